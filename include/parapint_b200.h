@@ -1,0 +1,137 @@
+/*
+ * parapint_b200.h -- C ABI of the B200-native Schur-complement KKT solver.
+ *
+ * The reference (sandialabs/parapint) has no FFI of its own: its hot path is Python calling
+ * SciPy/MA27/MUMPS.  These entry points are what a binding for that path binds instead; each cites
+ * the reference call site it replaces (paths relative to the reference root).  INTEGRATION.md shows
+ * the ctypes stub a parapint maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.  One handle per process / per GPU.
+ *  - every function returns a status code equal to parapint's LinearSolverStatus value
+ *    (parapint/linalg/results.py:4-9): 0 successful, 1 not_enough_memory, 2 singular, 3 error,
+ *    4 warning.  Nothing throws.  pp_last_error() gives a message for code 3.
+ *  - "local blocks" are the diagonal blocks K_i owned by this rank
+ *    (parapint/linalg/schur_complement/mpi_explicit_schur_complement.py:198-203); the coupling
+ *    matrix Q / S is replicated on every rank (:142-144, :352-360).
+ *  - value / vector buffers may live in host or device memory (`on_device` flag).  Host buffers
+ *    are staged through pinned memory owned by the handle; device buffers are used in place.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All work is enqueued on
+ *    it; functions that return a status or integers synchronise that stream before returning.
+ */
+#ifndef PARAPINT_B200_H
+#define PARAPINT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pp_handle pp_handle;
+
+enum {
+  PP_SUCCESSFUL = 0,
+  PP_NOT_ENOUGH_MEMORY = 1,
+  PP_SINGULAR = 2,
+  PP_ERROR = 3,
+  PP_WARNING = 4
+};
+
+/* Library / build identification (ABI version, compiled arch). */
+int pp_abi_version(void);
+const char *pp_build_info(void);
+const char *pp_last_error(void);
+
+/* Create / destroy a solver bound to CUDA device `device`. */
+int pp_create(int device, pp_handle **out);
+int pp_destroy(pp_handle *h);
+
+/* Tunables: name in {"pivot_tol", "panel_width", "use_graph", "refine_steps"}. */
+int pp_set_option(pp_handle *h, const char *name, double value);
+
+/*
+ * Symbolic phase.  Replaces SchurComplementLinearSolver.do_symbolic_factorization
+ * (linalg/schur_complement/explicit_schur_complement.py:44-78) and the structure discovery of
+ * MPISchurComplementLinearSolver._get_sc_structure (mpi_explicit_schur_complement.py:228-255).
+ *
+ *   n_local            number of diagonal blocks owned by this rank
+ *   block_n[i]         order n_i of local block i
+ *   border_ptr[i..i+1] range in border_rows of the nonzero rows of A_i (ascending coupling-row
+ *                      indices; `_BorderMatrix.nonzero_rows`, mpi_explicit_schur_complement.py:43-48)
+ *   m_c                coupling dimension (order of Q and S)
+ *   nvals              number of numeric input values per factorisation: the concatenation, in a
+ *                      caller-chosen fixed order, of the COO data of every local K_i, every local
+ *                      A_i and Q (duplicates and explicit zeros allowed,
+ *                      interfaces/interface.py:454-456,468-471)
+ *   dest_front[k]      destination of value k: local block index 0..n_local-1, n_local for the
+ *                      coupling matrix Q, or -1 to ignore the value (e.g. the strict upper triangle:
+ *                      like the MA27/MUMPS leaves only the lower triangle is read,
+ *                      linalg/mumps_interface.py:51,80, linalg/ma27_interface.py:114-116)
+ *   dest_row/dest_col  position inside that front (row >= col).  A front is the symmetric matrix
+ *                      [[K_i, .],[A_i(nonzero rows), 0]] of order n_i + m_i; border entry
+ *                      (nonzero row a, column j) therefore has row = n_i + a, col = j.
+ */
+int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
+                const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
+                const int32_t *dest_row, const int32_t *dest_col);
+
+/*
+ * Numeric phase, local part.  Replaces the per-block leaf factorisations and the Schur formation
+ * loop (explicit_schur_complement.py:99-121; mpi_explicit_schur_complement.py:292-333): assembles
+ * the fronts from `values`, runs the batched Bunch-Kaufman LDL^T of every local front and writes
+ * this rank's dense contribution  -sum_i A_i K_i^{-1} A_i^T  (m_c x m_c, column-major, lower
+ * triangle valid) to `schur_local_dev` (DEVICE pointer, caller owned, so that the caller can
+ * SUM-reduce it across ranks as mpi_explicit_schur_complement.py:343 does).
+ * Returns 0, 2 (a local block is singular) or 3.
+ */
+int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
+                     void *stream);
+
+/*
+ * Numeric phase, coupling part.  Replaces "S = Q - sum" and the coupling factorisation
+ * (explicit_schur_complement.py:108,122-128; mpi_explicit_schur_complement.py:347-358).
+ * `schur_sum_dev` is the (all-reduced) sum of the ranks' contributions (DEVICE pointer).
+ */
+int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream);
+
+/*
+ * Inertia (n_pos, n_neg, n_zero) from the pivots: local blocks and coupling matrix separately so
+ * the caller can SUM the local parts across ranks (explicit_schur_complement.py:157-172;
+ * mpi_explicit_schur_complement.py:404-436; consumer: algorithms/interior_point.py:371-382).
+ */
+int pp_inertia_local(pp_handle *h, int64_t out[3]);
+int pp_inertia_coupling(pp_handle *h, int64_t out[3]);
+
+/*
+ * Solve, phase 1 (explicit_schur_complement.py:141-145; mpi_explicit_schur_complement.py:381-385):
+ * forward substitution on every local front.  `rhs_local` is the concatenation of the local
+ * blocks' right-hand sides (sum n_i doubles).  Writes this rank's coupling contribution
+ * -sum_i A_i K_i^{-1} r_i  (m_c doubles) to `rc_local_dev` (DEVICE pointer, caller owned).
+ */
+int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, double *rc_local_dev,
+                     void *stream);
+
+/*
+ * Solve, phases 2+3 (explicit_schur_complement.py:147-153; mpi_explicit_schur_complement.py:386-398):
+ * x_c = S^{-1}(rhs_c + rc_sum), then back substitution on every local front.  `rc_sum_dev` is the
+ * all-reduced coupling contribution (DEVICE pointer).  `rhs_c`, `x_local` (sum n_i) and `x_c` (m_c)
+ * are host or device buffers according to `on_device`.
+ */
+int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_c, int on_device,
+                      double *x_local, double *x_c, void *stream);
+
+/* Sizes and introspection. */
+int64_t pp_factor_bytes(const pp_handle *h);  /* device bytes held by factors + workspaces */
+int64_t pp_local_dim(const pp_handle *h);     /* sum of n_i over local blocks */
+int64_t pp_kernel_launches(const pp_handle *h); /* kernels launched by this handle so far */
+
+/* Debug / test access: copy front `f` (0..n_local-1 local, n_local = coupling) to host,
+ * column-major with leading dimension *ld; piv/bsz receive the pivot records (n entries). */
+int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,
+                   int32_t *bsz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAPINT_B200_H */

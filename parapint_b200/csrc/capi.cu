@@ -1,0 +1,592 @@
+// C ABI of the B200-native Schur-complement KKT solver (see include/parapint_b200.h).
+//
+// Build (done by __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC \
+//        -I include -o parapint_b200/csrc/libparapint_b200.so parapint_b200/csrc/capi.cu
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/parapint_b200.h"
+#include "factor.cuh"
+#include "front.cuh"
+#include "solve.cuh"
+
+using namespace ppb;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaFail {
+  std::string msg;
+};
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaFail{std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +  \
+                     std::to_string(__LINE__) + ")"};                                              \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T> &h) {
+    alloc(h.size());
+    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+template <class T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count) {
+    if (count <= n) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = count;
+    CK(cudaMallocHost(&p, count * sizeof(T)));
+  }
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct pp_handle {
+  int device = 0;
+  int n_local = 0, m_c = 0;
+  bool have_symbolic = false, local_factored = false, coupling_factored = false, forward_done = false;
+  std::vector<int> n, m, nf, ld;  // n_local + 1 fronts (last = coupling)
+  int64_t local_dim = 0;
+  int nmax_local = 0, nfmax_local = 0;
+  // options
+  double pivot_tol = 0.0;
+  int panel_width = 64;
+  // device storage
+  DevBuf<double> arenaA, arenaW, arenaZ, vals, rhs, x, xc, crhs;
+  DevBuf<int> arenaI, flag;
+  DevBuf<Front> fronts;
+  std::vector<Front> hfronts;
+  DevBuf<unsigned long long> inertia;  // [0..2] local, [3..5] coupling
+  DevBuf<int64_t> asm_dst, asm_ptr, asm_src, src_ptr, brow_ptr, rhs_off;
+  DevBuf<int32_t> src_front, src_pos, brow;
+  PinBuf<double> pin_vals, pin_vec;
+  PinBuf<int> pin_flag;
+  PinBuf<unsigned long long> pin_inertia;
+  int64_t nvals = 0, nuniq = 0;
+  size_t arenaA_elems = 0;
+  int64_t launches = 0;
+  int64_t bytes = 0;
+};
+
+namespace {
+
+bool is_pinned_host(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Factor fronts [first, first+count): fixed schedule of (panel, interchange, update) launches.  A
+// panel eliminates NB-1 or NB columns, so after launch `it` front f has done at least
+// min(n_f, (it+1)(NB-1)) columns; that bounds the tile grid of the update from the host side.
+void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
+  if (count == 0) return;
+  const int NB = h->panel_width;
+  const Front *fr = h->fronts.p + first;
+  int nmax = 0;
+  for (int f = first; f < first + count; ++f) nmax = std::max(nmax, h->n[f]);
+  if (nmax == 0) return;
+  const int iters = (nmax + (NB - 2)) / (NB - 1);
+  for (int it = 0; it < iters; ++it) {
+    front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
+    h->launches++;
+    if (it > 0) {
+      dim3 g((nmax + 255) / 256, count);
+      front_swaps_left_kernel<<<g, 256, 0, st>>>(fr);
+      h->launches++;
+    }
+    int nt = 0;
+    for (int f = first; f < first + count; ++f) {
+      if (h->n[f] <= it * (NB - 1)) continue;  // finished in an earlier launch
+      const int done = std::min(h->n[f], (it + 1) * (NB - 1));
+      if (done >= h->nf[f]) continue;
+      nt = std::max(nt, (h->nf[f] + UT - 1) / UT - done / UT);
+    }
+    if (nt > 0) {
+      dim3 g(nt * (nt + 1) / 2, count);
+      front_update_kernel<<<g, UPD_THREADS, UPD_SMEM, st>>>(fr);
+      h->launches++;
+    }
+  }
+  CK(cudaGetLastError());
+}
+
+int read_flag(pp_handle *h, int first, int count, cudaStream_t st) {
+  if (count == 0) return 0;
+  collect_info_kernel<<<1, 256, 0, st>>>(h->fronts.p + first, count, h->flag.p);
+  h->launches++;
+  h->pin_flag.ensure(1);
+  CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return h->pin_flag.p[0];
+}
+
+size_t solve_smem(int nf) { return ((size_t)((nf + 1) & ~1) + SB * SPITCH) * sizeof(double); }
+
+template <class F>
+int guarded(F &&body) {
+  try {
+    return body();
+  } catch (const CudaFail &e) {
+    g_error = e.msg;
+    return PP_ERROR;
+  } catch (const std::bad_alloc &) {
+    g_error = "host allocation failed";
+    return PP_NOT_ENOUGH_MEMORY;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return PP_ERROR;
+  }
+}
+
+int fail(const std::string &msg) {
+  g_error = msg;
+  return PP_ERROR;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pp_abi_version(void) { return 1; }
+
+const char *pp_build_info(void) { return "parapint_b200 sm_100a fp64 dmma-m8n8k4 abi1"; }
+
+const char *pp_last_error(void) { return g_error.c_str(); }
+
+int pp_create(int device, pp_handle **out) {
+  if (!out) return fail("pp_create: null out pointer");
+  *out = nullptr;
+  return guarded([&]() {
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail("pp_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    auto *h = new pp_handle();
+    h->device = device;
+    h->flag.alloc(4);
+    h->inertia.alloc(8);
+    *out = h;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_destroy(pp_handle *h) {
+  if (!h) return PP_SUCCESSFUL;
+  cudaSetDevice(h->device);
+  delete h;
+  return PP_SUCCESSFUL;
+}
+
+int pp_set_option(pp_handle *h, const char *name, double value) {
+  if (!h || !name) return fail("pp_set_option: null argument");
+  const std::string key(name);
+  if (key == "pivot_tol") {
+    if (value < 0) return fail("pivot_tol must be >= 0");
+    h->pivot_tol = value;
+  } else if (key == "panel_width") {
+    const int nb = (int)value;
+    if (nb < 4 || nb > NBMAX) return fail("panel_width must be in [4, 64]");
+    h->panel_width = nb;
+  } else if (key == "use_graph" || key == "refine_steps") {
+    // accepted for forward compatibility; no effect in this build
+  } else {
+    return fail("pp_set_option: unknown option " + key);
+  }
+  return PP_SUCCESSFUL;
+}
+
+int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
+                const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
+                const int32_t *dest_row, const int32_t *dest_col) {
+  if (!h) return fail("pp_symbolic: null handle");
+  if (n_local < 0 || m_c < 0 || nvals < 0) return fail("pp_symbolic: negative size");
+  if (n_local > 0 && (!block_n || !border_ptr)) return fail("pp_symbolic: null block description");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    h->have_symbolic = h->local_factored = h->coupling_factored = h->forward_done = false;
+    const int nfronts = n_local + 1;
+    h->n_local = n_local;
+    h->m_c = m_c;
+    h->n.assign(nfronts, 0);
+    h->m.assign(nfronts, 0);
+    h->nf.assign(nfronts, 0);
+    h->ld.assign(nfronts, 0);
+    h->local_dim = 0;
+    h->nmax_local = h->nfmax_local = 0;
+    std::vector<int64_t> bptr(nfronts + 1, 0);
+    for (int f = 0; f < n_local; ++f) {
+      if (block_n[f] < 0) return fail("pp_symbolic: negative block order");
+      const int64_t mi = border_ptr[f + 1] - border_ptr[f];
+      if (mi < 0 || mi > m_c) return fail("pp_symbolic: bad border_ptr");
+      for (int64_t p = border_ptr[f]; p < border_ptr[f + 1]; ++p) {
+        if (border_rows[p] < 0 || border_rows[p] >= m_c) return fail("pp_symbolic: border row out of range");
+        if (p > border_ptr[f] && border_rows[p] <= border_rows[p - 1])
+          return fail("pp_symbolic: border rows must be strictly ascending");
+      }
+      h->n[f] = block_n[f];
+      h->m[f] = (int)mi;
+      h->local_dim += block_n[f];
+      bptr[f + 1] = bptr[f] + mi;
+    }
+    bptr[nfronts] = bptr[n_local];
+    h->n[n_local] = m_c;
+    h->m[n_local] = 0;
+    // storage layout
+    std::vector<size_t> offA(nfronts), offW(nfronts), offZ(nfronts), offI(nfronts);
+    size_t totA = 0, totW = 0, totZ = 0, totI = 0;
+    for (int f = 0; f < nfronts; ++f) {
+      h->nf[f] = h->n[f] + h->m[f];
+      h->ld[f] = std::max(16, round_up(h->nf[f], 16));
+      offA[f] = totA;
+      totA += (size_t)h->ld[f] * std::max(h->nf[f], 1);
+      offW[f] = totW;
+      totW += (size_t)h->ld[f] * NBMAX;
+      offZ[f] = totZ;
+      totZ += (size_t)round_up(h->n[f] + h->m[f] + 2, 16);
+      offI[f] = totI;
+      totI += (size_t)3 * round_up(h->n[f] + 1, 16) + 16;
+      if (f < n_local) {
+        h->nmax_local = std::max(h->nmax_local, h->n[f]);
+        h->nfmax_local = std::max(h->nfmax_local, h->nf[f]);
+      }
+      if (solve_smem(h->nf[f]) > 200 * 1024) return fail("pp_symbolic: front too large for the in-smem solve (nf > ~25000)");
+    }
+    h->arenaA_elems = totA;
+    h->arenaA.alloc(totA);
+    h->arenaW.alloc(totW);
+    h->arenaZ.alloc(totZ);
+    h->arenaI.alloc(totI);
+    CK(cudaMemset(h->arenaW.p, 0, totW * sizeof(double)));
+    CK(cudaMemset(h->arenaZ.p, 0, totZ * sizeof(double)));
+    CK(cudaMemset(h->arenaI.p, 0, totI * sizeof(int)));
+    std::vector<Front> hf(nfronts);
+    for (int f = 0; f < nfronts; ++f) {
+      Front &F = hf[f];
+      F.A = h->arenaA.p + offA[f];
+      F.W = h->arenaW.p + offW[f];
+      F.zbuf = h->arenaZ.p + offZ[f];
+      F.bvec = F.zbuf + h->n[f];
+      const int seg = round_up(h->n[f] + 1, 16);
+      F.ipiv = h->arenaI.p + offI[f];
+      F.bsz = F.ipiv + seg;
+      F.perm = F.bsz + seg;
+      F.state = F.perm + seg;
+      F.n = h->n[f];
+      F.m = h->m[f];
+      F.nf = h->nf[f];
+      F.ld = h->ld[f];
+    }
+    h->fronts.upload(hf);
+    h->hfronts = hf;
+
+    // ---- assembly map: group the input values by destination element ----
+    h->nvals = nvals;
+    std::vector<std::pair<int64_t, int64_t>> keyed;  // (arena offset, source index)
+    keyed.reserve((size_t)nvals);
+    for (int64_t k = 0; k < nvals; ++k) {
+      const int f = dest_front[k];
+      if (f < 0) continue;
+      if (f > n_local) return fail("pp_symbolic: dest_front out of range");
+      const int r = dest_row[k], c = dest_col[k];
+      if (r < 0 || c < 0 || r >= h->nf[f] || c > r) return fail("pp_symbolic: destination outside the lower triangle of its front");
+      keyed.emplace_back((int64_t)(offA[f] + (size_t)r + (size_t)c * h->ld[f]), k);
+    }
+    std::stable_sort(keyed.begin(), keyed.end(),
+                     [](const auto &a, const auto &b) { return a.first < b.first; });
+    std::vector<int64_t> dst, ptr, src(keyed.size());
+    for (size_t i = 0; i < keyed.size(); ++i) {
+      if (i == 0 || keyed[i].first != keyed[i - 1].first) {
+        dst.push_back(keyed[i].first);
+        ptr.push_back((int64_t)i);
+      }
+      src[i] = keyed[i].second;
+    }
+    ptr.push_back((int64_t)keyed.size());
+    h->nuniq = (int64_t)dst.size();
+    h->asm_dst.upload(dst);
+    h->asm_ptr.upload(ptr);
+    h->asm_src.upload(src);
+    h->vals.alloc((size_t)std::max<int64_t>(nvals, 1));
+
+    // ---- coupling-row sources: row r <- (front, position) in front order ----
+    std::vector<int32_t> brow((size_t)bptr[n_local]);
+    std::vector<int64_t> sptr((size_t)m_c + 1, 0);
+    for (int f = 0; f < n_local; ++f)
+      for (int64_t p = border_ptr[f]; p < border_ptr[f + 1]; ++p) {
+        brow[(size_t)(bptr[f] + (p - border_ptr[f]))] = border_rows[p];
+        sptr[(size_t)border_rows[p] + 1]++;
+      }
+    for (int r = 0; r < m_c; ++r) sptr[r + 1] += sptr[r];
+    std::vector<int32_t> sfront((size_t)bptr[n_local]), spos((size_t)bptr[n_local]);
+    std::vector<int64_t> fill(sptr.begin(), sptr.end() - 1);
+    for (int f = 0; f < n_local; ++f)
+      for (int a = 0; a < h->m[f]; ++a) {
+        const int r = brow[(size_t)bptr[f] + a];
+        sfront[(size_t)fill[r]] = f;
+        spos[(size_t)fill[r]] = a;
+        fill[r]++;
+      }
+    h->brow.upload(brow);
+    h->brow_ptr.upload(bptr);
+    h->src_ptr.upload(sptr);
+    h->src_front.upload(sfront);
+    h->src_pos.upload(spos);
+
+    // ---- solve buffers ----
+    std::vector<int64_t> roff(nfronts, 0);
+    for (int f = 1; f < n_local; ++f) roff[f] = roff[f - 1] + h->n[f - 1];
+    roff[n_local] = 0;
+    h->rhs_off.upload(roff);
+    h->rhs.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
+    h->x.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
+    h->xc.alloc((size_t)std::max(m_c, 1));
+    h->crhs.alloc((size_t)std::max(m_c, 1));
+    h->bytes = (int64_t)((totA + totW + totZ) * sizeof(double) + totI * sizeof(int));
+    h->have_symbolic = true;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
+                     void *stream) {
+  if (!h || !h->have_symbolic) return fail("pp_numeric_local: symbolic factorization required first");
+  if (h->nvals > 0 && !values) return fail("pp_numeric_local: null values");
+  if (h->m_c > 0 && !schur_local_dev) return fail("pp_numeric_local: null schur buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    h->local_factored = h->coupling_factored = h->forward_done = false;
+    const double *dvals = values;
+    if (!on_device && h->nvals > 0) {
+      const double *src = values;
+      if (!is_pinned_host(values)) {  // pageable caller memory: stage through the handle's pinned buffer
+        h->pin_vals.ensure((size_t)h->nvals);
+        std::memcpy(h->pin_vals.p, values, (size_t)h->nvals * sizeof(double));
+        src = h->pin_vals.p;
+      }
+      CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
+      dvals = h->vals.p;
+    }
+    CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
+    reset_fronts_kernel<<<h->n_local + 1, 256, 0, st>>>(h->fronts.p, h->inertia.p);
+    h->launches++;
+    if (h->nuniq > 0) {
+      assemble_kernel<<<(unsigned)((h->nuniq + 255) / 256), 256, 0, st>>>(dvals, h->asm_dst.p, h->asm_ptr.p,
+                                                                        h->asm_src.p, h->nuniq, h->arenaA.p);
+      h->launches++;
+    }
+    factor_fronts(h, 0, h->n_local, st);
+    if (h->m_c > 0) {
+      dim3 g((h->m_c + 127) / 128, h->m_c);
+      schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
+                                             h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
+      h->launches++;
+    }
+    if (h->n_local > 0) {
+      front_inertia_kernel<<<h->n_local, 256, 0, st>>>(h->fronts.p, h->inertia.p);
+      h->launches++;
+    }
+    CK(cudaGetLastError());
+    const int bad = read_flag(h, 0, h->n_local, st);
+    h->local_factored = true;
+    return bad ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream) {
+  if (!h || !h->local_factored) return fail("pp_numeric_coupling: pp_numeric_local required first");
+  if (h->m_c > 0 && !schur_sum_dev) return fail("pp_numeric_coupling: null schur buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    h->coupling_factored = h->forward_done = false;
+    const int mc = h->m_c;
+    if (mc > 0) {
+      const Front C = h->hfronts[h->n_local];
+      dim3 g((mc + 127) / 128, mc);
+      coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
+      h->launches++;
+      factor_fronts(h, h->n_local, 1, st);
+      front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
+      h->launches++;
+      CK(cudaGetLastError());
+    }
+    const int bad = mc > 0 ? read_flag(h, h->n_local, 1, st) : 0;
+    h->coupling_factored = true;
+    return bad ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+  });
+}
+
+static int read_inertia(pp_handle *h, int which, int64_t out[3]) {
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    h->pin_inertia.ensure(8);
+    CK(cudaMemcpy(h->pin_inertia.p, h->inertia.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->pin_inertia.p[which * 3 + k];
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_inertia_local(pp_handle *h, int64_t out[3]) {
+  if (!h || !out) return fail("pp_inertia_local: null argument");
+  if (!h->local_factored) return fail("pp_inertia_local: numeric factorization required first");
+  return read_inertia(h, 0, out);
+}
+
+int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
+  if (!h || !out) return fail("pp_inertia_coupling: null argument");
+  if (!h->coupling_factored) return fail("pp_inertia_coupling: numeric factorization required first");
+  return read_inertia(h, 1, out);
+}
+
+int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, double *rc_local_dev,
+                     void *stream) {
+  if (!h || !h->local_factored) return fail("pp_solve_forward: numeric factorization required first");
+  if (h->local_dim > 0 && !rhs_local) return fail("pp_solve_forward: null rhs");
+  if (h->m_c > 0 && !rc_local_dev) return fail("pp_solve_forward: null coupling buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *drhs = rhs_local;
+    if (!on_device && h->local_dim > 0) {
+      h->pin_vec.ensure((size_t)h->local_dim + (size_t)h->m_c);
+      std::memcpy(h->pin_vec.p, rhs_local, (size_t)h->local_dim * sizeof(double));
+      CK(cudaMemcpyAsync(h->rhs.p, h->pin_vec.p, (size_t)h->local_dim * sizeof(double), cudaMemcpyHostToDevice, st));
+      drhs = h->rhs.p;
+    }
+    if (h->n_local > 0) {
+      const size_t sm = solve_smem(h->nfmax_local);
+      CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      front_forward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, drhs, h->rhs_off.p);
+      h->launches++;
+    }
+    if (h->m_c > 0) {
+      rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p,
+                                                            h->src_pos.p, h->m_c, rc_local_dev);
+      h->launches++;
+    }
+    CK(cudaGetLastError());
+    h->forward_done = true;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_c, int on_device,
+                      double *x_local, double *x_c, void *stream) {
+  if (!h || !h->coupling_factored || !h->forward_done)
+    return fail("pp_solve_backward: numeric factorization and pp_solve_forward required first");
+  if (h->m_c > 0 && (!rc_sum_dev || !rhs_c || !x_c)) return fail("pp_solve_backward: null coupling argument");
+  if (h->local_dim > 0 && !x_local) return fail("pp_solve_backward: null solution buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mc = h->m_c;
+    double *dx = on_device ? x_local : h->x.p;
+    double *dxc = on_device ? x_c : h->xc.p;
+    if (mc > 0) {
+      const double *drc = rhs_c;
+      if (!on_device) {
+        h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
+        std::memcpy(h->pin_vec.p + h->local_dim, rhs_c, (size_t)mc * sizeof(double));
+        CK(cudaMemcpyAsync(h->xc.p, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double), cudaMemcpyHostToDevice, st));
+        drc = h->xc.p;
+      }
+      vec_add_kernel<<<(mc + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, mc, h->crhs.p);
+      const size_t sm = solve_smem(mc);
+      CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)std::max(sm, solve_smem(h->nfmax_local))));
+      CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)std::max(sm, solve_smem(h->nfmax_local))));
+      const Front *cf = h->fronts.p + h->n_local;
+      front_forward_kernel<512><<<1, 512, sm, st>>>(cf, h->crhs.p, h->rhs_off.p + h->n_local);
+      front_backward_kernel<512><<<1, 512, sm, st>>>(cf, nullptr, h->brow_ptr.p + h->n_local, h->brow.p, dxc,
+                                                    h->rhs_off.p + h->n_local);
+      h->launches += 3;
+    }
+    if (h->n_local > 0) {
+      const size_t sm = solve_smem(h->nfmax_local);
+      CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)std::max(sm, solve_smem(mc))));
+      front_backward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, dx,
+                                                             h->rhs_off.p);
+      h->launches++;
+    }
+    CK(cudaGetLastError());
+    if (!on_device) {
+      h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
+      if (h->local_dim > 0)
+        CK(cudaMemcpyAsync(h->pin_vec.p, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (mc > 0)
+        CK(cudaMemcpyAsync(h->pin_vec.p + h->local_dim, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h->local_dim > 0) std::memcpy(x_local, h->pin_vec.p, (size_t)h->local_dim * sizeof(double));
+      if (mc > 0) std::memcpy(x_c, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double));
+    }
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int64_t pp_factor_bytes(const pp_handle *h) { return h ? h->bytes : 0; }
+int64_t pp_local_dim(const pp_handle *h) { return h ? h->local_dim : 0; }
+int64_t pp_kernel_launches(const pp_handle *h) { return h ? h->launches : 0; }
+
+int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,
+                   int32_t *bsz) {
+  if (!h || !h->have_symbolic || f < 0 || f > h->n_local) return fail("pp_debug_front: bad front index");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    Front F;
+    CK(cudaMemcpy(&F, h->fronts.p + f, sizeof(Front), cudaMemcpyDeviceToHost));
+    const int64_t need = (int64_t)F.ld * F.nf;
+    if (ld) *ld = F.ld;
+    if (out) {
+      if (out_len < need) return fail("pp_debug_front: output buffer too small");
+      CK(cudaMemcpy(out, F.A, (size_t)need * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (piv) CK(cudaMemcpy(piv, F.ipiv, (size_t)F.n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (bsz) CK(cudaMemcpy(bsz, F.bsz, (size_t)F.n * sizeof(int), cudaMemcpyDeviceToHost));
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+}  // extern "C"

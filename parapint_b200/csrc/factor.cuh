@@ -1,0 +1,352 @@
+// Batched symmetric-indefinite LDL^T of fronts: Bunch-Kaufman panel + FP64 tensor-core update.
+//
+// One launch of front_panel_kernel eliminates up to NB columns of every front (one CTA per front),
+// choosing 1x1 / 2x2 pivots by the Bunch-Kaufman partial-pivoting rule among the first n rows.
+// Columns needed by the pivot search are brought up to date lazily against the panel computed so
+// far (W = L*D), so the O(n^2 NB) trailing work is left to front_update_kernel, a DMMA GEMM.
+// Row interchanges are applied to the whole row of L (front_swaps_left_kernel), i.e. the factors
+// satisfy P K P^T = L D L^T with one permutation, which keeps the triangular solves plain.
+#pragma once
+#include "front.cuh"
+
+namespace ppb {
+
+template <int NT>
+__device__ __forceinline__ void block_argmax(double &val, int &idx, double *sval, int *sidx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    double v2 = __shfl_down_sync(0xffffffffu, val, o);
+    int i2 = __shfl_down_sync(0xffffffffu, idx, o);
+    if (i2 >= 0 && (idx < 0 || v2 > val || (v2 == val && i2 < idx))) { val = v2; idx = i2; }
+  }
+  if (lane == 0) { sval[warp] = val; sidx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    val = lane < NT / 32 ? sval[lane] : -1.0;
+    idx = lane < NT / 32 ? sidx[lane] : -1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      double v2 = __shfl_down_sync(0xffffffffu, val, o);
+      int i2 = __shfl_down_sync(0xffffffffu, idx, o);
+      if (i2 >= 0 && (idx < 0 || v2 > val || (v2 == val && i2 < idx))) { val = v2; idx = i2; }
+    }
+    if (lane == 0) { sval[0] = val; sidx[0] = idx; }
+  }
+  __syncthreads();
+  val = sval[0];
+  idx = sidx[0];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel factorisation (one CTA per front).
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) front_panel_kernel(const Front *__restrict__ fronts, int NB,
+                                                         double pivtol) {
+  const Front F = fronts[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int n = F.n, nf = F.nf, ld = F.ld;
+  double *__restrict__ A = F.A;
+  double *__restrict__ W = F.W;
+  const int k0 = F.state[ST_KCUR];
+  if (k0 >= n) {
+    if (tid == 0) F.state[ST_KPREV] = k0;
+    return;
+  }
+  __shared__ double wrow[NBMAX];
+  __shared__ double sval[32];
+  __shared__ int sidx[32];
+  __shared__ double sh_d[4];
+
+  const bool last_panel = (n - k0 <= NB);
+  int k = k0;
+  while (k < n && (last_panel || (k - k0) < NB - 1)) {
+    const int kw = k - k0;
+    double *__restrict__ Wk = W + (size_t)kw * ld;
+    // ---- bring column k up to date:  W(:,kw) = A(:,k) - L(:,panel) * W(k,panel)^T ----
+    for (int j = tid; j < kw; j += NT) wrow[j] = W[k + (size_t)j * ld];
+    __syncthreads();
+    double best = -1.0;
+    int besti = -1;
+    for (int i = k + tid; i < nf; i += NT) {
+      double acc = A[i + (size_t)k * ld];
+      const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 4
+      for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+      Wk[i] = acc;
+      if (i > k && i < n) {
+        const double a = fabs(acc);
+        if (a > best) { best = a; besti = i; }
+      }
+      if (i == k) sh_d[0] = acc;
+    }
+    block_argmax<NT>(best, besti, sval, sidx);
+    const double colmax = besti >= 0 ? best : 0.0;
+    const int imax = besti;
+    const double akk = sh_d[0];
+    const double absakk = fabs(akk);
+
+    int kstep = 1, kp = k;
+    bool zero_pivot = false;
+    if (!(fmax(absakk, colmax) > pivtol)) {
+      zero_pivot = true;  // null (or NaN) column: record, keep going (LAPACK dsytf2 convention)
+    } else if (absakk >= BK_ALPHA * colmax) {
+      kp = k;
+    } else {
+      // ---- bring column imax up to date into W(:,kw+1) ----
+      double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      for (int j = tid; j < kw; j += NT) wrow[j] = W[imax + (size_t)j * ld];
+      __syncthreads();
+      double rbest = -1.0;
+      int rbesti = -1;
+      for (int i = k + tid; i < nf; i += NT) {
+        double acc = (i < imax) ? A[imax + (size_t)i * ld] : A[i + (size_t)imax * ld];
+        const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 4
+        for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+        Wk1[i] = acc;
+        if (i < n && i != imax) {
+          const double a = fabs(acc);
+          if (a > rbest) { rbest = a; rbesti = i; }
+        }
+        if (i == imax) sh_d[1] = acc;
+      }
+      block_argmax<NT>(rbest, rbesti, sval, sidx);
+      const double rowmax = rbesti >= 0 ? rbest : 0.0;
+      const double wimax = sh_d[1];
+      if (absakk >= BK_ALPHA * colmax * (colmax / rowmax)) {
+        kp = k;
+      } else if (fabs(wimax) >= BK_ALPHA * rowmax) {
+        kp = imax;  // 1x1 pivot taken from the diagonal at imax
+        for (int i = k + tid; i < nf; i += NT) Wk[i] = Wk1[i];
+      } else {
+        kp = imax;
+        kstep = 2;
+      }
+    }
+    __syncthreads();
+
+    const int kk = k + kstep - 1;
+    if (kp != kk) {
+      // Symmetric interchange of rows/columns kk and kp in the not-yet-updated trailing matrix
+      // (column kk itself is about to be overwritten by L), in the panel's L rows and in W.
+      if (tid == 0) {
+        A[kp + (size_t)kp * ld] = A[kk + (size_t)kk * ld];
+        const int t = F.perm[kk];
+        F.perm[kk] = F.perm[kp];
+        F.perm[kp] = t;
+      }
+      for (int j = kk + 1 + tid; j < kp; j += NT) A[kp + (size_t)j * ld] = A[j + (size_t)kk * ld];
+      for (int i = kp + 1 + tid; i < nf; i += NT) A[i + (size_t)kp * ld] = A[i + (size_t)kk * ld];
+      for (int j = tid; j < kw; j += NT) {
+        double *c = A + (size_t)(k0 + j) * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      for (int j = tid; j < kw + kstep; j += NT) {
+        double *c = W + (size_t)j * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      __syncthreads();
+    }
+
+    if (kstep == 1) {
+      const double d = Wk[k];
+      const bool bad = zero_pivot || !(fabs(d) > pivtol) || !isfinite(d);
+      const double rd = bad ? 0.0 : 1.0 / d;
+      for (int i = k + 1 + tid; i < nf; i += NT) A[i + (size_t)k * ld] = Wk[i] * rd;
+      if (tid == 0) {
+        A[k + (size_t)k * ld] = bad ? 0.0 : d;
+        F.ipiv[k] = kp;
+        F.bsz[k] = 1;
+        if (bad && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    } else {
+      const double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      const double e11 = Wk[k], e21 = Wk[k + 1], e22 = Wk1[k + 1];
+      // scaled inverse of the 2x2 pivot (as LAPACK dlasyf): robust when |e21| dominates
+      const double d11 = e22 / e21, d22 = e11 / e21;
+      const double t = 1.0 / (d11 * d22 - 1.0);
+      const double s = t / e21;
+      for (int i = k + 2 + tid; i < nf; i += NT) {
+        const double w0 = Wk[i], w1 = Wk1[i];
+        A[i + (size_t)k * ld] = s * (d11 * w0 - w1);
+        A[i + (size_t)(k + 1) * ld] = s * (d22 * w1 - w0);
+      }
+      if (tid == 0) {
+        A[k + (size_t)k * ld] = e11;
+        A[k + 1 + (size_t)k * ld] = e21;
+        A[k + 1 + (size_t)(k + 1) * ld] = e22;
+        F.ipiv[k] = kp;
+        F.ipiv[k + 1] = kp;
+        F.bsz[k] = 2;
+        F.bsz[k + 1] = 0;
+        if (!isfinite(s) && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    }
+    __syncthreads();
+    k += kstep;
+  }
+  if (tid == 0) {
+    F.state[ST_KPREV] = k0;
+    F.state[ST_KCUR] = k;
+  }
+}
+
+// Apply the interchanges of the last panel to the columns of L left of it (one thread per column).
+__global__ void front_swaps_left_kernel(const Front *__restrict__ fronts) {
+  const Front F = fronts[blockIdx.y];
+  const int k0 = F.state[ST_KPREV], k1 = F.state[ST_KCUR];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k0 || k0 == k1) return;
+  double *col = F.A + (size_t)c * F.ld;
+  for (int k = k0; k < k1; ++k) {
+    const int b = F.bsz[k];
+    if (b == 0) continue;
+    const int kk = k + b - 1, kp = F.ipiv[k];
+    if (kp != kk) {
+      const double t = col[kk];
+      col[kk] = col[kp];
+      col[kp] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trailing update  A(i,j) -= sum_k L(i,k) * W(j,k)   (i >= j >= kcur), FP64 DMMA m8n8k4.
+// 128 x 128 output tile per CTA, 16 warps of 32 x 32, whole panel (K <= NBMAX) staged in smem.
+// ---------------------------------------------------------------------------------------------
+constexpr int UT = 128;          // tile edge
+constexpr int UROW = UT + 4;     // smem row pitch (doubles): pitch % 16 == 4 -> conflict-free frags
+constexpr int UPD_THREADS = 512;
+constexpr size_t UPD_SMEM = (size_t)2 * NBMAX * UROW * sizeof(double);
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
+__global__ void __launch_bounds__(UPD_THREADS, 1) front_update_kernel(const Front *__restrict__ fronts) {
+  const Front F = fronts[blockIdx.y];
+  const int kprev = F.state[ST_KPREV], kcur = F.state[ST_KCUR];
+  const int kw = kcur - kprev;
+  const int nf = F.nf, ld = F.ld;
+  if (kw == 0 || kcur >= nf) return;
+  const int t0 = kcur / UT;
+  const int nt = (nf + UT - 1) / UT - t0;
+  if ((int)blockIdx.x >= nt * (nt + 1) / 2) return;
+  // linear index -> (ti >= tj) in the lower-triangular tile grid
+  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
+  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  const int row0 = (t0 + ti) * UT, col0 = (t0 + tj) * UT;
+
+  extern __shared__ __align__(16) double smem[];
+  double *sA = smem;                 // [kpad][UROW]  L(row0 + r, kprev + k)
+  double *sB = smem + NBMAX * UROW;  // [kpad][UROW]  W(col0 + c, k)
+  const int kpad = (kw + 3) & ~3;
+  const double *gA = F.A + (size_t)kprev * ld + row0;
+  const double *gB = F.W + col0;
+  for (int idx = threadIdx.x; idx < kpad * (UT / 2); idx += UPD_THREADS) {
+    const int k = idx / (UT / 2), r = (idx % (UT / 2)) * 2;
+    const bool pa_ok = k < kw && row0 + r < nf, pb_ok = k < kw && col0 + r < nf;
+    cp_async16(sA + k * UROW + r, pa_ok ? gA + (size_t)k * ld + r : F.A, pa_ok);
+    cp_async16(sB + k * UROW + r, pb_ok ? gB + (size_t)k * ld + r : F.A, pb_ok);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp & 3, wn = warp >> 2;
+  const bool active = !(ti == tj && wn > wm);  // warp tile strictly above the diagonal
+  const int g = lane >> 2, q = lane & 3;
+  const int rbase = row0 + wm * 32 + g;
+  const int cbase = col0 + wn * 32 + q * 2;
+  double acc[4][4][2];
+  if (active) {
+#pragma unroll
+    for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = rbase + fm * 8, c = cbase + fn * 8 + e;
+          const bool ok = r < nf && c >= kcur && r >= c;
+          acc[fm][fn][e] = ok ? F.A[r + (size_t)c * ld] : 0.0;
+        }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  if (!active) return;
+
+  const double *pa = sA + q * UROW + wm * 32 + g;
+  const double *pb = sB + q * UROW + wn * 32 + g;
+  for (int k = 0; k < kpad; k += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      a[f] = -pa[k * UROW + f * 8];
+      b[f] = pb[k * UROW + f * 8];
+    }
+#pragma unroll
+    for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+      for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a[fm], b[fn]);
+  }
+#pragma unroll
+  for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+    for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = rbase + fm * 8, c = cbase + fn * 8 + e;
+        if (r < nf && c >= kcur && r >= c) F.A[r + (size_t)c * ld] = acc[fm][fn][e];
+      }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inertia from the pivots: 1x1 by sign, 2x2 by determinant / trace.  out = {pos, neg, zero}.
+// ---------------------------------------------------------------------------------------------
+__global__ void front_inertia_kernel(const Front *__restrict__ fronts, unsigned long long *out) {
+  const Front F = fronts[blockIdx.x];
+  int pos = 0, neg = 0, zero = 0;
+  for (int k = threadIdx.x; k < F.n; k += blockDim.x) {
+    const int b = F.bsz[k];
+    if (b == 1) {
+      const double d = F.A[k + (size_t)k * F.ld];
+      pos += d > 0.0;
+      neg += d < 0.0;
+      zero += !(d > 0.0) && !(d < 0.0);
+    } else if (b == 2) {
+      const double a = F.A[k + (size_t)k * F.ld], o = F.A[k + 1 + (size_t)k * F.ld],
+                   c = F.A[k + 1 + (size_t)(k + 1) * F.ld];
+      // det = a*c - o^2, evaluated scaled by o^2 as in the factorisation
+      const double det = (a / o) * (c / o) - 1.0;
+      if (det < 0.0) { pos += 1; neg += 1; }
+      else if (det > 0.0) { if (a + c > 0.0) pos += 2; else neg += 2; }
+      else { zero += 1; if (a + c > 0.0) pos += 1; else if (a + c < 0.0) neg += 1; else zero += 1; }
+    }
+  }
+  __shared__ int s[3];
+  if (threadIdx.x < 3) s[threadIdx.x] = 0;
+  __syncthreads();
+  atomicAdd(&s[0], pos);
+  atomicAdd(&s[1], neg);
+  atomicAdd(&s[2], zero);
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(&out[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+
+}  // namespace ppb

@@ -1,0 +1,215 @@
+// Assembly, Schur gather and the triangular solves on fronts.
+//
+// The solve uses the border rows of L so that one forward and one backward sweep per front do the
+// work of the reference's two leaf solves per block (explicit_schur_complement.py:141-153):
+//   forward :  v = [P r ; 0],  v <- L^-1 v      =>  v[0:n] = z,  v[n:] = -L_A z = -(A K^-1 r)[rows]
+//   diagonal:  w = D^-1 z
+//   backward:  v = [w ; x_c[rows]],  v[0:n] <- L^-T-sweep  =>  x = P^T v[0:n] = K^-1 (r - A^T x_c)
+#pragma once
+#include "front.cuh"
+
+namespace ppb {
+
+// ---- assembly -------------------------------------------------------------------------------
+// Deterministic scatter-add of the input values into the (zeroed) front arena: destination u gets
+// the sum of its sources in input order (duplicates are legal in the KKT, interface.py:454-456).
+__global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *__restrict__ dst,
+                                const int64_t *__restrict__ ptr, const int64_t *__restrict__ src,
+                                int64_t nuniq, double *__restrict__ arena) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nuniq) return;
+  double s = 0.0;
+  for (int64_t p = ptr[u]; p < ptr[u + 1]; ++p) s += vals[src[p]];
+  arena[dst[u]] = s;
+}
+
+__global__ void reset_fronts_kernel(const Front *__restrict__ fronts, unsigned long long *inertia) {
+  const Front F = fronts[blockIdx.x];
+  for (int i = threadIdx.x; i < F.n; i += blockDim.x) {
+    F.perm[i] = i;
+    F.ipiv[i] = i;
+    F.bsz[i] = 1;
+  }
+  if (threadIdx.x < 4) F.state[threadIdx.x] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 3 && inertia) inertia[threadIdx.x] = 0ull;
+}
+
+// Worst info over a range of fronts -> flag[0] (0 = all fine).
+__global__ void collect_info_kernel(const Front *__restrict__ fronts, int count, int *flag) {
+  int bad = 0;
+  for (int f = threadIdx.x; f < count; f += blockDim.x)
+    if (fronts[f].state[ST_INFO] != 0) bad = 1;
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flag[0] = bad;
+}
+
+// ---- Schur gather ---------------------------------------------------------------------------
+// S_local(r,c) = sum over local fronts holding both coupling rows r and c of the front's trailing
+// block entry; sources are visited in front order, so the sum is reproducible.  Replaces the
+// scatter through sc_data_slices of mpi_explicit_schur_complement.py:249-254,329.
+__global__ void schur_gather_kernel(const Front *__restrict__ fronts, const int64_t *__restrict__ src_ptr,
+                                    const int32_t *__restrict__ src_front, const int32_t *__restrict__ src_pos,
+                                    const int64_t *__restrict__ brow_ptr, const int32_t *__restrict__ brow,
+                                    int m_c, double *__restrict__ S) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= m_c || r < c) return;
+  double s = 0.0;
+  for (int64_t p = src_ptr[r]; p < src_ptr[r + 1]; ++p) {
+    const int f = src_front[p], a = src_pos[p];
+    const int32_t *br = brow + brow_ptr[f];
+    int lo = 0, hi = a;  // c <= r  =>  position of c, if present, is <= a
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (br[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (br[lo] == c) {
+      const Front F = fronts[f];
+      s += F.A[(size_t)(F.n + a) + (size_t)(F.n + lo) * F.ld];
+    }
+  }
+  S[(size_t)r + (size_t)c * m_c] = s;
+  S[(size_t)c + (size_t)r * m_c] = s;
+}
+
+// coupling front (lower) += reduced Schur sum; Q was assembled into it already.
+__global__ void coupling_add_kernel(Front F, const double *__restrict__ Ssum, int m_c) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= m_c || r < c) return;
+  F.A[(size_t)r + (size_t)c * F.ld] += Ssum[(size_t)r + (size_t)c * m_c];
+}
+
+__global__ void rc_gather_kernel(const Front *__restrict__ fronts, const int64_t *__restrict__ src_ptr,
+                                 const int32_t *__restrict__ src_front, const int32_t *__restrict__ src_pos,
+                                 int m_c, double *__restrict__ rc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m_c) return;
+  double s = 0.0;
+  for (int64_t p = src_ptr[r]; p < src_ptr[r + 1]; ++p) s += fronts[src_front[p]].bvec[src_pos[p]];
+  rc[r] = s;
+}
+
+__global__ void vec_add_kernel(const double *__restrict__ a, const double *__restrict__ b, int n,
+                               double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+// ---- triangular solves ----------------------------------------------------------------------
+constexpr int SB = 32;         // columns per sweep block
+constexpr int SPITCH = SB + 1;
+
+__device__ __forceinline__ void load_tri(const Front &F, int kb, int bw, double *tri) {
+  for (int idx = threadIdx.x; idx < bw * bw; idx += blockDim.x) {
+    const int c = idx / bw, r = idx % bw;
+    double v = 0.0;
+    if (r > c && !(r == c + 1 && F.bsz[kb + c] == 2)) v = F.A[(size_t)(kb + r) + (size_t)(kb + c) * F.ld];
+    tri[c * SPITCH + r] = v;
+  }
+}
+
+// v lives in dynamic shared memory (nf doubles) followed by the SB x SPITCH diagonal block.
+template <int NT>
+__global__ void __launch_bounds__(NT) front_forward_kernel(const Front *__restrict__ fronts,
+                                                           const double *__restrict__ rhs,
+                                                           const int64_t *__restrict__ rhs_off) {
+  extern __shared__ double sm[];
+  const Front F = fronts[blockIdx.x];
+  const int n = F.n, nf = F.nf, ld = F.ld, tid = threadIdx.x;
+  double *v = sm;
+  double *tri = sm + ((nf + 1) & ~1);
+  const double *r = rhs + rhs_off[blockIdx.x];
+  for (int i = tid; i < nf; i += NT) v[i] = i < n ? r[F.perm[i]] : 0.0;
+  __syncthreads();
+  for (int kb = 0; kb < n; kb += SB) {
+    const int bw = min(SB, n - kb);
+    load_tri(F, kb, bw, tri);
+    __syncthreads();
+    if (tid < 32) {
+      double x = tid < bw ? v[kb + tid] : 0.0;
+      for (int c = 0; c < bw; ++c) {
+        const double xc = __shfl_sync(0xffffffffu, x, c);
+        if (tid > c && tid < bw) x -= tri[c * SPITCH + tid] * xc;
+      }
+      if (tid < bw) v[kb + tid] = x;
+    }
+    __syncthreads();
+    const bool straddle = F.bsz[kb + bw - 1] == 2;  // 2x2 pivot across the block edge
+    for (int i = kb + bw + tid; i < nf; i += NT) {
+      const double *__restrict__ Li = F.A + i + (size_t)kb * ld;
+      double acc = v[i];
+      const int cend = (straddle && i == kb + bw) ? bw - 1 : bw;
+#pragma unroll 4
+      for (int c = 0; c < cend; ++c) acc -= Li[(size_t)c * ld] * v[kb + c];
+      v[i] = acc;
+    }
+    __syncthreads();
+  }
+  // w = D^-1 z
+  for (int k = tid; k < n; k += NT) {
+    const int b = F.bsz[k];
+    if (b == 1) {
+      const double d = F.A[k + (size_t)k * ld];
+      F.zbuf[k] = d != 0.0 ? v[k] / d : 0.0;
+    } else if (b == 2) {
+      const double e21 = F.A[k + 1 + (size_t)k * ld];
+      const double akm1 = F.A[k + (size_t)k * ld] / e21, ak = F.A[k + 1 + (size_t)(k + 1) * ld] / e21;
+      const double denom = akm1 * ak - 1.0;
+      const double bkm1 = v[k] / e21, bk = v[k + 1] / e21;
+      F.zbuf[k] = (ak * bkm1 - bk) / denom;
+      F.zbuf[k + 1] = (akm1 * bk - bkm1) / denom;
+    }
+  }
+  for (int a = tid; a < F.m; a += NT) F.bvec[a] = v[n + a];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) front_backward_kernel(const Front *__restrict__ fronts,
+                                                            const double *__restrict__ xc,
+                                                            const int64_t *__restrict__ brow_ptr,
+                                                            const int32_t *__restrict__ brow,
+                                                            double *__restrict__ x,
+                                                            const int64_t *__restrict__ x_off) {
+  extern __shared__ double sm[];
+  const Front F = fronts[blockIdx.x];
+  const int n = F.n, nf = F.nf, ld = F.ld, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  double *v = sm;
+  double *tri = sm + ((nf + 1) & ~1);
+  for (int i = tid; i < n; i += NT) v[i] = F.zbuf[i];
+  if (F.m > 0) {
+    const int32_t *br = brow + brow_ptr[blockIdx.x];
+    for (int a = tid; a < F.m; a += NT) v[n + a] = xc[br[a]];
+  }
+  __syncthreads();
+  for (int kb = ((n - 1) / SB) * SB; kb >= 0; kb -= SB) {
+    const int bw = min(SB, n - kb);
+    load_tri(F, kb, bw, tri);
+    const bool straddle = F.bsz[kb + bw - 1] == 2;
+    // v[kb+c] -= L(kb+bw:nf, kb+c)^T v[kb+bw:nf]   (one warp per column, coalesced down the column)
+    for (int c = warp; c < bw; c += NT / 32) {
+      const double *__restrict__ Lc = F.A + (size_t)(kb + c) * ld;
+      const int ibeg = kb + bw + ((straddle && c == bw - 1) ? 1 : 0);
+      double acc = 0.0;
+      for (int i = ibeg + lane; i < nf; i += 32) acc += Lc[i] * v[i];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) v[kb + c] -= acc;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double y = tid < bw ? v[kb + tid] : 0.0;
+      for (int rr = bw - 1; rr > 0; --rr) {
+        const double xr = __shfl_sync(0xffffffffu, y, rr);
+        if (tid < rr) y -= tri[tid * SPITCH + rr] * xr;
+      }
+      if (tid < bw) v[kb + tid] = y;
+    }
+    __syncthreads();
+  }
+  double *out = x + x_off[blockIdx.x];
+  for (int i = tid; i < n; i += NT) out[F.perm[i]] = v[i];
+}
+
+}  // namespace ppb

@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI declared in ``include/parapint_b200.h``.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+CPU implementation behind this module: if the library is missing or no CUDA device is present the
+solver raises, it never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libparapint_b200.so")
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+#: every symbol the header declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "pp_abi_version": (C.c_int, []),
+    "pp_build_info": (C.c_char_p, []),
+    "pp_last_error": (C.c_char_p, []),
+    "pp_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "pp_destroy": (C.c_int, [_vp]),
+    "pp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "pp_symbolic": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp]),
+    "pp_numeric_local": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "pp_numeric_coupling": (C.c_int, [_vp, _vp, _vp]),
+    "pp_inertia_local": (C.c_int, [_vp, _i64p]),
+    "pp_inertia_coupling": (C.c_int, [_vp, _i64p]),
+    "pp_solve_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "pp_solve_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "pp_factor_bytes": (C.c_int64, [_vp]),
+    "pp_local_dim": (C.c_int64, [_vp]),
+    "pp_kernel_launches": (C.c_int64, [_vp]),
+    "pp_debug_front": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _vp, _vp]),
+}
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load ``libparapint_b200.so`` (once) and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pp_last_error().decode()
+
+
+def np_ptr(arr):
+    """void* of a C-contiguous numpy array (kept alive by the caller)."""
+    return arr.ctypes.data_as(_vp)

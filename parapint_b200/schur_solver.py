@@ -1,0 +1,277 @@
+"""``B200SchurComplementLinearSolver`` -- drop-in for parapint's Schur-complement linear solvers.
+
+Replaces ``SchurComplementLinearSolver``
+(reference ``parapint/linalg/schur_complement/explicit_schur_complement.py:16``) and
+``MPISchurComplementLinearSolver`` (``mpi_explicit_schur_complement.py:128``) *together with*
+their per-block sub-solvers behind the same ``LinearSolverInterface``
+(``base_linear_solver_interface.py:5-56``), so it plugs into ``ip_solve`` as
+``options.linalg.solver`` (``algorithms/interior_point.py:347,371,387,544,566``).
+
+Host code is Python; device buffers, streams and collectives come from PyTorch; all arithmetic
+runs in the hand-written sm_100a kernels behind the C ABI (``include/parapint_b200.h``).  There is
+no CPU fallback: constructing the solver without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import Optional
+
+import numpy as np
+
+from . import native, structure
+from .comm import Communicator
+from .interface import LinearSolverInterface, LinearSolverResults, LinearSolverStatus
+
+_OK = (LinearSolverStatus.successful, LinearSolverStatus.warning)
+
+
+class _NullTimer:
+    def start(self, name):
+        pass
+
+    def stop(self, name):
+        pass
+
+
+class CudaBackend:
+    """Owns the native handle and the PyTorch device / pinned buffers for one GPU."""
+
+    def __init__(self, device: Optional[int] = None, options: Optional[dict] = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200SchurComplementLinearSolver needs a CUDA device; there is no CPU fallback")
+        self.torch = torch
+        self.lib = native.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.handle = C.c_void_p()
+        self._check(self.lib.pp_create(self.device_index, C.byref(self.handle)), "pp_create")
+        for key, val in (options or {}).items():
+            self._check(self.lib.pp_set_option(self.handle, key.encode(), float(val)), "pp_set_option")
+        self.st = None
+
+    def _check(self, code, what):
+        if code == 3:
+            raise RuntimeError(f"{what} failed: {native.last_error()}")
+        return code
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.pp_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # -- buffers -----------------------------------------------------------------------------
+    def symbolic(self, st: structure.Structure):
+        torch = self.torch
+        self.st = st
+        code = self.lib.pp_symbolic(
+            self.handle, st.n_local, native.np_ptr(st.block_n), native.np_ptr(st.border_ptr),
+            native.np_ptr(st.border_rows), st.m_c, st.nvals, native.np_ptr(st.dest_front),
+            native.np_ptr(st.dest_row), native.np_ptr(st.dest_col))
+        self._check(code, "pp_symbolic")
+        mc = max(st.m_c, 1)
+        with torch.cuda.device(self.device):
+            self.schur = torch.zeros(mc * mc, dtype=torch.float64, device=self.device)
+            self.rc = torch.zeros(mc, dtype=torch.float64, device=self.device)
+            self.ints = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.values_pin = torch.empty(max(st.nvals, 1), dtype=torch.float64, pin_memory=True)
+        self.rhs_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
+        self.x_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
+        self.rhsc_pin = torch.empty(mc, dtype=torch.float64, pin_memory=True)
+        self.xc_pin = torch.empty(mc, dtype=torch.float64, pin_memory=True)
+        self.values = self.values_pin.numpy()
+        return code
+
+    # -- numeric -----------------------------------------------------------------------------
+    def numeric_local(self):
+        """Factor the local fronts from ``self.values``; returns (status code, device S_local)."""
+        code = self.lib.pp_numeric_local(self.handle, C.c_void_p(self.values_pin.data_ptr()), 0,
+                                         C.c_void_p(self.schur.data_ptr()), self._stream())
+        return self._check(code, "pp_numeric_local"), self.schur
+
+    def numeric_coupling(self, schur_sum):
+        code = self.lib.pp_numeric_coupling(self.handle, C.c_void_p(schur_sum.data_ptr()), self._stream())
+        return self._check(code, "pp_numeric_coupling")
+
+    def inertia_local(self):
+        out = (C.c_int64 * 3)()
+        self._check(self.lib.pp_inertia_local(self.handle, out), "pp_inertia_local")
+        return np.array(list(out), dtype=np.int64)
+
+    def inertia_coupling(self):
+        out = (C.c_int64 * 3)()
+        self._check(self.lib.pp_inertia_coupling(self.handle, out), "pp_inertia_coupling")
+        return np.array(list(out), dtype=np.int64)
+
+    # -- solve -------------------------------------------------------------------------------
+    def solve_forward(self):
+        """Forward sweep on ``self.rhs_pin``; returns the device coupling contribution."""
+        code = self.lib.pp_solve_forward(self.handle, C.c_void_p(self.rhs_pin.data_ptr()), 0,
+                                         C.c_void_p(self.rc.data_ptr()), self._stream())
+        self._check(code, "pp_solve_forward")
+        return self.rc
+
+    def solve_backward(self, rc_sum):
+        code = self.lib.pp_solve_backward(self.handle, C.c_void_p(rc_sum.data_ptr()),
+                                          C.c_void_p(self.rhsc_pin.data_ptr()), 0,
+                                          C.c_void_p(self.x_pin.data_ptr()), C.c_void_p(self.xc_pin.data_ptr()),
+                                          self._stream())
+        self._check(code, "pp_solve_backward")
+        return self.x_pin.numpy(), self.xc_pin.numpy()
+
+    def int_tensor(self, values):
+        t = self.ints[: len(values)]
+        t.copy_(self.torch.tensor(list(values), dtype=self.torch.int64))
+        return t
+
+    def kernel_launches(self):
+        return int(self.lib.pp_kernel_launches(self.handle))
+
+    def factor_bytes(self):
+        return int(self.lib.pp_factor_bytes(self.handle))
+
+
+class B200SchurComplementLinearSolver(LinearSolverInterface):
+    """Solve ``K x = b`` for block-bordered-diagonal symmetric ``K``::
+
+          K1          A1^T
+              K2      A2^T
+                  K3  A3^T
+          A1  A2  A3  Q
+
+    on one B200 per process.  Only the lower border ``A_i`` and the lower triangles of ``K_i`` and
+    ``Q`` are read (as the MA27 / MUMPS leaves do).
+
+    Parameters
+    ----------
+    subproblem_solvers, schur_complement_solver:
+        accepted for signature compatibility with the classes being replaced
+        (``explicit_schur_complement.py:28-29``) and ignored -- this solver owns its leaves.
+    device: CUDA device index (default: current device).
+    comm: ``Communicator`` (default: the ``torch.distributed`` world if initialised, else 1 rank).
+    options: native tunables, e.g. ``{"pivot_tol": 0.0, "panel_width": 64}``.
+    """
+
+    def __init__(self, subproblem_solvers=None, schur_complement_solver=None, device=None, comm=None,
+                 options=None, backend=None):
+        self.subproblem_solvers = subproblem_solvers
+        self.schur_complement_solver = schur_complement_solver
+        self.comm = comm if comm is not None else Communicator()
+        self.backend = backend if backend is not None else CudaBackend(device, options)
+        self.block_dim = 0
+        self.block_matrix = None
+        self.local_block_indices = []
+        self._st = None
+        self._status = None
+        self.logger = self.getLogger()
+
+    @classmethod
+    def getLoggerName(cls):
+        return "b200_schur"
+
+    # ---------------------------------------------------------------------------------------
+    def _finish(self, code, raise_on_error, what):
+        """Agree on the worst status across ranks (``_gather_results``, ``mpi...:19-30``)."""
+        if self.comm.size > 1:
+            t = self.backend.int_tensor([int(code)])
+            self.comm.allreduce_max_(t)
+            code = int(t[0].item())
+        res = LinearSolverResults()
+        res.status = LinearSolverStatus(int(code))
+        self._status = res.status
+        if res.status not in _OK and raise_on_error:
+            raise RuntimeError(f"{what} unsuccessful; status: {res.status}")
+        return res
+
+    def do_symbolic_factorization(self, matrix, raise_on_error=True, timer=None):
+        """Analyse the block structure and allocate the fronts (``explicit...:44-78``,
+        ``mpi...:165-255``).  Collective over the communicator."""
+        timer = timer or _NullTimer()
+        timer.start("sc_structure")
+        st = structure.analyse(matrix, self.comm.rank, self.comm.size)
+        self.block_dim = st.n_blocks + 1
+        self.local_block_indices = list(st.local_blocks)
+        self.backend.symbolic(st)
+        self._st = st
+        self._status = None
+        timer.stop("sc_structure")
+        return self._finish(0, raise_on_error, "Symbolic factorization")
+
+    def do_numeric_factorization(self, matrix, raise_on_error=True, timer=None):
+        """Factor every local front, all-reduce the Schur complement, factor it
+        (``explicit...:80-129``, ``mpi...:257-361``).  Collective."""
+        if self._st is None:
+            raise RuntimeError("do_symbolic_factorization must be called before do_numeric_factorization")
+        timer = timer or _NullTimer()
+        self.block_matrix = matrix
+        timer.start("form SC")
+        if not structure.gather_values(matrix, self._st, self.backend.values):
+            # COO pattern / ordering changed since the symbolic phase (happens after the first
+            # regularisation): analyse again, as mumps_interface.py:82-83 does.
+            self.logger.debug("nonzero pattern changed; repeating the symbolic phase")
+            st = structure.analyse(matrix, self.comm.rank, self.comm.size)
+            self.backend.symbolic(st)
+            self._st = st
+            if not structure.gather_values(matrix, st, self.backend.values):
+                raise RuntimeError("could not gather the matrix values after re-analysis")
+        timer.start("factorize")
+        code, schur_local = self.backend.numeric_local()
+        timer.stop("factorize")
+        res = self._finish(code, raise_on_error, "Numeric factorization")
+        if res.status not in _OK:
+            timer.stop("form SC")
+            return res
+        timer.start("communicate")
+        self.comm.allreduce_sum_(schur_local)
+        timer.stop("communicate")
+        timer.stop("form SC")
+        timer.start("factor SC")
+        code = self.backend.numeric_coupling(schur_local)
+        timer.stop("factor SC")
+        return self._finish(code, raise_on_error, "Numeric factorization")
+
+    def do_back_solve(self, rhs, timer=None):
+        """Three-phase block elimination (``explicit...:131-155``, ``mpi...:363-402``); returns a new
+        vector with the block structure of ``rhs``; ``rhs`` is not modified.  Collective."""
+        if self._status not in _OK or self.block_matrix is None:
+            raise RuntimeError("do_numeric_factorization must succeed before do_back_solve")
+        timer = timer or _NullTimer()
+        timer.start("back_solve")
+        st = self._st
+        structure.pack_rhs(rhs, st, self.backend.rhs_pin.numpy())
+        self.backend.rhsc_pin.numpy()[: st.m_c] = structure.coupling_rhs(rhs, st)
+        rc = self.backend.solve_forward()
+        self.comm.allreduce_sum_(rc)
+        x_local, x_c = self.backend.solve_backward(rc)
+        out = structure.unpack_solution(rhs, st, x_local, x_c[: st.m_c])
+        timer.stop("back_solve")
+        return out
+
+    def get_inertia(self):
+        """(num_pos, num_neg, num_zero) summed over all blocks and the Schur complement
+        (Haynsworth additivity; ``explicit...:157-172``, ``mpi...:404-436``).  Collective."""
+        if self._status not in _OK or self.block_matrix is None:
+            raise RuntimeError("The inertia is only available after a successful do_numeric_factorization.")
+        local = self.backend.inertia_local()
+        if self.comm.size > 1:
+            t = self.backend.int_tensor(local.tolist())
+            self.comm.allreduce_sum_(t)
+            local = t.cpu().numpy()
+        tot = local + self.backend.inertia_coupling()
+        return int(tot[0]), int(tot[1]), int(tot[2])
+
+    def increase_memory_allocation(self, factor):
+        """Factor storage is sized exactly in the symbolic phase, so ``not_enough_memory`` is never
+        returned and there is nothing to grow (``explicit...:174-177`` forwards to the leaves)."""
+        return None

@@ -1,0 +1,200 @@
+"""Host-side symbolic analysis of a block-bordered KKT matrix.
+
+Turns the PyNumero-style ``BlockMatrix`` the IPM hands to the linear solver
+(layout: reference ``explicit_schur_complement.py:17-27``; inputs described in
+SURVEY.md 3.6 / 8(b)) into the flat description the C ABI takes
+(``include/parapint_b200.h``, ``pp_symbolic``): which diagonal blocks this rank
+owns, the nonzero border rows of every owned block, and for every numeric input
+value the front position it is added into.
+
+Ownership follows ``mpi_explicit_schur_complement.py:198-203``: block ``i`` is
+local when ``rank_ownership[i, i] == rank`` or (``== -1`` and ``rank == 0``); a
+matrix without ``rank_ownership`` (serial ``BlockMatrix``) is split round-robin
+``i % size == rank`` (``mpi_sc_ip_interface.py:14-19``) when ``size > 1``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _coo(block):
+    """COO triplets of a leaf / nested block without summing duplicates."""
+    c = block.tocoo()
+    return np.asarray(c.row, dtype=np.int64), np.asarray(c.col, dtype=np.int64), np.asarray(c.data, dtype=np.float64), c.shape
+
+
+@dataclass
+class Structure:
+    n_blocks: int                      # N (number of diagonal blocks, all ranks)
+    m_c: int                           # coupling dimension
+    local_blocks: List[int]            # global indices of the blocks owned here
+    block_n: np.ndarray                # int32[n_local]
+    border_ptr: np.ndarray             # int64[n_local + 1]
+    border_rows: np.ndarray            # int32[sum m_i]
+    dest_front: np.ndarray             # int32[nvals]
+    dest_row: np.ndarray               # int32[nvals]
+    dest_col: np.ndarray               # int32[nvals]
+    segments: list = field(default_factory=list)   # (kind, block index, start, stop) per gathered COO array
+    patterns: list = field(default_factory=list)   # (row, col) arrays per segment, to detect pattern changes
+    rhs_offsets: np.ndarray = None     # int64[n_local + 1] offsets of local blocks in the packed rhs
+
+    @property
+    def nvals(self):
+        return int(self.dest_front.size)
+
+    @property
+    def n_local(self):
+        return len(self.local_blocks)
+
+    @property
+    def local_dim(self):
+        return int(self.rhs_offsets[-1])
+
+
+def local_block_indices(matrix, n_blocks, rank, size):
+    own = getattr(matrix, "rank_ownership", None)
+    if own is not None:
+        own = np.asarray(own)
+        return [i for i in range(n_blocks) if own[i, i] == rank or (own[i, i] == -1 and rank == 0)]
+    return [i for i in range(n_blocks) if i % size == rank]
+
+
+def analyse(matrix, rank=0, size=1) -> Structure:
+    nbr, nbc = matrix.bshape
+    if nbr != nbc:
+        raise ValueError("The block matrix provided is not square.")
+    if getattr(matrix, "rank_ownership", None) is None:
+        nrows, ncols = matrix.shape
+        if nrows != ncols:
+            raise ValueError("The block matrix provided is not square.")
+    N = nbr - 1
+    local = local_block_indices(matrix, N, rank, size)
+    Q = matrix.get_block(N, N)
+    if Q is None:
+        m_c = int(matrix.get_row_size(N))
+        q_row = q_col = np.zeros(0, dtype=np.int64)
+    else:
+        q_row, q_col, _, qshape = _coo(Q)
+        m_c = int(qshape[0])
+        if qshape[0] != qshape[1]:
+            raise ValueError("The coupling block is not square.")
+
+    block_n, border_ptr, border_rows = [], [0], []
+    dfront, drow, dcol = [], [], []
+    segments, patterns = [], []
+    pos = 0
+    for f, i in enumerate(local):
+        K = matrix.get_block(i, i)
+        if K is None:
+            raise ValueError(f"diagonal block {i} is missing on its owner")
+        kr, kc, _, kshape = _coo(K)
+        if kshape[0] != kshape[1]:
+            raise ValueError(f"diagonal block {i} is not square")
+        n_i = int(kshape[0])
+        block_n.append(n_i)
+        keep = kr >= kc  # lower triangle only, like the MA27 / MUMPS leaves (mumps_interface.py:51)
+        dfront.append(np.where(keep, f, -1))
+        drow.append(np.where(keep, kr, 0))
+        dcol.append(np.where(keep, kc, 0))
+        segments.append(("K", i, pos, pos + kr.size))
+        patterns.append((kr, kc))
+        pos += kr.size
+
+        A = matrix.get_block(N, i)
+        if A is None:
+            border_ptr.append(border_ptr[-1])
+            continue
+        ar, ac, _, ashape = _coo(A)
+        if ashape != (m_c, n_i):
+            raise ValueError(f"border block ({N},{i}) has shape {ashape}, expected {(m_c, n_i)}")
+        nz_rows = np.unique(ar)  # rows with stored entries (explicit zeros count, as in _BorderMatrix)
+        lookup = np.full(m_c, -1, dtype=np.int64)
+        lookup[nz_rows] = np.arange(nz_rows.size)
+        border_rows.append(nz_rows)
+        border_ptr.append(border_ptr[-1] + nz_rows.size)
+        dfront.append(np.full(ar.size, f, dtype=np.int64))
+        drow.append(n_i + lookup[ar])
+        dcol.append(ac)
+        segments.append(("A", i, pos, pos + ar.size))
+        patterns.append((ar, ac))
+        pos += ar.size
+
+    n_local = len(local)
+    if Q is not None:
+        keep = q_row >= q_col
+        dfront.append(np.where(keep, n_local, -1))
+        drow.append(np.where(keep, q_row, 0))
+        dcol.append(np.where(keep, q_col, 0))
+        segments.append(("Q", N, pos, pos + q_row.size))
+        patterns.append((q_row, q_col))
+        pos += q_row.size
+
+    def cat(parts, dtype):
+        return np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0), dtype=dtype)
+
+    offs = np.concatenate(([0], np.cumsum(block_n))).astype(np.int64) if block_n else np.zeros(1, dtype=np.int64)
+    return Structure(
+        n_blocks=N, m_c=m_c, local_blocks=local,
+        block_n=np.asarray(block_n, dtype=np.int32),
+        border_ptr=np.asarray(border_ptr, dtype=np.int64),
+        border_rows=cat(border_rows, np.int32),
+        dest_front=cat(dfront, np.int32), dest_row=cat(drow, np.int32), dest_col=cat(dcol, np.int32),
+        segments=segments, patterns=patterns, rhs_offsets=offs)
+
+
+def gather_values(matrix, st: Structure, out: np.ndarray) -> bool:
+    """Copy the numeric values of ``matrix`` into ``out`` in the order fixed by :func:`analyse`.
+
+    Returns False when a block's COO pattern differs from the analysed one (the caller then
+    re-runs the symbolic phase, as ``mumps_interface.py:82-83`` does)."""
+    N = st.n_blocks
+    for (kind, i, lo, hi), (prow, pcol) in zip(st.segments, st.patterns):
+        blk = matrix.get_block(i, i) if kind in ("K", "Q") else matrix.get_block(N, i)
+        if blk is None:
+            return False
+        c = blk.tocoo()
+        if c.data.size != hi - lo or not (np.array_equal(c.row, prow) and np.array_equal(c.col, pcol)):
+            return False
+        out[lo:hi] = c.data
+    return True
+
+
+def pack_rhs(rhs, st: Structure, out: np.ndarray):
+    for f, i in enumerate(st.local_blocks):
+        blk = rhs.get_block(i)
+        flat = blk.flatten() if hasattr(blk, "nblocks") else np.asarray(blk, dtype=np.float64).ravel()
+        lo, hi = st.rhs_offsets[f], st.rhs_offsets[f + 1]
+        if flat.size != hi - lo:
+            raise ValueError(f"rhs block {i} has size {flat.size}, expected {hi - lo}")
+        out[lo:hi] = flat
+
+
+def coupling_rhs(rhs, st: Structure) -> np.ndarray:
+    blk = rhs.get_block(st.n_blocks)
+    flat = blk.flatten() if hasattr(blk, "nblocks") else np.asarray(blk, dtype=np.float64).ravel()
+    if flat.size != st.m_c:
+        raise ValueError(f"coupling rhs has size {flat.size}, expected {st.m_c}")
+    return np.ascontiguousarray(flat, dtype=np.float64)
+
+
+def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray):
+    """New vector with the block structure of ``rhs`` (``mpi_explicit_schur_complement.py:390``;
+    nested blocks keep their structure as the SciPy leaf does, ``scipy_interface.py:57-60``)."""
+    out = rhs.copy_structure()
+
+    def shaped(template, flat):
+        if hasattr(template, "nblocks"):
+            blk = template.copy_structure()
+            blk.copyfrom(flat)
+            return blk
+        return np.array(flat, dtype=np.float64)
+
+    for f, i in enumerate(st.local_blocks):
+        lo, hi = st.rhs_offsets[f], st.rhs_offsets[f + 1]
+        out.set_block(i, shaped(rhs.get_block(i), x_local[lo:hi]))
+    out.set_block(st.n_blocks, shaped(rhs.get_block(st.n_blocks), x_c))
+    return out

@@ -1,0 +1,141 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.kkt_generator import EstimationModel
+from oracle.schur_oracle import SchurOracle, dense_inertia, sym_full
+from parapint_b200 import B200SchurComplementLinearSolver, LinearSolverStatus
+from tests.helpers import block_vector, bordered_from_dense, random_bordered
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(kkt, rhs, **kw):
+    s = B200SchurComplementLinearSolver(**kw)
+    assert s.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+    res = s.do_numeric_factorization(kkt)
+    assert res.status == LinearSolverStatus.successful
+    return s, s.do_back_solve(rhs)
+
+
+def _rel_residual(kkt, x, rhs):
+    K = sym_full(kkt)
+    b = rhs.flatten()
+    return np.linalg.norm(K @ x.flatten() - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", ["sym", "sym_q"])
+def test_known_answer_8x8(known_answers, name):
+    """reference test_explicit_schur_complement.py:13-55 / test_mpi_...:19-115 (symmetrised blocks)."""
+    dense = known_answers[f"kat_{name}_dense"]
+    rhs = block_vector(known_answers[f"kat_{name}_rhs"], [2, 2, 2, 2])
+    kkt = bordered_from_dense(dense, [2, 2, 2, 2])
+    s, x = _solve(kkt, rhs)
+    assert np.allclose(x.flatten(), known_answers[f"kat_{name}_x"], rtol=1e-12, atol=1e-13)
+    assert s.get_inertia() == tuple(known_answers[f"kat_{name}_inertia"])
+    # refactor + re-solve reuse (test_mpi_explicit_schur_complement.py:113-115)
+    assert s.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+    assert np.allclose(s.do_back_solve(rhs).flatten(), known_answers[f"kat_{name}_x"], rtol=1e-12, atol=1e-13)
+
+
+def test_leaf_3x3(known_answers):
+    """reference test_linear_solvers.py:63-79 through a 1-block system with an empty coupling row."""
+    dense = np.zeros((4, 4))
+    dense[:3, :3] = known_answers["leaf_dense"]
+    dense[3, 3] = 1.0
+    kkt = bordered_from_dense(dense, [3, 1])
+    s = B200SchurComplementLinearSolver()
+    zero = bordered_from_dense(dense, [3, 1])
+    assert s.do_symbolic_factorization(zero).status == LinearSolverStatus.successful
+    assert s.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+    for r, x in zip(known_answers["leaf_rhs"], known_answers["leaf_x"]):
+        sol = s.do_back_solve(block_vector(np.concatenate([r, [2.0]]), [3, 1]))
+        assert np.allclose(sol.flatten(), np.concatenate([x, [2.0]]), rtol=1e-12)
+    pos, neg, zero_ = known_answers["leaf_inertia"]
+    assert s.get_inertia() == (pos + 1, neg, zero_)
+
+
+@pytest.mark.parametrize("tag", ["g_3_20_2_5", "g_4_60_3_10"])
+def test_generator_small_vs_reference(generator_golden, tag):
+    g = generator_golden
+    args = tuple(int(v) for v in g[f"{tag}_args"])
+    m = EstimationModel(*args)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s, x = _solve(kkt, rhs)
+    ref = g[f"{tag}_x"]
+    assert np.linalg.norm(x.flatten() - ref) / np.linalg.norm(ref) <= 1e-8
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    assert s.get_inertia() == tuple(g[f"{tag}_inertia"]) == m.expected_inertia()
+    assert abs(m.check_result(x) - g[f"{tag}_max_err"]) <= 1e-8
+
+
+def test_generator_reference_golden():
+    """reference examples/tests/test_examples.py:76-99: max_err 0.3163456780448639 (7 places)."""
+    m = EstimationModel(3, 500, 12, 10)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s, x = _solve(kkt, rhs)
+    assert abs(m.check_result(x) - 0.3163456780448639) < 5e-8
+    assert s.get_inertia() == m.expected_inertia()
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+
+
+def test_config2_vs_oracle(generator_golden):
+    """BASELINE config 2: 64 blocks x 2000 rows x 50 coupling; full size, against the live oracle."""
+    m = EstimationModel(64, 150, 6, 50)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s, x = _solve(kkt, rhs)
+    o = SchurOracle()
+    o.symbolic(kkt)
+    assert o.numeric(kkt) == 0
+    x_ref = o.solve(rhs).flatten()
+    assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    assert s.get_inertia() == m.expected_inertia()
+    assert abs(m.check_result(x) - generator_golden["g_64_150_6_50_max_err"]) <= 1e-8
+    assert np.allclose(np.asarray(x.get_block(64)), generator_golden["g_64_150_6_50_xc"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("seed,n_blocks,n,m_c,rows", [(0, 3, 37, 5, None), (1, 5, 130, 9, 4), (2, 2, 300, 70, 33),
+                                                      (3, 4, [17, 64, 129, 200], 12, 7)])
+def test_random_general_border(seed, n_blocks, n, m_c, rows):
+    """General (non-selection) borders, ragged block sizes, partial border rows; vs oracle + dense."""
+    rng = np.random.default_rng(seed)
+    kkt = random_bordered(rng, n_blocks, n, m_c, density=0.08, border_nnz_rows=rows)
+    sizes = [kkt.get_block(i, i).shape[0] for i in range(n_blocks + 1)]
+    rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
+    s, x = _solve(kkt, rhs)
+    dense = sym_full(kkt).toarray()
+    x_ref = np.linalg.solve(dense, rhs.flatten())
+    assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    assert s.get_inertia() == dense_inertia(dense, "eigvalsh")
+    o = SchurOracle(compute_inertia=True, inertia_method="eigvalsh")
+    o.symbolic(kkt)
+    assert o.numeric(kkt) == 0
+    assert np.linalg.norm(x.flatten() - o.solve(rhs).flatten()) / np.linalg.norm(x_ref) <= 1e-8
+    assert s.get_inertia() == o.inertia()
+
+
+def test_singular_block_reports_singular():
+    dense = np.zeros((5, 5))
+    dense[:2, :2] = [[1.0, 2.0], [2.0, 4.0]]  # rank 1
+    dense[2:4, 2:4] = np.eye(2)
+    dense[4, 4] = 1.0
+    dense[4, 0] = dense[0, 4] = 1.0
+    kkt = bordered_from_dense(dense, [2, 2, 1])
+    s = B200SchurComplementLinearSolver()
+    s.do_symbolic_factorization(kkt)
+    res = s.do_numeric_factorization(kkt, raise_on_error=False)
+    assert res.status == LinearSolverStatus.singular
+    with pytest.raises(RuntimeError):
+        s.do_numeric_factorization(kkt, raise_on_error=True)
+    with pytest.raises(RuntimeError):
+        s.get_inertia()
+
+
+def test_non_square_rejected():
+    from parapint_b200 import BlockMatrix
+    bad = BlockMatrix(2, 3)
+    with pytest.raises(ValueError):
+        B200SchurComplementLinearSolver().do_symbolic_factorization(bad)
