@@ -1,0 +1,363 @@
+"""Benchmark of the hot path: KKT numeric factorisation + inertia + back-solve per IPM iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): the reference's own synthetic block-bordered KKT generator,
+``Model(64 * N, n_q=150, n_y_multiplier=6, n_theta=50)`` -> 64 blocks of 2000 rows per GPU and 50
+coupling variables (weak scaling: the block count grows with N, blocks are dealt round-robin as in
+reference ``mpi_sc_ip_interface.py:14-19``; the Schur complement and the coupling right-hand side are
+all-reduced over NCCL).  A step is one ``do_numeric_factorization`` + ``get_inertia`` +
+``do_back_solve`` (symbolic phase excluded and reported separately, as SURVEY.md 8(d) defines).
+
+One JSON line on stdout (rank 0).  ``value``: device-resident inputs/outputs; ``e2e``: the plugin API
+with host ``BlockMatrix`` / ``BlockVector`` objects, host<->device copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_Q, N_Y_MULT, N_THETA, BLOCKS_PER_GPU = 150, 6, 50, 64
+METRIC = "kkt_factor_solve_ms_per_ipm_iter"
+
+
+def workload_name(n_gpus):
+    return (f"parapint synthetic block-bordered KKT Model({BLOCKS_PER_GPU * n_gpus},{N_Q},{N_Y_MULT},{N_THETA}): "
+            f"{BLOCKS_PER_GPU * n_gpus} blocks x 2000 rows, 50 coupling vars; numeric factorization + inertia + back_solve")
+
+
+class ClockSampler(threading.Thread):
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.1)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=10)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        busy = [v for v in sm if v > 0.5 * float(self.rows[0][1])] or sm
+        reasons = []
+        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def update_flops(n, m, nb):
+    """Algorithmic flops of the DMMA trailing updates of one front: sum over panels of r^2 * kw, with
+    r the trailing order after the panel (lower triangle: r^2/2 entries, 2 flops per entry per column)."""
+    nf, k, tot, launches = n + m, 0, 0.0, 0
+    while k < n:
+        kw = min(nb - 1, n - k) if n - k > nb else n - k
+        k += kw
+        r = nf - k
+        if r > 0:
+            tot += float(r) * r * kw
+            launches += 1
+    return tot, launches
+
+
+def fp64_peak():
+    path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return d["cublas_dgemm_8192_tflops"], "cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json holds no FP64 figure"
+    except Exception:  # noqa: BLE001
+        return 37.0, "nominal B200 FP64 (no measured file)"
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def build_model(n_gpus, rank):
+    from oracle.kkt_generator import EstimationModel  # generator = input synthesis only
+    n_blocks = BLOCKS_PER_GPU * n_gpus
+    local = [i for i in range(n_blocks) if i % n_gpus == rank]
+    return EstimationModel(n_blocks, N_Q, N_Y_MULT, N_THETA, local_blocks=local)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: pyomo/mpi4py are absent so the
+    reference package itself cannot be imported; see oracle/__init__.py) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.parallel_baseline import PartitionedCpuSolver
+    model = build_model(1, 0) if args.gpus == 1 else None
+    if model is None:
+        from oracle.kkt_generator import EstimationModel
+        model = EstimationModel(BLOCKS_PER_GPU * args.gpus, N_Q, N_Y_MULT, N_THETA)
+    kkt, rhs = model.build_kkt(), model.build_rhs()
+    cores = os.cpu_count() or 1
+    with PartitionedCpuSolver(kkt, rhs, procs=cores) as solver:
+        for _ in range(args.warmup):
+            solver.factor_and_solve()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            status, blocks, x_c = solver.factor_and_solve()
+        dt = time.perf_counter() - t0
+        used = solver.procs
+    assert status == 0
+    ms = dt / args.steps * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (reference generator, built-in seeds)",
+        "config": {"workload": workload_name(args.gpus)},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": used, "kind": "port",
+                         "sample": f"full workload, {args.steps} steps; process-per-rank emulation of "
+                                   f"MPISchurComplementLinearSolver with SciPy SuperLU leaves on {used} processes "
+                                   "(mpirun/mpi4py/MUMPS absent from the image)"},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from parapint_b200 import B200SchurComplementLinearSolver, Communicator, LinearSolverStatus
+    from parapint_b200 import structure
+
+    comm = Communicator()
+    model = build_model(world, rank)
+    kkt, rhs = model.build_kkt(), model.build_rhs()
+    solver = B200SchurComplementLinearSolver(comm=comm, options={"profile": 1})
+    be = solver.backend
+
+    def sync_all():
+        torch.cuda.synchronize()
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+    torch.cuda.synchronize()
+    symbolic_ms = (time.perf_counter() - t0) * 1e3
+    st = solver._st
+
+    # ---- correctness gate (every timed run): inertia, residual --------------------------------
+    assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+    inertia = solver.get_inertia()
+    x = solver.do_back_solve(rhs)
+    assert inertia == model.expected_inertia(), (inertia, model.expected_inertia())
+    x_c = np.asarray(x.get_block(model.n_blocks))
+    border = model.border().tocsr()
+    res2 = np.zeros(2)
+    coupling_res = np.zeros(N_THETA)
+    for i in st.local_blocks:
+        K = kkt.get_block(i, i).tocsr()
+        xi, ri = np.asarray(x.get_block(i)), np.asarray(rhs.get_block(i))
+        res2[0] += np.sum((K @ xi + border.T @ x_c - ri) ** 2)
+        res2[1] += np.sum(ri ** 2)
+        coupling_res += border @ xi
+    red = torch.tensor(np.concatenate([res2, coupling_res]), device=dev)
+    comm.allreduce_sum_(red)
+    red = red.cpu().numpy()
+    rel_res = float(np.sqrt(red[0] + np.sum(red[2:] ** 2)) / np.sqrt(red[1]))
+    assert rel_res <= 1e-10, rel_res
+    max_err = model.check_result(x)
+
+    # ---- end-to-end through the plugin API (host buffers) ----------------------------------------
+    def e2e_step():
+        res = solver.do_numeric_factorization(kkt)
+        ine = solver.get_inertia()
+        sol = solver.do_back_solve(rhs)
+        return res, ine, sol
+
+    for _ in range(args.warmup):
+        e2e_step()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    sync_all()
+    e2e_wall_ms = (time.perf_counter() - tw) * 1e3 / args.steps
+    e2e_ms = max(ev0.elapsed_time(ev1) / args.steps, e2e_wall_ms)
+    h2d = (st.nvals + st.local_dim + st.m_c) * 8
+    d2h = (st.local_dim + st.m_c) * 8 + 4 * 2 + 6 * 8
+
+    # ---- device-resident hot path (`value`) --------------------------------------------------------
+    values_dev = be.values_pin.to(dev)
+    rhs_dev = be.rhs_pin.to(dev)
+    rhsc_dev = be.rhsc_pin.to(dev)
+    x_dev = torch.empty_like(rhs_dev)
+    xc_dev = torch.empty_like(rhsc_dev)
+
+    def dev_step():
+        code, s_local = be.numeric_local_device(values_dev)
+        comm.allreduce_sum_(s_local)
+        code2 = be.numeric_coupling(s_local)
+        loc = be.inertia_local()
+        cpl = be.inertia_coupling()
+        be.solve_device(rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=comm.allreduce_sum_)
+        return code, code2, loc, cpl
+
+    for _ in range(args.warmup):
+        dev_step()
+    sync_all()
+    be.profile(reset=True)
+    launches0 = be.kernel_launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        out = dev_step()
+    ev1.record()
+    sync_all()
+    clocks = sampler.finish() if sampler else None
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (be.kernel_launches() - launches0) // args.steps
+    prof = be.profile(reset=True)
+    assert out[0] == 0 and out[1] == 0
+    x_chk = x_dev.cpu().numpy()
+    assert np.allclose(x_chk, be.x_pin.numpy()[: x_chk.size], rtol=1e-12, atol=1e-12)
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    comm.allreduce_max_(t)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    per_step = {k: v["ms"] / args.steps for k, v in prof.items()}
+    dominant = max(per_step, key=per_step.get)
+    nb = 64
+    flops_front, upd_launches = update_flops(model.block_dim, N_THETA, nb)
+    if dominant == "update":
+        peak, peak_src = fp64_peak()
+        n_launch = max(prof["update"]["launches"] // args.steps, 1)
+        flops_per_launch = flops_front * st.n_local / upd_launches
+        avg_ms = per_step["update"] / n_launch
+        achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": "front_update_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic("front_update_kernel"),
+                    "peak_source": peak_src}
+    else:
+        # panel / sweep kernels stream L once per launch: HBM-bound in the roofline sense
+        peak, peak_src = hbm_peak()
+        nf = model.block_dim + N_THETA
+        if dominant == "panel":
+            # lazy column updates read the panel computed so far: ~ nb/2 * 8 B per trailing element and column
+            bytes_front = sum(8.0 * (nf - k) * ((k % (nb - 1)) + 2) for k in range(model.block_dim))
+            kname = "front_panel_kernel"
+        else:
+            bytes_front = 8.0 * nf * nf / 2
+            kname = {"forward": "front_forward_kernel", "backward": "front_backward_kernel"}.get(dominant, dominant)
+        n_launch = max(prof[dominant]["launches"] // args.steps, 1)
+        achieved = bytes_front * st.n_local / n_launch / (per_step[dominant] / n_launch * 1e-3) / 1e9
+        roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": ncu_traffic(kname), "peak_source": peak_src}
+    # the DMMA update is always reported too (it carries the n^3/3 flops of the factorisation)
+    peak64, _ = fp64_peak()
+    upd_tflops = flops_front * st.n_local / (per_step["update"] * 1e-3) / 1e12 if per_step["update"] > 0 else 0.0
+
+    line = {
+        "metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (reference generator create_model.Model, built-in seeds)",
+        "config": {"workload": workload_name(world), "blocks_per_gpu": BLOCKS_PER_GPU, "block_rows": model.block_dim,
+                   "coupling": N_THETA, "l2": "inputs larger than L2 (2.2 GB of fronts per GPU re-assembled every step)",
+                   "parallelism": f"blocks round-robin over {world} GPU(s); Schur complement + coupling rhs all-reduced (NCCL)"},
+        "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "wall_ms": e2e_wall_ms, "api": "B200SchurComplementLinearSolver.do_numeric_factorization + get_inertia + do_back_solve"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels_ms_per_step": per_step,
+        "update_kernel_tflops": upd_tflops, "update_kernel_frac_of_dgemm": upd_tflops / peak64,
+        "throughput": {"value": BLOCKS_PER_GPU * world / (dev_ms * 1e-3), "unit": "kkt_blocks/s"},
+        "symbolic_ms": symbolic_ms,
+        "check": {"inertia": list(inertia), "rel_residual": rel_res, "max_err": float(max_err)},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.parallel_baseline import time_serial
+        full_kkt, full_rhs = kkt, rhs
+        sec, reps, x_ref = time_serial(full_kkt, full_rhs, min_seconds=8.0)
+        rel = float(np.linalg.norm(x.flatten() - x_ref.flatten()) / np.linalg.norm(x_ref.flatten()))
+        assert rel <= 1e-8, rel
+        line["cpu_baseline"] = {"value": sec * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                                "sample": f"full workload, median of {reps} runs of the serial reference algorithm "
+                                          "(oracle port of SchurComplementLinearSolver + ScipyInterface/SuperLU leaves)"}
+        line["check"]["rel_diff_vs_cpu_reference"] = rel
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

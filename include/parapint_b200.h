@@ -47,7 +47,7 @@ const char *pp_last_error(void);
 int pp_create(int device, pp_handle **out);
 int pp_destroy(pp_handle *h);
 
-/* Tunables: name in {"pivot_tol", "panel_width", "use_graph", "refine_steps"}. */
+/* Tunables: name in {"pivot_tol", "panel_width", "profile", "use_graph", "refine_steps"}. */
 int pp_set_option(pp_handle *h, const char *name, double value);
 
 /*
@@ -125,6 +125,23 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
 int64_t pp_factor_bytes(const pp_handle *h);  /* device bytes held by factors + workspaces */
 int64_t pp_local_dim(const pp_handle *h);     /* sum of n_i over local blocks */
 int64_t pp_kernel_launches(const pp_handle *h); /* kernels launched by this handle so far */
+
+/*
+ * Per-kernel-class device timing (measurement aid; enabled with pp_set_option(h, "profile", 1)).
+ * CUDA events are recorded on the launching stream around every launch of each class; this call
+ * waits for them and returns accumulated milliseconds and launch counts per class.
+ */
+enum {
+  PP_PROF_ASSEMBLE = 0, /* arena clear + scatter-add of the input values */
+  PP_PROF_PANEL = 1,    /* Bunch-Kaufman panel factorisation */
+  PP_PROF_SWAPS = 2,    /* row interchanges left of the panel */
+  PP_PROF_UPDATE = 3,   /* DMMA trailing update */
+  PP_PROF_SCHUR = 4,    /* gather of the local Schur contribution */
+  PP_PROF_FORWARD = 5,  /* forward sweep on the local fronts */
+  PP_PROF_BACKWARD = 6, /* backward sweep on the local fronts */
+  PP_PROF_CLASSES = 8
+};
+int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset);
 
 /* Debug / test access: copy front `f` (0..n_local-1 local, n_local = coupling) to host,
  * column-major with leading dimension *ld; piv/bsz receive the pivot records (n entries). */

@@ -100,9 +100,65 @@ struct pp_handle {
   size_t arenaA_elems = 0;
   int64_t launches = 0;
   int64_t bytes = 0;
+  // optional per-kernel-class timing (option "profile"): CUDA events around every launch
+  bool profile = false;
+  struct Span { cudaEvent_t a, b; int cls; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[PP_PROF_CLASSES] = {0};
+  int64_t prof_launches[PP_PROF_CLASSES] = {0};
+  ~pp_handle() {
+    for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : event_pool) cudaEventDestroy(e);
+  }
 };
 
 namespace {
+
+cudaEvent_t take_event(pp_handle *h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  return e;
+}
+
+// RAII span: records an event pair around the launches of one kernel class when profiling is on.
+struct ProfSpan {
+  pp_handle *h;
+  cudaStream_t st;
+  pp_handle::Span s;
+  bool on;
+  ProfSpan(pp_handle *h_, int cls, cudaStream_t st_) : h(h_), st(st_), on(h_->profile) {
+    if (!on) return;
+    s.cls = cls;
+    s.a = take_event(h);
+    s.b = take_event(h);
+    cudaEventRecord(s.a, st);
+  }
+  ~ProfSpan() {
+    if (!on) return;
+    cudaEventRecord(s.b, st);
+    h->spans.push_back(s);
+  }
+};
+
+void resolve_profile(pp_handle *h) {
+  for (auto &s : h->spans) {
+    float ms = 0.f;
+    cudaEventSynchronize(s.b);
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      h->prof_ms[s.cls] += ms;
+      h->prof_launches[s.cls] += 1;
+    }
+    h->event_pool.push_back(s.a);
+    h->event_pool.push_back(s.b);
+  }
+  h->spans.clear();
+}
 
 bool is_pinned_host(const void *p) {
   cudaPointerAttributes at;
@@ -125,9 +181,13 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   if (nmax == 0) return;
   const int iters = (nmax + (NB - 2)) / (NB - 1);
   for (int it = 0; it < iters; ++it) {
-    front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
-    h->launches++;
+    {
+      ProfSpan sp(h, PP_PROF_PANEL, st);
+      front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
+      h->launches++;
+    }
     if (it > 0) {
+      ProfSpan sp(h, PP_PROF_SWAPS, st);
       dim3 g((nmax + 255) / 256, count);
       front_swaps_left_kernel<<<g, 256, 0, st>>>(fr);
       h->launches++;
@@ -140,6 +200,7 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
       nt = std::max(nt, (h->nf[f] + UT - 1) / UT - done / UT);
     }
     if (nt > 0) {
+      ProfSpan sp(h, PP_PROF_UPDATE, st);
       dim3 g(nt * (nt + 1) / 2, count);
       front_update_kernel<<<g, UPD_THREADS, UPD_SMEM, st>>>(fr);
       h->launches++;
@@ -204,6 +265,8 @@ int pp_create(int device, pp_handle **out) {
     h->device = device;
     h->flag.alloc(4);
     h->inertia.alloc(8);
+    CK(cudaMemset(h->inertia.p, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(h->flag.p, 0, 4 * sizeof(int)));
     *out = h;
     return (int)PP_SUCCESSFUL;
   });
@@ -226,6 +289,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     const int nb = (int)value;
     if (nb < 4 || nb > NBMAX) return fail("panel_width must be in [4, 64]");
     h->panel_width = nb;
+  } else if (key == "profile") {
+    h->profile = value != 0.0;
   } else if (key == "use_graph" || key == "refine_steps") {
     // accepted for forward compatibility; no effect in this build
   } else {
@@ -406,16 +471,20 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
       dvals = h->vals.p;
     }
-    CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
-    reset_fronts_kernel<<<h->n_local + 1, 256, 0, st>>>(h->fronts.p, h->inertia.p);
-    h->launches++;
-    if (h->nuniq > 0) {
-      assemble_kernel<<<(unsigned)((h->nuniq + 255) / 256), 256, 0, st>>>(dvals, h->asm_dst.p, h->asm_ptr.p,
-                                                                        h->asm_src.p, h->nuniq, h->arenaA.p);
+    {
+      ProfSpan sp(h, PP_PROF_ASSEMBLE, st);
+      CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
+      reset_fronts_kernel<<<h->n_local + 1, 256, 0, st>>>(h->fronts.p, h->inertia.p);
       h->launches++;
+      if (h->nuniq > 0) {
+        assemble_kernel<<<(unsigned)((h->nuniq + 255) / 256), 256, 0, st>>>(dvals, h->asm_dst.p, h->asm_ptr.p,
+                                                                          h->asm_src.p, h->nuniq, h->arenaA.p);
+        h->launches++;
+      }
     }
     factor_fronts(h, 0, h->n_local, st);
     if (h->m_c > 0) {
+      ProfSpan sp(h, PP_PROF_SCHUR, st);
       dim3 g((h->m_c + 127) / 128, h->m_c);
       schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
                                              h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
@@ -446,6 +515,7 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
       coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
       h->launches++;
       factor_fronts(h, h->n_local, 1, st);
+      CK(cudaMemsetAsync(h->inertia.p + 3, 0, 3 * sizeof(unsigned long long), st));
       front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
       h->launches++;
       CK(cudaGetLastError());
@@ -494,6 +564,7 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
       drhs = h->rhs.p;
     }
     if (h->n_local > 0) {
+      ProfSpan sp(h, PP_PROF_FORWARD, st);
       const size_t sm = solve_smem(h->nfmax_local);
       CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       front_forward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, drhs, h->rhs_off.p);
@@ -543,6 +614,7 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
       h->launches += 3;
     }
     if (h->n_local > 0) {
+      ProfSpan sp(h, PP_PROF_BACKWARD, st);
       const size_t sm = solve_smem(h->nfmax_local);
       CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)std::max(sm, solve_smem(mc))));
@@ -568,6 +640,20 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
 int64_t pp_factor_bytes(const pp_handle *h) { return h ? h->bytes : 0; }
 int64_t pp_local_dim(const pp_handle *h) { return h ? h->local_dim : 0; }
 int64_t pp_kernel_launches(const pp_handle *h) { return h ? h->launches : 0; }
+
+int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
+  if (!h) return fail("pp_profile: null handle");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    resolve_profile(h);
+    for (int c = 0; c < PP_PROF_CLASSES; ++c) {
+      if (ms) ms[c] = h->prof_ms[c];
+      if (launches) launches[c] = h->prof_launches[c];
+      if (reset) { h->prof_ms[c] = 0; h->prof_launches[c] = 0; }
+    }
+    return (int)PP_SUCCESSFUL;
+  });
+}
 
 int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,
                    int32_t *bsz) {

@@ -35,6 +35,7 @@ SIGNATURES = {
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),
     "pp_kernel_launches": (C.c_int64, [_vp]),
+    "pp_profile": (C.c_int, [_vp, _f64p, _i64p, C.c_int]),
     "pp_debug_front": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _vp, _vp]),
 }
 

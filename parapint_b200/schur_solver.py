@@ -130,6 +130,32 @@ class CudaBackend:
         self._check(code, "pp_solve_backward")
         return self.x_pin.numpy(), self.xc_pin.numpy()
 
+    # -- device-resident variants (inputs / outputs already in HBM; used by bench.py `value`) ----
+    def numeric_local_device(self, values_dev):
+        code = self.lib.pp_numeric_local(self.handle, C.c_void_p(values_dev.data_ptr()), 1,
+                                         C.c_void_p(self.schur.data_ptr()), self._stream())
+        return self._check(code, "pp_numeric_local"), self.schur
+
+    def solve_device(self, rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=None):
+        self._check(self.lib.pp_solve_forward(self.handle, C.c_void_p(rhs_dev.data_ptr()), 1,
+                                              C.c_void_p(self.rc.data_ptr()), self._stream()), "pp_solve_forward")
+        if reduce is not None:
+            reduce(self.rc)
+        self._check(self.lib.pp_solve_backward(self.handle, C.c_void_p(self.rc.data_ptr()),
+                                               C.c_void_p(rhsc_dev.data_ptr()), 1, C.c_void_p(x_dev.data_ptr()),
+                                               C.c_void_p(xc_dev.data_ptr()), self._stream()), "pp_solve_backward")
+
+    def set_option(self, name, value):
+        self._check(self.lib.pp_set_option(self.handle, name.encode(), float(value)), "pp_set_option")
+
+    def profile(self, reset=True):
+        """Accumulated device milliseconds and launch counts per kernel class (see pp_profile)."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        self._check(self.lib.pp_profile(self.handle, ms, cnt, 1 if reset else 0), "pp_profile")
+        names = ("assemble", "panel", "swaps", "update", "schur", "forward", "backward")
+        return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(names)}
+
     def int_tensor(self, values):
         t = self.ints[: len(values)]
         t.copy_(self.torch.tensor(list(values), dtype=self.torch.int64))
