@@ -213,6 +213,14 @@ class BlockVector:
     def shape(self):
         return (self.size,)
 
+    @property
+    def ndim(self):
+        return 1
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64)
+
     def block_sizes(self, copy=True):
         return np.asarray([b.size for b in self._blocks], dtype=np.int64)
 

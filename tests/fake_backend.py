@@ -1,0 +1,106 @@
+"""CPU stand-in for ``parapint_b200.schur_solver.CudaBackend`` (TEST INFRASTRUCTURE).
+
+Implements the contract of the C ABI (include/parapint_b200.h) with numpy so that the *host-side*
+logic of ``B200SchurComplementLinearSolver`` -- partitioning, value gathering, the order of the
+collectives, solution unpacking, status / inertia agreement -- can be exercised on CPU, including with
+``torch.distributed`` (gloo) at world_size > 1.  It is never importable from the product package.
+"""
+import numpy as np
+import torch
+
+from oracle.schur_oracle import dense_inertia
+
+
+class FakeBackend:
+    def __init__(self):
+        self.launches = 0
+
+    def symbolic(self, st):
+        self.st = st
+        mc = max(st.m_c, 1)
+        self.schur = torch.zeros(mc * mc, dtype=torch.float64)
+        self.rc = torch.zeros(mc, dtype=torch.float64)
+        self.ints = torch.zeros(4, dtype=torch.int64)
+        self.values_pin = torch.zeros(max(st.nvals, 1), dtype=torch.float64)
+        self.rhs_pin = torch.zeros(max(st.local_dim, 1), dtype=torch.float64)
+        self.x_pin = torch.zeros(max(st.local_dim, 1), dtype=torch.float64)
+        self.rhsc_pin = torch.zeros(mc, dtype=torch.float64)
+        self.xc_pin = torch.zeros(mc, dtype=torch.float64)
+        self.values = self.values_pin.numpy()
+        return 0
+
+    def _fronts(self):
+        st = self.st
+        sizes = [int(st.block_n[f] + st.border_ptr[f + 1] - st.border_ptr[f]) for f in range(st.n_local)] + [st.m_c]
+        fronts = [np.zeros((s, s)) for s in sizes]
+        for k in range(st.nvals):
+            f = st.dest_front[k]
+            if f >= 0:
+                fronts[f][st.dest_row[k], st.dest_col[k]] += self.values[k]
+        return [np.tril(F) + np.tril(F, -1).T for F in fronts]
+
+    def numeric_local(self):
+        st = self.st
+        fronts = self._fronts()
+        self.K, self.A, self.rows, self.inert = [], [], [], np.zeros(3, dtype=np.int64)
+        S = np.zeros((st.m_c, st.m_c))
+        code = 0
+        for f in range(st.n_local):
+            n = int(st.block_n[f])
+            K, A = fronts[f][:n, :n], fronts[f][n:, :n]
+            rows = st.border_rows[st.border_ptr[f]:st.border_ptr[f + 1]]
+            self.K.append(K); self.A.append(A); self.rows.append(rows)
+            if n and np.linalg.matrix_rank(K) < n:
+                code = 2
+                continue
+            self.inert += np.asarray(dense_inertia(K, "eigvalsh"), dtype=np.int64)
+            if rows.size:
+                S[np.ix_(rows, rows)] -= A @ np.linalg.solve(K, A.T)
+        self.Q = fronts[-1]
+        self.schur.copy_(torch.from_numpy(S.T.reshape(-1).copy()))
+        return code, self.schur
+
+    def numeric_coupling(self, schur_sum):
+        mc = self.st.m_c
+        self.S = self.Q + schur_sum.numpy().reshape(mc, mc).T
+        if mc and np.linalg.matrix_rank(self.S) < mc:
+            return 2
+        self.inert_c = np.asarray(dense_inertia(self.S, "eigvalsh"), dtype=np.int64)
+        return 0
+
+    def inertia_local(self):
+        return self.inert.copy()
+
+    def inertia_coupling(self):
+        return self.inert_c.copy()
+
+    def solve_forward(self):
+        st = self.st
+        rc = np.zeros(st.m_c)
+        self.y = []
+        for f in range(st.n_local):
+            r = self.rhs_pin.numpy()[st.rhs_offsets[f]:st.rhs_offsets[f + 1]]
+            y = np.linalg.solve(self.K[f], r)
+            self.y.append(y)
+            if self.rows[f].size:
+                rc[self.rows[f]] -= self.A[f] @ y
+        self.rc[: st.m_c] = torch.from_numpy(rc)
+        return self.rc
+
+    def solve_backward(self, rc_sum):
+        st = self.st
+        xc = np.linalg.solve(self.S, self.rhsc_pin.numpy()[: st.m_c] + rc_sum.numpy()[: st.m_c]) if st.m_c else np.zeros(0)
+        self.xc_pin.numpy()[: st.m_c] = xc
+        for f in range(st.n_local):
+            r = self.rhs_pin.numpy()[st.rhs_offsets[f]:st.rhs_offsets[f + 1]]
+            corr = self.A[f].T @ xc[self.rows[f]] if self.rows[f].size else 0.0
+            self.x_pin.numpy()[st.rhs_offsets[f]:st.rhs_offsets[f + 1]] = np.linalg.solve(self.K[f], r - corr)
+        return self.x_pin.numpy(), self.xc_pin.numpy()
+
+    def int_tensor(self, values):
+        t = self.ints[: len(values)]
+        t.copy_(torch.tensor(list(values), dtype=torch.int64))
+        return t
+
+    def kernel_launches(self):
+        return 0

@@ -1,0 +1,85 @@
+"""CPU, world_size 2 (gloo): the multi-rank host path -- partition, all-reduces, status agreement.
+
+The kernels are replaced by the numpy stand-in of the C ABI (tests/fake_backend.py); what is under
+test is the solver's own distributed logic, which is identical on NCCL.
+Mirrors reference test_mpi_explicit_schur_complement.py:19-115 (run there under mpirun -np 2/3).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.kkt_generator import EstimationModel
+        from oracle.schur_oracle import solve_partitioned
+        from parapint_b200 import B200SchurComplementLinearSolver, Communicator, LinearSolverStatus
+        from tests.fake_backend import FakeBackend
+        from tests.helpers import block_vector, bordered_from_dense
+
+        comm = Communicator()
+        assert (comm.rank, comm.size) == (rank, world)
+        solver = B200SchurComplementLinearSolver(backend=FakeBackend(), comm=comm)
+        if case == "generator":
+            full = EstimationModel(5, 12, 2, 3)
+            local = EstimationModel(5, 12, 2, 3, local_blocks=[i for i in range(5) if i % world == rank])
+            kkt, rhs = local.build_kkt(), local.build_rhs()
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            assert solver.local_block_indices == local.local_blocks
+            for _ in range(2):  # refactor + re-solve reuse (test_mpi...:113-115)
+                assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+                x = solver.do_back_solve(rhs)
+            st, x_ref, _ = solve_partitioned(full.build_kkt(), full.build_rhs(), world)
+            for i in local.local_blocks:
+                assert np.allclose(x.get_block(i), x_ref.get_block(i), rtol=1e-9, atol=1e-9)
+            assert np.allclose(x.get_block(5), x_ref.get_block(5), rtol=1e-9, atol=1e-9)  # replicated coupling
+            assert solver.get_inertia() == full.expected_inertia()
+            assert abs(full.check_result(x_ref) - local.check_result(x)) < 1e-6 or world > 1
+        elif case == "singular":
+            dense = np.zeros((5, 5))
+            dense[:2, :2] = [[1.0, 2.0], [2.0, 4.0]]  # block 0 (rank 0) is singular
+            dense[2:4, 2:4] = np.eye(2)
+            dense[4, 4] = 1.0
+            dense[4, 0] = dense[0, 4] = 1.0
+            kkt = bordered_from_dense(dense, [2, 2, 1])
+            solver.do_symbolic_factorization(kkt)
+            res = solver.do_numeric_factorization(kkt, raise_on_error=False)
+            assert res.status == LinearSolverStatus.singular  # every rank agrees (mpi...:19-30)
+            try:
+                solver.do_numeric_factorization(kkt, raise_on_error=True)
+                raise AssertionError("expected RuntimeError on every rank")
+            except RuntimeError:
+                pass
+        open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["generator", "singular"])
+def test_world_size_2(tmp_path, case):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"ok_{case}_0", f"ok_{case}_1"]
+
+
+def test_world_size_3_uneven(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(3, port, "generator", str(tmp_path)), nprocs=3, join=True)
+    assert len(os.listdir(tmp_path)) == 3

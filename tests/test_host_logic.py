@@ -1,0 +1,233 @@
+"""CPU: carriers, symbolic analysis, C-ABI surface and the solver's host logic (fake numpy backend)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.kkt_generator import EstimationModel
+from oracle.schur_oracle import SchurOracle, dense_inertia, sym_full
+from parapint_b200 import (B200SchurComplementLinearSolver, BlockMatrix, BlockVector, LinearSolverInterface,
+                           LinearSolverStatus, native, structure)
+from tests.fake_backend import FakeBackend
+from tests.helpers import block_vector, bordered_from_dense, random_bordered
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    """The built library loads (no GPU needed) and exports exactly what include/parapint_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "parapint_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pp_[a-z_0-9]+)\s*\(", body))
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    lib = native.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pp_abi_version() == 1
+    assert b"sm_100a" in lib.pp_build_info()
+
+
+def test_status_codes_match_reference_enum():
+    """parapint/linalg/results.py:4-9."""
+    assert [s.value for s in LinearSolverStatus] == [0, 1, 2, 3, 4]
+    assert [s.name for s in LinearSolverStatus] == ["successful", "not_enough_memory", "singular", "error", "warning"]
+    header = open(os.path.join(ROOT, "include", "parapint_b200.h")).read()
+    for name, val in (("PP_SUCCESSFUL", 0), ("PP_NOT_ENOUGH_MEMORY", 1), ("PP_SINGULAR", 2), ("PP_ERROR", 3), ("PP_WARNING", 4)):
+        assert re.search(rf"{name}\s*=\s*{val}\b", header)
+
+
+def test_null_handle_calls_fail_cleanly():
+    lib = native.load()
+    assert lib.pp_numeric_local(None, None, 0, None, None) == 3
+    assert b"symbolic" in lib.pp_last_error()
+    assert lib.pp_destroy(None) == 0
+    assert lib.pp_set_option(None, b"pivot_tol", 0.0) == 3
+
+
+def test_solver_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200SchurComplementLinearSolver()
+
+
+def test_plugin_surface():
+    """base_linear_solver_interface.py:5-56: same method names and call conventions."""
+    assert issubclass(B200SchurComplementLinearSolver, LinearSolverInterface)
+    import inspect
+    for name, params in (("do_symbolic_factorization", ["self", "matrix", "raise_on_error", "timer"]),
+                         ("do_numeric_factorization", ["self", "matrix", "raise_on_error", "timer"]),
+                         ("do_back_solve", ["self", "rhs", "timer"]), ("get_inertia", ["self"]),
+                         ("increase_memory_allocation", ["self", "factor"])):
+        assert list(inspect.signature(getattr(B200SchurComplementLinearSolver, name)).parameters) == params
+
+
+# ---- carriers ------------------------------------------------------------------------------------
+def test_block_matrix_nested_and_duplicates():
+    inner = BlockMatrix(2, 2)
+    inner.set_block(0, 0, sp.coo_matrix(([1.0, 2.0], ([0, 0], [0, 0])), shape=(2, 2)))  # duplicate entry
+    inner.set_block(1, 0, sp.coo_matrix(np.array([[0.0, 5.0]])))
+    inner.set_col_size(1, 1)
+    outer = BlockMatrix(2, 2)
+    outer.set_block(0, 0, inner)
+    outer.set_block(1, 1, sp.identity(2, format="coo"))
+    assert outer.shape == (5, 5) and outer.bshape == (2, 2)
+    coo = outer.tocoo()
+    assert coo.nnz == 5  # duplicates preserved
+    dense = outer.toarray()
+    assert dense[0, 0] == 3.0 and dense[2, 1] == 5.0 and dense[3, 3] == 1.0
+    assert np.array_equal(outer.transpose().toarray(), dense.T)
+    assert outer.copy_structure().get_block(0, 0) is None and outer.copy().toarray()[0, 0] == 3.0
+
+
+def test_block_vector_structure_ops():
+    inner = BlockVector(2)
+    inner.set_block(0, np.array([1.0, 2.0]))
+    inner.set_block(1, np.array([3.0]))
+    v = BlockVector(2)
+    v.set_block(0, inner)
+    v.set_block(1, np.array([4.0, 5.0]))
+    assert v.size == 5 and np.array_equal(v.flatten(), [1, 2, 3, 4, 5])
+    w = v - np.ones(5)
+    assert w.get_block(0).nblocks == 2 and np.array_equal(w.flatten(), [0, 1, 2, 3, 4])
+    c = v.copy_structure()
+    c.copyfrom(np.arange(5.0))
+    assert np.array_equal(c.get_block(0).get_block(1), [2.0])
+    assert np.array_equal(sp.identity(5, format="csr").dot(v), v.flatten())
+
+
+# ---- symbolic analysis -----------------------------------------------------------------------------
+def test_analyse_generator_structure():
+    m = EstimationModel(3, 20, 2, 5)
+    kkt = m.build_kkt()
+    st = structure.analyse(kkt)
+    assert st.n_blocks == 3 and st.m_c == 5 and st.local_blocks == [0, 1, 2]
+    assert list(st.block_n) == [m.block_dim] * 3
+    assert list(st.border_ptr) == [0, 5, 10, 15] and list(st.border_rows[:5]) == [0, 1, 2, 3, 4]
+    # border entries land in rows n..n+m-1 of their front, on the last n_theta columns (create_model.py:107-110)
+    kind, i, lo, hi = st.segments[1]
+    assert kind == "A" and np.array_equal(st.dest_row[lo:hi], m.block_dim + np.arange(5))
+    assert np.array_equal(st.dest_col[lo:hi], m.block_dim - 5 + np.arange(5))
+    # strict upper triangle of K is dropped
+    kind, i, lo, hi = st.segments[0]
+    c = kkt.get_block(0, 0).tocoo()
+    assert np.array_equal(st.dest_front[lo:hi] >= 0, c.row >= c.col)
+    vals = np.zeros(st.nvals)
+    assert structure.gather_values(kkt, st, vals)
+    assert np.array_equal(vals[lo:hi], c.data)
+
+
+def test_analyse_partitions_round_robin_and_by_ownership():
+    m = EstimationModel(5, 10, 2, 3)
+    kkt = m.build_kkt()
+    assert structure.analyse(kkt, rank=1, size=2).local_blocks == [1, 3]
+    kkt.rank_ownership = -np.ones((6, 6), dtype=np.int64)
+    for i, o in enumerate([1, 1, 0, 0, 1]):
+        kkt.rank_ownership[i, i] = o
+    assert structure.analyse(kkt, rank=1, size=2).local_blocks == [0, 1, 4]
+    kkt.rank_ownership[2, 2] = -1
+    assert structure.analyse(kkt, rank=0, size=2).local_blocks == [2, 3]  # -1 belongs to rank 0 (mpi...:201-202)
+
+
+def test_pattern_change_is_detected():
+    m = EstimationModel(2, 10, 2, 3)
+    kkt = m.build_kkt()
+    st = structure.analyse(kkt)
+    vals = np.zeros(st.nvals)
+    k0 = kkt.get_block(0, 0).tocoo()
+    shuffled = sp.coo_matrix((k0.data[::-1], (k0.row[::-1], k0.col[::-1])), shape=k0.shape)
+    kkt.set_block(0, 0, shuffled)
+    assert not structure.gather_values(kkt, st, vals)
+
+
+def test_non_square_rejected():
+    with pytest.raises(ValueError, match="not square"):
+        structure.analyse(BlockMatrix(2, 3))
+
+
+# ---- solver host logic on the fake backend ---------------------------------------------------------
+def _fake_solver(**kw):
+    return B200SchurComplementLinearSolver(backend=FakeBackend(), **kw)
+
+
+def test_host_logic_known_answer(known_answers):
+    dense = known_answers["kat_sym_q_dense"]
+    kkt = bordered_from_dense(dense, [2, 2, 2, 2])
+    rhs = block_vector(known_answers["kat_sym_q_rhs"], [2, 2, 2, 2])
+    before = rhs.flatten().copy()
+    s = _fake_solver()
+    assert s.do_symbolic_factorization(matrix=kkt, raise_on_error=False, timer=None).status == LinearSolverStatus.successful
+    assert s.do_numeric_factorization(matrix=kkt, raise_on_error=False, timer=None).status == LinearSolverStatus.successful
+    x = s.do_back_solve(rhs)
+    assert np.allclose(x.flatten(), known_answers["kat_sym_q_x"])
+    assert np.array_equal(rhs.flatten(), before)  # rhs is not mutated (unlike explicit...:141,145)
+    assert s.get_inertia() == tuple(known_answers["kat_sym_q_inertia"])
+    assert x.nblocks == 4
+
+
+def test_host_logic_nested_blocks_and_reanalysis():
+    """Nested BlockMatrix / BlockVector blocks (sc_ip_interface.py:1248-1266) and a COO re-ordering."""
+    rng = np.random.default_rng(5)
+    flat = random_bordered(rng, 2, 6, 3)
+    kkt = BlockMatrix(3, 3)
+    for i in range(2):
+        K = flat.get_block(i, i).toarray()
+        nest = BlockMatrix(2, 2)
+        nest.set_block(0, 0, sp.coo_matrix(K[:4, :4])); nest.set_block(0, 1, sp.coo_matrix(K[:4, 4:]))
+        nest.set_block(1, 0, sp.coo_matrix(K[4:, :4])); nest.set_block(1, 1, sp.coo_matrix(K[4:, 4:]))
+        kkt.set_block(i, i, nest)
+        kkt.set_block(2, i, flat.get_block(2, i))
+    kkt.set_block(2, 2, flat.get_block(2, 2))
+    rhs = BlockVector(3)
+    for i in range(2):
+        nest = BlockVector(2)
+        nest.set_block(0, rng.standard_normal(4)); nest.set_block(1, rng.standard_normal(2))
+        rhs.set_block(i, nest)
+    rhs.set_block(2, rng.standard_normal(3))
+    s = _fake_solver()
+    s.do_symbolic_factorization(kkt)
+    s.do_numeric_factorization(kkt)
+    x = s.do_back_solve(rhs)
+    assert x.get_block(0).nblocks == 2  # structure preserved for set_primal_dual_kkt_solution
+    assert np.allclose(sym_full(flat) @ x.flatten(), rhs.flatten())
+    # same matrix, different COO order in one block -> silently re-analysed (mumps_interface.py:82-83)
+    A = kkt.get_block(2, 0).tocoo()
+    kkt.set_block(2, 0, sp.coo_matrix((A.data[::-1], (A.row[::-1], A.col[::-1])), shape=A.shape))
+    assert s.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+    assert np.allclose(s.do_back_solve(rhs).flatten(), x.flatten())
+
+
+def test_host_logic_error_conventions():
+    dense = np.zeros((5, 5))
+    dense[:2, :2] = [[1.0, 2.0], [2.0, 4.0]]
+    dense[2:4, 2:4] = np.eye(2); dense[4, 4] = 1.0; dense[4, 0] = dense[0, 4] = 1.0
+    kkt = bordered_from_dense(dense, [2, 2, 1])
+    s = _fake_solver()
+    with pytest.raises(RuntimeError):
+        s.do_numeric_factorization(kkt)  # before symbolic
+    s.do_symbolic_factorization(kkt)
+    with pytest.raises(RuntimeError):
+        s.get_inertia()  # before numeric (ma27_interface.py:197-200)
+    assert s.do_numeric_factorization(kkt, raise_on_error=False).status == LinearSolverStatus.singular
+    with pytest.raises(RuntimeError, match="singular"):
+        s.do_numeric_factorization(kkt, raise_on_error=True)
+    with pytest.raises(RuntimeError):
+        s.do_back_solve(block_vector(np.ones(5), [2, 2, 1]))
+    assert s.increase_memory_allocation(2) is None
+
+
+def test_host_logic_generator_vs_oracle():
+    m = EstimationModel(4, 12, 2, 3)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s = _fake_solver()
+    s.do_symbolic_factorization(kkt)
+    s.do_numeric_factorization(kkt)
+    o = SchurOracle()
+    o.symbolic(kkt); o.numeric(kkt)
+    assert np.allclose(s.do_back_solve(rhs).flatten(), o.solve(rhs).flatten(), rtol=1e-9, atol=1e-9)
+    assert s.get_inertia() == m.expected_inertia()
