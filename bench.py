@@ -35,41 +35,50 @@ def workload_name(n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML while the timed region runs."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.power, self.reason_bits = [], [], 0
+        self.sm_max = None
         self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
 
     def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:  # noqa: BLE001
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.005)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=10)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        busy = [v for v in sm if v > 0.5 * float(self.rows[0][1])] or sm
-        reasons = []
-        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
-            if any(r[k].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+        reasons = [n for n, attr in names if self.reason_bits & int(getattr(nv, attr, 0))]
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(self.power)}
 
 
 def update_flops(n, m, nb):
@@ -181,6 +190,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from parapint_b200 import B200SchurComplementLinearSolver, Communicator, LinearSolverStatus
