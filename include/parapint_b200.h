@@ -47,7 +47,9 @@ const char *pp_last_error(void);
 int pp_create(int device, pp_handle **out);
 int pp_destroy(pp_handle *h);
 
-/* Tunables: name in {"pivot_tol", "panel_width", "profile", "use_graph", "refine_steps"}. */
+/* Tunables: "pivot_tol" (absolute zero-pivot tolerance), "panel_width" (dense panel, <= 64),
+ * "sparse" (0/1: multifrontal subtree path), "pivot_threshold" (u of the threshold test in subtree
+ * fronts, default 0.01), "sparse_fmax", "sparse_dmax", "sparse_min_n", "profile". */
 int pp_set_option(pp_handle *h, const char *name, double value);
 
 /*
@@ -139,9 +141,33 @@ enum {
   PP_PROF_SCHUR = 4,    /* gather of the local Schur contribution */
   PP_PROF_FORWARD = 5,  /* forward sweep on the local fronts */
   PP_PROF_BACKWARD = 6, /* backward sweep on the local fronts */
+  PP_PROF_SUBTREE = 7,  /* multifrontal factorisation of the subtree fronts (one CTA per block) */
   PP_PROF_CLASSES = 8
 };
 int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset);
+
+/*
+ * Symbolic statistics of local block `block`: out = {plan id, subtree supernodes, root columns,
+ * delayed-pivot slots, static nnz(L) of the subtree part, largest subtree front, factor doubles,
+ * stack doubles, number of distinct plans, 1 if the sparse path overflowed and the handle fell back
+ * to dense fronts, delayed pivots that reached the root in the last factorisation, failure flag}.
+ */
+int pp_plan_stats(pp_handle *h, int32_t block, int64_t out[12]);
+
+/*
+ * Host-only access to the symbolic analysis of ONE block (no GPU needed): minimum-degree ordering,
+ * supernodes, subtree / root split and the destination of every input entry.  `rows`/`cols` are
+ * lower-triangular positions in the front [K | border rows] (row >= n: border row `row - n`).
+ * Arrays: rootcols, col_ptr, cols, row_ptr, rows, rel, parent, nchild, dcap, ent_ptr, tgt_row,
+ * tgt_col, tgt_src_ptr, tgt_src, root_row, root_col, root_src.  Scalars: n, m, nT, DR, ns, nnz_l,
+ * max_front, l_total, stack_cap.  Pass fmax / dmax / min_sparse_n < 0 for the defaults.
+ */
+typedef struct pp_plan pp_plan;
+int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols,
+                   int32_t fmax, int32_t dmax, int32_t min_sparse_n, pp_plan **out);
+int pp_plan_get(const pp_plan *plan, const char *name, const int32_t **data, int64_t *len);
+int pp_plan_scalar(const pp_plan *plan, const char *name, int64_t *value);
+int pp_plan_destroy(pp_plan *plan);
 
 /* Debug / test access: copy front `f` (0..n_local-1 local, n_local = coupling) to host,
  * column-major with leading dimension *ld; piv/bsz receive the pivot records (n entries). */

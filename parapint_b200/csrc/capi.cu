@@ -15,6 +15,9 @@
 #include "factor.cuh"
 #include "front.cuh"
 #include "solve.cuh"
+#include "sparse.cuh"
+#include "symbolic.hpp"
+#include <map>
 
 using namespace ppb;
 
@@ -82,16 +85,35 @@ struct pp_handle {
   std::vector<int> n, m, nf, ld;  // n_local + 1 fronts (last = coupling)
   int64_t local_dim = 0;
   int nmax_local = 0, nfmax_local = 0;
+  std::vector<int> block_n;       // original order of every local block
   // options
   double pivot_tol = 0.0;
   int panel_width = 64;
+  double pivot_threshold = 0.01;  // u of the threshold test in the subtree fronts
+  bool use_sparse = true;
+  bool sparse_failed = false;     // a block overflowed its delayed-pivot capacity: all blocks were redone dense
+  PlanOptions plan_opt;
+  // saved symbolic inputs (for the dense re-analysis after a sparse-path overflow)
+  std::vector<int32_t> in_block_n, in_border_rows, in_dest_front, in_dest_row, in_dest_col;
+  std::vector<int64_t> in_border_ptr;
+  // multifrontal (subtree) part
+  std::vector<PatternPlan> plans;
+  std::vector<int> block_plan;
+  DevBuf<int> planI;              // all integer tables of all plans
+  DevBuf<long long> planL;
+  DevBuf<PlanDev> plans_dev;
+  DevBuf<SparseBlock> blocks_dev;
+  DevBuf<double> arenaL, arenaStack, ywork, root_rhs, root_x;
+  DevBuf<int> arenaBI;
+  DevBuf<long long> vec_off, root_off;
+  int64_t root_total = 0;
   // device storage
   DevBuf<double> arenaA, arenaW, arenaZ, vals, rhs, x, xc, crhs;
   DevBuf<int> arenaI, flag;
   DevBuf<Front> fronts;
   std::vector<Front> hfronts;
   DevBuf<unsigned long long> inertia;  // [0..2] local, [3..5] coupling
-  DevBuf<int64_t> asm_dst, asm_ptr, asm_src, src_ptr, brow_ptr, rhs_off;
+  DevBuf<int64_t> asm_dst, asm_ptr, asm_src, src_ptr, brow_ptr, rhs_off, root_off64;
   DevBuf<int32_t> src_front, src_pos, brow;
   PinBuf<double> pin_vals, pin_vec;
   PinBuf<int> pin_flag;
@@ -213,8 +235,8 @@ int read_flag(pp_handle *h, int first, int count, cudaStream_t st) {
   if (count == 0) return 0;
   collect_info_kernel<<<1, 256, 0, st>>>(h->fronts.p + first, count, h->flag.p);
   h->launches++;
-  h->pin_flag.ensure(1);
-  CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  h->pin_flag.ensure(4);
+  CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return h->pin_flag.p[0];
 }
@@ -261,6 +283,9 @@ int pp_create(int device, pp_handle **out) {
     if (device < 0 || device >= count) return fail("pp_create: no such CUDA device");
     CK(cudaSetDevice(device));
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
+    CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
+    CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
     auto *h = new pp_handle();
     h->device = device;
     h->flag.alloc(4);
@@ -289,6 +314,17 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     const int nb = (int)value;
     if (nb < 4 || nb > NBMAX) return fail("panel_width must be in [4, 64]");
     h->panel_width = nb;
+  } else if (key == "sparse") {
+    h->use_sparse = value != 0.0;
+  } else if (key == "pivot_threshold") {
+    if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
+    h->pivot_threshold = value;
+  } else if (key == "sparse_fmax") {
+    h->plan_opt.fmax = std::max(8, std::min((int)value, SF_SBUF - 8));
+  } else if (key == "sparse_dmax") {
+    h->plan_opt.dmax = std::max(0, std::min((int)value, SF_SBUF / 2));
+  } else if (key == "sparse_min_n") {
+    h->plan_opt.min_sparse_n = (int)value;
   } else if (key == "profile") {
     h->profile = value != 0.0;
   } else if (key == "use_graph" || key == "refine_steps") {
@@ -299,25 +335,289 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   return PP_SUCCESSFUL;
 }
 
+// Builds every device structure from the saved symbolic inputs.  force_dense: no subtree part.
+static int do_symbolic(pp_handle *h, bool force_dense) {
+  const int n_local = h->n_local, m_c = h->m_c;
+  const int64_t nvals = h->nvals;
+  const int32_t *block_n = h->in_block_n.data();
+  const int64_t *border_ptr = h->in_border_ptr.data();
+  const int32_t *border_rows = h->in_border_rows.data();
+  const int32_t *dest_front = h->in_dest_front.data();
+  const int32_t *dest_row = h->in_dest_row.data();
+  const int32_t *dest_col = h->in_dest_col.data();
+  h->have_symbolic = h->local_factored = h->coupling_factored = h->forward_done = false;
+  const int nfronts = n_local + 1;
+  h->block_n.assign(block_n, block_n + n_local);
+  h->local_dim = 0;
+  std::vector<int64_t> bptr(nfronts + 1, 0);
+  std::vector<int> mloc(n_local, 0);
+  for (int f = 0; f < n_local; ++f) {
+    mloc[f] = (int)(border_ptr[f + 1] - border_ptr[f]);
+    h->local_dim += block_n[f];
+    bptr[f + 1] = bptr[f] + mloc[f];
+  }
+  bptr[nfronts] = bptr[n_local];
+
+  // ---- per-block entry lists and pattern de-duplication ----
+  std::vector<std::vector<int>> e_row(n_local), e_col(n_local), e_src(n_local);
+  std::vector<int64_t> first_k(n_local, -1);
+  std::vector<int64_t> coupling_k;
+  for (int64_t k = 0; k < nvals; ++k) {
+    const int f = dest_front[k];
+    if (f < 0) continue;
+    if (f > n_local) return fail("pp_symbolic: dest_front out of range");
+    const int r = dest_row[k], c = dest_col[k];
+    if (f == n_local) {
+      if (r < 0 || c < 0 || r >= m_c || c > r) return fail("pp_symbolic: coupling entry outside the lower triangle");
+      coupling_k.push_back(k);
+      continue;
+    }
+    if (r < 0 || c < 0 || r >= block_n[f] + mloc[f] || c > r || c >= block_n[f])
+      return fail("pp_symbolic: destination outside the lower triangle of its front");
+    if (first_k[f] < 0) first_k[f] = k;
+    if (k - first_k[f] > 0x7fffffff) return fail("pp_symbolic: block values span more than 2^31 entries");
+    e_row[f].push_back(r);
+    e_col[f].push_back(c);
+    e_src[f].push_back((int)(k - first_k[f]));
+  }
+  h->plans.clear();
+  h->block_plan.assign(n_local, -1);
+  {
+    std::map<std::vector<int>, int> seen;
+    for (int f = 0; f < n_local; ++f) {
+      std::vector<int> key;
+      key.reserve(3 * e_row[f].size() + 2);
+      key.push_back(block_n[f]);
+      key.push_back(mloc[f]);
+      key.insert(key.end(), e_row[f].begin(), e_row[f].end());
+      key.insert(key.end(), e_col[f].begin(), e_col[f].end());
+      key.insert(key.end(), e_src[f].begin(), e_src[f].end());
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        const int id = (int)h->plans.size();
+        h->plans.push_back(build_plan(block_n[f], mloc[f], e_row[f], e_col[f], e_src[f], h->plan_opt,
+                                      force_dense || !h->use_sparse));
+        seen.emplace(std::move(key), id);
+        h->block_plan[f] = id;
+      } else {
+        h->block_plan[f] = it->second;
+      }
+    }
+  }
+
+  // ---- dense fronts: one root per block + the coupling front ----
+  h->n.assign(nfronts, 0);
+  h->m.assign(nfronts, 0);
+  h->nf.assign(nfronts, 0);
+  h->ld.assign(nfronts, 0);
+  h->nmax_local = h->nfmax_local = 0;
+  for (int f = 0; f < n_local; ++f) {
+    const PatternPlan &P = h->plans[h->block_plan[f]];
+    h->n[f] = P.nT + P.DR;
+    h->m[f] = mloc[f];
+  }
+  h->n[n_local] = m_c;
+  h->m[n_local] = 0;
+  std::vector<size_t> offA(nfronts), offW(nfronts), offZ(nfronts), offI(nfronts);
+  size_t totA = 0, totW = 0, totZ = 0, totI = 0;
+  for (int f = 0; f < nfronts; ++f) {
+    h->nf[f] = h->n[f] + h->m[f];
+    h->ld[f] = std::max(16, round_up(h->nf[f], 16));
+    offA[f] = totA;
+    totA += (size_t)h->ld[f] * std::max(h->nf[f], 1);
+    offW[f] = totW;
+    totW += (size_t)h->ld[f] * NBMAX;
+    offZ[f] = totZ;
+    totZ += (size_t)round_up(h->n[f] + h->m[f] + 2, 16);
+    offI[f] = totI;
+    totI += (size_t)3 * round_up(h->n[f] + 1, 16) + 16;
+    if (f < n_local) {
+      h->nmax_local = std::max(h->nmax_local, h->n[f]);
+      h->nfmax_local = std::max(h->nfmax_local, h->nf[f]);
+    }
+    if (solve_smem(h->nf[f]) > 200 * 1024) return fail("pp_symbolic: dense front too large for the in-smem solve (nf > ~25000)");
+  }
+  h->arenaA_elems = totA;
+  h->arenaA.alloc(totA);
+  h->arenaW.alloc(totW);
+  h->arenaZ.alloc(totZ);
+  h->arenaI.alloc(totI);
+  CK(cudaMemset(h->arenaW.p, 0, totW * sizeof(double)));
+  CK(cudaMemset(h->arenaZ.p, 0, totZ * sizeof(double)));
+  CK(cudaMemset(h->arenaI.p, 0, totI * sizeof(int)));
+  std::vector<Front> hf(nfronts);
+  for (int f = 0; f < nfronts; ++f) {
+    Front &F = hf[f];
+    F.A = h->arenaA.p + offA[f];
+    F.W = h->arenaW.p + offW[f];
+    F.zbuf = h->arenaZ.p + offZ[f];
+    F.bvec = F.zbuf + h->n[f];
+    const int seg = round_up(h->n[f] + 1, 16);
+    F.ipiv = h->arenaI.p + offI[f];
+    F.bsz = F.ipiv + seg;
+    F.perm = F.bsz + seg;
+    F.state = F.perm + seg;
+    F.n = h->n[f];
+    F.m = h->m[f];
+    F.nf = h->nf[f];
+    F.ld = h->ld[f];
+  }
+  h->fronts.upload(hf);
+  h->hfronts = hf;
+
+  // ---- dense assembly map (root entries of every block + Q): group values by destination ----
+  std::vector<std::pair<int64_t, int64_t>> keyed;
+  for (int f = 0; f < n_local; ++f) {
+    const PatternPlan &P = h->plans[h->block_plan[f]];
+    for (size_t i = 0; i < P.root_row.size(); ++i)
+      keyed.emplace_back((int64_t)(offA[f] + (size_t)P.root_row[i] + (size_t)P.root_col[i] * h->ld[f]),
+                         first_k[f] + P.root_src[i]);
+  }
+  for (int64_t k : coupling_k)
+    keyed.emplace_back((int64_t)(offA[n_local] + (size_t)dest_row[k] + (size_t)dest_col[k] * h->ld[n_local]), k);
+  std::stable_sort(keyed.begin(), keyed.end(), [](const auto &a, const auto &b) {
+    return a.first != b.first ? a.first < b.first : a.second < b.second;
+  });
+  std::vector<int64_t> dst, ptr, src(keyed.size());
+  for (size_t i = 0; i < keyed.size(); ++i) {
+    if (i == 0 || keyed[i].first != keyed[i - 1].first) {
+      dst.push_back(keyed[i].first);
+      ptr.push_back((int64_t)i);
+    }
+    src[i] = keyed[i].second;
+  }
+  ptr.push_back((int64_t)keyed.size());
+  h->nuniq = (int64_t)dst.size();
+  h->asm_dst.upload(dst);
+  h->asm_ptr.upload(ptr);
+  h->asm_src.upload(src);
+  if (h->vals.n < (size_t)std::max<int64_t>(nvals, 1)) h->vals.alloc((size_t)std::max<int64_t>(nvals, 1));
+
+  // ---- plans on the device: one int table, one int64 table ----
+  std::vector<int> ti;
+  std::vector<long long> tl;
+  struct Off { size_t rootcols, col_ptr, cols, row_ptr, rows, rel, parent, nchild, dcap, fid_off, fs_off, ent_ptr, tgt_row, tgt_col, tgt_src_ptr, tgt_src, l_off; };
+  std::vector<Off> offs(h->plans.size());
+  auto put = [&](const std::vector<int> &v) { const size_t o = ti.size(); ti.insert(ti.end(), v.begin(), v.end()); ti.push_back(0); return o; };
+  for (size_t q = 0; q < h->plans.size(); ++q) {
+    const PatternPlan &P = h->plans[q];
+    Off &o = offs[q];
+    o.rootcols = put(P.rootcols); o.col_ptr = put(P.col_ptr); o.cols = put(P.cols); o.row_ptr = put(P.row_ptr);
+    o.rows = put(P.rows); o.rel = put(P.rel); o.parent = put(P.parent); o.nchild = put(P.nchild); o.dcap = put(P.dcap);
+    o.fid_off = put(P.fid_off); o.fs_off = put(P.fs_off); o.ent_ptr = put(P.ent_ptr); o.tgt_row = put(P.tgt_row);
+    o.tgt_col = put(P.tgt_col); o.tgt_src_ptr = put(P.tgt_src_ptr); o.tgt_src = put(P.tgt_src);
+    o.l_off = tl.size();
+    for (int64_t v : P.l_off) tl.push_back((long long)v);
+    tl.push_back(0);
+  }
+  h->planI.upload(ti);
+  h->planL.upload(tl);
+  std::vector<PlanDev> pd(h->plans.size());
+  for (size_t q = 0; q < h->plans.size(); ++q) {
+    const PatternPlan &P = h->plans[q];
+    const Off &o = offs[q];
+    PlanDev &D = pd[q];
+    const int *b = h->planI.p;
+    D.n = P.n; D.m = P.m; D.nT = P.nT; D.DR = P.DR; D.ns = P.ns; D.pad = 0;
+    D.rootcols = b + o.rootcols; D.col_ptr = b + o.col_ptr; D.cols = b + o.cols; D.row_ptr = b + o.row_ptr;
+    D.rows = b + o.rows; D.rel = b + o.rel; D.parent = b + o.parent; D.nchild = b + o.nchild; D.dcap = b + o.dcap;
+    D.fid_off = b + o.fid_off; D.fs_off = b + o.fs_off; D.ent_ptr = b + o.ent_ptr; D.tgt_row = b + o.tgt_row;
+    D.tgt_col = b + o.tgt_col; D.tgt_src_ptr = b + o.tgt_src_ptr; D.tgt_src = b + o.tgt_src;
+    D.l_off = h->planL.p + o.l_off;
+  }
+  h->plans_dev.upload(pd);
+
+  // ---- per-block storage of the subtree part ----
+  size_t totL = 0, totS = 0, totBI = 0;
+  std::vector<size_t> oL(n_local), oS(n_local), oBI(n_local);
+  std::vector<long long> voff(n_local + 1, 0), roff_root(n_local + 1, 0);
+  for (int f = 0; f < n_local; ++f) {
+    const PatternPlan &P = h->plans[h->block_plan[f]];
+    oL[f] = totL; totL += (size_t)P.l_total + 8;
+    oS[f] = totS; totS += (size_t)P.stack_cap + 8;
+    oBI[f] = totBI; totBI += (size_t)P.fid_total + P.fs_total + 2 * P.ns + P.nT + P.DR + 16;
+    voff[f + 1] = voff[f] + block_n[f];
+    roff_root[f + 1] = roff_root[f] + P.nT + P.DR;
+  }
+  h->root_total = roff_root[n_local];
+  h->arenaL.alloc(std::max<size_t>(totL, 1));
+  h->arenaStack.alloc(std::max<size_t>(totS, 1));
+  h->arenaBI.alloc(std::max<size_t>(totBI, 1));
+  CK(cudaMemset(h->arenaBI.p, 0, std::max<size_t>(totBI, 1) * sizeof(int)));
+  std::vector<SparseBlock> sb(n_local);
+  for (int f = 0; f < n_local; ++f) {
+    const PatternPlan &P = h->plans[h->block_plan[f]];
+    SparseBlock &B = sb[f];
+    B.plan = h->block_plan[f];
+    B.root = f;
+    B.val_off = first_k[f] < 0 ? 0 : first_k[f];
+    B.L = h->arenaL.p + oL[f];
+    B.stack = h->arenaStack.p + oS[f];
+    B.stack_cap = P.stack_cap;
+    int *bi = h->arenaBI.p + oBI[f];
+    B.fid = bi; bi += P.fid_total;
+    B.pbz = bi; bi += P.fs_total;
+    B.meta = bi; bi += 2 * P.ns;
+    B.rootids = bi; bi += P.nT + P.DR;
+    B.info = bi;
+  }
+  h->blocks_dev.upload(sb);
+  h->vec_off.upload(voff);
+  h->root_off.upload(roff_root);
+  {
+    std::vector<int64_t> r64(roff_root.begin(), roff_root.end());
+    h->root_off64.upload(r64);
+  }
+  h->ywork.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
+  h->root_rhs.alloc((size_t)std::max<int64_t>(h->root_total, 1));
+  h->root_x.alloc((size_t)std::max<int64_t>(h->root_total, 1));
+
+  // ---- coupling-row sources: row r <- (front, position) in front order ----
+  std::vector<int32_t> brow((size_t)bptr[n_local]);
+  std::vector<int64_t> sptr((size_t)m_c + 1, 0);
+  for (int f = 0; f < n_local; ++f)
+    for (int64_t p2 = border_ptr[f]; p2 < border_ptr[f + 1]; ++p2) {
+      brow[(size_t)(bptr[f] + (p2 - border_ptr[f]))] = border_rows[p2];
+      sptr[(size_t)border_rows[p2] + 1]++;
+    }
+  for (int r = 0; r < m_c; ++r) sptr[r + 1] += sptr[r];
+  std::vector<int32_t> sfront((size_t)bptr[n_local]), spos((size_t)bptr[n_local]);
+  std::vector<int64_t> fill(sptr.begin(), sptr.end() - 1);
+  for (int f = 0; f < n_local; ++f)
+    for (int a = 0; a < h->m[f]; ++a) {
+      const int r = brow[(size_t)bptr[f] + a];
+      sfront[(size_t)fill[r]] = f;
+      spos[(size_t)fill[r]] = a;
+      fill[r]++;
+    }
+  h->brow.upload(brow);
+  h->brow_ptr.upload(bptr);
+  h->src_ptr.upload(sptr);
+  h->src_front.upload(sfront);
+  h->src_pos.upload(spos);
+
+  // ---- solve buffers ----
+  std::vector<int64_t> zero_off(nfronts + 1, 0);
+  h->rhs_off.upload(zero_off);
+  h->rhs.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
+  h->x.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
+  h->xc.alloc((size_t)std::max(m_c, 1));
+  h->crhs.alloc((size_t)std::max(m_c, 1));
+  h->bytes = (int64_t)((totA + totW + totZ + totL + totS) * sizeof(double) + (totI + totBI) * sizeof(int));
+  h->have_symbolic = true;
+  return (int)PP_SUCCESSFUL;
+}
+
 int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
                 const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
                 const int32_t *dest_row, const int32_t *dest_col) {
   if (!h) return fail("pp_symbolic: null handle");
   if (n_local < 0 || m_c < 0 || nvals < 0) return fail("pp_symbolic: negative size");
   if (n_local > 0 && (!block_n || !border_ptr)) return fail("pp_symbolic: null block description");
+  if (nvals > 0 && (!dest_front || !dest_row || !dest_col)) return fail("pp_symbolic: null destination arrays");
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
-    h->have_symbolic = h->local_factored = h->coupling_factored = h->forward_done = false;
-    const int nfronts = n_local + 1;
-    h->n_local = n_local;
-    h->m_c = m_c;
-    h->n.assign(nfronts, 0);
-    h->m.assign(nfronts, 0);
-    h->nf.assign(nfronts, 0);
-    h->ld.assign(nfronts, 0);
-    h->local_dim = 0;
-    h->nmax_local = h->nfmax_local = 0;
-    std::vector<int64_t> bptr(nfronts + 1, 0);
+    h->have_symbolic = false;
     for (int f = 0; f < n_local; ++f) {
       if (block_n[f] < 0) return fail("pp_symbolic: negative block order");
       const int64_t mi = border_ptr[f + 1] - border_ptr[f];
@@ -327,128 +627,58 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
         if (p > border_ptr[f] && border_rows[p] <= border_rows[p - 1])
           return fail("pp_symbolic: border rows must be strictly ascending");
       }
-      h->n[f] = block_n[f];
-      h->m[f] = (int)mi;
-      h->local_dim += block_n[f];
-      bptr[f + 1] = bptr[f] + mi;
     }
-    bptr[nfronts] = bptr[n_local];
-    h->n[n_local] = m_c;
-    h->m[n_local] = 0;
-    // storage layout
-    std::vector<size_t> offA(nfronts), offW(nfronts), offZ(nfronts), offI(nfronts);
-    size_t totA = 0, totW = 0, totZ = 0, totI = 0;
-    for (int f = 0; f < nfronts; ++f) {
-      h->nf[f] = h->n[f] + h->m[f];
-      h->ld[f] = std::max(16, round_up(h->nf[f], 16));
-      offA[f] = totA;
-      totA += (size_t)h->ld[f] * std::max(h->nf[f], 1);
-      offW[f] = totW;
-      totW += (size_t)h->ld[f] * NBMAX;
-      offZ[f] = totZ;
-      totZ += (size_t)round_up(h->n[f] + h->m[f] + 2, 16);
-      offI[f] = totI;
-      totI += (size_t)3 * round_up(h->n[f] + 1, 16) + 16;
-      if (f < n_local) {
-        h->nmax_local = std::max(h->nmax_local, h->n[f]);
-        h->nfmax_local = std::max(h->nfmax_local, h->nf[f]);
-      }
-      if (solve_smem(h->nf[f]) > 200 * 1024) return fail("pp_symbolic: front too large for the in-smem solve (nf > ~25000)");
-    }
-    h->arenaA_elems = totA;
-    h->arenaA.alloc(totA);
-    h->arenaW.alloc(totW);
-    h->arenaZ.alloc(totZ);
-    h->arenaI.alloc(totI);
-    CK(cudaMemset(h->arenaW.p, 0, totW * sizeof(double)));
-    CK(cudaMemset(h->arenaZ.p, 0, totZ * sizeof(double)));
-    CK(cudaMemset(h->arenaI.p, 0, totI * sizeof(int)));
-    std::vector<Front> hf(nfronts);
-    for (int f = 0; f < nfronts; ++f) {
-      Front &F = hf[f];
-      F.A = h->arenaA.p + offA[f];
-      F.W = h->arenaW.p + offW[f];
-      F.zbuf = h->arenaZ.p + offZ[f];
-      F.bvec = F.zbuf + h->n[f];
-      const int seg = round_up(h->n[f] + 1, 16);
-      F.ipiv = h->arenaI.p + offI[f];
-      F.bsz = F.ipiv + seg;
-      F.perm = F.bsz + seg;
-      F.state = F.perm + seg;
-      F.n = h->n[f];
-      F.m = h->m[f];
-      F.nf = h->nf[f];
-      F.ld = h->ld[f];
-    }
-    h->fronts.upload(hf);
-    h->hfronts = hf;
-
-    // ---- assembly map: group the input values by destination element ----
+    h->n_local = n_local;
+    h->m_c = m_c;
     h->nvals = nvals;
-    std::vector<std::pair<int64_t, int64_t>> keyed;  // (arena offset, source index)
-    keyed.reserve((size_t)nvals);
-    for (int64_t k = 0; k < nvals; ++k) {
-      const int f = dest_front[k];
-      if (f < 0) continue;
-      if (f > n_local) return fail("pp_symbolic: dest_front out of range");
-      const int r = dest_row[k], c = dest_col[k];
-      if (r < 0 || c < 0 || r >= h->nf[f] || c > r) return fail("pp_symbolic: destination outside the lower triangle of its front");
-      keyed.emplace_back((int64_t)(offA[f] + (size_t)r + (size_t)c * h->ld[f]), k);
-    }
-    std::stable_sort(keyed.begin(), keyed.end(),
-                     [](const auto &a, const auto &b) { return a.first < b.first; });
-    std::vector<int64_t> dst, ptr, src(keyed.size());
-    for (size_t i = 0; i < keyed.size(); ++i) {
-      if (i == 0 || keyed[i].first != keyed[i - 1].first) {
-        dst.push_back(keyed[i].first);
-        ptr.push_back((int64_t)i);
-      }
-      src[i] = keyed[i].second;
-    }
-    ptr.push_back((int64_t)keyed.size());
-    h->nuniq = (int64_t)dst.size();
-    h->asm_dst.upload(dst);
-    h->asm_ptr.upload(ptr);
-    h->asm_src.upload(src);
-    h->vals.alloc((size_t)std::max<int64_t>(nvals, 1));
-
-    // ---- coupling-row sources: row r <- (front, position) in front order ----
-    std::vector<int32_t> brow((size_t)bptr[n_local]);
-    std::vector<int64_t> sptr((size_t)m_c + 1, 0);
-    for (int f = 0; f < n_local; ++f)
-      for (int64_t p = border_ptr[f]; p < border_ptr[f + 1]; ++p) {
-        brow[(size_t)(bptr[f] + (p - border_ptr[f]))] = border_rows[p];
-        sptr[(size_t)border_rows[p] + 1]++;
-      }
-    for (int r = 0; r < m_c; ++r) sptr[r + 1] += sptr[r];
-    std::vector<int32_t> sfront((size_t)bptr[n_local]), spos((size_t)bptr[n_local]);
-    std::vector<int64_t> fill(sptr.begin(), sptr.end() - 1);
-    for (int f = 0; f < n_local; ++f)
-      for (int a = 0; a < h->m[f]; ++a) {
-        const int r = brow[(size_t)bptr[f] + a];
-        sfront[(size_t)fill[r]] = f;
-        spos[(size_t)fill[r]] = a;
-        fill[r]++;
-      }
-    h->brow.upload(brow);
-    h->brow_ptr.upload(bptr);
-    h->src_ptr.upload(sptr);
-    h->src_front.upload(sfront);
-    h->src_pos.upload(spos);
-
-    // ---- solve buffers ----
-    std::vector<int64_t> roff(nfronts, 0);
-    for (int f = 1; f < n_local; ++f) roff[f] = roff[f - 1] + h->n[f - 1];
-    roff[n_local] = 0;
-    h->rhs_off.upload(roff);
-    h->rhs.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
-    h->x.alloc((size_t)std::max<int64_t>(h->local_dim, 1));
-    h->xc.alloc((size_t)std::max(m_c, 1));
-    h->crhs.alloc((size_t)std::max(m_c, 1));
-    h->bytes = (int64_t)((totA + totW + totZ) * sizeof(double) + totI * sizeof(int));
-    h->have_symbolic = true;
-    return (int)PP_SUCCESSFUL;
+    h->in_block_n.assign(block_n, block_n + n_local);
+    h->in_border_ptr.assign(border_ptr, border_ptr + n_local + 1);
+    if (n_local == 0) h->in_border_ptr.assign(1, 0);
+    h->in_border_rows.assign(border_rows, border_rows + (n_local ? border_ptr[n_local] : 0));
+    h->in_dest_front.assign(dest_front, dest_front + nvals);
+    h->in_dest_row.assign(dest_row, dest_row + nvals);
+    h->in_dest_col.assign(dest_col, dest_col + nvals);
+    h->sparse_failed = false;
+    return do_symbolic(h, false);
   });
+}
+
+static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_local_dev, cudaStream_t st,
+                              int *sparse_bad) {
+  {
+    ProfSpan sp(h, PP_PROF_ASSEMBLE, st);
+    CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
+    reset_fronts_kernel<<<h->n_local + 1, 256, 0, st>>>(h->fronts.p, h->inertia.p);
+    h->launches++;
+    if (h->nuniq > 0) {
+      assemble_kernel<<<(unsigned)((h->nuniq + 255) / 256), 256, 0, st>>>(dvals, h->asm_dst.p, h->asm_ptr.p,
+                                                                        h->asm_src.p, h->nuniq, h->arenaA.p);
+      h->launches++;
+    }
+  }
+  if (h->n_local > 0) {
+    ProfSpan sp(h, PP_PROF_SUBTREE, st);
+    subtree_factor_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->fronts.p, dvals,
+                                                             h->pivot_threshold, h->pivot_tol, h->inertia.p);
+    h->launches++;
+  }
+  factor_fronts(h, 0, h->n_local, st);
+  if (h->m_c > 0) {
+    ProfSpan sp(h, PP_PROF_SCHUR, st);
+    dim3 g((h->m_c + 127) / 128, h->m_c);
+    schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
+                                           h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
+    h->launches++;
+  }
+  if (h->n_local > 0) {
+    front_inertia_kernel<<<h->n_local, 256, 0, st>>>(h->fronts.p, h->inertia.p);
+    collect_sparse_info_kernel<<<1, 256, 0, st>>>(h->blocks_dev.p, h->n_local, h->flag.p);
+    h->launches += 2;
+  }
+  CK(cudaGetLastError());
+  const int bad = read_flag(h, 0, h->n_local, st);
+  *sparse_bad = h->n_local > 0 ? h->pin_flag.p[1] : 0;
+  return bad;
 }
 
 int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
@@ -471,31 +701,17 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
       dvals = h->vals.p;
     }
-    {
-      ProfSpan sp(h, PP_PROF_ASSEMBLE, st);
-      CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
-      reset_fronts_kernel<<<h->n_local + 1, 256, 0, st>>>(h->fronts.p, h->inertia.p);
-      h->launches++;
-      if (h->nuniq > 0) {
-        assemble_kernel<<<(unsigned)((h->nuniq + 255) / 256), 256, 0, st>>>(dvals, h->asm_dst.p, h->asm_ptr.p,
-                                                                          h->asm_src.p, h->nuniq, h->arenaA.p);
-        h->launches++;
-      }
+    int sparse_bad = 0;
+    int bad = numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad);
+    if (sparse_bad) {
+      // A block ran out of delayed-pivot capacity (or front buffer): redo the analysis with whole
+      // blocks as dense fronts -- slower, but pivoting is then unrestricted -- and factor again.
+      h->sparse_failed = true;
+      const int rc = do_symbolic(h, true);
+      if (rc != PP_SUCCESSFUL) return rc;
+      bad = numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad);
+      if (sparse_bad) return fail("pp_numeric_local: internal error in the dense re-factorisation");
     }
-    factor_fronts(h, 0, h->n_local, st);
-    if (h->m_c > 0) {
-      ProfSpan sp(h, PP_PROF_SCHUR, st);
-      dim3 g((h->m_c + 127) / 128, h->m_c);
-      schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
-                                             h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
-      h->launches++;
-    }
-    if (h->n_local > 0) {
-      front_inertia_kernel<<<h->n_local, 256, 0, st>>>(h->fronts.p, h->inertia.p);
-      h->launches++;
-    }
-    CK(cudaGetLastError());
-    const int bad = read_flag(h, 0, h->n_local, st);
     h->local_factored = true;
     return bad ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
   });
@@ -565,10 +781,12 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
     }
     if (h->n_local > 0) {
       ProfSpan sp(h, PP_PROF_FORWARD, st);
+      subtree_forward_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+                                                                h->ywork.p, h->root_rhs.p, h->root_off.p);
       const size_t sm = solve_smem(h->nfmax_local);
       CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      front_forward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, drhs, h->rhs_off.p);
-      h->launches++;
+      front_forward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, h->root_rhs.p, h->root_off64.p);
+      h->launches += 2;
     }
     if (h->m_c > 0) {
       rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p,
@@ -618,9 +836,11 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
       const size_t sm = solve_smem(h->nfmax_local);
       CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)std::max(sm, solve_smem(mc))));
-      front_backward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, dx,
-                                                             h->rhs_off.p);
-      h->launches++;
+      front_backward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, dxc, h->brow_ptr.p, h->brow.p,
+                                                             h->root_x.p, h->root_off64.p);
+      subtree_backward_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+                                                                 h->vec_off.p, h->root_x.p, h->root_off.p, dx);
+      h->launches += 2;
     }
     CK(cudaGetLastError());
     if (!on_device) {
@@ -653,6 +873,108 @@ int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
     }
     return (int)PP_SUCCESSFUL;
   });
+}
+
+int pp_plan_stats(pp_handle *h, int32_t block, int64_t out[12]) {
+  if (!h || !h->have_symbolic || block < 0 || block >= h->n_local || !out) return fail("pp_plan_stats: bad argument");
+  const PatternPlan &P = h->plans[h->block_plan[block]];
+  out[0] = h->block_plan[block];
+  out[1] = P.ns;
+  out[2] = P.nT;
+  out[3] = P.DR;
+  out[4] = P.nnz_l;
+  out[5] = P.max_front;
+  out[6] = P.l_total;
+  out[7] = P.stack_cap;
+  out[8] = (int64_t)h->plans.size();
+  out[9] = h->sparse_failed ? 1 : 0;
+  out[10] = 0;
+  out[11] = 0;
+  if (P.ns > 0) {  // delayed pivots that reached the root in the last factorisation
+    int info[2] = {0, 0};
+    std::vector<SparseBlock> sb(1);
+    if (cudaMemcpy(sb.data(), h->blocks_dev.p + block, sizeof(SparseBlock), cudaMemcpyDeviceToHost) == cudaSuccess &&
+        cudaMemcpy(info, sb[0].info, sizeof(info), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      out[10] = info[1];
+      out[11] = info[0];
+    }
+  }
+  return PP_SUCCESSFUL;
+}
+
+// ---- host-only access to the symbolic analysis (tests, documentation of the plan format) ----
+struct pp_plan {
+  PatternPlan P;
+};
+
+int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols, int32_t fmax,
+                   int32_t dmax, int32_t min_sparse_n, pp_plan **out) {
+  if (!out || n < 0 || m < 0 || nent < 0 || (nent > 0 && (!rows || !cols))) return fail("pp_plan_create: bad argument");
+  *out = nullptr;
+  return guarded([&]() {
+    std::vector<int> r(rows, rows + nent), c(cols, cols + nent), src((size_t)nent);
+    std::iota(src.begin(), src.end(), 0);
+    for (int64_t k = 0; k < nent; ++k)
+      if (r[k] < c[k] || c[k] < 0 || c[k] >= n || r[k] >= n + m) return fail("pp_plan_create: entry outside the lower triangle");
+    PlanOptions opt;
+    if (fmax > 0) opt.fmax = std::max(8, std::min((int)fmax, SF_SBUF - 8));
+    if (dmax >= 0) opt.dmax = std::max(0, std::min((int)dmax, SF_SBUF / 2));
+    if (min_sparse_n >= 0) opt.min_sparse_n = min_sparse_n;
+    auto *pl = new pp_plan();
+    pl->P = build_plan(n, m, r, c, src, opt, false);
+    *out = pl;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_plan_get(const pp_plan *pl, const char *name, const int32_t **data, int64_t *len) {
+  if (!pl || !name || !data || !len) return fail("pp_plan_get: null argument");
+  const PatternPlan &P = pl->P;
+  const std::string k(name);
+  const std::vector<int> *v = nullptr;
+  if (k == "rootcols") v = &P.rootcols;
+  else if (k == "col_ptr") v = &P.col_ptr;
+  else if (k == "cols") v = &P.cols;
+  else if (k == "row_ptr") v = &P.row_ptr;
+  else if (k == "rows") v = &P.rows;
+  else if (k == "rel") v = &P.rel;
+  else if (k == "parent") v = &P.parent;
+  else if (k == "nchild") v = &P.nchild;
+  else if (k == "dcap") v = &P.dcap;
+  else if (k == "ent_ptr") v = &P.ent_ptr;
+  else if (k == "tgt_row") v = &P.tgt_row;
+  else if (k == "tgt_col") v = &P.tgt_col;
+  else if (k == "tgt_src_ptr") v = &P.tgt_src_ptr;
+  else if (k == "tgt_src") v = &P.tgt_src;
+  else if (k == "root_row") v = &P.root_row;
+  else if (k == "root_col") v = &P.root_col;
+  else if (k == "root_src") v = &P.root_src;
+  else return fail("pp_plan_get: unknown array " + k);
+  *data = v->data();
+  *len = (int64_t)v->size();
+  return PP_SUCCESSFUL;
+}
+
+int pp_plan_scalar(const pp_plan *pl, const char *name, int64_t *value) {
+  if (!pl || !name || !value) return fail("pp_plan_scalar: null argument");
+  const PatternPlan &P = pl->P;
+  const std::string k(name);
+  if (k == "n") *value = P.n;
+  else if (k == "m") *value = P.m;
+  else if (k == "nT") *value = P.nT;
+  else if (k == "DR") *value = P.DR;
+  else if (k == "ns") *value = P.ns;
+  else if (k == "nnz_l") *value = P.nnz_l;
+  else if (k == "max_front") *value = P.max_front;
+  else if (k == "l_total") *value = P.l_total;
+  else if (k == "stack_cap") *value = P.stack_cap;
+  else return fail("pp_plan_scalar: unknown scalar " + k);
+  return PP_SUCCESSFUL;
+}
+
+int pp_plan_destroy(pp_plan *pl) {
+  delete pl;
+  return PP_SUCCESSFUL;
 }
 
 int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,

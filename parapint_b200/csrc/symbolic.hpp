@@ -1,0 +1,377 @@
+// Host-side symbolic analysis of one diagonal KKT block for the multifrontal path.
+//
+// The reference leaves do this inside SuperLU / MA27 / MUMPS (COLAMD / AMD + elimination tree,
+// scipy_interface.py:30, ma27_interface.py:79, mumps_interface.py:59).  Here: a quotient-graph
+// minimum-degree ordering of K_i (columns touched by the border A_i are kept for last), relaxed
+// supernode amalgamation, and a split of the assembly tree into
+//   * SUBTREE supernodes: small fronts (<= fmax rows) that one CTA factors in shared memory, and
+//   * the ROOT: every remaining column (ancestor-closed top of the tree, incl. the border-touched
+//     columns), handled as ONE dense front [root cols | delayed-pivot slots | border rows] by the
+//     batched Bunch-Kaufman kernels of factor.cuh.
+// All index lists use ORIGINAL column numbers of the block.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <set>
+#include <vector>
+
+namespace ppb {
+
+struct PatternPlan {
+  int n = 0, m = 0;     // block order, number of (nonzero) border rows
+  int nT = 0, DR = 0;   // root front: nT static columns, DR delayed-pivot slots
+  int ns = 0;           // subtree supernodes (postorder)
+  std::vector<int> rootcols;          // [nT] original ids in root order
+  std::vector<int> col_ptr, cols;     // own columns per supernode
+  std::vector<int> row_ptr, rows;     // static contribution rows per supernode (original ids)
+  std::vector<int> rel;               // aligned with rows: position in the parent's [cols|rows] list, or in rootcols
+  std::vector<int> parent, nchild, dcap;
+  std::vector<int64_t> l_off;         // offset of the supernode's L block in the per-block factor arena
+  std::vector<int> fid_off, fs_off;   // offsets of the id / pivot-flag lists
+  int64_t l_total = 0;
+  int fid_total = 0, fs_total = 0;
+  int64_t stack_cap = 0;              // doubles needed by the contribution-block stack
+  int max_front = 0;                  // largest subtree front incl. delayed capacity actually allowed
+  int64_t nnz_l = 0;                  // static entries of L in the subtree part (statistics)
+  // original entries grouped by destination: unique targets with their sources (relative value index)
+  std::vector<int> ent_ptr;           // [ns+1] ranges into tgt_*
+  std::vector<int> tgt_row, tgt_col;  // local (row >= nc means contribution row index + nc)
+  std::vector<int> tgt_src_ptr;       // [ntargets+1] into tgt_src
+  std::vector<int> tgt_src;           // relative value indices
+  // root entries (dense front positions; border rows already offset by nT + DR)
+  std::vector<int> root_row, root_col, root_src;  // one per input entry kept
+};
+
+namespace detail {
+
+// Minimum-degree ordering on a quotient graph with element absorption and exact external degrees.
+// Vertices with hold[v] != 0 are never eliminated.  Returns the elimination order of the others and,
+// for each eliminated vertex, its column structure (the variables adjacent at elimination time).
+inline void minimum_degree(int n, const std::vector<std::vector<int>> &adj, const std::vector<char> &hold,
+                           std::vector<int> &order, std::vector<std::vector<int>> &lstruct) {
+  std::vector<std::vector<int>> vadj(adj), eadj(n), evars(n);
+  std::vector<char> eliminated(n, 0), ealive(n, 0);
+  std::vector<int> mark(n, -1), degree(n, 0);
+  int stamp = 0;
+  std::set<std::pair<int, int>> heap;
+  for (int v = 0; v < n; ++v) {
+    degree[v] = (int)vadj[v].size();
+    if (!hold[v]) heap.insert({degree[v], v});
+  }
+  lstruct.assign(n, {});
+  order.clear();
+  std::vector<int> reach;
+  while (!heap.empty()) {
+    const int p = heap.begin()->second;
+    heap.erase(heap.begin());
+    // reach set of p
+    ++stamp;
+    mark[p] = stamp;
+    reach.clear();
+    for (int v : vadj[p])
+      if (!eliminated[v] && mark[v] != stamp) { mark[v] = stamp; reach.push_back(v); }
+    for (int e : eadj[p])
+      if (ealive[e])
+        for (int v : evars[e])
+          if (!eliminated[v] && mark[v] != stamp) { mark[v] = stamp; reach.push_back(v); }
+    std::sort(reach.begin(), reach.end());
+    lstruct[p] = reach;
+    eliminated[p] = 1;
+    order.push_back(p);
+    for (int e : eadj[p]) ealive[e] = 0;  // absorbed into the new element p
+    ealive[p] = 1;
+    evars[p] = reach;
+    const int pstamp = stamp;  // members of the new element carry mark == pstamp
+    for (int v : reach) {
+      // prune variable edges now covered by element p, and dead elements
+      auto &va = vadj[v];
+      va.erase(std::remove_if(va.begin(), va.end(), [&](int w) { return w == p || mark[w] == pstamp || eliminated[w]; }),
+               va.end());
+      auto &ea = eadj[v];
+      ea.erase(std::remove_if(ea.begin(), ea.end(), [&](int e) { return !ealive[e]; }), ea.end());
+      ea.push_back(p);
+    }
+    for (int v : reach) {
+      // exact external degree of v
+      ++stamp;
+      mark[v] = stamp;
+      int d = 0;
+      for (int w : vadj[v])
+        if (mark[w] != stamp) { mark[w] = stamp; ++d; }
+      for (int e : eadj[v])
+        for (int w : evars[e])
+          if (!eliminated[w] && mark[w] != stamp) { mark[w] = stamp; ++d; }
+      if (!hold[v]) {
+        heap.erase({degree[v], v});
+        heap.insert({d, v});
+      }
+      degree[v] = d;
+    }
+    // restore the element-membership stamp for the next prune (marks were overwritten above)
+    stamp += 1;
+  }
+}
+
+}  // namespace detail
+
+struct PlanOptions {
+  int fmax = 64;        // largest static subtree front (own columns + contribution rows)
+  int dmax = 32;        // delayed-pivot capacity per front / per root
+  int sbuf = 96;        // rows of the shared-memory front buffer
+  int relax_zeros = 24; // explicit zeros tolerated when merging a child supernode into its parent
+  int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front
+  double max_density = 0.20; // ... as are blocks whose factor would fill more than this share of n^2/2
+};
+
+// rows/cols: lower-triangular positions (row >= col) of the block's input entries inside the front
+// [K | border]: row < n is a K entry, row >= n a border entry (row - n = border row index).
+// entries with keep[k] == 0 are ignored.  src[k] = relative value index of entry k.
+inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
+                              const std::vector<int> &src, const PlanOptions &opt, bool force_dense) {
+  PatternPlan P;
+  P.n = n;
+  P.m = m;
+  const size_t ne = rows.size();
+  std::vector<char> hold(n, 0);
+  std::vector<std::vector<int>> adj(n);
+  for (size_t k = 0; k < ne; ++k) {
+    const int r = rows[k], c = cols[k];
+    if (r >= n) hold[c] = 1;  // border-touched column: must stay in the root
+    else if (r != c) { adj[r].push_back(c); adj[c].push_back(r); }
+  }
+  for (auto &a : adj) {
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+  }
+  bool dense = force_dense || n < opt.min_sparse_n;
+  std::vector<int> order;
+  std::vector<std::vector<int>> lstruct;
+  if (!dense) {
+    detail::minimum_degree(n, adj, hold, order, lstruct);
+    double fill = 0;
+    for (int p : order) fill += (double)lstruct[p].size() + 1;
+    const double held = (double)(n - (int)order.size());
+    fill += held * (held + 1) / 2;
+    if (fill > opt.max_density * 0.5 * (double)n * n) dense = true;
+  }
+  if (dense) {
+    order.clear();
+    lstruct.assign(n, {});
+  }
+  std::vector<int> pos(n, -1);
+  for (size_t k = 0; k < order.size(); ++k) pos[order[k]] = (int)k;
+  const int big = 1 << 30;
+  auto epos = [&](int v) { return pos[v] < 0 ? big + v : pos[v]; };  // held columns come last
+
+  // ---- supernodes by relaxed amalgamation along the elimination tree ----
+  const int ne_cols = (int)order.size();
+  std::vector<int> sn_of(n, -1), colparent(n, -1);
+  struct SN { std::vector<int> cols, rows; int parent = -1; bool dead = false; bool top = false; };
+  std::vector<SN> sn(ne_cols);
+  for (int k = 0; k < ne_cols; ++k) {
+    const int p = order[k];
+    sn[k].cols = {p};
+    sn[k].rows = lstruct[p];
+    std::sort(sn[k].rows.begin(), sn[k].rows.end(), [&](int a, int b) { return epos(a) < epos(b); });
+    sn_of[p] = k;
+    colparent[p] = sn[k].rows.empty() ? -1 : sn[k].rows.front();
+  }
+  auto find = [&](int s) { while (sn[s].dead) s = sn[s].parent; return s; };
+  for (int k = 0; k < ne_cols; ++k) {
+    if (sn[k].dead) continue;
+    const int q = colparent[sn[k].cols.back()];
+    if (q < 0 || pos[q] < 0) { sn[k].parent = -1; continue; }  // parent is a held column -> root
+    const int ps = find(sn_of[q]);
+    sn[k].parent = ps;
+    // merge k into ps when q is the FIRST column of ps (k's columns are eliminated right before it)
+    if (sn[ps].cols.front() != q) continue;
+    const int nc = (int)sn[k].cols.size(), ncb = (int)sn[k].rows.size();
+    const int pc = (int)sn[ps].cols.size(), pcb = (int)sn[ps].rows.size();
+    const long zeros = (long)nc * (pc + pcb - ncb);
+    if (nc + pc + pcb > opt.fmax) continue;
+    if (zeros > opt.relax_zeros && zeros * 4 > (long)(nc + pc) * (nc + pc + pcb)) continue;
+    std::vector<int> merged(sn[k].cols);
+    merged.insert(merged.end(), sn[ps].cols.begin(), sn[ps].cols.end());
+    sn[ps].cols.swap(merged);
+    sn[k].dead = true;  // parent pointer keeps the forwarding address
+    for (int c : sn[k].cols) sn_of[c] = ps;
+  }
+  // resolve parents after merging
+  for (int k = 0; k < ne_cols; ++k)
+    if (!sn[k].dead && sn[k].parent >= 0) sn[k].parent = find(sn[k].parent);
+  // ---- top of the tree: big fronts and everything above them go to the dense root ----
+  for (int k = 0; k < ne_cols; ++k) {
+    if (sn[k].dead) continue;
+    if ((int)(sn[k].cols.size() + sn[k].rows.size()) > opt.fmax) sn[k].top = true;
+    if (sn[k].top && sn[k].parent >= 0) sn[sn[k].parent].top = true;  // parents come later in elimination order
+  }
+  // elimination order is topological (children first), so one forward pass closes T upwards
+  // ---- DFS postorder of the surviving subtree supernodes ----
+  std::vector<std::vector<int>> kids(ne_cols);
+  std::vector<int> roots;
+  for (int k = 0; k < ne_cols; ++k) {
+    if (sn[k].dead || sn[k].top) continue;
+    const int p = sn[k].parent;
+    if (p >= 0 && !sn[p].top) kids[p].push_back(k); else roots.push_back(k);
+  }
+  std::vector<int> post, newid(ne_cols, -1);
+  {
+    std::vector<std::pair<int, size_t>> st;
+    for (int r : roots) {
+      st.push_back({r, 0});
+      while (!st.empty()) {
+        auto &[v, i] = st.back();
+        if (i < kids[v].size()) { const int c = kids[v][i++]; st.push_back({c, 0}); }
+        else { newid[v] = (int)post.size(); post.push_back(v); st.pop_back(); }
+      }
+    }
+  }
+  // ---- root columns ----
+  std::vector<int> rootpos(n, -1);
+  for (int k = 0; k < ne_cols; ++k)
+    if (!sn[k].dead && sn[k].top)
+      for (int c : sn[k].cols) { rootpos[c] = (int)P.rootcols.size(); P.rootcols.push_back(c); }
+  for (int v = 0; v < n; ++v)
+    if (pos[v] < 0) { rootpos[v] = (int)P.rootcols.size(); P.rootcols.push_back(v); }
+  P.nT = (int)P.rootcols.size();
+  P.ns = (int)post.size();
+  P.DR = P.ns > 0 ? opt.dmax : 0;
+
+  // ---- static per-supernode tables ----
+  P.col_ptr.assign(1, 0);
+  P.row_ptr.assign(1, 0);
+  P.parent.resize(P.ns);
+  P.nchild.assign(P.ns, 0);
+  P.dcap.resize(P.ns);
+  P.l_off.resize(P.ns);
+  P.fid_off.resize(P.ns);
+  P.fs_off.resize(P.ns);
+  std::vector<int> below(P.ns, 0);  // columns strictly below each supernode
+  std::vector<int> localpos(n, -1);
+  for (int s = 0; s < P.ns; ++s) {
+    const SN &S = sn[post[s]];
+    const int pp = (S.parent >= 0 && !sn[S.parent].top) ? newid[S.parent] : -1;
+    P.parent[s] = pp;
+    if (pp >= 0) { P.nchild[pp]++; }
+    P.cols.insert(P.cols.end(), S.cols.begin(), S.cols.end());
+    P.rows.insert(P.rows.end(), S.rows.begin(), S.rows.end());
+    P.col_ptr.push_back((int)P.cols.size());
+    P.row_ptr.push_back((int)P.rows.size());
+  }
+  for (int s = 0; s < P.ns; ++s) {
+    const int nc = P.col_ptr[s + 1] - P.col_ptr[s];
+    if (P.parent[s] >= 0) below[P.parent[s]] += below[s] + nc;
+  }
+  P.rel.resize(P.rows.size());
+  for (int s = 0; s < P.ns; ++s) {
+    const int pp = P.parent[s];
+    if (pp >= 0) {
+      int k = 0;
+      for (int i = P.col_ptr[pp]; i < P.col_ptr[pp + 1]; ++i) localpos[P.cols[i]] = k++;
+      for (int i = P.row_ptr[pp]; i < P.row_ptr[pp + 1]; ++i) localpos[P.rows[i]] = k++;
+      for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) P.rel[i] = localpos[P.rows[i]];
+    } else {
+      for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) P.rel[i] = rootpos[P.rows[i]];
+    }
+  }
+  // capacities, factor layout, stack bound
+  int64_t stack = 0, peak = 0;
+  std::vector<int64_t> rec(P.ns, 0);
+  for (int s = 0; s < P.ns; ++s) {
+    const int nc = P.col_ptr[s + 1] - P.col_ptr[s], ncb = P.row_ptr[s + 1] - P.row_ptr[s];
+    P.dcap[s] = std::min(opt.dmax, std::min(below[s], opt.sbuf - nc - ncb));
+    if (P.dcap[s] < 0) P.dcap[s] = 0;
+    const int cap_rows = nc + P.dcap[s] + ncb, cap_fs = nc + P.dcap[s];
+    P.l_off[s] = P.l_total;
+    P.l_total += (int64_t)cap_rows * cap_fs;
+    P.fid_off[s] = P.fid_total;
+    P.fid_total += cap_rows;
+    P.fs_off[s] = P.fs_total;
+    P.fs_total += cap_fs;
+    P.max_front = std::max(P.max_front, cap_rows);
+    P.nnz_l += (int64_t)nc * (nc + 1) / 2 + (int64_t)nc * ncb;
+    // stack simulation with capacity-sized records: children are popped, own record pushed
+    const int dim = ncb + cap_fs;  // nothing eliminated in the worst case
+    rec[s] = (int64_t)dim * dim + dim + 8;
+    // children records were pushed earlier; pop them
+    // (postorder: the children of s are exactly the most recent unpopped records)
+    // we do not track identities here: subtract the sizes of the direct children
+  }
+  {
+    std::vector<int64_t> child_sum(P.ns, 0);
+    for (int s = 0; s < P.ns; ++s) {
+      peak = std::max(peak, stack + 0);
+      stack -= child_sum[s];
+      if (P.parent[s] >= 0) { stack += rec[s]; child_sum[P.parent[s]] += rec[s]; }
+      peak = std::max(peak, stack);
+    }
+  }
+  P.stack_cap = peak + 16;
+
+  // ---- where every input entry goes ----
+  struct Tgt { int s, row, col, src; };
+  std::vector<Tgt> tg;
+  tg.reserve(ne);
+  for (int s = 0; s < P.ns; ++s) {
+    for (int i = P.col_ptr[s]; i < P.col_ptr[s + 1]; ++i) sn_of[P.cols[i]] = s;  // reuse: column -> new supernode id
+  }
+  std::vector<char> in_sub(n, 0);
+  for (int c : P.cols) in_sub[c] = 1;
+  // local position of a variable inside supernode s: computed on demand via a scratch table
+  std::vector<int> lp(n, -1);
+  std::vector<std::vector<int>> ent_of(P.ns);
+  for (size_t k = 0; k < ne; ++k) {
+    const int r = rows[k], c = cols[k];
+    if (r >= n) {  // border entry -> root, below the delayed slots
+      P.root_row.push_back(P.nT + P.DR + (r - n));
+      P.root_col.push_back(rootpos[c]);
+      P.root_src.push_back(src[k]);
+      continue;
+    }
+    const bool rs = in_sub[r], cs = in_sub[c];
+    if (!rs && !cs) {
+      const int a = rootpos[r], b = rootpos[c];
+      P.root_row.push_back(std::max(a, b));
+      P.root_col.push_back(std::min(a, b));
+      P.root_src.push_back(src[k]);
+      continue;
+    }
+    // the entry belongs to the front of whichever endpoint is eliminated first
+    int first = c, other = r;
+    if (!cs || (rs && epos(r) < epos(c))) { first = r; other = c; }
+    ent_of[sn_of[first]].push_back((int)k);
+    (void)other;
+  }
+  P.ent_ptr.assign(1, 0);
+  P.tgt_src_ptr.assign(1, 0);
+  for (int s = 0; s < P.ns; ++s) {
+    int kk = 0;
+    for (int i = P.col_ptr[s]; i < P.col_ptr[s + 1]; ++i) lp[P.cols[i]] = kk++;
+    for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) lp[P.rows[i]] = kk++;
+    std::vector<Tgt> loc;
+    for (int k : ent_of[s]) {
+      int a = lp[rows[k]], b = lp[cols[k]];
+      if (a < b) std::swap(a, b);
+      loc.push_back({s, a, b, src[k]});
+    }
+    std::stable_sort(loc.begin(), loc.end(), [](const Tgt &x, const Tgt &y) {
+      return x.col != y.col ? x.col < y.col : x.row < y.row;
+    });
+    for (size_t i = 0; i < loc.size(); ++i) {
+      if (i == 0 || loc[i].row != loc[i - 1].row || loc[i].col != loc[i - 1].col) {
+        if (i) P.tgt_src_ptr.push_back((int)P.tgt_src.size());
+        P.tgt_row.push_back(loc[i].row);
+        P.tgt_col.push_back(loc[i].col);
+      }
+      P.tgt_src.push_back(loc[i].src);
+    }
+    if (!loc.empty()) P.tgt_src_ptr.push_back((int)P.tgt_src.size());
+    P.ent_ptr.push_back((int)P.tgt_row.size());
+    for (int i = P.col_ptr[s]; i < P.col_ptr[s + 1]; ++i) lp[P.cols[i]] = -1;
+    for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) lp[P.rows[i]] = -1;
+  }
+  return P;
+}
+
+}  // namespace ppb

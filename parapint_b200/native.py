@@ -36,6 +36,11 @@ SIGNATURES = {
     "pp_local_dim": (C.c_int64, [_vp]),
     "pp_kernel_launches": (C.c_int64, [_vp]),
     "pp_profile": (C.c_int, [_vp, _f64p, _i64p, C.c_int]),
+    "pp_plan_stats": (C.c_int, [_vp, C.c_int32, _i64p]),
+    "pp_plan_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "pp_plan_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32p), _i64p]),
+    "pp_plan_scalar": (C.c_int, [_vp, C.c_char_p, _i64p]),
+    "pp_plan_destroy": (C.c_int, [_vp]),
     "pp_debug_front": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _vp, _vp]),
 }
 
@@ -71,3 +76,34 @@ def last_error() -> str:
 def np_ptr(arr):
     """void* of a C-contiguous numpy array (kept alive by the caller)."""
     return arr.ctypes.data_as(_vp)
+
+
+PLAN_ARRAYS = ("rootcols", "col_ptr", "cols", "row_ptr", "rows", "rel", "parent", "nchild", "dcap", "ent_ptr",
+               "tgt_row", "tgt_col", "tgt_src_ptr", "tgt_src", "root_row", "root_col", "root_src")
+PLAN_SCALARS = ("n", "m", "nT", "DR", "ns", "nnz_l", "max_front", "l_total", "stack_cap")
+
+
+def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1):
+    """Run the host symbolic analysis of one block and return its tables as a dict of numpy arrays."""
+    import numpy as np
+    lib = load()
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    plan = _vp()
+    if lib.pp_plan_create(n, m, rows.size, np_ptr(rows), np_ptr(cols), fmax, dmax, min_sparse_n, C.byref(plan)) != 0:
+        raise RuntimeError(last_error())
+    try:
+        out = {}
+        for name in PLAN_ARRAYS:
+            ptr, ln = _i32p(), C.c_int64()
+            if lib.pp_plan_get(plan, name.encode(), C.byref(ptr), C.byref(ln)) != 0:
+                raise RuntimeError(last_error())
+            out[name] = np.ctypeslib.as_array(ptr, shape=(ln.value,)).copy() if ln.value else np.zeros(0, dtype=np.int32)
+        for name in PLAN_SCALARS:
+            val = C.c_int64()
+            if lib.pp_plan_scalar(plan, name.encode(), C.byref(val)) != 0:
+                raise RuntimeError(last_error())
+            out[name] = int(val.value)
+        return out
+    finally:
+        lib.pp_plan_destroy(plan)

@@ -153,8 +153,15 @@ class CudaBackend:
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
         self._check(self.lib.pp_profile(self.handle, ms, cnt, 1 if reset else 0), "pp_profile")
-        names = ("assemble", "panel", "swaps", "update", "schur", "forward", "backward")
+        names = ("assemble", "panel", "swaps", "update", "schur", "forward", "backward", "subtree")
         return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(names)}
+
+    def plan_stats(self, block=0):
+        out = (C.c_int64 * 12)()
+        self._check(self.lib.pp_plan_stats(self.handle, block, out), "pp_plan_stats")
+        keys = ("plan", "supernodes", "root_cols", "delay_slots", "nnz_l_subtree", "max_front", "factor_doubles",
+                "stack_doubles", "n_plans", "fell_back_dense", "delayed_to_root", "failed")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def int_tensor(self, values):
         t = self.ints[: len(values)]

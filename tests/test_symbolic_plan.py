@@ -1,0 +1,96 @@
+"""CPU: the host symbolic analysis (minimum degree, supernodes, subtree/root split, entry targets)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.kkt_generator import EstimationModel
+from parapint_b200 import native
+from tests.multifrontal_emulation import emulate
+
+
+def _lower_entries(K, A):
+    """Entries of the front [K | A] as the solver passes them: lower triangle of K, then the border rows."""
+    n = K.shape[0]
+    Kc = sp.tril(K).tocoo()
+    rows, cols, vals = list(Kc.row), list(Kc.col), list(Kc.data)
+    Ac = sp.coo_matrix(A)
+    nz = np.unique(Ac.row)
+    look = {r: i for i, r in enumerate(nz)}
+    rows += [n + look[r] for r in Ac.row]
+    cols += list(Ac.col)
+    vals += list(Ac.data)
+    return np.asarray(rows), np.asarray(cols), np.asarray(vals, dtype=float), len(nz)
+
+
+def _check_plan_invariants(plan, n):
+    ns = plan["ns"]
+    seen = np.zeros(n, dtype=int)
+    seen[plan["rootcols"]] += 1
+    seen[plan["cols"]] += 1
+    assert np.all(seen == 1)  # every column is eliminated exactly once: in a subtree front or in the root
+    for s in range(ns):
+        p = plan["parent"][s]
+        assert p == -1 or p > s  # postorder
+        rel = plan["rel"][plan["row_ptr"][s]:plan["row_ptr"][s + 1]]
+        assert len(set(rel)) == len(rel) and np.all(rel >= 0)
+        if p >= 0:
+            size_p = (plan["col_ptr"][p + 1] - plan["col_ptr"][p]) + (plan["row_ptr"][p + 1] - plan["row_ptr"][p])
+            assert np.all(rel < size_p)
+        else:
+            assert np.all(rel < plan["nT"])
+
+
+@pytest.mark.parametrize("seed,n,m,density", [(0, 300, 7, 0.01), (1, 500, 20, 0.006), (2, 400, 0, 0.005)])
+def test_plan_reproduces_schur_complement(seed, n, m, density):
+    rng = np.random.default_rng(seed)
+    M = sp.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal)
+    K = (M + M.T).tolil()
+    K.setdiag(np.abs(K).sum(axis=1).A1 + 1.0)  # diagonally dominant: any pivot order is safe
+    K = K.tocsr()
+    A = np.zeros((max(m, 1), n))
+    if m:
+        for a in range(m):
+            A[a, rng.choice(n, size=3, replace=False)] = rng.standard_normal(3)
+    else:
+        A = np.zeros((0, n))
+    rows, cols, vals, mm = _lower_entries(K, A)
+    assert mm == m
+    plan = native.build_plan(n, m, rows, cols, min_sparse_n=64)
+    assert plan["ns"] > 0 and plan["nT"] < n
+    _check_plan_invariants(plan, n)
+    root, pivots = emulate(plan, vals, n, m)
+    assert np.all(pivots > 0)
+    # finish the root densely and compare the trailing block with -A K^-1 A^T
+    nr = plan["nT"] + plan["DR"]
+    R = np.tril(root) + np.tril(root, -1).T
+    schur = R[nr:, nr:] - R[nr:, :nr] @ np.linalg.solve(R[:nr, :nr], R[:nr, nr:])
+    expect = -A @ np.linalg.solve(K.toarray(), A.T)
+    assert np.allclose(schur, expect, rtol=1e-9, atol=1e-11)
+
+
+def test_plan_generator_block():
+    """BASELINE config-2 block (n = 2000, nnz 8176): most columns leave the dense root."""
+    m = EstimationModel(1, 150, 6, 50)
+    K = m.blocks[0].kkt().tocsr()
+    A = m.border().toarray()
+    rows, cols, vals, mm = _lower_entries(K, A)
+    plan = native.build_plan(2000, mm, rows, cols)
+    _check_plan_invariants(plan, 2000)
+    assert plan["nT"] >= 50 and plan["nT"] < 400  # the 50 border-touched columns stay in the root
+    assert plan["max_front"] <= 96
+    assert set(np.where(A.any(axis=0))[0]) <= set(plan["rootcols"])
+
+
+def test_small_or_dense_blocks_stay_dense():
+    n = 40
+    K = sp.csr_matrix(np.ones((n, n)))
+    rows, cols, vals, mm = _lower_entries(K, np.zeros((0, n)))
+    plan = native.build_plan(n, 0, rows, cols)
+    assert plan["ns"] == 0 and plan["nT"] == n and plan["DR"] == 0
+    assert np.array_equal(plan["rootcols"], np.arange(n))
+    n = 400
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((n, n))
+    rows, cols, vals, mm = _lower_entries(sp.csr_matrix(D + D.T), np.zeros((0, n)))
+    plan = native.build_plan(n, 0, rows, cols)
+    assert plan["ns"] == 0  # fill would exceed the density cut-off
