@@ -100,13 +100,15 @@ struct pp_handle {
   std::vector<PatternPlan> plans;
   std::vector<int> block_plan;
   DevBuf<int> planI;              // all integer tables of all plans
-  DevBuf<long long> planL;
+  DevBuf<SnHead> planH;
+  DevBuf<int2> planT;
   DevBuf<PlanDev> plans_dev;
   DevBuf<SparseBlock> blocks_dev;
   DevBuf<double> arenaL, arenaStack, ywork, root_rhs, root_x;
   DevBuf<int> arenaBI;
   DevBuf<long long> vec_off, root_off;
   int64_t root_total = 0;
+  int max_leaves = 0;             // most level-0 small fronts in any local block
   // device storage
   DevBuf<double> arenaA, arenaW, arenaZ, vals, rhs, x, xc, crhs;
   DevBuf<int> arenaI, flag;
@@ -284,8 +286,11 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaSetDevice(device));
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
-    CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
-    CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
+    CK(cudaFuncSetAttribute(subtree_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
+    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
+    CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
+    CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
     auto *h = new pp_handle();
     h->device = device;
     h->flag.alloc(4);
@@ -493,37 +498,60 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->asm_src.upload(src);
   if (h->vals.n < (size_t)std::max<int64_t>(nvals, 1)) h->vals.alloc((size_t)std::max<int64_t>(nvals, 1));
 
-  // ---- plans on the device: one int table, one int64 table ----
+  // ---- plans on the device: supernode headers, packed entry targets, one int table ----
   std::vector<int> ti;
-  std::vector<long long> tl;
-  struct Off { size_t rootcols, col_ptr, cols, row_ptr, rows, rel, parent, nchild, dcap, fid_off, fs_off, ent_ptr, tgt_row, tgt_col, tgt_src_ptr, tgt_src, l_off; };
+  std::vector<SnHead> heads;
+  std::vector<int2> tgts;
+  struct Off { size_t heads, tgt, rootcols, cols, rows, rel, child_idx, root_children, tiny_ptr, tiny_idx, big_ptr, big_idx, tgt_src; };
   std::vector<Off> offs(h->plans.size());
   auto put = [&](const std::vector<int> &v) { const size_t o = ti.size(); ti.insert(ti.end(), v.begin(), v.end()); ti.push_back(0); return o; };
   for (size_t q = 0; q < h->plans.size(); ++q) {
     const PatternPlan &P = h->plans[q];
     Off &o = offs[q];
-    o.rootcols = put(P.rootcols); o.col_ptr = put(P.col_ptr); o.cols = put(P.cols); o.row_ptr = put(P.row_ptr);
-    o.rows = put(P.rows); o.rel = put(P.rel); o.parent = put(P.parent); o.nchild = put(P.nchild); o.dcap = put(P.dcap);
-    o.fid_off = put(P.fid_off); o.fs_off = put(P.fs_off); o.ent_ptr = put(P.ent_ptr); o.tgt_row = put(P.tgt_row);
-    o.tgt_col = put(P.tgt_col); o.tgt_src_ptr = put(P.tgt_src_ptr); o.tgt_src = put(P.tgt_src);
-    o.l_off = tl.size();
-    for (int64_t v : P.l_off) tl.push_back((long long)v);
-    tl.push_back(0);
+    o.rootcols = put(P.rootcols); o.cols = put(P.cols); o.rows = put(P.rows); o.rel = put(P.rel);
+    o.child_idx = put(P.child_idx); o.root_children = put(P.root_children); o.tiny_ptr = put(P.tiny_ptr);
+    o.tiny_idx = put(P.tiny_idx); o.big_ptr = put(P.big_ptr); o.big_idx = put(P.big_idx); o.tgt_src = put(P.tgt_src);
+    o.heads = heads.size();
+    o.tgt = tgts.size();
+    for (int sidx = 0; sidx < P.ns; ++sidx) {
+      SnHead H;
+      H.c0 = P.col_ptr[sidx]; H.nc = P.col_ptr[sidx + 1] - P.col_ptr[sidx];
+      H.r0 = P.row_ptr[sidx]; H.ncb = P.row_ptr[sidx + 1] - P.row_ptr[sidx];
+      H.ch0 = P.child_ptr[sidx]; H.nch = P.child_ptr[sidx + 1] - P.child_ptr[sidx];
+      H.dcap = P.dcap[sidx]; H.dslot = P.dslot[sidx];
+      H.fid_off = P.fid_off[sidx]; H.fs_off = P.fs_off[sidx]; H.vec_off = P.vec_off[sidx];
+      H.ent0 = P.ent_ptr[sidx]; H.nent = P.ent_ptr[sidx + 1] - P.ent_ptr[sidx];
+      H.parent = P.parent[sidx]; H.pad0 = H.pad1 = 0;
+      H.l_off = P.l_off[sidx]; H.cb_off = P.cb_off[sidx];
+      heads.push_back(H);
+    }
+    for (size_t e = 0; e < P.tgt_row.size(); ++e) {
+      const int cntv = P.tgt_src_ptr[e + 1] - P.tgt_src_ptr[e];
+      if (cntv > 32767 || P.tgt_row[e] > 255 || P.tgt_col[e] > 255) return fail("pp_symbolic: entry target does not fit its packed record");
+      int2 t;
+      t.x = P.tgt_row[e] | (P.tgt_col[e] << 8) | (cntv << 16);
+      t.y = cntv == 1 ? P.tgt_src[P.tgt_src_ptr[e]] : P.tgt_src_ptr[e];
+      tgts.push_back(t);
+    }
   }
+  if (heads.empty()) heads.push_back(SnHead{});
+  if (tgts.empty()) tgts.push_back(int2{0, 0});
   h->planI.upload(ti);
-  h->planL.upload(tl);
+  h->planH.upload(heads);
+  h->planT.upload(tgts);
   std::vector<PlanDev> pd(h->plans.size());
   for (size_t q = 0; q < h->plans.size(); ++q) {
     const PatternPlan &P = h->plans[q];
     const Off &o = offs[q];
     PlanDev &D = pd[q];
     const int *b = h->planI.p;
-    D.n = P.n; D.m = P.m; D.nT = P.nT; D.DR = P.DR; D.ns = P.ns; D.pad = 0;
-    D.rootcols = b + o.rootcols; D.col_ptr = b + o.col_ptr; D.cols = b + o.cols; D.row_ptr = b + o.row_ptr;
-    D.rows = b + o.rows; D.rel = b + o.rel; D.parent = b + o.parent; D.nchild = b + o.nchild; D.dcap = b + o.dcap;
-    D.fid_off = b + o.fid_off; D.fs_off = b + o.fs_off; D.ent_ptr = b + o.ent_ptr; D.tgt_row = b + o.tgt_row;
-    D.tgt_col = b + o.tgt_col; D.tgt_src_ptr = b + o.tgt_src_ptr; D.tgt_src = b + o.tgt_src;
-    D.l_off = h->planL.p + o.l_off;
+    D.n = P.n; D.m = P.m; D.nT = P.nT; D.DR = P.DR; D.ns = P.ns; D.nlevels = P.nlevels;
+    D.nrootch = (int)P.root_children.size(); D.pad = 0;
+    D.heads = h->planH.p + o.heads;
+    D.tgt = h->planT.p + o.tgt;
+    D.rootcols = b + o.rootcols; D.cols = b + o.cols; D.rows = b + o.rows; D.rel = b + o.rel;
+    D.child_idx = b + o.child_idx; D.root_children = b + o.root_children; D.tiny_ptr = b + o.tiny_ptr;
+    D.tiny_idx = b + o.tiny_idx; D.big_ptr = b + o.big_ptr; D.big_idx = b + o.big_idx; D.tgt_src = b + o.tgt_src;
   }
   h->plans_dev.upload(pd);
 
@@ -534,16 +562,22 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   for (int f = 0; f < n_local; ++f) {
     const PatternPlan &P = h->plans[h->block_plan[f]];
     oL[f] = totL; totL += (size_t)P.l_total + 8;
-    oS[f] = totS; totS += (size_t)P.stack_cap + 8;
-    oBI[f] = totBI; totBI += (size_t)P.fid_total + P.fs_total + 2 * P.ns + P.nT + P.DR + 16;
+    oS[f] = totS; totS += (size_t)P.cb_total + (size_t)P.vec_total + 16;
+    oBI[f] = totBI; totBI += (size_t)P.fid_total + 2 * (size_t)P.fs_total + 3 * (size_t)P.ns + P.nT + P.DR + 16;
     voff[f + 1] = voff[f] + block_n[f];
     roff_root[f + 1] = roff_root[f] + P.nT + P.DR;
   }
   h->root_total = roff_root[n_local];
+  h->max_leaves = 0;
+  for (int f = 0; f < n_local; ++f) {
+    const PatternPlan &P = h->plans[h->block_plan[f]];
+    if (P.nlevels > 0) h->max_leaves = std::max(h->max_leaves, P.tiny_ptr[1] - P.tiny_ptr[0]);
+  }
   h->arenaL.alloc(std::max<size_t>(totL, 1));
   h->arenaStack.alloc(std::max<size_t>(totS, 1));
   h->arenaBI.alloc(std::max<size_t>(totBI, 1));
   CK(cudaMemset(h->arenaBI.p, 0, std::max<size_t>(totBI, 1) * sizeof(int)));
+  CK(cudaMemset(h->arenaStack.p, 0, std::max<size_t>(totS, 1) * sizeof(double)));
   std::vector<SparseBlock> sb(n_local);
   for (int f = 0; f < n_local; ++f) {
     const PatternPlan &P = h->plans[h->block_plan[f]];
@@ -552,12 +586,13 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     B.root = f;
     B.val_off = first_k[f] < 0 ? 0 : first_k[f];
     B.L = h->arenaL.p + oL[f];
-    B.stack = h->arenaStack.p + oS[f];
-    B.stack_cap = P.stack_cap;
+    B.cb = h->arenaStack.p + oS[f];
+    B.vec = B.cb + P.cb_total + 8;
     int *bi = h->arenaBI.p + oBI[f];
     B.fid = bi; bi += P.fid_total;
     B.pbz = bi; bi += P.fs_total;
-    B.meta = bi; bi += 2 * P.ns;
+    B.opos = bi; bi += P.fs_total;
+    B.meta = bi; bi += 3 * P.ns;
     B.rootids = bi; bi += P.nT + P.DR;
     B.info = bi;
   }
@@ -658,6 +693,12 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
   }
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_SUBTREE, st);
+    if (h->max_leaves > 0) {
+      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
+      subtree_leaf_kernel<<<g, LF_NT, LF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold,
+                                                     h->pivot_tol, h->inertia.p);
+      h->launches++;
+    }
     subtree_factor_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->fronts.p, dvals,
                                                              h->pivot_threshold, h->pivot_tol, h->inertia.p);
     h->launches++;
@@ -781,7 +822,13 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
     }
     if (h->n_local > 0) {
       ProfSpan sp(h, PP_PROF_FORWARD, st);
-      subtree_forward_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+      if (h->max_leaves > 0) {
+        dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
+        subtree_leaf_forward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+                                                               h->ywork.p);
+        h->launches++;
+      }
+      subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
                                                                 h->ywork.p, h->root_rhs.p, h->root_off.p);
       const size_t sm = solve_smem(h->nfmax_local);
       CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -838,8 +885,14 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
                               (int)std::max(sm, solve_smem(mc))));
       front_backward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, dxc, h->brow_ptr.p, h->brow.p,
                                                              h->root_x.p, h->root_off64.p);
-      subtree_backward_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+      subtree_backward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
                                                                  h->vec_off.p, h->root_x.p, h->root_off.p, dx);
+      if (h->max_leaves > 0) {
+        dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
+        subtree_leaf_backward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+                                                                h->vec_off.p, dx);
+        h->launches++;
+      }
       h->launches += 2;
     }
     CK(cudaGetLastError());
@@ -940,6 +993,14 @@ int pp_plan_get(const pp_plan *pl, const char *name, const int32_t **data, int64
   else if (k == "rel") v = &P.rel;
   else if (k == "parent") v = &P.parent;
   else if (k == "nchild") v = &P.nchild;
+  else if (k == "dslot") v = &P.dslot;
+  else if (k == "child_ptr") v = &P.child_ptr;
+  else if (k == "child_idx") v = &P.child_idx;
+  else if (k == "root_children") v = &P.root_children;
+  else if (k == "tiny_ptr") v = &P.tiny_ptr;
+  else if (k == "tiny_idx") v = &P.tiny_idx;
+  else if (k == "big_ptr") v = &P.big_ptr;
+  else if (k == "big_idx") v = &P.big_idx;
   else if (k == "dcap") v = &P.dcap;
   else if (k == "ent_ptr") v = &P.ent_ptr;
   else if (k == "tgt_row") v = &P.tgt_row;
@@ -968,6 +1029,7 @@ int pp_plan_scalar(const pp_plan *pl, const char *name, int64_t *value) {
   else if (k == "max_front") *value = P.max_front;
   else if (k == "l_total") *value = P.l_total;
   else if (k == "stack_cap") *value = P.stack_cap;
+  else if (k == "nlevels") *value = P.nlevels;
   else return fail("pp_plan_scalar: unknown scalar " + k);
   return PP_SUCCESSFUL;
 }

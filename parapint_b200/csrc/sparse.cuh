@@ -1,44 +1,118 @@
 // Multifrontal factorisation / solves of the SUBTREE part of every diagonal block (one CTA per block).
 //
-// The CTA walks its block's assembly tree in postorder.  Each small front is assembled in shared
-// memory (original entries + the contribution blocks of its children, popped from a per-block stack
-// in HBM), partially factorised with threshold pivoting among its fully-summed rows (1x1 and 2x2
-// pivots; columns that find no acceptable pivot are DELAYED to the parent, MA57-style), its L/D
-// columns are written to the block's factor arena and its contribution block is pushed for the
-// parent -- or, for children of the root, added into the block's dense root front, which the batched
-// Bunch-Kaufman kernels of factor.cuh then finish (they also see the delayed columns, so no pivot is
-// ever forced: inertia stays exact).
+// The block's assembly tree is processed level by level (level 0 = leaves).  Fronts of one level
+// are independent: small ones are taken by single warps concurrently, larger ones by the whole CTA.
+// A front is assembled in shared memory (original entries + the contribution blocks of its
+// children, read from per-front slots in HBM), partially factorised with threshold pivoting among
+// its fully-summed rows (1x1 and 2x2 pivots; columns that find no acceptable pivot are DELAYED to the
+// parent, MA57-style), its L/D columns go to the block's factor arena and its contribution block to
+// its slot.  Children of the root are finally added into the block's dense root front, which the
+// batched Bunch-Kaufman kernels of factor.cuh finish (they also see the delayed columns, so no pivot
+// is ever forced: the inertia stays exact).  All sums run in a fixed order: results are reproducible.
 #pragma once
 #include "front.cuh"
 
 namespace ppb {
 
+// Static description of one supernode, fetched with a single 80-byte load.
+struct __align__(16) SnHead {
+  int c0, nc, r0, ncb;            // own columns: cols[c0..c0+nc); contribution rows: rows[r0..r0+ncb)
+  int ch0, nch, dcap, dslot;      // children: child_idx[ch0..ch0+nch); delayed-in / delayed-out capacity
+  int fid_off, fs_off, vec_off, ent0;
+  int nent, parent, pad0, pad1;   // original-entry targets: tgt[ent0..ent0+nent)
+  long long l_off, cb_off;
+};
+
 struct PlanDev {
-  int n, m, nT, DR, ns, pad;
-  const int *rootcols;
-  const int *col_ptr, *cols, *row_ptr, *rows, *rel, *parent, *nchild, *dcap, *fid_off, *fs_off;
-  const long long *l_off;
-  const int *ent_ptr, *tgt_row, *tgt_col, *tgt_src_ptr, *tgt_src;
+  int n, m, nT, DR, ns, nlevels, nrootch, pad;
+  const SnHead *heads;
+  const int *rootcols, *cols, *rows, *rel, *child_idx, *root_children;
+  const int *tiny_ptr, *tiny_idx, *big_ptr, *big_idx;
+  const int2 *tgt;      // .x = row | col << 8 | count << 16,  .y = source index (count == 1) or offset into tgt_src
+  const int *tgt_src;
 };
 
 struct SparseBlock {
   int plan, root;        // plan index; index of the dense root front
   long long val_off;     // base index of this block's input values
   double *L;             // factor arena of the subtree supernodes
-  double *stack;         // contribution-block stack
-  long long stack_cap;
+  double *cb;            // contribution slots
+  double *vec;           // forward-solve contribution vectors
   int *fid;              // per supernode: original ids of the front rows after pivoting
   int *pbz;              // per supernode: pivot flags (1, 2, 0) of the eliminated columns
-  int *meta;             // per supernode: {ne, S}
+  int *opos;             // per supernode: pre-pivoting position of every fully-summed row
+  int *meta;             // per supernode: {ne, S, nd_out}
   int *rootids;          // [nT + DR] original id per root position, -1 for unused delayed slots
-  int *info;             // [0] overflow / failure flag, [1] delayed pivots that reached the root
+  int *info;             // [0] failure flag, [1] delayed pivots that reached the root
 };
 
-constexpr int SF_NT = 128;           // threads per CTA in the subtree kernels
-constexpr int SF_SBUF = 96;          // largest front held in shared memory
+constexpr int SF_NT = 512;           // threads per CTA in the subtree kernels
+constexpr int SF_NW = SF_NT / 32;
+constexpr int SF_SBUF = 96;          // largest front held in shared memory (whole CTA)
 constexpr int SF_LDF = SF_SBUF + 1;  // odd pitch: conflict-free row and column walks
-constexpr size_t SF_SMEM = (size_t)SF_SBUF * SF_LDF * sizeof(double) + 3 * SF_SBUF * sizeof(double) +
-                           4 * SF_SBUF * sizeof(int) + 64;
+constexpr int SF_TBUF = 24;          // largest front held by a single warp
+constexpr int SF_TLD = SF_TBUF + 1;
+
+// shared-memory work area of one group (a warp or the whole CTA)
+struct FrontBuf {
+  double *F;   // cap x ld, lower triangle
+  double *w0, *w1;
+  int *fid, *opos, *bsz, *map;
+  int *sh;     // 8 ints of scratch
+  int ld, cap;
+};
+
+__host__ __device__ constexpr size_t fb_bytes(int cap, int ld) {
+  return (size_t)cap * ld * 8 + 2 * (size_t)cap * 8 + 4 * (size_t)cap * 4 + 32;
+}
+constexpr size_t SF_BIG_BYTES = fb_bytes(SF_SBUF, SF_LDF);
+constexpr size_t SF_TINY_BYTES = (fb_bytes(SF_TBUF, SF_TLD) + 15) / 16 * 16;
+// staging area used when a front has many small children: their contribution entries are fetched
+// by all threads at once (one child per thread) and then applied in child order by a single warp
+constexpr int SF_STG = 2048;     // staged entries
+constexpr int SF_MAXCH = 512;    // children per staging batch
+constexpr int SF_CHDIM = 12;     // largest child contribution block that is staged
+constexpr size_t SF_STG_BYTES = (size_t)SF_STG * 12 + (size_t)(3 * SF_MAXCH + 16) * 4;
+constexpr size_t SF_WORK = SF_BIG_BYTES > SF_NW * SF_TINY_BYTES ? SF_BIG_BYTES : SF_NW * SF_TINY_BYTES;
+constexpr size_t SF_SMEM = SF_WORK + 16 * sizeof(int) + 64 * sizeof(int) + SF_STG_BYTES;
+
+struct Stage {
+  double *val;   // [SF_STG]
+  int *tgt;      // [SF_STG] offset into F (or position in v)
+  int *cnt;      // [SF_MAXCH + 1] entry offsets per child
+  int *ndo;      // [SF_MAXCH] delayed columns per child / running offsets
+  int *big;      // [SF_MAXCH] children handled one by one afterwards
+};
+
+__device__ __forceinline__ Stage carve_stage(unsigned char *base) {
+  Stage g;
+  g.val = reinterpret_cast<double *>(base);
+  g.tgt = reinterpret_cast<int *>(g.val + SF_STG);
+  g.cnt = g.tgt + SF_STG;
+  g.ndo = g.cnt + SF_MAXCH + 8;
+  g.big = g.ndo + SF_MAXCH;
+  return g;
+}
+
+__device__ __forceinline__ FrontBuf carve(unsigned char *base, int cap, int ld) {
+  FrontBuf b;
+  b.F = reinterpret_cast<double *>(base);
+  b.w0 = b.F + (size_t)cap * ld;
+  b.w1 = b.w0 + cap;
+  b.fid = reinterpret_cast<int *>(b.w1 + cap);
+  b.opos = b.fid + cap;
+  b.bsz = b.opos + cap;
+  b.map = b.bsz + cap;
+  b.sh = b.map + cap;
+  b.ld = ld;
+  b.cap = cap;
+  return b;
+}
+
+template <int G> __device__ __forceinline__ int gtid() { return G == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+template <int G> __device__ __forceinline__ void gsync() {
+  if (G == 32) __syncwarp(); else __syncthreads();
+}
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -55,61 +129,69 @@ __device__ __forceinline__ void warp_argmax(double &v, int &i) {
   }
 }
 
-__device__ __forceinline__ double &fent(double *F, int r, int c) {  // lower-triangle accessor
-  return r >= c ? F[r + c * SF_LDF] : F[c + r * SF_LDF];
+__device__ __forceinline__ double &fent(double *F, int ld, int r, int c) {  // lower-triangle accessor
+  return r >= c ? F[r + c * ld] : F[c + r * ld];
 }
 
-// symmetric interchange of positions a < b in the lower-stored front (L rows included)
-__device__ __forceinline__ void front_swap(double *F, int S, int a, int b, int *fid) {
+// symmetric interchange of positions a < b in the lower-stored front (rows of L included)
+template <int G>
+__device__ __forceinline__ void front_swap(const FrontBuf &B, int S, int a, int b) {
   if (a == b) return;
-  for (int i = threadIdx.x; i < S; i += SF_NT) {
+  double *F = B.F;
+  const int ld = B.ld;
+  for (int i = gtid<G>(); i < S; i += G) {
     double *p, *q;
-    if (i < a) { p = &F[a + i * SF_LDF]; q = &F[b + i * SF_LDF]; }
-    else if (i == a) { p = &F[a + a * SF_LDF]; q = &F[b + b * SF_LDF]; }
-    else if (i < b) { p = &F[i + a * SF_LDF]; q = &F[b + i * SF_LDF]; }
+    if (i < a) { p = &F[a + i * ld]; q = &F[b + i * ld]; }
+    else if (i == a) { p = &F[a + a * ld]; q = &F[b + b * ld]; }
+    else if (i < b) { p = &F[i + a * ld]; q = &F[b + i * ld]; }
     else if (i == b) continue;
-    else { p = &F[i + a * SF_LDF]; q = &F[i + b * SF_LDF]; }
+    else { p = &F[i + a * ld]; q = &F[i + b * ld]; }
     const double t = *p;
     *p = *q;
     *q = t;
   }
-  if (threadIdx.x == 0) { const int t = fid[a]; fid[a] = fid[b]; fid[b] = t; }
-  __syncthreads();
+  if (gtid<G>() == 0) {
+    int t = B.fid[a]; B.fid[a] = B.fid[b]; B.fid[b] = t;
+    t = B.opos[a]; B.opos[a] = B.opos[b]; B.opos[b] = t;
+  }
+  gsync<G>();
 }
 
-// Partial factorisation of the S x S front in shared memory; the first fs rows are fully summed.
-// Returns the number of eliminated columns; inertia counts are accumulated by thread 0 in cnt[3].
-__device__ int factor_front(double *F, int S, int fs, int *fid, int *bsz, double *w0, double *w1, double u,
-                            double pivtol, int *cnt, int *sh_i) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = SF_NT / 32;
+// Partial factorisation of the S x S front; the first fs rows are fully summed.  Returns the number
+// of eliminated columns; inertia counts go to cnt[3] (shared, atomics on integers).
+template <int G>
+__device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double pivtol, int *cnt) {
+  const int tid = gtid<G>(), lane = tid & 31, gw = tid >> 5;
+  constexpr int NW = G / 32;
+  double *F = B.F;
+  const int ld = B.ld;
   int t = 0;
   while (t < fs) {
-    if (warp == 0) {
+    if (gw == 0) {
       int kind = 0, pc = -1, pr = -1;
       for (int c = t; c < fs; ++c) {
         double cmax = 0.0, fbest = -1.0;
         int r = -1;
         for (int i = t + lane; i < S; i += 32) {
           if (i == c) continue;
-          const double v = fabs(fent(F, i, c));
+          const double v = fabs(fent(F, ld, i, c));
           cmax = fmax(cmax, v);
           if (i < fs && v > fbest) { fbest = v; r = i; }
         }
         cmax = warp_max(cmax);
         warp_argmax(fbest, r);
-        const double dcc = F[c + c * SF_LDF];
+        const double dcc = F[c + c * ld];
         if (fabs(dcc) > pivtol && fabs(dcc) >= u * cmax) { kind = 1; pc = c; break; }
         if (r >= 0 && fbest > pivtol) {
           double cm_c = 0.0, cm_r = 0.0;
           for (int i = t + lane; i < S; i += 32) {
             if (i == c || i == r) continue;
-            cm_c = fmax(cm_c, fabs(fent(F, i, c)));
-            cm_r = fmax(cm_r, fabs(fent(F, i, r)));
+            cm_c = fmax(cm_c, fabs(fent(F, ld, i, c)));
+            cm_r = fmax(cm_r, fabs(fent(F, ld, i, r)));
           }
           cm_c = warp_max(cm_c);
           cm_r = warp_max(cm_r);
-          const double drr = F[r + r * SF_LDF], b = fent(F, r, c);
+          const double drr = F[r + r * ld], b = fent(F, ld, r, c);
           const double det = dcc * drr - b * b;
           const double g1 = (fabs(drr) * cm_c + fabs(b) * cm_r) / fabs(det);
           const double g2 = (fabs(b) * cm_c + fabs(dcc) * cm_r) / fabs(det);
@@ -117,71 +199,269 @@ __device__ int factor_front(double *F, int S, int fs, int *fid, int *bsz, double
           if (fabs(drr) > pivtol && fabs(drr) >= u * fmax(cm_r, fabs(b))) { kind = 1; pc = r; break; }
         }
       }
-      if (lane == 0) { sh_i[0] = kind; sh_i[1] = pc; sh_i[2] = pr; }
+      if (lane == 0) { B.sh[0] = kind; B.sh[1] = pc; B.sh[2] = pr; }
     }
-    __syncthreads();
-    const int kind = sh_i[0];
-    int pc = sh_i[1], pr = sh_i[2];
-    __syncthreads();
+    gsync<G>();
+    const int kind = B.sh[0];
+    int pc = B.sh[1], pr = B.sh[2];
+    gsync<G>();
     if (kind == 0) break;
     if (kind == 2 && pr < pc) { const int x = pc; pc = pr; pr = x; }
-    front_swap(F, S, t, pc, fid);
+    front_swap<G>(B, S, t, pc);
     if (kind == 1) {
-      const double d = F[t + t * SF_LDF];
-      for (int i = t + 1 + tid; i < S; i += SF_NT) w0[i] = F[i + t * SF_LDF];
-      __syncthreads();
+      const double d = F[t + t * ld];
+      for (int i = t + 1 + tid; i < S; i += G) B.w0[i] = F[i + t * ld];
+      gsync<G>();
       const double rd = 1.0 / d;
-      for (int j = t + 1 + warp; j < S; j += NW) {
-        const double wj = w0[j] * rd;
-        for (int i = j + lane; i < S; i += 32) F[i + j * SF_LDF] -= w0[i] * wj;
+      for (int j = t + 1 + gw; j < S; j += NW) {
+        const double wj = B.w0[j] * rd;
+        for (int i = j + lane; i < S; i += 32) F[i + j * ld] -= B.w0[i] * wj;
       }
-      for (int i = t + 1 + tid; i < S; i += SF_NT) F[i + t * SF_LDF] = w0[i] * rd;
+      for (int i = t + 1 + tid; i < S; i += G) F[i + t * ld] = B.w0[i] * rd;
       if (tid == 0) {
-        bsz[t] = 1;
-        cnt[d > 0.0 ? 0 : (d < 0.0 ? 1 : 2)]++;
+        B.bsz[t] = 1;
+        atomicAdd(&cnt[d > 0.0 ? 0 : (d < 0.0 ? 1 : 2)], 1);
       }
-      __syncthreads();
+      gsync<G>();
       t += 1;
     } else {
-      front_swap(F, S, t + 1, pr, fid);
-      const double e11 = F[t + t * SF_LDF], e21 = F[t + 1 + t * SF_LDF], e22 = F[t + 1 + (t + 1) * SF_LDF];
-      for (int i = t + 2 + tid; i < S; i += SF_NT) {
-        w0[i] = F[i + t * SF_LDF];
-        w1[i] = F[i + (t + 1) * SF_LDF];
+      front_swap<G>(B, S, t + 1, pr);
+      const double e11 = F[t + t * ld], e21 = F[t + 1 + t * ld], e22 = F[t + 1 + (t + 1) * ld];
+      for (int i = t + 2 + tid; i < S; i += G) {
+        B.w0[i] = F[i + t * ld];
+        B.w1[i] = F[i + (t + 1) * ld];
       }
-      __syncthreads();
+      gsync<G>();
       const double d11 = e22 / e21, d22 = e11 / e21;
       const double sc = (1.0 / (d11 * d22 - 1.0)) / e21;
-      for (int j = t + 2 + warp; j < S; j += NW) {
-        const double a0 = w0[j], a1 = w1[j];
+      for (int j = t + 2 + gw; j < S; j += NW) {
+        const double a0 = B.w0[j], a1 = B.w1[j];
         for (int i = j + lane; i < S; i += 32) {
-          const double l0 = sc * (d11 * w0[i] - w1[i]), l1 = sc * (d22 * w1[i] - w0[i]);
-          F[i + j * SF_LDF] -= l0 * a0 + l1 * a1;
+          const double l0 = sc * (d11 * B.w0[i] - B.w1[i]), l1 = sc * (d22 * B.w1[i] - B.w0[i]);
+          F[i + j * ld] -= l0 * a0 + l1 * a1;
         }
       }
-      for (int i = t + 2 + tid; i < S; i += SF_NT) {
-        F[i + t * SF_LDF] = sc * (d11 * w0[i] - w1[i]);
-        F[i + (t + 1) * SF_LDF] = sc * (d22 * w1[i] - w0[i]);
+      for (int i = t + 2 + tid; i < S; i += G) {
+        F[i + t * ld] = sc * (d11 * B.w0[i] - B.w1[i]);
+        F[i + (t + 1) * ld] = sc * (d22 * B.w1[i] - B.w0[i]);
       }
       if (tid == 0) {
-        bsz[t] = 2;
-        bsz[t + 1] = 0;
+        B.bsz[t] = 2;
+        B.bsz[t + 1] = 0;
         const double det = d11 * d22 - 1.0;  // sign of the determinant (scaled by e21^2 > 0)
-        if (det < 0.0) { cnt[0]++; cnt[1]++; }
-        else if (det > 0.0) { if (e11 + e22 > 0.0) cnt[0] += 2; else cnt[1] += 2; }
-        else { cnt[2]++; cnt[e11 + e22 > 0.0 ? 0 : 1]++; }
+        if (det < 0.0) { atomicAdd(&cnt[0], 1); atomicAdd(&cnt[1], 1); }
+        else if (det > 0.0) atomicAdd(&cnt[e11 + e22 > 0.0 ? 0 : 1], 2);
+        else { atomicAdd(&cnt[2], 1); atomicAdd(&cnt[e11 + e22 > 0.0 ? 0 : 1], 1); }
       }
-      __syncthreads();
+      gsync<G>();
       t += 2;
     }
   }
   return t;
 }
 
-// record layout on the contribution stack (doubles):  [ids: dim ints, padded][dim*dim matrix][footer 2]
-// footer = {dim | nd_out<<16 | supernode<<32 ... } stored as three ints + padding in two doubles
-__device__ __forceinline__ long long rec_size(int dim) {
-  return (long long)((dim + 1) / 2) + (long long)dim * dim + 2;
+enum { PF_OK = 0, PF_DEFER = 1, PF_FAIL = 2 };
+
+// Assemble, factor and store supernode s with group G.  PF_DEFER: the front (with its delayed
+// columns) does not fit this group's buffer; nothing was written.
+template <int G>
+__device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const double *__restrict__ vals, int s,
+                             const FrontBuf &B, double u, double pivtol, int *cnt, const Stage &stg) {
+  const int tid = gtid<G>();
+  const SnHead H = P.heads[s];
+  const int nc = H.nc, ncb = H.ncb;
+  const bool staged = G != 32 && H.nch >= 4 && H.nch <= SF_MAXCH;
+  int nd_in = 0;
+  if (staged) {
+    // one child per thread: delayed count and staged-entry count; serial prefix by thread 0
+    for (int k = tid; k < H.nch; k += G) {
+      const int c = P.child_idx[H.ch0 + k];
+      const int dim = Bk.meta[3 * c + 1] - Bk.meta[3 * c];
+      stg.ndo[k] = Bk.meta[3 * c + 2];
+      stg.cnt[k] = dim <= SF_CHDIM ? dim * (dim + 1) / 2 : -1;
+    }
+    gsync<G>();
+    if (tid == 0) {
+      int off = 0, ent = 0, nbig = 0;
+      for (int k = 0; k < H.nch; ++k) {
+        const int d = stg.ndo[k], e = stg.cnt[k];
+        stg.ndo[k] = off;
+        off += d;
+        if (e < 0 || ent + e > SF_STG) { stg.big[nbig++] = k; stg.cnt[k] = ent; }  // handled one by one
+        else { stg.cnt[k] = ent; ent += e; }
+        if (k + 1 == H.nch) stg.cnt[k + 1] = ent;
+      }
+      B.sh[4] = off;
+      B.sh[5] = nbig;
+    }
+    gsync<G>();
+    nd_in = B.sh[4];
+  } else {
+    for (int k = 0; k < H.nch; ++k) nd_in += Bk.meta[3 * P.child_idx[H.ch0 + k] + 2];
+  }
+  const int fs = nc + nd_in, S = fs + ncb;
+  if (S > B.cap) return G == 32 ? PF_DEFER : PF_FAIL;
+  if (nd_in > H.dcap) return PF_FAIL;
+  double *F = B.F;
+  const int ld = B.ld;
+  for (int j = 0; j < S; ++j)
+    for (int i = j + tid; i < S; i += G) F[i + j * ld] = 0.0;
+  for (int i = tid; i < nc; i += G) B.fid[i] = P.cols[H.c0 + i];
+  for (int i = tid; i < ncb; i += G) B.fid[fs + i] = P.rows[H.r0 + i];
+  for (int i = tid; i < fs; i += G) B.opos[i] = i;
+  gsync<G>();
+  // original entries: unique targets, sources summed in input order
+  for (int e = tid; e < H.nent; e += G) {
+    const int2 t = P.tgt[H.ent0 + e];
+    const int cntv = t.x >> 16;
+    double v;
+    if (cntv == 1) v = vals[Bk.val_off + t.y];
+    else {
+      v = 0.0;
+      for (int p = 0; p < cntv; ++p) v += vals[Bk.val_off + P.tgt_src[t.y + p]];
+    }
+    int r = t.x & 255;
+    if (r >= nc) r += nd_in;
+    F[r + ((t.x >> 8) & 255) * ld] = v;
+  }
+  gsync<G>();
+  // children: fixed order (staged small ones in index order, then the others in index order)
+  if (staged) {
+    const int nbig = B.sh[5];
+    for (int k = tid; k < H.nch; k += G) {
+      const int e0 = stg.cnt[k], e1 = stg.cnt[k + 1];
+      if (e1 == e0) continue;  // big child (or empty contribution)
+      const int c = P.child_idx[H.ch0 + k];
+      const SnHead C = P.heads[c];
+      const int cne = Bk.meta[3 * c], ndo = Bk.meta[3 * c + 2];
+      const int dim = Bk.meta[3 * c + 1] - cne;
+      const int *ids = Bk.fid + C.fid_off + cne;
+      const int *crel = P.rel + C.r0;
+      const double *M = Bk.cb + C.cb_off;
+      const int off = stg.ndo[k];
+      int mp[SF_CHDIM];
+#pragma unroll
+      for (int i = 0; i < SF_CHDIM; ++i) {
+        if (i < dim) {
+          if (i < ndo) { mp[i] = nc + off + i; B.fid[nc + off + i] = ids[i]; }
+          else { const int rr = crel[i - ndo]; mp[i] = rr < nc ? rr : rr + nd_in; }
+        }
+      }
+      int e = e0;
+#pragma unroll
+      for (int j = 0; j < SF_CHDIM; ++j)
+#pragma unroll
+        for (int i = j; i < SF_CHDIM; ++i)
+          if (i < dim) {
+            const int a = mp[i] >= mp[j] ? mp[i] : mp[j], b = mp[i] >= mp[j] ? mp[j] : mp[i];
+            stg.tgt[e] = a + b * ld;
+            stg.val[e] = M[i + j * dim];
+            ++e;
+          }
+    }
+    gsync<G>();
+    if (tid < 32) {
+      for (int k = 0; k < H.nch; ++k) {
+        for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) F[stg.tgt[e]] += stg.val[e];
+        __syncwarp();
+      }
+    }
+    gsync<G>();
+    for (int q = 0; q < nbig; ++q) {
+      const int k = stg.big[q];
+      const int c = P.child_idx[H.ch0 + k];
+      const SnHead C = P.heads[c];
+      const int cne = Bk.meta[3 * c], cS = Bk.meta[3 * c + 1], ndo = Bk.meta[3 * c + 2];
+      const int dim = cS - cne, off = stg.ndo[k];
+      const int *ids = Bk.fid + C.fid_off + cne;
+      const int *crel = P.rel + C.r0;
+      const double *M = Bk.cb + C.cb_off;
+      for (int i = tid; i < dim; i += G) {
+        if (i < ndo) { B.map[i] = nc + off + i; B.fid[nc + off + i] = ids[i]; }
+        else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
+      }
+      gsync<G>();
+      for (int j = 0; j < dim; ++j) {
+        const int mj = B.map[j];
+        for (int i = j + tid; i < dim; i += G) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+      }
+      gsync<G>();
+    }
+  } else {
+    int off = 0;
+    for (int k = 0; k < H.nch; ++k) {
+      const int c = P.child_idx[H.ch0 + k];
+      const SnHead C = P.heads[c];
+      const int cne = Bk.meta[3 * c], cS = Bk.meta[3 * c + 1], ndo = Bk.meta[3 * c + 2];
+      const int dim = cS - cne;
+      const int *ids = Bk.fid + C.fid_off + cne;
+      const int *crel = P.rel + C.r0;
+      const double *M = Bk.cb + C.cb_off;
+      for (int i = tid; i < dim; i += G) {
+        if (i < ndo) { B.map[i] = nc + off + i; B.fid[nc + off + i] = ids[i]; }
+        else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
+      }
+      gsync<G>();
+      for (int j = 0; j < dim; ++j) {
+        const int mj = B.map[j];
+        for (int i = j + tid; i < dim; i += G) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+      }
+      gsync<G>();
+      off += ndo;
+    }
+  }
+  const int ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
+  const int ndo = fs - ne, dim = S - ne;
+  if (ndo > H.dslot) {
+    if (tid == 0) { Bk.meta[3 * s] = 0; Bk.meta[3 * s + 1] = 0; Bk.meta[3 * s + 2] = 0; }
+    return PF_FAIL;
+  }
+  const int caprows = nc + H.dcap + ncb;
+  double *Ls = Bk.L + H.l_off;
+  for (int j = 0; j < ne; ++j)
+    for (int i = j + tid; i < S; i += G) Ls[i + (long long)j * caprows] = F[i + j * ld];
+  for (int i = tid; i < S; i += G) Bk.fid[H.fid_off + i] = B.fid[i];
+  for (int i = tid; i < fs; i += G) {
+    Bk.opos[H.fs_off + i] = B.opos[i];
+    if (i < ne) Bk.pbz[H.fs_off + i] = B.bsz[i];
+  }
+  double *M = Bk.cb + H.cb_off;
+  for (int j = 0; j < dim; ++j)
+    for (int i = j + tid; i < dim; i += G) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
+  if (tid == 0) { Bk.meta[3 * s] = ne; Bk.meta[3 * s + 1] = S; Bk.meta[3 * s + 2] = ndo; }
+  gsync<G>();
+  return PF_OK;
+}
+
+// Level-0 small fronts have no children, hence no dependencies at all: one warp per (block, leaf),
+// spread over the whole GPU.  grid = (ceil(max leaves / LF_NW), blocks).
+constexpr int LF_NT = 256, LF_NW = LF_NT / 32;
+constexpr size_t LF_SMEM = LF_NW * SF_TINY_BYTES + 16;
+
+__global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *__restrict__ blocks,
+                                                             const PlanDev *__restrict__ plans,
+                                                             const double *__restrict__ vals, double u, double pivtol,
+                                                             unsigned long long *inertia) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __shared__ int cnt[4];
+  const SparseBlock Bk = blocks[blockIdx.y];
+  const PlanDev P = plans[Bk.plan];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.nlevels == 0) return;
+  const int nleaf = P.tiny_ptr[1] - P.tiny_ptr[0];
+  if ((int)blockIdx.x * LF_NW >= nleaf) return;
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int k = blockIdx.x * LF_NW + warp;
+  if (k < nleaf) {
+    const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
+    Stage none;
+    none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr;
+    const int rc = process_front<32>(Bk, P, vals, P.tiny_idx[P.tiny_ptr[0] + k], mine, u, pivtol, cnt, none);
+    if (rc != PF_OK && lane == 0) Bk.info[2] = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && cnt[threadIdx.x]) atomicAdd(&inertia[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock *__restrict__ blocks,
@@ -190,143 +470,89 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
                                                                const double *__restrict__ vals, double u,
                                                                double pivtol, unsigned long long *inertia) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  double *F = reinterpret_cast<double *>(sm_raw);
-  double *w0 = F + SF_SBUF * SF_LDF;
-  double *w1 = w0 + SF_SBUF;
-  int *fid = reinterpret_cast<int *>(w1 + 2 * SF_SBUF);  // (one spare row of doubles keeps alignment simple)
-  int *bsz = fid + SF_SBUF;
-  int *map = bsz + SF_SBUF;
-  int *sh_i = map + SF_SBUF;  // 16 ints of scratch
+  int *cnt = reinterpret_cast<int *>(sm_raw + SF_WORK);  // [0..2] inertia, [3] failed, [4] deferred count
+  int *deferred = cnt + 16;                              // up to 64 deferred fronts per level
+  const Stage stg = carve_stage(sm_raw + SF_WORK + 80 * sizeof(int));
+  const SparseBlock Bk = blocks[blockIdx.x];
+  const PlanDev P = plans[Bk.plan];
+  const Front R = fronts[Bk.root];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const FrontBuf big = carve(sm_raw, SF_SBUF, SF_LDF);
+  const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
+  if (tid < 8) cnt[tid] = 0;
+  __syncthreads();
 
-  const SparseBlock B = blocks[blockIdx.x];
-  const PlanDev P = plans[B.plan];
-  const Front R = fronts[B.root];
-  const int tid = threadIdx.x;
-  int *cnt = sh_i + 8;
-  if (tid < 3) cnt[tid] = 0;
-  long long sp = 0;  // stack pointer (doubles)
-  int ndroot = 0;
-  bool failed = false;
-
-  for (int s = 0; s < P.ns && !failed; ++s) {
-    const int c0 = P.col_ptr[s], nc = P.col_ptr[s + 1] - c0;
-    const int r0 = P.row_ptr[s], ncb = P.row_ptr[s + 1] - r0;
-    const int nch = P.nchild[s];
-    // ---- incoming delayed pivots: walk the children's footers from the top of the stack ----
-    int nd_in = 0;
-    {
-      long long q = sp;
-      for (int c = 0; c < nch; ++c) {
-        const int *ft = reinterpret_cast<const int *>(B.stack + q - 2);
-        nd_in += ft[1];
-        q -= rec_size(ft[0]);
+  for (int l = 0; l < P.nlevels; ++l) {
+    // ---- small fronts: one warp each, all warps concurrently (the leaves were done by
+    //      subtree_leaf_kernel, spread over the whole GPU) ----
+    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+      const int s = P.tiny_idx[k];
+      const int rc = process_front<32>(Bk, P, vals, s, mine, u, pivtol, cnt, stg);
+      if (lane == 0) {
+        if (rc == PF_DEFER) {
+          const int pos = atomicAdd(&cnt[4], 1);
+          if (pos < 64) deferred[pos] = s; else cnt[3] = 1;
+        } else if (rc == PF_FAIL) cnt[3] = 1;
       }
-    }
-    const int fs = nc + nd_in, S = fs + ncb;
-    if (S > SF_SBUF || nd_in > P.dcap[s]) { failed = true; break; }
-    for (int idx = tid; idx < S * S; idx += SF_NT) {
-      const int j = idx / S, i = idx - j * S;
-      if (i >= j) F[i + j * SF_LDF] = 0.0;
-    }
-    for (int i = tid; i < nc; i += SF_NT) fid[i] = P.cols[c0 + i];
-    for (int i = tid; i < ncb; i += SF_NT) fid[fs + i] = P.rows[r0 + i];
-    __syncthreads();
-    // ---- original entries (unique targets; sources summed in input order) ----
-    for (int e = P.ent_ptr[s] + tid; e < P.ent_ptr[s + 1]; e += SF_NT) {
-      double v = 0.0;
-      for (int p = P.tgt_src_ptr[e]; p < P.tgt_src_ptr[e + 1]; ++p) v += vals[B.val_off + P.tgt_src[p]];
-      int r = P.tgt_row[e];
-      const int c = P.tgt_col[e];
-      if (r >= nc) r += nd_in;
-      F[r + c * SF_LDF] = v;
     }
     __syncthreads();
-    // ---- extend-add the children (top of stack first) ----
-    int off = 0;
-    for (int c = 0; c < nch; ++c) {
-      const int *ft = reinterpret_cast<const int *>(B.stack + sp - 2);
-      const int dim = ft[0], ndo = ft[1], child = ft[2];
-      const long long base = sp - rec_size(dim);
-      const int *ids = reinterpret_cast<const int *>(B.stack + base);
-      const double *M = B.stack + base + (dim + 1) / 2;
-      const int *crel = P.rel + P.row_ptr[child];
-      for (int i = tid; i < dim; i += SF_NT) {
-        if (i < ndo) { map[i] = nc + off + i; fid[nc + off + i] = ids[i]; }
-        else { const int rr = crel[i - ndo]; map[i] = rr < nc ? rr : rr + nd_in; }
-      }
+    // ---- larger fronts (and small ones that grew through delayed pivots): whole CTA, one by one ----
+    const int ndef = min(cnt[4], 64);
+    for (int k = 0; k < ndef; ++k) {
+      int best = -1;  // deterministic order: ascending supernode index
+      for (int q = 0; q < ndef; ++q)
+        if (deferred[q] >= 0 && (best < 0 || deferred[q] < deferred[best])) best = q;
+      const int s = deferred[best];
       __syncthreads();
-      for (int idx = tid; idx < dim * dim; idx += SF_NT) {
-        const int j = idx / dim, i = idx - j * dim;
-        if (i < j) continue;
-        const int a = map[i], b = map[j];
-        fent(F, a, b) += M[i + (long long)j * dim];
-      }
+      if (tid == 0) deferred[best] = -1;
+      if (process_front<SF_NT>(Bk, P, vals, s, big, u, pivtol, cnt, stg) != PF_OK && tid == 0) cnt[3] = 1;
       __syncthreads();
-      off += ndo;
-      sp = base;
     }
-    // ---- partial factorisation ----
-    const int ne = factor_front(F, S, fs, fid, bsz, w0, w1, u, pivtol, cnt, sh_i);
-    const int ndo = fs - ne, dim = S - ne;
-    // ---- store L / D, ids, pivot flags ----
-    {
-      const int caprows = nc + P.dcap[s] + ncb;
-      double *Ls = B.L + P.l_off[s];
-      for (int idx = tid; idx < S * ne; idx += SF_NT) {
-        const int j = idx / S, i = idx - j * S;
-        if (i >= j) Ls[i + (long long)j * caprows] = F[i + j * SF_LDF];
-      }
-      int *fo = B.fid + P.fid_off[s];
-      for (int i = tid; i < S; i += SF_NT) fo[i] = fid[i];
-      int *po = B.pbz + P.fs_off[s];
-      for (int i = tid; i < ne; i += SF_NT) po[i] = bsz[i];
-      if (tid == 0) { B.meta[2 * s] = ne; B.meta[2 * s + 1] = S; }
-    }
-    // ---- contribution block: to the parent's stack record, or into the dense root front ----
-    if (P.parent[s] >= 0) {
-      const long long need = rec_size(dim);
-      if (sp + need > B.stack_cap) { failed = true; break; }
-      int *ids = reinterpret_cast<int *>(B.stack + sp);
-      double *M = B.stack + sp + (dim + 1) / 2;
-      for (int i = tid; i < ndo; i += SF_NT) ids[i] = fid[ne + i];
-      for (int idx = tid; idx < dim * dim; idx += SF_NT) {
-        const int j = idx / dim, i = idx - j * dim;
-        if (i >= j) M[i + (long long)j * dim] = F[(ne + i) + (ne + j) * SF_LDF];
-      }
-      if (tid == 0) {
-        int *ft = reinterpret_cast<int *>(B.stack + sp + need - 2);
-        ft[0] = dim; ft[1] = ndo; ft[2] = s; ft[3] = 0;
-      }
-      sp += need;
-    } else {
-      if (ndroot + ndo > P.DR) { failed = true; break; }
-      const int *crel = P.rel + r0;
-      for (int i = tid; i < dim; i += SF_NT) {
-        if (i < ndo) { map[i] = P.nT + ndroot + i; B.rootids[P.nT + ndroot + i] = fid[ne + i]; }
-        else map[i] = crel[i - ndo];
-      }
+    for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+      if (process_front<SF_NT>(Bk, P, vals, P.big_idx[k], big, u, pivtol, cnt, stg) != PF_OK && tid == 0) cnt[3] = 1;
       __syncthreads();
-      for (int idx = tid; idx < dim * dim; idx += SF_NT) {
-        const int j = idx / dim, i = idx - j * dim;
-        if (i < j) continue;
-        int a = map[i], b = map[j];
-        if (a < b) { const int x = a; a = b; b = x; }
-        R.A[(size_t)a + (size_t)b * R.ld] += F[(ne + i) + (ne + j) * SF_LDF];
-      }
-      ndroot += ndo;
     }
+    if (tid == 0) cnt[4] = 0;
     __syncthreads();
+    if (cnt[3]) break;
   }
-  // ---- finish the root: identity on unused delayed slots, ids of the static columns ----
-  for (int i = tid; i < P.nT; i += SF_NT) B.rootids[i] = P.rootcols[i];
+  // ---- children of the root: add their contribution blocks into the dense root front ----
+  int ndroot = 0;
+  bool failed = cnt[3] != 0 || Bk.info[2] != 0;
+  for (int k = 0; k < P.nrootch && !failed; ++k) {
+    const int s = P.root_children[k];
+    const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], ndo = Bk.meta[3 * s + 2];
+    const int dim = S - ne;
+    if (ndroot + ndo > P.DR) { failed = true; break; }
+    const SnHead H = P.heads[s];
+    const int *ids = Bk.fid + H.fid_off + ne;
+    const int *crel = P.rel + H.r0;
+    const double *M = Bk.cb + H.cb_off;
+    for (int i = tid; i < dim; i += SF_NT) {
+      if (i < ndo) { big.map[i] = P.nT + ndroot + i; Bk.rootids[P.nT + ndroot + i] = ids[i]; }
+      else big.map[i] = crel[i - ndo];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < dim * dim; idx += SF_NT) {
+      const int j = idx / dim, i = idx - j * dim;
+      if (i < j) continue;
+      int a = big.map[i], b = big.map[j];
+      if (a < b) { const int x = a; a = b; b = x; }
+      R.A[(size_t)a + (size_t)b * R.ld] += M[i + j * dim];
+    }
+    __syncthreads();
+    ndroot += ndo;
+  }
+  for (int i = tid; i < P.nT; i += SF_NT) Bk.rootids[i] = P.rootcols[i];
   for (int t = ndroot + tid; t < P.DR; t += SF_NT) {
-    B.rootids[P.nT + t] = -1;
-    R.A[(size_t)(P.nT + t) + (size_t)(P.nT + t) * R.ld] = 1.0;
+    Bk.rootids[P.nT + t] = -1;
+    R.A[(size_t)(P.nT + t) + (size_t)(P.nT + t) * R.ld] = 1.0;  // unused delayed slot: identity pivot
   }
   __syncthreads();
   if (tid == 0) {
-    B.info[0] = failed ? 1 : 0;
-    B.info[1] = ndroot;
+    Bk.info[0] = failed ? 1 : 0;
+    Bk.info[1] = ndroot;
+    Bk.info[2] = 0;  // leaf-failure flag consumed
     // the DR - ndroot identity slots will be counted as positive pivots by the root: cancel them here
     const long long pos = (long long)cnt[0] - (long long)(P.DR - ndroot);
     atomicAdd(&inertia[0], (unsigned long long)pos);
@@ -336,8 +562,205 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
 }
 
 // ---- solves on the subtree part ---------------------------------------------------------------
-// forward: y <- rhs; for every front (postorder) z = L11^-1 y[elim], y[rest] -= L21 z; then the root
-// right-hand side is gathered.  y keeps z for the backward sweep.
+// Per front (after pivoting): rows [0,ne) eliminated, [ne,fs) delayed, [fs,S) contribution rows.
+//   forward : v = rhs on own rows + children's vectors;  z = L11^-1 v[0:ne];  out = v[ne:] - L21 z
+//   backward: x[0:ne] = L11^-T (D^-1 z - L21^T x[ne:])
+struct SolveBuf {
+  double *Ls, *z, *v;
+  int *fid, *inv, *bsz, *map;
+  int ld, cap;
+};
+__host__ __device__ constexpr size_t sb_bytes(int cap, int ld) {
+  return (size_t)cap * ld * 8 + 2 * (size_t)cap * 8 + 4 * (size_t)cap * 4;
+}
+constexpr size_t SV_TINY_BYTES = (sb_bytes(SF_TBUF, SF_TLD) + 15) / 16 * 16;
+constexpr size_t SV_BIG_BYTES = sb_bytes(SF_SBUF, SF_LDF);
+constexpr size_t SV_WORK = (SV_BIG_BYTES > SF_NW * SV_TINY_BYTES ? SV_BIG_BYTES : SF_NW * SV_TINY_BYTES) / 16 * 16 + 16;
+constexpr size_t SV_SMEM = SV_WORK + SF_STG_BYTES;
+
+__device__ __forceinline__ SolveBuf carve_solve(unsigned char *base, int cap, int ld) {
+  SolveBuf b;
+  b.Ls = reinterpret_cast<double *>(base);
+  b.z = b.Ls + (size_t)cap * ld;
+  b.v = b.z + cap;
+  b.fid = reinterpret_cast<int *>(b.v + cap);
+  b.inv = b.fid + cap;
+  b.bsz = b.inv + cap;
+  b.map = b.bsz + cap;
+  b.ld = ld;
+  b.cap = cap;
+  return b;
+}
+
+template <int G>
+__device__ void load_front(const SparseBlock &Bk, const SnHead &H, const SolveBuf &B, int ne, int S) {
+  const int tid = gtid<G>();
+  const int caprows = H.nc + H.dcap + H.ncb;
+  const double *Lg = Bk.L + H.l_off;
+  for (int j = 0; j < ne; ++j)
+    for (int i = j + tid; i < S; i += G) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
+  for (int i = tid; i < S; i += G) B.fid[i] = Bk.fid[H.fid_off + i];
+  for (int i = tid; i < ne; i += G) B.bsz[i] = Bk.pbz[H.fs_off + i];
+}
+
+template <int G>
+__device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, const SolveBuf &B,
+                              const double *__restrict__ rhs, double *__restrict__ y, const Stage &stg) {
+  const int tid = gtid<G>(), lane = tid & 31;
+  const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], fs = ne + Bk.meta[3 * s + 2];
+  if (S == 0) return;
+  const SnHead H = P.heads[s];
+  const int nc = H.nc;
+  const int nd_in = fs - nc;
+  load_front<G>(Bk, H, B, ne, S);
+  for (int i = tid; i < fs; i += G) B.inv[Bk.opos[H.fs_off + i]] = i;  // pre-pivot -> stored position
+  gsync<G>();
+  for (int i = tid; i < S; i += G)
+    B.v[i] = (i < fs && Bk.opos[H.fs_off + i] < nc) ? rhs[B.fid[i]] : 0.0;
+  gsync<G>();
+  if (G != 32 && H.nch >= 4 && H.nch <= SF_MAXCH) {
+    // many children: fetch their vectors concurrently (one child per thread), apply in child order
+    for (int k = tid; k < H.nch; k += G) {
+      const int c = P.child_idx[H.ch0 + k];
+      stg.ndo[k] = Bk.meta[3 * c + 2];
+      stg.cnt[k] = Bk.meta[3 * c + 1] - Bk.meta[3 * c];
+    }
+    gsync<G>();
+    if (tid == 0) {
+      int off = 0, ent = 0;
+      for (int k = 0; k < H.nch; ++k) {
+        const int d = stg.ndo[k], e = stg.cnt[k];
+        stg.ndo[k] = off;
+        off += d;
+        stg.cnt[k] = ent;
+        ent += e;
+      }
+      stg.cnt[H.nch] = ent;
+    }
+    gsync<G>();
+    const int total = stg.cnt[H.nch];
+    if (total <= SF_STG) {
+      for (int k = tid; k < H.nch; k += G) {
+        const int c = P.child_idx[H.ch0 + k];
+        const SnHead C = P.heads[c];
+        const int ndo = Bk.meta[3 * c + 2], dim = stg.cnt[k + 1] - stg.cnt[k], off = stg.ndo[k];
+        const int *crel = P.rel + C.r0;
+        const double *uc = Bk.vec + C.vec_off;
+        for (int i = 0; i < dim; ++i) {
+          int q;
+          if (i < ndo) q = nc + off + i;
+          else { const int rr = crel[i - ndo]; q = rr < nc ? rr : rr + nd_in; }
+          stg.tgt[stg.cnt[k] + i] = q < fs ? B.inv[q] : q;
+          stg.val[stg.cnt[k] + i] = uc[i];
+        }
+      }
+      gsync<G>();
+      if (tid < 32) {
+        for (int k = 0; k < H.nch; ++k) {
+          for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) B.v[stg.tgt[e]] += stg.val[e];
+          __syncwarp();
+        }
+      }
+      gsync<G>();
+    } else {
+      for (int k = 0; k < H.nch; ++k) {
+        const int c = P.child_idx[H.ch0 + k];
+        const SnHead C = P.heads[c];
+        const int ndo = Bk.meta[3 * c + 2], dim = stg.cnt[k + 1] - stg.cnt[k], off = stg.ndo[k];
+        const int *crel = P.rel + C.r0;
+        const double *uc = Bk.vec + C.vec_off;
+        for (int i = tid; i < dim; i += G) {
+          int q;
+          if (i < ndo) q = nc + off + i;
+          else { const int rr = crel[i - ndo]; q = rr < nc ? rr : rr + nd_in; }
+          B.v[q < fs ? B.inv[q] : q] += uc[i];
+        }
+        gsync<G>();
+      }
+    }
+  } else {
+    int off = 0;
+    for (int k = 0; k < H.nch; ++k) {
+      const int c = P.child_idx[H.ch0 + k];
+      const SnHead C = P.heads[c];
+      const int cne = Bk.meta[3 * c], cS = Bk.meta[3 * c + 1], ndo = Bk.meta[3 * c + 2];
+      const int dim = cS - cne;
+      const int *crel = P.rel + C.r0;
+      const double *uc = Bk.vec + C.vec_off;
+      for (int i = tid; i < dim; i += G) {
+        int q;
+        if (i < ndo) q = nc + off + i;
+        else { const int rr = crel[i - ndo]; q = rr < nc ? rr : rr + nd_in; }
+        B.v[q < fs ? B.inv[q] : q] += uc[i];
+      }
+      gsync<G>();
+      off += ndo;
+    }
+  }
+  if (tid < 32) {
+    for (int c = 0; c < ne; ++c) {
+      const double zc = B.v[c];
+      const int skip = B.bsz[c] == 2 ? c + 1 : -1;
+      for (int i = c + 1 + lane; i < ne; i += 32)
+        if (i != skip) B.v[i] -= B.Ls[i + c * B.ld] * zc;
+      __syncwarp();
+    }
+  }
+  gsync<G>();
+  double *out = Bk.vec + H.vec_off;
+  for (int i = ne + tid; i < S; i += G) {
+    double acc = 0.0;
+    for (int c = 0; c < ne; ++c) acc += B.Ls[i + c * B.ld] * B.v[c];
+    out[i - ne] = B.v[i] - acc;
+  }
+  for (int i = tid; i < ne; i += G) y[B.fid[i]] = B.v[i];
+  gsync<G>();
+}
+
+template <int G>
+__device__ void backward_front(const SparseBlock &Bk, const PlanDev &P, int s, const SolveBuf &B,
+                               const double *__restrict__ y, double *__restrict__ x) {
+  const int tid = gtid<G>(), lane = tid & 31;
+  const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1];
+  if (ne == 0) return;
+  const SnHead H = P.heads[s];
+  load_front<G>(Bk, H, B, ne, S);
+  gsync<G>();
+  for (int i = ne + tid; i < S; i += G) B.v[i] = x[B.fid[i]];
+  for (int k = tid; k < ne; k += G) {  // w = D^-1 z
+    const int b = B.bsz[k];
+    if (b == 1) {
+      const double d = B.Ls[k + k * B.ld];
+      B.z[k] = d != 0.0 ? y[B.fid[k]] / d : 0.0;
+    } else if (b == 2) {
+      const double e21 = B.Ls[k + 1 + k * B.ld];
+      const double akm1 = B.Ls[k + k * B.ld] / e21, ak = B.Ls[k + 1 + (k + 1) * B.ld] / e21;
+      const double denom = akm1 * ak - 1.0;
+      const double bkm1 = y[B.fid[k]] / e21, bk = y[B.fid[k + 1]] / e21;
+      B.z[k] = (ak * bkm1 - bk) / denom;
+      B.z[k + 1] = (akm1 * bk - bkm1) / denom;
+    }
+  }
+  gsync<G>();
+  for (int c = tid; c < ne; c += G) {
+    double acc = 0.0;
+    for (int i = ne; i < S; ++i) acc += B.Ls[i + c * B.ld] * B.v[i];
+    B.z[c] -= acc;
+  }
+  gsync<G>();
+  if (tid < 32) {
+    for (int rr = ne - 1; rr > 0; --rr) {
+      const double xv = B.z[rr];
+      for (int c = lane; c < rr; c += 32)
+        if (!(B.bsz[c] == 2 && rr == c + 1)) B.z[c] -= B.Ls[rr + c * B.ld] * xv;
+      __syncwarp();
+    }
+  }
+  gsync<G>();
+  for (int i = tid; i < ne; i += G) x[B.fid[i]] = B.z[i];
+  gsync<G>();
+}
+
 __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBlock *__restrict__ blocks,
                                                                 const PlanDev *__restrict__ plans,
                                                                 const double *__restrict__ rhs,
@@ -346,59 +769,48 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
                                                                 double *__restrict__ root_rhs,
                                                                 const long long *__restrict__ root_off) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  double *Ls = reinterpret_cast<double *>(sm_raw);  // S x ne block, pitch SF_LDF
-  double *z = Ls + SF_SBUF * SF_LDF;
-  int *fid = reinterpret_cast<int *>(z + SF_SBUF);
-  int *bsz = fid + SF_SBUF;
-  const SparseBlock B = blocks[blockIdx.x];
-  const PlanDev P = plans[B.plan];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const SparseBlock Bk = blocks[blockIdx.x];
+  const PlanDev P = plans[Bk.plan];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
+  const Stage stg = carve_stage(sm_raw + SV_WORK);
   const double *r = rhs + vec_off[blockIdx.x];
   double *y = ywork + vec_off[blockIdx.x];
-  for (int i = tid; i < P.n; i += SF_NT) y[i] = r[i];
-  __syncthreads();
-  for (int s = 0; s < P.ns; ++s) {
-    const int ne = B.meta[2 * s], S = B.meta[2 * s + 1];
-    if (ne == 0) continue;
-    const int nc = P.col_ptr[s + 1] - P.col_ptr[s], ncb = P.row_ptr[s + 1] - P.row_ptr[s];
-    const int caprows = nc + P.dcap[s] + ncb;
-    const double *Lg = B.L + P.l_off[s];
-    for (int idx = tid; idx < S * ne; idx += SF_NT) {
-      const int j = idx / S, i = idx - j * S;
-      if (i > j) Ls[i + j * SF_LDF] = Lg[i + (long long)j * caprows];
-    }
-    for (int i = tid; i < S; i += SF_NT) fid[i] = B.fid[P.fid_off[s] + i];
-    for (int i = tid; i < ne; i += SF_NT) bsz[i] = B.pbz[P.fs_off[s] + i];
-    __syncthreads();
-    for (int i = tid; i < ne; i += SF_NT) z[i] = y[fid[i]];
-    __syncthreads();
-    if (tid < 32) {
-      for (int c = 0; c < ne; ++c) {
-        const double zc = z[c];
-        const int skip = bsz[c] == 2 ? c + 1 : -1;
-        for (int i = c + 1 + lane; i < ne; i += 32)
-          if (i != skip) z[i] -= Ls[i + c * SF_LDF] * zc;
-        __syncwarp();
-      }
+  for (int l = 0; l < P.nlevels; ++l) {
+    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+      const int s = P.tiny_idx[k];
+      if (Bk.meta[3 * s + 1] <= SF_TBUF) forward_front<32>(Bk, P, s, mine, r, y, stg);
     }
     __syncthreads();
-    for (int i = ne + tid; i < S; i += SF_NT) {
-      double acc = 0.0;
-      for (int c = 0; c < ne; ++c) acc += Ls[i + c * SF_LDF] * z[c];
-      y[fid[i]] -= acc;
+    for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {  // small fronts that outgrew a warp
+      const int s = P.tiny_idx[k];
+      if (Bk.meta[3 * s + 1] > SF_TBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
     }
-    for (int i = tid; i < ne; i += SF_NT) y[fid[i]] = z[i];
+    for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+      forward_front<SF_NT>(Bk, P, P.big_idx[k], big, r, y, stg);
+      __syncthreads();
+    }
     __syncthreads();
   }
+  // root right-hand side: own entries + contributions of the root's children (fixed order)
   double *rr = root_rhs + root_off[blockIdx.x];
-  for (int p = tid; p < P.nT + P.DR; p += SF_NT) {
-    const int id = B.rootids[p];
-    rr[p] = id >= 0 ? y[id] : 0.0;
+  for (int p = tid; p < P.nT + P.DR; p += SF_NT) rr[p] = p < P.nT ? r[P.rootcols[p]] : 0.0;
+  __syncthreads();
+  int ndroot = 0;
+  for (int k = 0; k < P.nrootch; ++k) {
+    const int s = P.root_children[k];
+    const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], ndo = Bk.meta[3 * s + 2];
+    const int dim = S - ne;
+    const SnHead H = P.heads[s];
+    const int *crel = P.rel + H.r0;
+    const double *uc = Bk.vec + H.vec_off;
+    for (int i = tid; i < dim; i += SF_NT) rr[i < ndo ? P.nT + ndroot + i : crel[i - ndo]] += uc[i];
+    __syncthreads();
+    ndroot += ndo;
   }
 }
 
-// backward: x[root ids] <- root solution; for every front in reverse postorder
-//   x[elim] = L11^-T (D^-1 z - L21^T x[rest]).
 __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlock *__restrict__ blocks,
                                                                  const PlanDev *__restrict__ plans,
                                                                  const double *__restrict__ ywork,
@@ -407,71 +819,72 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
                                                                  const long long *__restrict__ root_off,
                                                                  double *__restrict__ xout) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  double *Ls = reinterpret_cast<double *>(sm_raw);
-  double *z = Ls + SF_SBUF * SF_LDF;
-  double *xr = z + SF_SBUF;
-  int *fid = reinterpret_cast<int *>(xr + SF_SBUF);
-  int *bsz = fid + SF_SBUF;
-  const SparseBlock B = blocks[blockIdx.x];
-  const PlanDev P = plans[B.plan];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const SparseBlock Bk = blocks[blockIdx.x];
+  const PlanDev P = plans[Bk.plan];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
   const double *y = ywork + vec_off[blockIdx.x];
   double *x = xout + vec_off[blockIdx.x];
   const double *rx = root_x + root_off[blockIdx.x];
   for (int p = tid; p < P.nT + P.DR; p += SF_NT) {
-    const int id = B.rootids[p];
+    const int id = Bk.rootids[p];
     if (id >= 0) x[id] = rx[p];
   }
   __syncthreads();
-  for (int s = P.ns - 1; s >= 0; --s) {
-    const int ne = B.meta[2 * s], S = B.meta[2 * s + 1];
-    if (ne == 0) continue;
-    const int nc = P.col_ptr[s + 1] - P.col_ptr[s], ncb = P.row_ptr[s + 1] - P.row_ptr[s];
-    const int caprows = nc + P.dcap[s] + ncb;
-    const double *Lg = B.L + P.l_off[s];
-    for (int idx = tid; idx < S * ne; idx += SF_NT) {
-      const int j = idx / S, i = idx - j * S;
-      if (i >= j) Ls[i + j * SF_LDF] = Lg[i + (long long)j * caprows];
+  for (int l = P.nlevels - 1; l >= 0; --l) {
+    for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+      backward_front<SF_NT>(Bk, P, P.big_idx[k], big, y, x);
+      __syncthreads();
     }
-    for (int i = tid; i < S; i += SF_NT) fid[i] = B.fid[P.fid_off[s] + i];
-    for (int i = tid; i < ne; i += SF_NT) bsz[i] = B.pbz[P.fs_off[s] + i];
-    __syncthreads();
-    for (int i = ne + tid; i < S; i += SF_NT) xr[i] = x[fid[i]];
-    // w = D^-1 z
-    for (int k = tid; k < ne; k += SF_NT) {
-      const int b = bsz[k];
-      if (b == 1) {
-        const double d = Ls[k + k * SF_LDF];
-        z[k] = d != 0.0 ? y[fid[k]] / d : 0.0;
-      } else if (b == 2) {
-        const double e21 = Ls[k + 1 + k * SF_LDF];
-        const double akm1 = Ls[k + k * SF_LDF] / e21, ak = Ls[k + 1 + (k + 1) * SF_LDF] / e21;
-        const double denom = akm1 * ak - 1.0;
-        const double bkm1 = y[fid[k]] / e21, bk = y[fid[k + 1]] / e21;
-        z[k] = (ak * bkm1 - bk) / denom;
-        z[k + 1] = (akm1 * bk - bkm1) / denom;
-      }
+    for (int k = P.tiny_ptr[l]; k < P.tiny_ptr[l + 1]; ++k) {
+      const int s = P.tiny_idx[k];
+      if (Bk.meta[3 * s + 1] > SF_TBUF) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
     }
     __syncthreads();
-    // z[c] -= L21(:,c)^T xr
-    for (int c = tid; c < ne; c += SF_NT) {
-      double acc = 0.0;
-      for (int i = ne; i < S; ++i) acc += Ls[i + c * SF_LDF] * xr[i];
-      z[c] -= acc;
+    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+      const int s = P.tiny_idx[k];
+      if (Bk.meta[3 * s + 1] <= SF_TBUF) backward_front<32>(Bk, P, s, mine, y, x);
     }
-    __syncthreads();
-    if (tid < 32) {
-      for (int rr = ne - 1; rr > 0; --rr) {
-        const double xv = z[rr];
-        for (int c = lane; c < rr; c += 32)
-          if (!(bsz[c] == 2 && rr == c + 1)) z[c] -= Ls[rr + c * SF_LDF] * xv;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < ne; i += SF_NT) x[fid[i]] = z[i];
     __syncthreads();
   }
+}
+
+// leaves of the solves: one warp per (block, leaf) over the whole GPU
+constexpr size_t LS_SMEM = LF_NW * SV_TINY_BYTES + 16;
+
+__global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const SparseBlock *__restrict__ blocks,
+                                                                     const PlanDev *__restrict__ plans,
+                                                                     const double *__restrict__ rhs,
+                                                                     const long long *__restrict__ vec_off,
+                                                                     double *__restrict__ ywork) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const SparseBlock Bk = blocks[blockIdx.y];
+  const PlanDev P = plans[Bk.plan];
+  const int warp = threadIdx.x >> 5;
+  if (P.nlevels == 0) return;
+  const int k = blockIdx.x * LF_NW + warp;
+  if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
+  Stage none;
+  none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr;
+  forward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, rhs + vec_off[blockIdx.y], ywork + vec_off[blockIdx.y], none);
+}
+
+__global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const SparseBlock *__restrict__ blocks,
+                                                                      const PlanDev *__restrict__ plans,
+                                                                      const double *__restrict__ ywork,
+                                                                      const long long *__restrict__ vec_off,
+                                                                      double *__restrict__ xout) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const SparseBlock Bk = blocks[blockIdx.y];
+  const PlanDev P = plans[Bk.plan];
+  const int warp = threadIdx.x >> 5;
+  if (P.nlevels == 0) return;
+  const int k = blockIdx.x * LF_NW + warp;
+  if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
+  backward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, ywork + vec_off[blockIdx.y], xout + vec_off[blockIdx.y]);
 }
 
 // worst failure flag over the sparse blocks -> flag[1]

@@ -31,7 +31,17 @@ struct PatternPlan {
   std::vector<int> fid_off, fs_off;   // offsets of the id / pivot-flag lists
   int64_t l_total = 0;
   int fid_total = 0, fs_total = 0;
-  int64_t stack_cap = 0;              // doubles needed by the contribution-block stack
+  int64_t stack_cap = 0;              // (unused by the level-scheduled kernels; kept for statistics)
+  std::vector<int> child_ptr, child_idx;   // children of every supernode, ascending
+  std::vector<int> root_children;          // supernodes whose parent is the dense root, ascending
+  std::vector<int> dslot;                  // delayed columns a supernode may pass up
+  std::vector<int64_t> cb_off;             // contribution slot (dim <= ncb + dslot, stored dim x dim)
+  std::vector<int> vec_off;                // forward-solve contribution vector slot
+  int64_t cb_total = 0;
+  int vec_total = 0;
+  int nlevels = 0;                         // height classes: level 0 = leaves
+  std::vector<int> tiny_ptr, tiny_idx;     // per level: fronts small enough for one warp
+  std::vector<int> big_ptr, big_idx;       // per level: fronts factored by the whole CTA
   int max_front = 0;                  // largest subtree front incl. delayed capacity actually allowed
   int64_t nnz_l = 0;                  // static entries of L in the subtree part (statistics)
   // original entries grouped by destination: unique targets with their sources (relative value index)
@@ -120,6 +130,10 @@ struct PlanOptions {
   int dmax = 32;        // delayed-pivot capacity per front / per root
   int sbuf = 96;        // rows of the shared-memory front buffer
   int relax_zeros = 24; // explicit zeros tolerated when merging a child supernode into its parent
+  int merge_max = 16;   // largest front produced by a merge that introduces explicit zeros
+  int dslot = 8;        // delayed columns one front may hand to its parent
+  int tiny = 16;        // largest static front handled by a single warp
+  int tiny_max_children = 8;  // fronts with more children are assembled by the whole CTA (staged fetch)
   int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front
   double max_density = 0.20; // ... as are blocks whose factor would fill more than this share of n^2/2
 };
@@ -178,24 +192,47 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
     colparent[p] = sn[k].rows.empty() ? -1 : sn[k].rows.front();
   }
   auto find = [&](int s) { while (sn[s].dead) s = sn[s].parent; return s; };
+  // singleton tree, heights (children precede parents in elimination order)
+  std::vector<std::vector<int>> ch(ne_cols);
+  std::vector<int> height(ne_cols, 0);
   for (int k = 0; k < ne_cols; ++k) {
-    if (sn[k].dead) continue;
     const int q = colparent[sn[k].cols.back()];
-    if (q < 0 || pos[q] < 0) { sn[k].parent = -1; continue; }  // parent is a held column -> root
-    const int ps = find(sn_of[q]);
-    sn[k].parent = ps;
-    // merge k into ps when q is the FIRST column of ps (k's columns are eliminated right before it)
-    if (sn[ps].cols.front() != q) continue;
-    const int nc = (int)sn[k].cols.size(), ncb = (int)sn[k].rows.size();
-    const int pc = (int)sn[ps].cols.size(), pcb = (int)sn[ps].rows.size();
-    const long zeros = (long)nc * (pc + pcb - ncb);
-    if (nc + pc + pcb > opt.fmax) continue;
-    if (zeros > opt.relax_zeros && zeros * 4 > (long)(nc + pc) * (nc + pc + pcb)) continue;
-    std::vector<int> merged(sn[k].cols);
-    merged.insert(merged.end(), sn[ps].cols.begin(), sn[ps].cols.end());
-    sn[ps].cols.swap(merged);
-    sn[k].dead = true;  // parent pointer keeps the forwarding address
-    for (int c : sn[k].cols) sn_of[c] = ps;
+    sn[k].parent = (q < 0 || pos[q] < 0) ? -1 : pos[q];
+    if (sn[k].parent >= 0) {
+      ch[sn[k].parent].push_back(k);
+      height[sn[k].parent] = std::max(height[sn[k].parent], height[k] + 1);
+    }
+  }
+  // Greedy amalgamation from the top down: a node repeatedly absorbs its TALLEST child (the one on
+  // the critical path), which shortens the level schedule of the numeric kernels; explicit zeros are
+  // bounded, and merged fronts stay small enough for one warp unless the merge is free of zeros.
+  for (int p2 = ne_cols - 1; p2 >= 0; --p2) {
+    if (sn[p2].dead) continue;
+    while (!ch[p2].empty()) {
+      int bi = 0;
+      for (int i = 1; i < (int)ch[p2].size(); ++i) {
+        const int a = ch[p2][i], b = ch[p2][bi];
+        if (height[a] > height[b] || (height[a] == height[b] && a > b)) bi = i;
+      }
+      const int c = ch[p2][bi];
+      const int nc = (int)sn[c].cols.size(), ncb = (int)sn[c].rows.size();
+      const int pc = (int)sn[p2].cols.size(), pcb = (int)sn[p2].rows.size();
+      const long zeros = (long)nc * (pc + pcb - ncb);
+      const int size = nc + pc + pcb;
+      bool ok = size <= opt.fmax;
+      if (ok && zeros > 0)
+        ok = size <= opt.merge_max && (zeros <= opt.relax_zeros || zeros * 4 <= (long)(nc + pc) * size);
+      if (!ok) break;
+      std::vector<int> merged(sn[c].cols);
+      merged.insert(merged.end(), sn[p2].cols.begin(), sn[p2].cols.end());
+      sn[p2].cols.swap(merged);
+      sn[c].dead = true;
+      sn[c].parent = p2;  // forwarding address
+      for (int col : sn[c].cols) sn_of[col] = p2;
+      ch[p2].erase(ch[p2].begin() + bi);
+      for (int g : ch[c]) { sn[g].parent = p2; ch[p2].push_back(g); }
+      ch[c].clear();
+    }
   }
   // resolve parents after merging
   for (int k = 0; k < ne_cols; ++k)
@@ -275,13 +312,31 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
       for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) P.rel[i] = rootpos[P.rows[i]];
     }
   }
-  // capacities, factor layout, stack bound
-  int64_t stack = 0, peak = 0;
-  std::vector<int64_t> rec(P.ns, 0);
+  // children lists and levels
+  P.child_ptr.assign(P.ns + 1, 0);
+  for (int s = 0; s < P.ns; ++s)
+    if (P.parent[s] >= 0) P.child_ptr[P.parent[s] + 1]++; else P.root_children.push_back(s);
+  for (int s = 0; s < P.ns; ++s) P.child_ptr[s + 1] += P.child_ptr[s];
+  P.child_idx.resize(P.child_ptr[P.ns]);
+  {
+    std::vector<int> fillp(P.child_ptr.begin(), P.child_ptr.end() - 1);
+    for (int s = 0; s < P.ns; ++s)
+      if (P.parent[s] >= 0) P.child_idx[fillp[P.parent[s]]++] = s;
+  }
+  std::vector<int> level(P.ns, 0);
+  for (int s = 0; s < P.ns; ++s)
+    if (P.parent[s] >= 0) level[P.parent[s]] = std::max(level[P.parent[s]], level[s] + 1);
+  // capacities and storage layout (children precede parents in postorder)
+  P.dslot.resize(P.ns);
+  P.cb_off.resize(P.ns);
+  P.vec_off.resize(P.ns);
+  std::vector<char> is_tiny(P.ns, 0);
   for (int s = 0; s < P.ns; ++s) {
     const int nc = P.col_ptr[s + 1] - P.col_ptr[s], ncb = P.row_ptr[s + 1] - P.row_ptr[s];
-    P.dcap[s] = std::min(opt.dmax, std::min(below[s], opt.sbuf - nc - ncb));
-    if (P.dcap[s] < 0) P.dcap[s] = 0;
+    int incoming = 0;
+    for (int k = P.child_ptr[s]; k < P.child_ptr[s + 1]; ++k) incoming += P.dslot[P.child_idx[k]];
+    P.dcap[s] = std::max(0, std::min(std::min(opt.dmax, incoming), opt.sbuf - nc - ncb));
+    P.dslot[s] = std::min(opt.dslot, nc + P.dcap[s]);
     const int cap_rows = nc + P.dcap[s] + ncb, cap_fs = nc + P.dcap[s];
     P.l_off[s] = P.l_total;
     P.l_total += (int64_t)cap_rows * cap_fs;
@@ -289,25 +344,29 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
     P.fid_total += cap_rows;
     P.fs_off[s] = P.fs_total;
     P.fs_total += cap_fs;
+    const int cbdim = ncb + P.dslot[s];
+    P.cb_off[s] = P.cb_total;
+    P.cb_total += (int64_t)cbdim * cbdim;
+    P.vec_off[s] = P.vec_total;
+    P.vec_total += cbdim;
     P.max_front = std::max(P.max_front, cap_rows);
     P.nnz_l += (int64_t)nc * (nc + 1) / 2 + (int64_t)nc * ncb;
-    // stack simulation with capacity-sized records: children are popped, own record pushed
-    const int dim = ncb + cap_fs;  // nothing eliminated in the worst case
-    rec[s] = (int64_t)dim * dim + dim + 8;
-    // children records were pushed earlier; pop them
-    // (postorder: the children of s are exactly the most recent unpopped records)
-    // we do not track identities here: subtract the sizes of the direct children
+    is_tiny[s] = (nc + ncb) <= opt.tiny && (P.child_ptr[s + 1] - P.child_ptr[s]) < opt.tiny_max_children;
+    P.nlevels = std::max(P.nlevels, level[s] + 1);
   }
+  P.stack_cap = P.cb_total;
+  P.tiny_ptr.assign(P.nlevels + 1, 0);
+  P.big_ptr.assign(P.nlevels + 1, 0);
+  for (int s = 0; s < P.ns; ++s) (is_tiny[s] ? P.tiny_ptr : P.big_ptr)[level[s] + 1]++;
+  for (int l = 0; l < P.nlevels; ++l) { P.tiny_ptr[l + 1] += P.tiny_ptr[l]; P.big_ptr[l + 1] += P.big_ptr[l]; }
+  P.tiny_idx.resize(P.tiny_ptr[P.nlevels]);
+  P.big_idx.resize(P.big_ptr[P.nlevels]);
   {
-    std::vector<int64_t> child_sum(P.ns, 0);
+    std::vector<int> ft(P.tiny_ptr.begin(), P.tiny_ptr.end() - 1), fb(P.big_ptr.begin(), P.big_ptr.end() - 1);
     for (int s = 0; s < P.ns; ++s) {
-      peak = std::max(peak, stack + 0);
-      stack -= child_sum[s];
-      if (P.parent[s] >= 0) { stack += rec[s]; child_sum[P.parent[s]] += rec[s]; }
-      peak = std::max(peak, stack);
+      if (is_tiny[s]) P.tiny_idx[ft[level[s]]++] = s; else P.big_idx[fb[level[s]]++] = s;
     }
   }
-  P.stack_cap = peak + 16;
 
   // ---- where every input entry goes ----
   struct Tgt { int s, row, col, src; };

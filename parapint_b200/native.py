@@ -78,9 +78,10 @@ def np_ptr(arr):
     return arr.ctypes.data_as(_vp)
 
 
-PLAN_ARRAYS = ("rootcols", "col_ptr", "cols", "row_ptr", "rows", "rel", "parent", "nchild", "dcap", "ent_ptr",
+PLAN_ARRAYS = ("rootcols", "col_ptr", "cols", "row_ptr", "rows", "rel", "parent", "nchild", "dcap", "dslot", "child_ptr",
+               "child_idx", "root_children", "tiny_ptr", "tiny_idx", "big_ptr", "big_idx", "ent_ptr",
                "tgt_row", "tgt_col", "tgt_src_ptr", "tgt_src", "root_row", "root_col", "root_src")
-PLAN_SCALARS = ("n", "m", "nT", "DR", "ns", "nnz_l", "max_front", "l_total", "stack_cap")
+PLAN_SCALARS = ("n", "m", "nT", "DR", "ns", "nnz_l", "max_front", "l_total", "stack_cap", "nlevels")
 
 
 def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1):
