@@ -91,6 +91,7 @@ struct pp_handle {
   int panel_width = 64;
   double pivot_threshold = 0.01;  // u of the threshold test in the subtree fronts
   bool use_sparse = true;
+  bool no_fallback = false;
   bool sparse_failed = false;     // a block overflowed its delayed-pivot capacity: all blocks were redone dense
   PlanOptions plan_opt;
   // saved symbolic inputs (for the dense re-analysis after a sparse-path overflow)
@@ -324,6 +325,10 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   } else if (key == "pivot_threshold") {
     if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
+  } else if (key == "no_fallback") {
+    h->no_fallback = value != 0.0;
+  } else if (key == "sparse_dslot") {
+    h->plan_opt.dslot = std::max(0, std::min((int)value, 32));
   } else if (key == "sparse_fmax") {
     h->plan_opt.fmax = std::max(8, std::min((int)value, SF_SBUF - 8));
   } else if (key == "sparse_dmax") {
@@ -744,6 +749,7 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
     }
     int sparse_bad = 0;
     int bad = numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad);
+    if (sparse_bad && h->no_fallback) return fail("pp_numeric_local: sparse path overflow (fallback disabled)");
     if (sparse_bad) {
       // A block ran out of delayed-pivot capacity (or front buffer): redo the analysis with whole
       // blocks as dense fronts -- slower, but pivoting is then unrestricted -- and factor again.
@@ -944,12 +950,12 @@ int pp_plan_stats(pp_handle *h, int32_t block, int64_t out[12]) {
   out[10] = 0;
   out[11] = 0;
   if (P.ns > 0) {  // delayed pivots that reached the root in the last factorisation
-    int info[2] = {0, 0};
+    int info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<SparseBlock> sb(1);
     if (cudaMemcpy(sb.data(), h->blocks_dev.p + block, sizeof(SparseBlock), cudaMemcpyDeviceToHost) == cudaSuccess &&
         cudaMemcpy(info, sb[0].info, sizeof(info), cudaMemcpyDeviceToHost) == cudaSuccess) {
       out[10] = info[1];
-      out[11] = info[0];
+      out[11] = info[0] + 10 * info[3] + 1000 * (int64_t)info[4] + 100000000ll * info[5];
     }
   }
   return PP_SUCCESSFUL;

@@ -300,8 +300,14 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     for (int k = 0; k < H.nch; ++k) nd_in += Bk.meta[3 * P.child_idx[H.ch0 + k] + 2];
   }
   const int fs = nc + nd_in, S = fs + ncb;
-  if (S > B.cap) return G == 32 ? PF_DEFER : PF_FAIL;
-  if (nd_in > H.dcap) return PF_FAIL;
+  if (S > B.cap) {
+    if (G != 32 && tid == 0) { Bk.info[3] = 1; Bk.info[4] = s; Bk.info[5] = S; }
+    return G == 32 ? PF_DEFER : PF_FAIL;
+  }
+  if (nd_in > H.dcap) {
+    if (tid == 0) { Bk.info[3] = 2; Bk.info[4] = s; Bk.info[5] = nd_in; }
+    return PF_FAIL;
+  }
   double *F = B.F;
   const int ld = B.ld;
   for (int j = 0; j < S; ++j)
@@ -413,7 +419,10 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   const int ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
   const int ndo = fs - ne, dim = S - ne;
   if (ndo > H.dslot) {
-    if (tid == 0) { Bk.meta[3 * s] = 0; Bk.meta[3 * s + 1] = 0; Bk.meta[3 * s + 2] = 0; }
+    if (tid == 0) {
+      Bk.meta[3 * s] = 0; Bk.meta[3 * s + 1] = 0; Bk.meta[3 * s + 2] = 0;
+      Bk.info[3] = 3; Bk.info[4] = s; Bk.info[5] = ndo;
+    }
     return PF_FAIL;
   }
   const int caprows = nc + H.dcap + ncb;
@@ -480,6 +489,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
   const FrontBuf big = carve(sm_raw, SF_SBUF, SF_LDF);
   const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
   if (tid < 8) cnt[tid] = 0;
+  if (tid == 0) Bk.info[3] = 0;
   __syncthreads();
 
   for (int l = 0; l < P.nlevels; ++l) {
@@ -523,7 +533,11 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     const int s = P.root_children[k];
     const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], ndo = Bk.meta[3 * s + 2];
     const int dim = S - ne;
-    if (ndroot + ndo > P.DR) { failed = true; break; }
+    if (ndroot + ndo > P.DR) {
+      if (tid == 0) { Bk.info[3] = 4; Bk.info[4] = s; Bk.info[5] = ndroot + ndo; }
+      failed = true;
+      break;
+    }
     const SnHead H = P.heads[s];
     const int *ids = Bk.fid + H.fid_off + ne;
     const int *crel = P.rel + H.r0;

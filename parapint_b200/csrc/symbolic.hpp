@@ -127,11 +127,11 @@ inline void minimum_degree(int n, const std::vector<std::vector<int>> &adj, cons
 
 struct PlanOptions {
   int fmax = 64;        // largest static subtree front (own columns + contribution rows)
-  int dmax = 32;        // delayed-pivot capacity per front / per root
+  int dmax = 48;        // delayed-pivot capacity per front / per root
   int sbuf = 96;        // rows of the shared-memory front buffer
   int relax_zeros = 24; // explicit zeros tolerated when merging a child supernode into its parent
   int merge_max = 16;   // largest front produced by a merge that introduces explicit zeros
-  int dslot = 8;        // delayed columns one front may hand to its parent
+  int dslot = 16;       // delayed columns one front may hand to its parent
   int tiny = 16;        // largest static front handled by a single warp
   int tiny_max_children = 8;  // fronts with more children are assembled by the whole CTA (staged fetch)
   int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front

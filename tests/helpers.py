@@ -44,3 +44,50 @@ def random_bordered(rng, n_blocks, n, m_c, density=0.05, border_nnz_rows=None, d
     Qh = rng.standard_normal((m_c, m_c))
     kkt.set_block(n_blocks, n_blocks, sp.coo_matrix(Qh + Qh.T))
     return kkt
+
+
+def ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, barrier_span=(1e-4, 1e4), hess_shift=1.0):
+    """Parapint-shaped primal-dual KKT of one scenario ("family P"):
+    order [x, s, lam_eq, lam_in, lam_link]  (interfaces/interface.py:475-489 wrapped with the linking rows of
+    interfaces/schur_complement/sc_ip_interface.py:1248-1266).  Returns (K sparse symmetric, n)."""
+    band = sp.diags([rng.standard_normal(n_x - 2) * 0.3, rng.standard_normal(n_x - 1) * 0.5,
+                     np.abs(rng.standard_normal(n_x)) + hess_shift,
+                     rng.standard_normal(n_x - 1) * 0.0, rng.standard_normal(n_x - 2) * 0.0], [-2, -1, 0, 1, 2]).tocsr()
+    H = sp.tril(band) + sp.tril(band, -1).T
+    lo, hi = np.log(barrier_span[0]), np.log(barrier_span[1])
+    sig_x = np.exp(rng.uniform(lo, hi, n_x))
+    sig_s = np.exp(rng.uniform(lo, hi, n_in))
+    assert n_fs + n_eq + n_in <= n_x
+    # full row rank by construction: the identity parts of L, J_eq and J_in sit on disjoint primal columns
+    J_eq = (sp.eye(n_eq, n_x, k=n_fs) + sp.diags([rng.standard_normal(n_eq) * 0.5], [n_fs + 1], shape=(n_eq, n_x))
+            + sp.diags([rng.standard_normal(n_eq) * 0.3], [n_fs - 1], shape=(n_eq, n_x))).tocsr()
+    J_in = (sp.random(n_in, n_x, density=2.0 / n_x, random_state=rng, data_rvs=rng.standard_normal) * 0.3
+            + sp.eye(n_in, n_x, k=n_x - n_in)).tocsr()
+    L = sp.eye(n_fs, n_x).tocsr()  # linking rows select the first n_fs primals
+    Z = lambda a, b: sp.csr_matrix((a, b))
+    I_in = sp.identity(n_in, format="csr")
+    K = sp.bmat([
+        [H + sp.diags(sig_x), Z(n_x, n_in), J_eq.T, J_in.T, L.T],
+        [Z(n_in, n_x), sp.diags(sig_s), Z(n_in, n_eq), -I_in, Z(n_in, n_fs)],
+        [J_eq, Z(n_eq, n_in), Z(n_eq, n_eq), Z(n_eq, n_in), Z(n_eq, n_fs)],
+        [J_in, -I_in, Z(n_in, n_eq), Z(n_in, n_in), Z(n_in, n_fs)],
+        [L, Z(n_fs, n_in), Z(n_fs, n_eq), Z(n_fs, n_in), Z(n_fs, n_fs)],
+    ]).tocoo()
+    return K, n_x + n_in + n_eq + n_in + n_fs
+
+
+def stochastic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_fs, **kw):
+    """Block-bordered KKT of a two-stage stochastic NLP: border = [0 | -I] on the linking multipliers
+    (sc_ip_interface.py:1275-1280), Q = 0 (:1282-1284)."""
+    kkt = BlockMatrix(n_blocks + 1, n_blocks + 1)
+    sizes = []
+    for i in range(n_blocks):
+        rng = np.random.default_rng(1000 * seed + i)
+        K, n = ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, **kw)
+        sizes.append(n)
+        kkt.set_block(i, i, K)
+        A = sp.coo_matrix((-np.ones(n_fs), (np.arange(n_fs), n - n_fs + np.arange(n_fs))), shape=(n_fs, n))
+        kkt.set_block(n_blocks, i, A)
+    kkt.set_block(n_blocks, n_blocks, sp.coo_matrix((n_fs, n_fs)))
+    sizes.append(n_fs)
+    return kkt, sizes

@@ -139,3 +139,37 @@ def test_non_square_rejected():
     bad = BlockMatrix(2, 3)
     with pytest.raises(ValueError):
         B200SchurComplementLinearSolver().do_symbolic_factorization(bad)
+
+
+@pytest.mark.parametrize("seed,n_blocks,n_x,n_eq,n_in,n_fs", [(0, 4, 300, 240, 30, 10), (1, 3, 600, 500, 20, 25),
+                                                               (2, 6, 220, 100, 60, 8)])
+def test_ipm_shaped_stochastic_kkt(seed, n_blocks, n_x, n_eq, n_in, n_fs):
+    """Family P: primal-dual KKT blocks with zero (2,2) blocks and barrier diagonals spread over
+    eight orders of magnitude -- exercises 2x2 pivots and delayed pivots of the multifrontal path."""
+    from tests.helpers import stochastic_ipm_system
+    kkt, sizes = stochastic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_fs)
+    rng = np.random.default_rng(seed)
+    rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
+    s, x = _solve(kkt, rhs)
+    stats = s.backend.plan_stats(0)
+    assert stats["supernodes"] > 0 and not stats["fell_back_dense"]
+    dense = sym_full(kkt).toarray()
+    x_ref = np.linalg.solve(dense, rhs.flatten())
+    assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    expect = dense_inertia(dense, "ldl")
+    assert s.get_inertia() == expect == dense_inertia(dense, "eigvalsh")  # what interior_point.py:379 tests
+
+
+def test_delayed_pivot_overflow_falls_back_to_dense():
+    """With no delayed-pivot capacity the sparse path must notice and redo the block densely, not return garbage."""
+    from tests.helpers import stochastic_ipm_system
+    kkt, sizes = stochastic_ipm_system(3, 2, 300, 240, 30, 10)
+    rng = np.random.default_rng(3)
+    rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
+    s, x = _solve(kkt, rhs, options={"sparse_dmax": 0})
+    dense = sym_full(kkt).toarray()
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    assert s.get_inertia() == dense_inertia(dense, "ldl")
+    st = s.backend.plan_stats(0)
+    assert st["fell_back_dense"] == 1 or st["delayed_to_root"] == 0
