@@ -22,9 +22,9 @@ import scipy.sparse as sp
 
 
 def _coo(block):
-    """COO triplets of a leaf / nested block without summing duplicates."""
+    """COO triplets of a leaf / nested block without summing duplicates (index arrays are not copied)."""
     c = block.tocoo()
-    return np.asarray(c.row, dtype=np.int64), np.asarray(c.col, dtype=np.int64), np.asarray(c.data, dtype=np.float64), c.shape
+    return c.row, c.col, np.asarray(c.data, dtype=np.float64), c.shape
 
 
 @dataclass
@@ -157,7 +157,10 @@ def gather_values(matrix, st: Structure, out: np.ndarray) -> bool:
         if blk is None:
             return False
         c = blk.tocoo()
-        if c.data.size != hi - lo or not (np.array_equal(c.row, prow) and np.array_equal(c.col, pcol)):
+        if c.data.size != hi - lo:
+            return False
+        # same index arrays as analysed (the usual case: values updated in place) -> nothing to compare
+        if not ((c.row is prow or np.array_equal(c.row, prow)) and (c.col is pcol or np.array_equal(c.col, pcol))):
             return False
         out[lo:hi] = c.data
     return True
