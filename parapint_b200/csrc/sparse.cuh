@@ -109,9 +109,12 @@ __device__ __forceinline__ FrontBuf carve(unsigned char *base, int cap, int ld) 
   return b;
 }
 
+// groups: a warp (32), the first four warps of the CTA (128, named barrier 1) or the whole CTA
 template <int G> __device__ __forceinline__ int gtid() { return G == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
 template <int G> __device__ __forceinline__ void gsync() {
-  if (G == 32) __syncwarp(); else __syncthreads();
+  if (G == 32) __syncwarp();
+  else if (G == 128) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else __syncthreads();
 }
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -168,35 +171,44 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
   int t = 0;
   while (t < fs) {
     if (gw == 0) {
+      // Pivot search.  Column maxima only feed threshold tests, so they are reduced on the high 32
+      // bits of |value| (monotone, one redux.sync each) and widened to an upper bound; the partner
+      // row for a 2x2 pivot is the (near-)largest fully-summed entry, lowest index on ties.
       int kind = 0, pc = -1, pr = -1;
       for (int c = t; c < fs; ++c) {
-        double cmax = 0.0, fbest = -1.0;
-        int r = -1;
+        unsigned kmax = 0u, kbest = 0u;
         for (int i = t + lane; i < S; i += 32) {
           if (i == c) continue;
-          const double v = fabs(fent(F, ld, i, c));
-          cmax = fmax(cmax, v);
-          if (i < fs && v > fbest) { fbest = v; r = i; }
+          const unsigned hi = (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu;
+          kmax = max(kmax, hi);
+          if (i < fs) kbest = max(kbest, (hi & 0xffffff80u) | (unsigned)(127 - i));
         }
-        cmax = warp_max(cmax);
-        warp_argmax(fbest, r);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        kbest = __reduce_max_sync(0xffffffffu, kbest);
+        const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
         const double dcc = F[c + c * ld];
         if (fabs(dcc) > pivtol && fabs(dcc) >= u * cmax) { kind = 1; pc = c; break; }
-        if (r >= 0 && fbest > pivtol) {
-          double cm_c = 0.0, cm_r = 0.0;
-          for (int i = t + lane; i < S; i += 32) {
-            if (i == c || i == r) continue;
-            cm_c = fmax(cm_c, fabs(fent(F, ld, i, c)));
-            cm_r = fmax(cm_r, fabs(fent(F, ld, i, r)));
+        if (kbest != 0u) {
+          const int r = 127 - (int)(kbest & 127u);
+          const double b = fent(F, ld, r, c);
+          if (fabs(b) > pivtol) {
+            unsigned kc = 0u, kr = 0u;
+            for (int i = t + lane; i < S; i += 32) {
+              if (i == c || i == r) continue;
+              kc = max(kc, (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu);
+              kr = max(kr, (unsigned)__double2hiint(fent(F, ld, i, r)) & 0x7fffffffu);
+            }
+            kc = __reduce_max_sync(0xffffffffu, kc);
+            kr = __reduce_max_sync(0xffffffffu, kr);
+            const double cm_c = kc ? __hiloint2double((int)kc, -1) : 0.0;
+            const double cm_r = kr ? __hiloint2double((int)kr, -1) : 0.0;
+            const double drr = F[r + r * ld];
+            const double det = dcc * drr - b * b;
+            const double g1 = (fabs(drr) * cm_c + fabs(b) * cm_r) / fabs(det);
+            const double g2 = (fabs(b) * cm_c + fabs(dcc) * cm_r) / fabs(det);
+            if (g1 * u <= 1.0 && g2 * u <= 1.0) { kind = 2; pc = c; pr = r; break; }
+            if (fabs(drr) > pivtol && fabs(drr) >= u * fmax(cm_r, fabs(b))) { kind = 1; pc = r; break; }
           }
-          cm_c = warp_max(cm_c);
-          cm_r = warp_max(cm_r);
-          const double drr = F[r + r * ld], b = fent(F, ld, r, c);
-          const double det = dcc * drr - b * b;
-          const double g1 = (fabs(drr) * cm_c + fabs(b) * cm_r) / fabs(det);
-          const double g2 = (fabs(b) * cm_c + fabs(dcc) * cm_r) / fabs(det);
-          if (g1 * u <= 1.0 && g2 * u <= 1.0) { kind = 2; pc = c; pr = r; break; }
-          if (fabs(drr) > pivtol && fabs(drr) >= u * fmax(cm_r, fabs(b))) { kind = 1; pc = r; break; }
         }
       }
       if (lane == 0) { B.sh[0] = kind; B.sh[1] = pc; B.sh[2] = pr; }
@@ -366,10 +378,25 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
           }
     }
     gsync<G>();
-    if (tid < 32) {
-      for (int k = 0; k < H.nch; ++k) {
-        for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) F[stg.tgt[e]] += stg.val[e];
-        __syncwarp();
+    {
+      const int total = stg.cnt[H.nch];
+      if (S * (S + 1) / 2 <= G) {
+        // one thread per target entry sums its matches in staged (= child) order: parallel and reproducible
+        int a = 0, b = 0, left = tid;
+        while (b < S && left >= S - b) { left -= S - b; ++b; }
+        a = b + left;
+        if (b < S) {
+          const int mine = a + b * ld;
+          double acc = F[mine];
+          for (int e = 0; e < total; ++e)
+            if (stg.tgt[e] == mine) acc += stg.val[e];
+          F[mine] = acc;
+        }
+      } else if (tid < 32) {
+        for (int k = 0; k < H.nch; ++k) {
+          for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) F[stg.tgt[e]] += stg.val[e];
+          __syncwarp();
+        }
       }
     }
     gsync<G>();
@@ -416,7 +443,19 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       off += ndo;
     }
   }
-  const int ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
+  int ne;
+  if (G == SF_NT && S <= 48) {
+    // small front assembled by the whole CTA: the pivot loop runs on four warps with a named barrier
+    // (block-wide barriers of 16 warps would dominate it)
+    if (tid < 128) {
+      ne = factor_front<128>(B, S, fs, u, pivtol, cnt);
+      if (tid == 0) B.sh[6] = ne;
+    }
+    __syncthreads();
+    ne = B.sh[6];
+  } else {
+    ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
+  }
   const int ndo = fs - ne, dim = S - ne;
   if (ndo > H.dslot) {
     if (tid == 0) {
