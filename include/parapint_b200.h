@@ -49,7 +49,8 @@ int pp_destroy(pp_handle *h);
 
 /* Tunables: "pivot_tol" (absolute zero-pivot tolerance), "panel_width" (dense panel, <= 64),
  * "sparse" (0/1: multifrontal subtree path), "pivot_threshold" (u of the threshold test in subtree
- * fronts, default 0.01), "sparse_fmax", "sparse_dmax", "sparse_min_n", "profile". */
+ * fronts, default 0.01), "ordering" (0 auto, 1 minimum degree, 2 nested dissection), "nd_leaf",
+ * "sparse_fmax", "sparse_dmax", "sparse_dslot", "sparse_min_n", "no_fallback", "profile". */
 int pp_set_option(pp_handle *h, const char *name, double value);
 
 /*
@@ -165,6 +166,7 @@ int pp_plan_stats(pp_handle *h, int32_t block, int64_t out[12]);
 typedef struct pp_plan pp_plan;
 int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols,
                    int32_t fmax, int32_t dmax, int32_t min_sparse_n, pp_plan **out);
+int pp_plan_set_ordering(int32_t ordering); /* for pp_plan_create: 0 auto, 1 minimum degree, 2 nested dissection */
 int pp_plan_get(const pp_plan *plan, const char *name, const int32_t **data, int64_t *len);
 int pp_plan_scalar(const pp_plan *plan, const char *name, int64_t *value);
 int pp_plan_destroy(pp_plan *plan);

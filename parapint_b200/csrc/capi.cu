@@ -329,6 +329,10 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->no_fallback = value != 0.0;
   } else if (key == "sparse_dslot") {
     h->plan_opt.dslot = std::max(0, std::min((int)value, 32));
+  } else if (key == "ordering") {
+    h->plan_opt.ordering = (int)value;
+  } else if (key == "nd_leaf") {
+    h->plan_opt.nd_leaf = std::max(4, (int)value);
   } else if (key == "sparse_fmax") {
     h->plan_opt.fmax = std::max(8, std::min((int)value, SF_SBUF - 8));
   } else if (key == "sparse_dmax") {
@@ -507,7 +511,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   std::vector<int> ti;
   std::vector<SnHead> heads;
   std::vector<int2> tgts;
-  struct Off { size_t heads, tgt, rootcols, cols, rows, rel, child_idx, root_children, tiny_ptr, tiny_idx, big_ptr, big_idx, tgt_src; };
+  struct Off { size_t heads, tgt, rootcols, cols, rows, rel, child_idx, root_children, tiny_ptr, tiny_idx, med_ptr, med_idx, big_ptr, big_idx, tgt_src; };
   std::vector<Off> offs(h->plans.size());
   auto put = [&](const std::vector<int> &v) { const size_t o = ti.size(); ti.insert(ti.end(), v.begin(), v.end()); ti.push_back(0); return o; };
   for (size_t q = 0; q < h->plans.size(); ++q) {
@@ -515,7 +519,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     Off &o = offs[q];
     o.rootcols = put(P.rootcols); o.cols = put(P.cols); o.rows = put(P.rows); o.rel = put(P.rel);
     o.child_idx = put(P.child_idx); o.root_children = put(P.root_children); o.tiny_ptr = put(P.tiny_ptr);
-    o.tiny_idx = put(P.tiny_idx); o.big_ptr = put(P.big_ptr); o.big_idx = put(P.big_idx); o.tgt_src = put(P.tgt_src);
+    o.tiny_idx = put(P.tiny_idx); o.med_ptr = put(P.med_ptr); o.med_idx = put(P.med_idx); o.big_ptr = put(P.big_ptr);
+    o.big_idx = put(P.big_idx); o.tgt_src = put(P.tgt_src);
     o.heads = heads.size();
     o.tgt = tgts.size();
     for (int sidx = 0; sidx < P.ns; ++sidx) {
@@ -556,7 +561,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     D.tgt = h->planT.p + o.tgt;
     D.rootcols = b + o.rootcols; D.cols = b + o.cols; D.rows = b + o.rows; D.rel = b + o.rel;
     D.child_idx = b + o.child_idx; D.root_children = b + o.root_children; D.tiny_ptr = b + o.tiny_ptr;
-    D.tiny_idx = b + o.tiny_idx; D.big_ptr = b + o.big_ptr; D.big_idx = b + o.big_idx; D.tgt_src = b + o.tgt_src;
+    D.tiny_idx = b + o.tiny_idx; D.med_ptr = b + o.med_ptr; D.med_idx = b + o.med_idx; D.big_ptr = b + o.big_ptr;
+    D.big_idx = b + o.big_idx; D.tgt_src = b + o.tgt_src;
   }
   h->plans_dev.upload(pd);
 
@@ -966,6 +972,12 @@ struct pp_plan {
   PatternPlan P;
 };
 
+static int g_plan_ordering = 0;
+int pp_plan_set_ordering(int32_t ordering) {
+  g_plan_ordering = ordering;
+  return PP_SUCCESSFUL;
+}
+
 int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols, int32_t fmax,
                    int32_t dmax, int32_t min_sparse_n, pp_plan **out) {
   if (!out || n < 0 || m < 0 || nent < 0 || (nent > 0 && (!rows || !cols))) return fail("pp_plan_create: bad argument");
@@ -979,6 +991,7 @@ int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, cons
     if (fmax > 0) opt.fmax = std::max(8, std::min((int)fmax, SF_SBUF - 8));
     if (dmax >= 0) opt.dmax = std::max(0, std::min((int)dmax, SF_SBUF / 2));
     if (min_sparse_n >= 0) opt.min_sparse_n = min_sparse_n;
+    opt.ordering = g_plan_ordering;
     auto *pl = new pp_plan();
     pl->P = build_plan(n, m, r, c, src, opt, false);
     *out = pl;
@@ -1005,6 +1018,8 @@ int pp_plan_get(const pp_plan *pl, const char *name, const int32_t **data, int64
   else if (k == "root_children") v = &P.root_children;
   else if (k == "tiny_ptr") v = &P.tiny_ptr;
   else if (k == "tiny_idx") v = &P.tiny_idx;
+  else if (k == "med_ptr") v = &P.med_ptr;
+  else if (k == "med_idx") v = &P.med_idx;
   else if (k == "big_ptr") v = &P.big_ptr;
   else if (k == "big_idx") v = &P.big_idx;
   else if (k == "dcap") v = &P.dcap;

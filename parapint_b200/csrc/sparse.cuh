@@ -27,7 +27,7 @@ struct PlanDev {
   int n, m, nT, DR, ns, nlevels, nrootch, pad;
   const SnHead *heads;
   const int *rootcols, *cols, *rows, *rel, *child_idx, *root_children;
-  const int *tiny_ptr, *tiny_idx, *big_ptr, *big_idx;
+  const int *tiny_ptr, *tiny_idx, *med_ptr, *med_idx, *big_ptr, *big_idx;
   const int2 *tgt;      // .x = row | col << 8 | count << 16,  .y = source index (count == 1) or offset into tgt_src
   const int *tgt_src;
 };
@@ -72,25 +72,39 @@ constexpr size_t SF_TINY_BYTES = (fb_bytes(SF_TBUF, SF_TLD) + 15) / 16 * 16;
 constexpr int SF_STG = 2048;     // staged entries
 constexpr int SF_MAXCH = 512;    // children per staging batch
 constexpr int SF_CHDIM = 12;     // largest child contribution block that is staged
-constexpr size_t SF_STG_BYTES = (size_t)SF_STG * 12 + (size_t)(3 * SF_MAXCH + 16) * 4;
-constexpr size_t SF_WORK = SF_BIG_BYTES > SF_NW * SF_TINY_BYTES ? SF_BIG_BYTES : SF_NW * SF_TINY_BYTES;
-constexpr size_t SF_SMEM = SF_WORK + 16 * sizeof(int) + 64 * sizeof(int) + SF_STG_BYTES;
+// quarter-CTA groups: fronts of up to SF_MBUF rows, each group with its own staging area
+constexpr int SF_MBUF = 32, SF_MLD = SF_MBUF + 1, SF_MSTG = 1024, SF_MMAXCH = 256, SF_NG = 4;
+
 
 struct Stage {
-  double *val;   // [SF_STG]
-  int *tgt;      // [SF_STG] offset into F (or position in v)
-  int *cnt;      // [SF_MAXCH + 1] entry offsets per child
-  int *ndo;      // [SF_MAXCH] delayed columns per child / running offsets
-  int *big;      // [SF_MAXCH] children handled one by one afterwards
+  double *val;   // [cap] staged values
+  int *tgt;      // [cap] offset into F (or position in v)
+  int *cnt;      // [maxch + 1] entry offsets per child
+  int *ndo;      // [maxch] delayed columns per child / running offsets
+  int *big;      // [maxch] children handled one by one afterwards
+  int cap, maxch;
 };
 
-__device__ __forceinline__ Stage carve_stage(unsigned char *base) {
+__host__ __device__ constexpr size_t stage_bytes(int cap, int maxch) {
+  return ((size_t)cap * 12 + (size_t)(3 * maxch + 16) * 4 + 15) / 16 * 16;
+}
+__host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) / 16 * 16; }
+__host__ __device__ constexpr size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+constexpr size_t SF_BIG_FB = align16(fb_bytes(SF_SBUF, SF_LDF));
+constexpr size_t SF_MED_FB = align16(fb_bytes(SF_MBUF, SF_MLD));
+constexpr size_t SF_MED_BYTES = SF_MED_FB + stage_bytes(SF_MSTG, SF_MMAXCH);
+constexpr size_t SF_WORK = max3(SF_BIG_FB + stage_bytes(SF_STG, SF_MAXCH), SF_NG * SF_MED_BYTES, SF_NW * SF_TINY_BYTES);
+constexpr size_t SF_SMEM = SF_WORK + 96 * sizeof(int);
+
+__device__ __forceinline__ Stage carve_stage(unsigned char *base, int cap = SF_STG, int maxch = SF_MAXCH) {
   Stage g;
   g.val = reinterpret_cast<double *>(base);
-  g.tgt = reinterpret_cast<int *>(g.val + SF_STG);
-  g.cnt = g.tgt + SF_STG;
-  g.ndo = g.cnt + SF_MAXCH + 8;
-  g.big = g.ndo + SF_MAXCH;
+  g.tgt = reinterpret_cast<int *>(g.val + cap);
+  g.cnt = g.tgt + cap;
+  g.ndo = g.cnt + maxch + 8;
+  g.big = g.ndo + maxch;
+  g.cap = cap;
+  g.maxch = maxch;
   return g;
 }
 
@@ -109,11 +123,13 @@ __device__ __forceinline__ FrontBuf carve(unsigned char *base, int cap, int ld) 
   return b;
 }
 
-// groups: a warp (32), the first four warps of the CTA (128, named barrier 1) or the whole CTA
-template <int G> __device__ __forceinline__ int gtid() { return G == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+// groups: a warp (32), a quarter-CTA of four warps (128, named barrier 1 + group index) or the whole CTA
+template <int G> __device__ __forceinline__ int gtid() {
+  return G == 32 ? (int)(threadIdx.x & 31) : (G == 128 ? (int)(threadIdx.x & 127) : (int)threadIdx.x);
+}
 template <int G> __device__ __forceinline__ void gsync() {
   if (G == 32) __syncwarp();
-  else if (G == 128) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else if (G == 128) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
   else __syncthreads();
 }
 
@@ -282,7 +298,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   const int tid = gtid<G>();
   const SnHead H = P.heads[s];
   const int nc = H.nc, ncb = H.ncb;
-  const bool staged = G != 32 && H.nch >= 4 && H.nch <= SF_MAXCH;
+  const bool staged = G != 32 && H.nch >= 4 && H.nch <= stg.maxch;
   int nd_in = 0;
   if (staged) {
     // one child per thread: delayed count and staged-entry count; serial prefix by thread 0
@@ -299,7 +315,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
         const int d = stg.ndo[k], e = stg.cnt[k];
         stg.ndo[k] = off;
         off += d;
-        if (e < 0 || ent + e > SF_STG) { stg.big[nbig++] = k; stg.cnt[k] = ent; }  // handled one by one
+        if (e < 0 || ent + e > stg.cap) { stg.big[nbig++] = k; stg.cnt[k] = ent; }  // handled one by one
         else { stg.cnt[k] = ent; ent += e; }
         if (k + 1 == H.nch) stg.cnt[k + 1] = ent;
       }
@@ -313,8 +329,8 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   }
   const int fs = nc + nd_in, S = fs + ncb;
   if (S > B.cap) {
-    if (G != 32 && tid == 0) { Bk.info[3] = 1; Bk.info[4] = s; Bk.info[5] = S; }
-    return G == 32 ? PF_DEFER : PF_FAIL;
+    if (G == SF_NT && tid == 0) { Bk.info[3] = 1; Bk.info[4] = s; Bk.info[5] = S; }
+    return G == SF_NT ? PF_FAIL : PF_DEFER;
   }
   if (nd_in > H.dcap) {
     if (tid == 0) { Bk.info[3] = 2; Bk.info[4] = s; Bk.info[5] = nd_in; }
@@ -504,7 +520,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *
   if (k < nleaf) {
     const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
     Stage none;
-    none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr;
+    none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0; none.cap = 0; none.maxch = 0;
     const int rc = process_front<32>(Bk, P, vals, P.tiny_idx[P.tiny_ptr[0] + k], mine, u, pivtol, cnt, none);
     if (rc != PF_OK && lane == 0) Bk.info[2] = 1;
   }
@@ -520,12 +536,15 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
   extern __shared__ __align__(16) unsigned char sm_raw[];
   int *cnt = reinterpret_cast<int *>(sm_raw + SF_WORK);  // [0..2] inertia, [3] failed, [4] deferred count
   int *deferred = cnt + 16;                              // up to 64 deferred fronts per level
-  const Stage stg = carve_stage(sm_raw + SF_WORK + 80 * sizeof(int));
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
   const Front R = fronts[Bk.root];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = tid >> 7;
+  // the three work areas alias each other: the passes of a level are separated by block barriers
   const FrontBuf big = carve(sm_raw, SF_SBUF, SF_LDF);
+  const Stage stg = carve_stage(sm_raw + SF_BIG_FB, SF_STG, SF_MAXCH);
+  const FrontBuf med = carve(sm_raw + (size_t)grp * SF_MED_BYTES, SF_MBUF, SF_MLD);
+  const Stage mstg = carve_stage(sm_raw + (size_t)grp * SF_MED_BYTES + SF_MED_FB, SF_MSTG, SF_MMAXCH);
   const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
   if (tid < 8) cnt[tid] = 0;
   if (tid == 0) Bk.info[3] = 0;
@@ -536,7 +555,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     //      subtree_leaf_kernel, spread over the whole GPU) ----
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
       const int s = P.tiny_idx[k];
-      const int rc = process_front<32>(Bk, P, vals, s, mine, u, pivtol, cnt, stg);
+      const int rc = process_front<32>(Bk, P, vals, s, mine, u, pivtol, cnt, mstg);
       if (lane == 0) {
         if (rc == PF_DEFER) {
           const int pos = atomicAdd(&cnt[4], 1);
@@ -545,7 +564,19 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
       }
     }
     __syncthreads();
-    // ---- larger fronts (and small ones that grew through delayed pivots): whole CTA, one by one ----
+    // ---- medium fronts (up to 32 rows, any number of children): four warps each, four at a time ----
+    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+      const int s = P.med_idx[k];
+      const int rc = process_front<128>(Bk, P, vals, s, med, u, pivtol, cnt, mstg);
+      if ((tid & 127) == 0) {
+        if (rc == PF_DEFER) {
+          const int pos = atomicAdd(&cnt[4], 1);
+          if (pos < 64) deferred[pos] = s; else cnt[3] = 1;
+        } else if (rc == PF_FAIL) cnt[3] = 1;
+      }
+    }
+    __syncthreads();
+    // ---- larger fronts (and smaller ones that grew through delayed pivots): whole CTA, one by one ----
     const int ndef = min(cnt[4], 64);
     for (int k = 0; k < ndef; ++k) {
       int best = -1;  // deterministic order: ascending supernode index
@@ -626,10 +657,11 @@ struct SolveBuf {
 __host__ __device__ constexpr size_t sb_bytes(int cap, int ld) {
   return (size_t)cap * ld * 8 + 2 * (size_t)cap * 8 + 4 * (size_t)cap * 4;
 }
-constexpr size_t SV_TINY_BYTES = (sb_bytes(SF_TBUF, SF_TLD) + 15) / 16 * 16;
-constexpr size_t SV_BIG_BYTES = sb_bytes(SF_SBUF, SF_LDF);
-constexpr size_t SV_WORK = (SV_BIG_BYTES > SF_NW * SV_TINY_BYTES ? SV_BIG_BYTES : SF_NW * SV_TINY_BYTES) / 16 * 16 + 16;
-constexpr size_t SV_SMEM = SV_WORK + SF_STG_BYTES;
+constexpr size_t SV_TINY_BYTES = align16(sb_bytes(SF_TBUF, SF_TLD));
+constexpr size_t SV_BIG_SB = align16(sb_bytes(SF_SBUF, SF_LDF));
+constexpr size_t SV_MED_SB = align16(sb_bytes(SF_MBUF, SF_MLD));
+constexpr size_t SV_MED_BYTES = SV_MED_SB + stage_bytes(SF_MSTG, SF_MMAXCH);
+constexpr size_t SV_SMEM = max3(SV_BIG_SB + stage_bytes(SF_STG, SF_MAXCH), SF_NG * SV_MED_BYTES, SF_NW * SV_TINY_BYTES);
 
 __device__ __forceinline__ SolveBuf carve_solve(unsigned char *base, int cap, int ld) {
   SolveBuf b;
@@ -671,7 +703,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
   for (int i = tid; i < S; i += G)
     B.v[i] = (i < fs && Bk.opos[H.fs_off + i] < nc) ? rhs[B.fid[i]] : 0.0;
   gsync<G>();
-  if (G != 32 && H.nch >= 4 && H.nch <= SF_MAXCH) {
+  if (G != 32 && H.nch >= 4 && H.nch <= stg.maxch) {
     // many children: fetch their vectors concurrently (one child per thread), apply in child order
     for (int k = tid; k < H.nch; k += G) {
       const int c = P.child_idx[H.ch0 + k];
@@ -692,7 +724,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
     }
     gsync<G>();
     const int total = stg.cnt[H.nch];
-    if (total <= SF_STG) {
+    if (total <= stg.cap) {
       for (int k = tid; k < H.nch; k += G) {
         const int c = P.child_idx[H.ch0 + k];
         const SnHead C = P.heads[c];
@@ -824,21 +856,32 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, grp = tid >> 7;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
+  const Stage stg = carve_stage(sm_raw + SV_BIG_SB, SF_STG, SF_MAXCH);
+  const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
+  const Stage mstg = carve_stage(sm_raw + (size_t)grp * SV_MED_BYTES + SV_MED_SB, SF_MSTG, SF_MMAXCH);
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
-  const Stage stg = carve_stage(sm_raw + SV_WORK);
   const double *r = rhs + vec_off[blockIdx.x];
   double *y = ywork + vec_off[blockIdx.x];
   for (int l = 0; l < P.nlevels; ++l) {
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
       const int s = P.tiny_idx[k];
-      if (Bk.meta[3 * s + 1] <= SF_TBUF) forward_front<32>(Bk, P, s, mine, r, y, stg);
+      if (Bk.meta[3 * s + 1] <= SF_TBUF) forward_front<32>(Bk, P, s, mine, r, y, mstg);
     }
     __syncthreads();
-    for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {  // small fronts that outgrew a warp
+    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+      const int s = P.med_idx[k];
+      if (Bk.meta[3 * s + 1] <= SF_MBUF) forward_front<128>(Bk, P, s, med, r, y, mstg);
+    }
+    __syncthreads();
+    for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {  // fronts that outgrew their group
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] > SF_TBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
+    }
+    for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) {
+      const int s = P.med_idx[k];
+      if (Bk.meta[3 * s + 1] > SF_MBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
     }
     for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
       forward_front<SF_NT>(Bk, P, P.big_idx[k], big, r, y, stg);
@@ -874,8 +917,9 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, grp = tid >> 7;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
+  const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
   const double *y = ywork + vec_off[blockIdx.x];
   double *x = xout + vec_off[blockIdx.x];
@@ -890,9 +934,18 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
       backward_front<SF_NT>(Bk, P, P.big_idx[k], big, y, x);
       __syncthreads();
     }
-    for (int k = P.tiny_ptr[l]; k < P.tiny_ptr[l + 1]; ++k) {
+    for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) {
+      const int s = P.med_idx[k];
+      if (Bk.meta[3 * s + 1] > SF_MBUF) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
+    }
+    for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] > SF_TBUF) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
+    }
+    __syncthreads();
+    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+      const int s = P.med_idx[k];
+      if (Bk.meta[3 * s + 1] <= SF_MBUF) backward_front<128>(Bk, P, s, med, y, x);
     }
     __syncthreads();
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
@@ -920,7 +973,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const Spars
   if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
   Stage none;
-  none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr;
+  none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0;
   forward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, rhs + vec_off[blockIdx.y], ywork + vec_off[blockIdx.y], none);
 }
 

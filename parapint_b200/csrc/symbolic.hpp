@@ -41,6 +41,7 @@ struct PatternPlan {
   int vec_total = 0;
   int nlevels = 0;                         // height classes: level 0 = leaves
   std::vector<int> tiny_ptr, tiny_idx;     // per level: fronts small enough for one warp
+  std::vector<int> med_ptr, med_idx;       // per level: fronts for a quarter-CTA (<= medium rows, any children)
   std::vector<int> big_ptr, big_idx;       // per level: fronts factored by the whole CTA
   int max_front = 0;                  // largest subtree front incl. delayed capacity actually allowed
   int64_t nnz_l = 0;                  // static entries of L in the subtree part (statistics)
@@ -58,16 +59,22 @@ namespace detail {
 // Minimum-degree ordering on a quotient graph with element absorption and exact external degrees.
 // Vertices with hold[v] != 0 are never eliminated.  Returns the elimination order of the others and,
 // for each eliminated vertex, its column structure (the variables adjacent at elimination time).
+// `stage` (optional) constrains the order: all vertices of stage k are eliminated before any of stage
+// k+1, minimum degree decides inside a stage (nested dissection supplies the stages).
 inline void minimum_degree(int n, const std::vector<std::vector<int>> &adj, const std::vector<char> &hold,
-                           std::vector<int> &order, std::vector<std::vector<int>> &lstruct) {
+                           const std::vector<int> &stage, std::vector<int> &order,
+                           std::vector<std::vector<int>> &lstruct) {
   std::vector<std::vector<int>> vadj(adj), eadj(n), evars(n);
   std::vector<char> eliminated(n, 0), ealive(n, 0);
   std::vector<int> mark(n, -1), degree(n, 0);
   int stamp = 0;
-  std::set<std::pair<int, int>> heap;
+  const bool staged = !stage.empty();
+  const long long SM = 1ll << 32;  // key = stage * 2^32 + degree
+  auto key = [&](int v, int d) { return (staged ? (long long)stage[v] * SM : 0ll) + d; };
+  std::set<std::pair<long long, int>> heap;
   for (int v = 0; v < n; ++v) {
     degree[v] = (int)vadj[v].size();
-    if (!hold[v]) heap.insert({degree[v], v});
+    if (!hold[v]) heap.insert({key(v, degree[v]), v});
   }
   lstruct.assign(n, {});
   order.clear();
@@ -113,13 +120,123 @@ inline void minimum_degree(int n, const std::vector<std::vector<int>> &adj, cons
         for (int w : evars[e])
           if (!eliminated[w] && mark[w] != stamp) { mark[w] = stamp; ++d; }
       if (!hold[v]) {
-        heap.erase({degree[v], v});
-        heap.insert({d, v});
+        heap.erase({key(v, degree[v]), v});
+        heap.insert({key(v, d), v});
       }
       degree[v] = d;
     }
     // restore the element-membership stamp for the next prune (marks were overwritten above)
     stamp += 1;
+  }
+}
+
+// Nested dissection by breadth-first level structures (George): recursively split every connected
+// component at the level set nearest its middle, thinned to the vertices that touch the next level.
+// Produces a stage number per vertex: the two halves (recursively) come before their separator.
+// Held vertices are not part of the graph.  Banded / time-like structures, which minimum degree turns
+// into one long dependency chain, become shallow trees.
+inline void nested_dissection_stages(int n, const std::vector<std::vector<int>> &adj,
+                                     const std::vector<char> &hold, int leaf_size, std::vector<int> &stage) {
+  stage.assign(n, -1);
+  std::vector<int> region(n, -1);  // current region id of every still-unassigned vertex
+  for (int v = 0; v < n; ++v) region[v] = hold[v] ? -2 : 0;
+  int next_region = 1, next_stage = 0;
+  std::vector<int> dist(n, -1), queue;
+  struct Task { std::vector<int> verts; int id; bool emit_only; };
+  std::vector<Task> stack;
+  {
+    Task t0;
+    t0.id = 0;
+    t0.emit_only = false;
+    for (int v = 0; v < n; ++v)
+      if (!hold[v]) t0.verts.push_back(v);
+    if (t0.verts.empty()) return;
+    stack.push_back(std::move(t0));
+  }
+  auto bfs = [&](int start, int id, std::vector<int> &visited) {
+    visited.clear();
+    visited.push_back(start);
+    dist[start] = 0;
+    for (size_t h = 0; h < visited.size(); ++h) {
+      const int v = visited[h];
+      for (int w : adj[v])
+        if (region[w] == id && dist[w] < 0) { dist[w] = dist[v] + 1; visited.push_back(w); }
+    }
+  };
+  while (!stack.empty()) {
+    Task t = std::move(stack.back());
+    stack.pop_back();
+    if (t.emit_only || (int)t.verts.size() <= leaf_size) {
+      for (int v : t.verts) { stage[v] = next_stage; region[v] = -3; }
+      ++next_stage;
+      continue;
+    }
+    // connected component of the first vertex
+    std::vector<int> comp;
+    bfs(t.verts[0], t.id, comp);
+    if (comp.size() < t.verts.size()) {
+      // several components: peel this one off, keep the rest as a task of its own
+      const int cid = next_region++;
+      Task rest;
+      rest.id = t.id;
+      rest.emit_only = false;
+      for (int v : comp) { region[v] = cid; dist[v] = -1; }
+      for (int v : t.verts)
+        if (region[v] == t.id) rest.verts.push_back(v);
+      Task c;
+      c.id = cid;
+      c.emit_only = false;
+      c.verts = comp;
+      stack.push_back(std::move(rest));
+      stack.push_back(std::move(c));
+      continue;
+    }
+    // pseudo-peripheral start: repeat BFS from the farthest vertex a few times
+    int start = comp.back();
+    std::vector<int> lev;
+    for (int it = 0; it < 3; ++it) {
+      for (int v : comp) dist[v] = -1;
+      bfs(start, t.id, lev);
+      const int far = lev.back();
+      if (it < 2 && dist[far] > 0) start = far;
+    }
+    const int depth = dist[lev.back()];
+    if (depth < 2) {  // no useful separator: one leaf
+      for (int v : comp) dist[v] = -1;
+      t.emit_only = true;
+      stack.push_back(std::move(t));
+      continue;
+    }
+    // middle level by cumulative size
+    std::vector<int> count(depth + 1, 0);
+    for (int v : lev) count[dist[v]]++;
+    int j = 1, acc = count[0];
+    const int half = (int)lev.size() / 2;
+    while (j < depth - 1 && acc + count[j] < half) acc += count[j++];
+    const int aid = next_region++, bid = next_region++, sid = next_region++;
+    Task A, B, S;
+    A.id = aid; B.id = bid; S.id = sid;
+    A.emit_only = B.emit_only = false;
+    S.emit_only = true;
+    for (int v : lev) {
+      const int d = dist[v];
+      if (d < j) A.verts.push_back(v);
+      else if (d > j) B.verts.push_back(v);
+      else {
+        bool touches_next = false;
+        for (int w : adj[v])
+          if (region[w] == t.id && dist[w] == j + 1) { touches_next = true; break; }
+        (touches_next ? S.verts : A.verts).push_back(v);
+      }
+    }
+    for (int v : A.verts) region[v] = aid;
+    for (int v : B.verts) region[v] = bid;
+    for (int v : S.verts) region[v] = sid;
+    for (int v : lev) dist[v] = -1;
+    // LIFO: halves are processed (and numbered) before the separator
+    stack.push_back(std::move(S));
+    if (!B.verts.empty()) stack.push_back(std::move(B));
+    if (!A.verts.empty()) stack.push_back(std::move(A));
   }
 }
 
@@ -133,7 +250,10 @@ struct PlanOptions {
   int merge_max = 16;   // largest front produced by a merge that introduces explicit zeros
   int dslot = 16;       // delayed columns one front may hand to its parent
   int tiny = 16;        // largest static front handled by a single warp
+  int medium = 24;      // largest static front handled by four warps
   int tiny_max_children = 8;  // fronts with more children are assembled by the whole CTA (staged fetch)
+  int nd_leaf = 48;     // nested dissection stops at components of this many vertices
+  int ordering = 0;     // 0 = pick the cheaper of minimum degree and nested dissection, 1 = MD, 2 = ND
   int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front
   double max_density = 0.20; // ... as are blocks whose factor would fill more than this share of n^2/2
 };
@@ -141,8 +261,9 @@ struct PlanOptions {
 // rows/cols: lower-triangular positions (row >= col) of the block's input entries inside the front
 // [K | border]: row < n is a K entry, row >= n a border entry (row - n = border row index).
 // entries with keep[k] == 0 are ignored.  src[k] = relative value index of entry k.
-inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
-                              const std::vector<int> &src, const PlanOptions &opt, bool force_dense) {
+inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
+                                   const std::vector<int> &src, const PlanOptions &opt, bool force_dense,
+                                   bool dissect) {
   PatternPlan P;
   P.n = n;
   P.m = m;
@@ -162,7 +283,9 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
   std::vector<int> order;
   std::vector<std::vector<int>> lstruct;
   if (!dense) {
-    detail::minimum_degree(n, adj, hold, order, lstruct);
+    std::vector<int> stage;
+    if (dissect) detail::nested_dissection_stages(n, adj, hold, opt.nd_leaf, stage);
+    detail::minimum_degree(n, adj, hold, stage, order, lstruct);
     double fill = 0;
     for (int p : order) fill += (double)lstruct[p].size() + 1;
     const double held = (double)(n - (int)order.size());
@@ -330,7 +453,7 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
   P.dslot.resize(P.ns);
   P.cb_off.resize(P.ns);
   P.vec_off.resize(P.ns);
-  std::vector<char> is_tiny(P.ns, 0);
+  std::vector<char> cls(P.ns, 2);  // 0 tiny, 1 medium, 2 big
   for (int s = 0; s < P.ns; ++s) {
     const int nc = P.col_ptr[s + 1] - P.col_ptr[s], ncb = P.row_ptr[s + 1] - P.row_ptr[s];
     int incoming = 0;
@@ -351,21 +474,22 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
     P.vec_total += cbdim;
     P.max_front = std::max(P.max_front, cap_rows);
     P.nnz_l += (int64_t)nc * (nc + 1) / 2 + (int64_t)nc * ncb;
-    is_tiny[s] = (nc + ncb) <= opt.tiny && (P.child_ptr[s + 1] - P.child_ptr[s]) < opt.tiny_max_children;
+    const int nch = P.child_ptr[s + 1] - P.child_ptr[s];
+    cls[s] = ((nc + ncb) <= opt.tiny && nch < opt.tiny_max_children) ? 0 : ((nc + ncb) <= opt.medium ? 1 : 2);
     P.nlevels = std::max(P.nlevels, level[s] + 1);
   }
   P.stack_cap = P.cb_total;
-  P.tiny_ptr.assign(P.nlevels + 1, 0);
-  P.big_ptr.assign(P.nlevels + 1, 0);
-  for (int s = 0; s < P.ns; ++s) (is_tiny[s] ? P.tiny_ptr : P.big_ptr)[level[s] + 1]++;
-  for (int l = 0; l < P.nlevels; ++l) { P.tiny_ptr[l + 1] += P.tiny_ptr[l]; P.big_ptr[l + 1] += P.big_ptr[l]; }
-  P.tiny_idx.resize(P.tiny_ptr[P.nlevels]);
-  P.big_idx.resize(P.big_ptr[P.nlevels]);
-  {
-    std::vector<int> ft(P.tiny_ptr.begin(), P.tiny_ptr.end() - 1), fb(P.big_ptr.begin(), P.big_ptr.end() - 1);
-    for (int s = 0; s < P.ns; ++s) {
-      if (is_tiny[s]) P.tiny_idx[ft[level[s]]++] = s; else P.big_idx[fb[level[s]]++] = s;
-    }
+  std::vector<int> *ptrs[3] = {&P.tiny_ptr, &P.med_ptr, &P.big_ptr};
+  std::vector<int> *idxs[3] = {&P.tiny_idx, &P.med_idx, &P.big_idx};
+  for (int c = 0; c < 3; ++c) {
+    ptrs[c]->assign(P.nlevels + 1, 0);
+    for (int s = 0; s < P.ns; ++s)
+      if (cls[s] == c) (*ptrs[c])[level[s] + 1]++;
+    for (int l = 0; l < P.nlevels; ++l) (*ptrs[c])[l + 1] += (*ptrs[c])[l];
+    idxs[c]->resize((*ptrs[c])[P.nlevels]);
+    std::vector<int> fillp(ptrs[c]->begin(), ptrs[c]->end() - 1);
+    for (int s = 0; s < P.ns; ++s)
+      if (cls[s] == c) (*idxs[c])[fillp[level[s]]++] = s;
   }
 
   // ---- where every input entry goes ----
@@ -431,6 +555,40 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
     for (int i = P.row_ptr[s]; i < P.row_ptr[s + 1]; ++i) lp[P.rows[i]] = -1;
   }
   return P;
+}
+
+}  // namespace ppb
+
+namespace ppb {
+
+// Estimated time of the level-scheduled numeric kernels, in "front latencies": every level costs a
+// fixed front overhead plus the pivots of its widest front (fronts of a level run concurrently).
+inline double plan_schedule_cost(const PatternPlan &P) {
+  // per level: warps share the tiny fronts 16 at a time, quarter-CTAs the medium ones 4 at a time,
+  // big fronts run one after the other; a front costs a fixed overhead plus its pivots
+  double cost = 0;
+  auto width = [&](int s) { return (double)(P.col_ptr[s + 1] - P.col_ptr[s]); };
+  for (int l = 1; l < P.nlevels; ++l) {
+    double t = 0, m = 0, b = 0, tmax = 0, mmax = 0;
+    for (int k = P.tiny_ptr[l]; k < P.tiny_ptr[l + 1]; ++k) { t += 6.0 + width(P.tiny_idx[k]); tmax = std::max(tmax, 6.0 + width(P.tiny_idx[k])); }
+    for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) { m += 8.0 + width(P.med_idx[k]); mmax = std::max(mmax, 8.0 + width(P.med_idx[k])); }
+    for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) b += 10.0 + 2.0 * width(P.big_idx[k]);
+    cost += std::max(t / 16.0, tmax) + std::max(m / 4.0, mmax) + b + 2.0;
+  }
+  return cost + 0.02 * (double)(P.nT + P.DR) * (P.nT + P.DR) / 64.0;  // dense root panel steps
+}
+
+// Minimum degree minimises fill, nested dissection the depth of the tree; build both, keep the one
+// with the shorter schedule unless it costs much more fill.
+inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
+                              const std::vector<int> &src, const PlanOptions &opt, bool force_dense) {
+  PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, false);
+  if (force_dense || md.ns == 0 || opt.ordering == 1) return md;
+  PatternPlan nd = build_plan_with(n, m, rows, cols, src, opt, force_dense, true);
+  if (opt.ordering == 2) return nd;
+  if (nd.ns == 0) return md;
+  const bool fill_ok = (double)nd.nnz_l <= 2.5 * (double)md.nnz_l + 1000.0 && nd.nT <= md.nT + 64;
+  return (fill_ok && plan_schedule_cost(nd) < 0.8 * plan_schedule_cost(md)) ? nd : md;
 }
 
 }  // namespace ppb

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pp_profile": (C.c_int, [_vp, _f64p, _i64p, C.c_int]),
     "pp_plan_stats": (C.c_int, [_vp, C.c_int32, _i64p]),
     "pp_plan_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "pp_plan_set_ordering": (C.c_int, [C.c_int32]),
     "pp_plan_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32p), _i64p]),
     "pp_plan_scalar": (C.c_int, [_vp, C.c_char_p, _i64p]),
     "pp_plan_destroy": (C.c_int, [_vp]),
@@ -79,15 +80,16 @@ def np_ptr(arr):
 
 
 PLAN_ARRAYS = ("rootcols", "col_ptr", "cols", "row_ptr", "rows", "rel", "parent", "nchild", "dcap", "dslot", "child_ptr",
-               "child_idx", "root_children", "tiny_ptr", "tiny_idx", "big_ptr", "big_idx", "ent_ptr",
+               "child_idx", "root_children", "tiny_ptr", "tiny_idx", "med_ptr", "med_idx", "big_ptr", "big_idx", "ent_ptr",
                "tgt_row", "tgt_col", "tgt_src_ptr", "tgt_src", "root_row", "root_col", "root_src")
 PLAN_SCALARS = ("n", "m", "nT", "DR", "ns", "nnz_l", "max_front", "l_total", "stack_cap", "nlevels")
 
 
-def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1):
+def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1, ordering=0):
     """Run the host symbolic analysis of one block and return its tables as a dict of numpy arrays."""
     import numpy as np
     lib = load()
+    lib.pp_plan_set_ordering(ordering)
     rows = np.ascontiguousarray(rows, dtype=np.int32)
     cols = np.ascontiguousarray(cols, dtype=np.int32)
     plan = _vp()
