@@ -201,14 +201,19 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   if (count == 0) return;
   const int NB = h->panel_width;
   const Front *fr = h->fronts.p + first;
-  int nmax = 0;
-  for (int f = first; f < first + count; ++f) nmax = std::max(nmax, h->n[f]);
+  int nmax = 0, nfmax = 0;
+  for (int f = first; f < first + count; ++f) {
+    nmax = std::max(nmax, h->n[f]);
+    nfmax = std::max(nfmax, h->nf[f]);
+  }
   if (nmax == 0) return;
+  const bool small = nfmax <= 384;  // short columns: four warps per front keep the block reductions cheap
   const int iters = (nmax + (NB - 2)) / (NB - 1);
   for (int it = 0; it < iters; ++it) {
     {
       ProfSpan sp(h, PP_PROF_PANEL, st);
-      front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
+      if (small) front_panel_kernel<128><<<count, 128, 0, st>>>(fr, NB, h->pivot_tol);
+      else front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
       h->launches++;
     }
     if (it > 0) {
@@ -475,6 +480,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     F.m = h->m[f];
     F.nf = h->nf[f];
     F.ld = h->ld[f];
+    F.nb = h->n[f];
+    F.pad = 0;
   }
   h->fronts.upload(hf);
   h->hfronts = hf;

@@ -25,7 +25,8 @@ struct Front {
   int *bsz;      // n: 1 = 1x1 pivot, 2 = first column of a 2x2 pivot, 0 = second column
   int *perm;     // n: perm[i] = original row now at position i   (P K P^T = L D L^T)
   int *state;    // [0] columns eliminated, [1] start of the last panel, [2] info, [3] reserved
-  int n, m, nf, ld;
+  int n, m, nf, ld;  // n = pivot candidates (rows [0,n)); for a block root n = nT + delayed columns, set on the device
+  int nb, pad;        // first border row (static): rows [n, nb) are unused delayed-pivot slots, rows [nb, nf) the border
 };
 
 constexpr int ST_KCUR = 0, ST_KPREV = 1, ST_INFO = 2;

@@ -25,7 +25,7 @@ __global__ void assemble_kernel(const double *__restrict__ vals, const int64_t *
 
 __global__ void reset_fronts_kernel(const Front *__restrict__ fronts, unsigned long long *inertia) {
   const Front F = fronts[blockIdx.x];
-  for (int i = threadIdx.x; i < F.n; i += blockDim.x) {
+  for (int i = threadIdx.x; i < F.nb; i += blockDim.x) {
     F.perm[i] = i;
     F.ipiv[i] = i;
     F.bsz[i] = 1;
@@ -65,7 +65,7 @@ __global__ void schur_gather_kernel(const Front *__restrict__ fronts, const int6
     }
     if (br[lo] == c) {
       const Front F = fronts[f];
-      s += F.A[(size_t)(F.n + a) + (size_t)(F.n + lo) * F.ld];
+      s += F.A[(size_t)(F.nb + a) + (size_t)(F.nb + lo) * F.ld];
     }
   }
   S[(size_t)r + (size_t)c * m_c] = s;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT) front_forward_kernel(const Front *__restri
       F.zbuf[k + 1] = (akm1 * bk - bkm1) / denom;
     }
   }
-  for (int a = tid; a < F.m; a += NT) F.bvec[a] = v[n + a];
+  for (int a = tid; a < F.m; a += NT) F.bvec[a] = v[F.nb + a];
 }
 
 template <int NT>
@@ -177,10 +177,10 @@ __global__ void __launch_bounds__(NT) front_backward_kernel(const Front *__restr
   const int lane = tid & 31, warp = tid >> 5;
   double *v = sm;
   double *tri = sm + ((nf + 1) & ~1);
-  for (int i = tid; i < n; i += NT) v[i] = F.zbuf[i];
+  for (int i = tid; i < F.nb; i += NT) v[i] = i < n ? F.zbuf[i] : 0.0;
   if (F.m > 0) {
     const int32_t *br = brow + brow_ptr[blockIdx.x];
-    for (int a = tid; a < F.m; a += NT) v[n + a] = xc[br[a]];
+    for (int a = tid; a < F.m; a += NT) v[F.nb + a] = xc[br[a]];
   }
   __syncthreads();
   for (int kb = ((n - 1) / SB) * SB; kb >= 0; kb -= SB) {

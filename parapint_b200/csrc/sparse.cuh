@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *
 
 __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock *__restrict__ blocks,
                                                                const PlanDev *__restrict__ plans,
-                                                               const Front *__restrict__ fronts,
+                                                               Front *__restrict__ fronts,
                                                                const double *__restrict__ vals, double u,
                                                                double pivtol, unsigned long long *inertia) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -628,18 +628,14 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     ndroot += ndo;
   }
   for (int i = tid; i < P.nT; i += SF_NT) Bk.rootids[i] = P.rootcols[i];
-  for (int t = ndroot + tid; t < P.DR; t += SF_NT) {
-    Bk.rootids[P.nT + t] = -1;
-    R.A[(size_t)(P.nT + t) + (size_t)(P.nT + t) * R.ld] = 1.0;  // unused delayed slot: identity pivot
-  }
+  for (int t = ndroot + tid; t < P.DR; t += SF_NT) Bk.rootids[P.nT + t] = -1;  // unused delayed slots
   __syncthreads();
   if (tid == 0) {
     Bk.info[0] = failed ? 1 : 0;
     Bk.info[1] = ndroot;
     Bk.info[2] = 0;  // leaf-failure flag consumed
-    // the DR - ndroot identity slots will be counted as positive pivots by the root: cancel them here
-    const long long pos = (long long)cnt[0] - (long long)(P.DR - ndroot);
-    atomicAdd(&inertia[0], (unsigned long long)pos);
+    fronts[Bk.root].n = P.nT + ndroot;  // pivot candidates of the dense root: static columns + delayed ones
+    atomicAdd(&inertia[0], (unsigned long long)cnt[0]);
     atomicAdd(&inertia[1], (unsigned long long)cnt[1]);
     atomicAdd(&inertia[2], (unsigned long long)cnt[2]);
   }
