@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                 self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:  # noqa: BLE001
                 pass
-            self._halt.wait(0.005)
+            self._halt.wait(0.02)  # NVML queries contend with kernel launches for the driver lock: keep them sparse
 
     def finish(self):
         self._halt.set()
@@ -171,7 +171,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,7 +190,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN") else None
+        # (NCCL prints a version banner on stdout at VERSION/WARN level; stdout must stay the one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     from parapint_b200 import B200SchurComplementLinearSolver, Communicator, LinearSolverStatus
@@ -277,14 +278,14 @@ def main():
         be.solve_device(rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=comm.allreduce_sum_)
         return code, code2, loc, cpl
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # NVML init takes milliseconds: before the barrier
     for _ in range(args.warmup):
         dev_step()
-    sync_all()
     be.profile(reset=True)
     launches0 = be.kernel_launches()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    sync_all()
     ev0.record()
     for _ in range(args.steps):
         out = dev_step()

@@ -256,6 +256,10 @@ class BlockVector:
             out._blocks[i] = b.copy_structure() if is_block_vector(b) else np.zeros(b.size, dtype=np.float64)
         return out
 
+    def empty_like_structure(self):
+        """Same number of blocks, nothing allocated (the caller sets every block it owns)."""
+        return BlockVector(self.nblocks)
+
     def copyfrom(self, other):
         flat = other.flatten() if is_block_vector(other) else np.asarray(other, dtype=np.float64).ravel()
         if flat.size != self.size:

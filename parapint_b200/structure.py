@@ -152,17 +152,22 @@ def gather_values(matrix, st: Structure, out: np.ndarray) -> bool:
     Returns False when a block's COO pattern differs from the analysed one (the caller then
     re-runs the symbolic phase, as ``mumps_interface.py:82-83`` does)."""
     N = st.n_blocks
+    get = matrix.get_block
     for (kind, i, lo, hi), (prow, pcol) in zip(st.segments, st.patterns):
-        blk = matrix.get_block(i, i) if kind in ("K", "Q") else matrix.get_block(N, i)
+        blk = get(i, i) if kind != "A" else get(N, i)
         if blk is None:
             return False
-        c = blk.tocoo()
-        if c.data.size != hi - lo:
+        # fast path: a COO leaf that still carries the analysed index arrays (values updated in place)
+        if getattr(blk, "format", None) == "coo" and blk.row is prow and blk.col is pcol:
+            data = blk.data
+        else:
+            c = blk.tocoo()
+            if not ((c.row is prow or np.array_equal(c.row, prow)) and (c.col is pcol or np.array_equal(c.col, pcol))):
+                return False
+            data = c.data
+        if data.size != hi - lo:
             return False
-        # same index arrays as analysed (the usual case: values updated in place) -> nothing to compare
-        if not ((c.row is prow or np.array_equal(c.row, prow)) and (c.col is pcol or np.array_equal(c.col, pcol))):
-            return False
-        out[lo:hi] = c.data
+        out[lo:hi] = data
     return True
 
 
@@ -186,18 +191,26 @@ def coupling_rhs(rhs, st: Structure) -> np.ndarray:
 
 def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray):
     """New vector with the block structure of ``rhs`` (``mpi_explicit_schur_complement.py:390``;
-    nested blocks keep their structure as the SciPy leaf does, ``scipy_interface.py:57-60``)."""
-    out = rhs.copy_structure()
-
-    def shaped(template, flat):
+    nested blocks keep their structure as the SciPy leaf does, ``scipy_interface.py:57-60``).
+    The blocks are views of one freshly allocated array (nothing aliases solver buffers)."""
+    out = rhs.empty_like_structure() if hasattr(rhs, "empty_like_structure") else rhs.copy_structure()
+    flat = np.array(x_local[: st.local_dim], dtype=np.float64)  # one copy out of the pinned buffer
+    offs = st.rhs_offsets
+    get, put = rhs.get_block, out.set_block
+    for f, i in enumerate(st.local_blocks):
+        template = get(i)
+        seg = flat[offs[f]:offs[f + 1]]
         if hasattr(template, "nblocks"):
             blk = template.copy_structure()
-            blk.copyfrom(flat)
-            return blk
-        return np.array(flat, dtype=np.float64)
-
-    for f, i in enumerate(st.local_blocks):
-        lo, hi = st.rhs_offsets[f], st.rhs_offsets[f + 1]
-        out.set_block(i, shaped(rhs.get_block(i), x_local[lo:hi]))
-    out.set_block(st.n_blocks, shaped(rhs.get_block(st.n_blocks), x_c))
+            blk.copyfrom(seg)
+            put(i, blk)
+        else:
+            put(i, seg)
+    template = get(st.n_blocks)
+    if hasattr(template, "nblocks"):
+        blk = template.copy_structure()
+        blk.copyfrom(x_c)
+        put(st.n_blocks, blk)
+    else:
+        put(st.n_blocks, np.array(x_c, dtype=np.float64))
     return out
