@@ -293,3 +293,36 @@ def sym_full(kkt):
         put(A.transpose(), off[i], off[N])
     n = off[-1]
     return sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+
+
+class OraclePlugin:
+    """The reference's serial ``SchurComplementLinearSolver`` + ``ScipyInterface(compute_inertia=True)`` leaves
+    behind the four-method plugin surface (``base_linear_solver_interface.py:26-51``), for driving the flat IPM
+    restatement (``oracle/ipm.py``) with the reference algorithm."""
+
+    def __init__(self, inertia_method="eigvals"):
+        from parapint_b200.interface import LinearSolverResults, LinearSolverStatus
+        self._Results, self._Status = LinearSolverResults, LinearSolverStatus
+        self.oracle = SchurOracle(compute_inertia=True, inertia_method=inertia_method)
+        self.n_numeric = 0
+
+    def _res(self, code):
+        r = self._Results()
+        r.status = self._Status(code)
+        return r
+
+    def do_symbolic_factorization(self, matrix, raise_on_error=True, timer=None):
+        return self._res(self.oracle.symbolic(matrix))
+
+    def do_numeric_factorization(self, matrix, raise_on_error=True, timer=None):
+        self.n_numeric += 1
+        return self._res(self.oracle.numeric(matrix))
+
+    def do_back_solve(self, rhs):
+        return self.oracle.solve(rhs)
+
+    def get_inertia(self):
+        return self.oracle.inertia()
+
+    def increase_memory_allocation(self, factor):
+        pass
