@@ -596,3 +596,29 @@ def farmer_scenarios():
             rows.append(r); g_lb.append(0.0); g_ub.append(price_quota[i])
         scen.append(QuadraticScenario(c, lb, ub, sp.coo_matrix(np.asarray(rows)), g_lb, g_ub))
     return scen, [[0, 1, 2]] * 3, crops
+
+
+def random_stochastic_qp(seed, n_scen, n_x, n_eq, n_in, n_fs, negative_curvature=0.0):
+    """A separable two-stage QP in the farmer mould, scaled up (SURVEY.md 8(d) "end-to-end inputs"): banded
+    Hessians (optionally with some negative curvature so that the inertia-correction loop has work to do),
+    banded equality rows, a few sparse inequality rows, box bounds on every variable; the first ``n_fs`` variables
+    of every scenario are the first-stage variables."""
+    scen = []
+    for i in range(n_scen):
+        rng = np.random.default_rng(7919 * seed + i)
+        d = rng.uniform(0.5, 2.0, n_x)
+        if negative_curvature > 0:
+            pick = rng.random(n_x) < negative_curvature
+            d[pick] = -rng.uniform(0.1, 0.5, pick.sum())
+        off = rng.standard_normal(n_x - 1) * 0.2
+        H = sp.diags([off, d, off], [-1, 0, 1]).tocoo()
+        c = rng.standard_normal(n_x)
+        A_eq = (sp.eye(n_eq, n_x, k=n_fs) + sp.diags([rng.standard_normal(n_eq) * 0.5], [n_fs + 1], shape=(n_eq, n_x))).tocoo()
+        x_feas = rng.uniform(-1.0, 1.0, n_x)
+        b_eq = A_eq @ x_feas
+        A_in = (sp.random(n_in, n_x, density=3.0 / n_x, random_state=rng, data_rvs=rng.standard_normal)
+                + sp.eye(n_in, n_x, k=n_x - n_in)).tocoo()
+        g_mid = A_in @ x_feas
+        scen.append(QuadraticScenario(c, np.full(n_x, -5.0), np.full(n_x, 5.0), A_in, g_mid - 2.0, g_mid + 3.0,
+                                      A_eq=A_eq, b_eq=b_eq, H=H))
+    return scen, [list(range(n_fs))] * n_scen

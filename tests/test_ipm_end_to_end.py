@@ -51,3 +51,27 @@ def test_farmer_same_trajectory_on_b200():
     assert [(r[1], r[2], r[3], r[4]) for r in out["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
     for (i1, o1, *_), (i2, o2, *_) in zip(out["history"], ref["history"]):
         assert i1 == i2 and abs(o1 - o2) <= 1e-6 * max(1.0, abs(o2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [(0, 4, 60, 20, 8, 5, 0.0), (1, 4, 60, 20, 8, 5, 0.3), (2, 6, 220, 120, 12, 6, 0.15)])
+def test_stochastic_qp_same_trajectory_on_b200(args):
+    """Scaled-up two-stage QPs; with negative curvature the inertia-correction loop refactorises dozens of times
+    (interior_point.py:369-395) and the Hessian regularisation changes the COO pattern (interface.py:610-619), which
+    the solver must notice.  The 370-row blocks of the last case take the multifrontal path."""
+    from oracle.ipm import random_stochastic_qp
+    from parapint_b200 import B200SchurComplementLinearSolver
+
+    def run(solver):
+        scen, first_stage = random_stochastic_qp(*args)
+        return ip_solve(StochasticInterface(scen, first_stage), solver)
+
+    ref = run(OraclePlugin(inertia_method="ldl"))
+    solver = B200SchurComplementLinearSolver()
+    out = run(solver)
+    assert ref["status"] == out["status"] == "optimal"
+    assert out["iterations"] == ref["iterations"]
+    assert abs(out["objective"] - ref["objective"]) <= 1e-8 * max(1.0, abs(ref["objective"]))
+    assert [(r[1], r[2], r[3], r[4]) for r in out["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
+    if args[2] >= 200:
+        assert solver.backend.plan_stats(0)["supernodes"] > 0
