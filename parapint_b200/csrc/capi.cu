@@ -92,6 +92,7 @@ struct pp_handle {
   double pivot_threshold = 0.01;  // u of the threshold test in the subtree fronts
   bool use_sparse = true;
   bool no_fallback = false;
+  bool use_cluster = true;
   bool sparse_failed = false;     // a block overflowed its delayed-pivot capacity: all blocks were redone dense
   PlanOptions plan_opt;
   // saved symbolic inputs (for the dense re-analysis after a sparse-path overflow)
@@ -208,12 +209,33 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   }
   if (nmax == 0) return;
   const bool small = nfmax <= 384;  // short columns: four warps per front keep the block reductions cheap
+  // tall fronts: a cluster of CTAs per front, as many as fill the GPU once (8 is the portable maximum)
+  int csize = 1;
+  if (h->use_cluster && nfmax >= 1024)
+    while (csize < 8 && count * csize * 2 <= 128 && PC_NT * csize * 2 <= nfmax + PC_NT) csize *= 2;
   const int iters = (nmax + (NB - 2)) / (NB - 1);
   for (int it = 0; it < iters; ++it) {
     {
       ProfSpan sp(h, PP_PROF_PANEL, st);
-      if (small) front_panel_kernel<128><<<count, 128, 0, st>>>(fr, NB, h->pivot_tol);
-      else front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
+      if (small) {
+        front_panel_kernel<128><<<count, 128, 0, st>>>(fr, NB, h->pivot_tol);
+      } else if (csize > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(count * csize);
+        cfg.blockDim = dim3(PC_NT);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_kernel, fr, NB, h->pivot_tol));
+      } else {
+        front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
+      }
       h->launches++;
     }
     if (it > 0) {
@@ -330,6 +352,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   } else if (key == "pivot_threshold") {
     if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
+  } else if (key == "cluster_panel") {
+    h->use_cluster = value != 0.0;
   } else if (key == "no_fallback") {
     h->no_fallback = value != 0.0;
   } else if (key == "sparse_dslot") {

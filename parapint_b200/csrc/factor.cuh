@@ -7,6 +7,7 @@
 // Row interchanges are applied to the whole row of L (front_swaps_left_kernel), i.e. the factors
 // satisfy P K P^T = L D L^T with one permutation, which keeps the triangular solves plain.
 #pragma once
+#include <cooperative_groups.h>
 #include "front.cuh"
 
 namespace ppb {
@@ -193,6 +194,204 @@ __global__ void __launch_bounds__(NT) front_panel_kernel(const Front *__restrict
     k += kstep;
   }
   if (tid == 0) {
+    F.state[ST_KPREV] = k0;
+    F.state[ST_KCUR] = k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel factorisation for tall fronts: one thread-block CLUSTER per front.  The rows of the panel are
+// dealt over the CTAs of the cluster, so the bandwidth-bound column updates (each pivot step reads the
+// panel computed so far) run on up to 8 SMs instead of one; arg-max results are exchanged through
+// distributed shared memory, global data is handed over at cluster barriers.  Same algorithm and the
+// same pivot choices as front_panel_kernel (ties resolve to the lowest row index).
+// ---------------------------------------------------------------------------------------------
+constexpr int PC_NT = 512;
+
+__device__ __forceinline__ void cluster_argmax(cooperative_groups::cluster_group &cl, double &val, int &idx,
+                                               double &extra, double *sval, int *sidx, double *xval, int *xidx,
+                                               double *xextra, int &parity) {
+  // block-level reduce, then every CTA reads every CTA's result over DSMEM (one lane per remote CTA).
+  // The exchange slots are double-buffered, so one cluster barrier per call suffices.
+  block_argmax<PC_NT>(val, idx, sval, sidx);
+  const int p = parity;
+  parity ^= 1;
+  if (threadIdx.x == 0) { xval[p] = val; xidx[p] = idx; xextra[p] = extra; }
+  cl.sync();
+  if (threadIdx.x < 32) {
+    const unsigned nb = cl.num_blocks();
+    double v = -1.0, e = 0.0;
+    int i = -1;
+    if (threadIdx.x < nb) {
+      v = *cl.map_shared_rank(xval + p, threadIdx.x);
+      i = *cl.map_shared_rank(xidx + p, threadIdx.x);
+      if (threadIdx.x == 0) e = *cl.map_shared_rank(xextra + p, 0);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double v2 = __shfl_down_sync(0xffffffffu, v, o);
+      const int i2 = __shfl_down_sync(0xffffffffu, i, o);
+      if (i2 >= 0 && (i < 0 || v2 > v || (v2 == v && i2 < i))) { v = v2; i = i2; }
+    }
+    if (threadIdx.x == 0) { sval[0] = v; sidx[0] = i; sval[1] = e; }
+  }
+  __syncthreads();
+  val = sval[0];
+  idx = sidx[0];
+  extra = sval[1];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front *__restrict__ fronts, int NB,
+                                                                    double pivtol) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  const Front F = fronts[blockIdx.x / C];
+  const int tid = threadIdx.x;
+  const int gtid = rank * PC_NT + tid, GT = C * PC_NT;
+  const int n = F.n, nf = F.nf, ld = F.ld;
+  double *__restrict__ A = F.A;
+  double *__restrict__ W = F.W;
+  const int k0 = F.state[ST_KCUR];
+  if (k0 >= n) {
+    if (gtid == 0) F.state[ST_KPREV] = k0;
+    return;  // uniform over the cluster
+  }
+  __shared__ double wrow[NBMAX];
+  __shared__ double sval[32];
+  __shared__ int sidx[32];
+  __shared__ double xval[2], xextra[2];
+  __shared__ int xidx[2];
+  int parity = 0;
+
+  const bool last_panel = (n - k0 <= NB);
+  int k = k0;
+  while (k < n && (last_panel || (k - k0) < NB - 1)) {
+    const int kw = k - k0;
+    double *__restrict__ Wk = W + (size_t)kw * ld;
+    for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[k + (size_t)j * ld];
+    __syncthreads();
+    double best = -1.0, akk = 0.0;
+    int besti = -1;
+    for (int i = k + gtid; i < nf; i += GT) {
+      double acc = A[i + (size_t)k * ld];
+      const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 8
+      for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+      Wk[i] = acc;
+      if (i > k && i < n) {
+        const double a = fabs(acc);
+        if (a > best) { best = a; besti = i; }
+      }
+      if (i == k) akk = acc;  // gtid 0 (rank 0, thread 0)
+    }
+    cluster_argmax(cl, best, besti, akk, sval, sidx, xval, xidx, xextra, parity);
+    const double colmax = besti >= 0 ? best : 0.0;
+    const int imax = besti;
+    const double absakk = fabs(akk);
+
+    int kstep = 1, kp = k;
+    bool zero_pivot = false;
+    if (!(fmax(absakk, colmax) > pivtol)) {
+      zero_pivot = true;
+    } else if (absakk >= BK_ALPHA * colmax) {
+      kp = k;
+    } else {
+      double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[imax + (size_t)j * ld];
+      __syncthreads();
+      double rbest = -1.0, wimax = 0.0;
+      int rbesti = -1;
+      for (int i = k + gtid; i < nf; i += GT) {
+        double acc = (i < imax) ? A[imax + (size_t)i * ld] : A[i + (size_t)imax * ld];
+        const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 8
+        for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+        Wk1[i] = acc;
+        if (i < n && i != imax) {
+          const double a = fabs(acc);
+          if (a > rbest) { rbest = a; rbesti = i; }
+        }
+      }
+      double dummy = 0.0;
+      cluster_argmax(cl, rbest, rbesti, dummy, sval, sidx, xval, xidx, xextra, parity);
+      wimax = Wk1[imax];  // written before the cluster barrier inside cluster_argmax
+      const double rowmax = rbesti >= 0 ? rbest : 0.0;
+      if (absakk >= BK_ALPHA * colmax * (colmax / rowmax)) {
+        kp = k;
+      } else if (fabs(wimax) >= BK_ALPHA * rowmax) {
+        kp = imax;
+        for (int i = k + gtid; i < nf; i += GT) Wk[i] = Wk1[i];
+      } else {
+        kp = imax;
+        kstep = 2;
+      }
+    }
+    cl.sync();
+
+    const int kk = k + kstep - 1;
+    if (kp != kk) {
+      if (gtid == 0) {
+        A[kp + (size_t)kp * ld] = A[kk + (size_t)kk * ld];
+        const int t = F.perm[kk];
+        F.perm[kk] = F.perm[kp];
+        F.perm[kp] = t;
+      }
+      for (int j = kk + 1 + gtid; j < kp; j += GT) A[kp + (size_t)j * ld] = A[j + (size_t)kk * ld];
+      for (int i = kp + 1 + gtid; i < nf; i += GT) A[i + (size_t)kp * ld] = A[i + (size_t)kk * ld];
+      for (int j = gtid; j < kw; j += GT) {
+        double *c = A + (size_t)(k0 + j) * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      for (int j = gtid; j < kw + kstep; j += GT) {
+        double *c = W + (size_t)j * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      cl.sync();
+    }
+
+    if (kstep == 1) {
+      const double d = Wk[k];
+      const bool bad = zero_pivot || !(fabs(d) > pivtol) || !isfinite(d);
+      const double rd = bad ? 0.0 : 1.0 / d;
+      for (int i = k + 1 + gtid; i < nf; i += GT) A[i + (size_t)k * ld] = Wk[i] * rd;
+      if (gtid == 0) {
+        A[k + (size_t)k * ld] = bad ? 0.0 : d;
+        F.ipiv[k] = kp;
+        F.bsz[k] = 1;
+        if (bad && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    } else {
+      const double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      const double e11 = Wk[k], e21 = Wk[k + 1], e22 = Wk1[k + 1];
+      const double d11 = e22 / e21, d22 = e11 / e21;
+      const double t = 1.0 / (d11 * d22 - 1.0);
+      const double sc = t / e21;
+      for (int i = k + 2 + gtid; i < nf; i += GT) {
+        const double w0 = Wk[i], w1 = Wk1[i];
+        A[i + (size_t)k * ld] = sc * (d11 * w0 - w1);
+        A[i + (size_t)(k + 1) * ld] = sc * (d22 * w1 - w0);
+      }
+      if (gtid == 0) {
+        A[k + (size_t)k * ld] = e11;
+        A[k + 1 + (size_t)k * ld] = e21;
+        A[k + 1 + (size_t)(k + 1) * ld] = e22;
+        F.ipiv[k] = kp;
+        F.ipiv[k + 1] = kp;
+        F.bsz[k] = 2;
+        F.bsz[k + 1] = 0;
+        if (!isfinite(sc) && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    }
+    cl.sync();
+    k += kstep;
+  }
+  if (gtid == 0) {
     F.state[ST_KPREV] = k0;
     F.state[ST_KCUR] = k;
   }

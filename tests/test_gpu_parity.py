@@ -173,3 +173,21 @@ def test_delayed_pivot_overflow_falls_back_to_dense():
     assert s.get_inertia() == dense_inertia(dense, "ldl")
     st = s.backend.plan_stats(0)
     assert st["fell_back_dense"] == 1 or st["delayed_to_root"] == 0
+
+
+@pytest.mark.parametrize("cluster", [1, 0])
+def test_large_dense_fronts(cluster):
+    """Dense blocks tall enough for the cluster panel kernel (and, with cluster_panel=0, the single-CTA one):
+    both must make the same pivot choices, so inertia and solution agree with LAPACK."""
+    rng = np.random.default_rng(11)
+    n, m_c, nb = 1300, 40, 2
+    kkt = random_bordered(rng, nb, n, m_c, density=0.6, border_nnz_rows=25)
+    sizes = [n] * nb + [m_c]
+    rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
+    s, x = _solve(kkt, rhs, options={"cluster_panel": cluster})
+    assert s.backend.plan_stats(0)["supernodes"] == 0  # dense plan
+    dense = sym_full(kkt).toarray()
+    x_ref = np.linalg.solve(dense, rhs.flatten())
+    assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    assert s.get_inertia() == dense_inertia(dense, "ldl")
