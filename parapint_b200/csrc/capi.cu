@@ -83,6 +83,7 @@ struct pp_handle {
   int n_local = 0, m_c = 0;
   bool have_symbolic = false, local_factored = false, coupling_factored = false, forward_done = false;
   std::vector<int> n, m, nf, ld;  // n_local + 1 fronts (last = coupling)
+  std::vector<int> nmin;          // pivots every factorisation is sure to eliminate in the front (static columns)
   int64_t local_dim = 0;
   int nmax_local = 0, nfmax_local = 0;
   std::vector<int> block_n;       // original order of every local block
@@ -244,16 +245,18 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
       front_swaps_left_kernel<<<g, 256, 0, st>>>(fr);
       h->launches++;
     }
-    int nt = 0;
+    int ntiles = 0;
     for (int f = first; f < first + count; ++f) {
       if (h->n[f] <= it * (NB - 1)) continue;  // finished in an earlier launch
-      const int done = std::min(h->n[f], (it + 1) * (NB - 1));
+      // lower bound on the columns done: a root eliminates at least its static columns (nmin), the
+      // delayed-pivot slots may be unused
+      const int done = std::min(h->nmin[f], (it + 1) * (NB - 1));
       if (done >= h->nf[f]) continue;
-      nt = std::max(nt, (h->nf[f] + UT - 1) / UT - done / UT);
+      ntiles = std::max(ntiles, update_tile_count(h->nf[f], done));
     }
-    if (nt > 0) {
+    if (ntiles > 0) {
       ProfSpan sp(h, PP_PROF_UPDATE, st);
-      dim3 g(nt * (nt + 1) / 2, count);
+      dim3 g(ntiles, count);
       front_update_kernel<<<g, UPD_THREADS, UPD_SMEM, st>>>(fr);
       h->launches++;
     }
@@ -450,6 +453,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
 
   // ---- dense fronts: one root per block + the coupling front ----
   h->n.assign(nfronts, 0);
+  h->nmin.assign(nfronts, 0);
   h->m.assign(nfronts, 0);
   h->nf.assign(nfronts, 0);
   h->ld.assign(nfronts, 0);
@@ -457,9 +461,11 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   for (int f = 0; f < n_local; ++f) {
     const PatternPlan &P = h->plans[h->block_plan[f]];
     h->n[f] = P.nT + P.DR;
+    h->nmin[f] = P.nT;
     h->m[f] = mloc[f];
   }
   h->n[n_local] = m_c;
+  h->nmin[n_local] = m_c;
   h->m[n_local] = 0;
   std::vector<size_t> offA(nfronts), offW(nfronts), offZ(nfronts), offI(nfronts);
   size_t totA = 0, totW = 0, totZ = 0, totI = 0;

@@ -420,10 +420,12 @@ __global__ void front_swaps_left_kernel(const Front *__restrict__ fronts) {
 // Trailing update  A(i,j) -= sum_k L(i,k) * W(j,k)   (i >= j >= kcur), FP64 DMMA m8n8k4.
 // 128 x 128 output tile per CTA, 16 warps of 32 x 32, whole panel (K <= NBMAX) staged in smem.
 // ---------------------------------------------------------------------------------------------
-constexpr int UT = 128;          // tile edge
-constexpr int UROW = UT + 4;     // smem row pitch (doubles): pitch % 16 == 4 -> conflict-free frags
-constexpr int UPD_THREADS = 512;
-constexpr size_t UPD_SMEM = (size_t)2 * NBMAX * UROW * sizeof(double);
+constexpr int UT = 128;          // tile rows
+constexpr int UTN = 64;          // tile columns
+constexpr int UROW = UT + 4;     // smem pitches (doubles): pitch % 16 == 4 -> conflict-free fragment loads
+constexpr int UCOL = UTN + 4;
+constexpr int UPD_THREADS = 256;
+constexpr size_t UPD_SMEM = (size_t)NBMAX * (UROW + UCOL) * sizeof(double);  // 100 KB: two CTAs per SM
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -437,39 +439,54 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
 }
 
-__global__ void __launch_bounds__(UPD_THREADS, 1) front_update_kernel(const Front *__restrict__ fronts) {
+// number of (128 x 64) tiles of the lower-triangular trailing region that starts at `kcur` in a
+// front of `nf` rows; tiles are anchored at absolute multiples of the tile size
+__host__ __device__ inline int update_tile_count(int nf, int kcur) {
+  const int t0 = kcur / UT, c0 = kcur / UTN, tend = (nf + UT - 1) / UT;
+  int total = 0;
+  for (int t = t0; t < tend; ++t) total += min(2 * t + 2, (nf + UTN - 1) / UTN) - c0;
+  return total;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS, 2) front_update_kernel(const Front *__restrict__ fronts) {
   const Front F = fronts[blockIdx.y];
   const int kprev = F.state[ST_KPREV], kcur = F.state[ST_KCUR];
   const int kw = kcur - kprev;
   const int nf = F.nf, ld = F.ld;
   if (kw == 0 || kcur >= nf) return;
-  const int t0 = kcur / UT;
-  const int nt = (nf + UT - 1) / UT - t0;
-  if ((int)blockIdx.x >= nt * (nt + 1) / 2) return;
-  // linear index -> (ti >= tj) in the lower-triangular tile grid
-  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
-  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
-  const int tj = blockIdx.x - ti * (ti + 1) / 2;
-  const int row0 = (t0 + ti) * UT, col0 = (t0 + tj) * UT;
+  // linear index -> (row tile ti, column tile tj) with 64*tj <= 128*ti + 127
+  const int t0 = kcur / UT, c0 = kcur / UTN, tend = (nf + UT - 1) / UT, cend = (nf + UTN - 1) / UTN;
+  int rem = blockIdx.x, ti = t0;
+  for (; ti < tend; ++ti) {
+    const int cnt = min(2 * ti + 2, cend) - c0;
+    if (rem < cnt) break;
+    rem -= cnt;
+  }
+  if (ti >= tend) return;
+  const int tj = c0 + rem;
+  const int row0 = ti * UT, col0 = tj * UTN;
 
   extern __shared__ __align__(16) double smem[];
   double *sA = smem;                 // [kpad][UROW]  L(row0 + r, kprev + k)
-  double *sB = smem + NBMAX * UROW;  // [kpad][UROW]  W(col0 + c, k)
+  double *sB = smem + NBMAX * UROW;  // [kpad][UCOL]  W(col0 + c, k)
   const int kpad = (kw + 3) & ~3;
   const double *gA = F.A + (size_t)kprev * ld + row0;
   const double *gB = F.W + col0;
   for (int idx = threadIdx.x; idx < kpad * (UT / 2); idx += UPD_THREADS) {
     const int k = idx / (UT / 2), r = (idx % (UT / 2)) * 2;
-    const bool pa_ok = k < kw && row0 + r < nf, pb_ok = k < kw && col0 + r < nf;
-    cp_async16(sA + k * UROW + r, pa_ok ? gA + (size_t)k * ld + r : F.A, pa_ok);
-    cp_async16(sB + k * UROW + r, pb_ok ? gB + (size_t)k * ld + r : F.A, pb_ok);
+    const bool ok = k < kw && row0 + r < nf;
+    cp_async16(sA + k * UROW + r, ok ? gA + (size_t)k * ld + r : F.A, ok);
+  }
+  for (int idx = threadIdx.x; idx < kpad * (UTN / 2); idx += UPD_THREADS) {
+    const int k = idx / (UTN / 2), r = (idx % (UTN / 2)) * 2;
+    const bool ok = k < kw && col0 + r < nf;
+    cp_async16(sB + k * UCOL + r, ok ? gB + (size_t)k * ld + r : F.A, ok);
   }
   asm volatile("cp.async.commit_group;\n" ::);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp & 3, wn = warp >> 2;
-  const bool active = !(ti == tj && wn > wm);  // warp tile strictly above the diagonal
+  const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps of 32 x 32
+  const bool active = row0 + wm * 32 + 31 >= col0 + wn * 32;  // not strictly above the diagonal
   const int g = lane >> 2, q = lane & 3;
   const int rbase = row0 + wm * 32 + g;
   const int cbase = col0 + wn * 32 + q * 2;
@@ -491,13 +508,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) front_update_kernel(const Fron
   if (!active) return;
 
   const double *pa = sA + q * UROW + wm * 32 + g;
-  const double *pb = sB + q * UROW + wn * 32 + g;
+  const double *pb = sB + q * UCOL + wn * 32 + g;
   for (int k = 0; k < kpad; k += 4) {
     double a[4], b[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       a[f] = -pa[k * UROW + f * 8];
-      b[f] = pb[k * UROW + f * 8];
+      b[f] = pb[k * UCOL + f * 8];
     }
 #pragma unroll
     for (int fm = 0; fm < 4; ++fm)
