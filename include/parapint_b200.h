@@ -85,9 +85,13 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
  * the fronts from `values`, runs the batched Bunch-Kaufman LDL^T of every local front and writes
  * this rank's dense contribution  -sum_i A_i K_i^{-1} A_i^T  (m_c x m_c, column-major, lower
  * triangle valid) to `schur_local_dev` (DEVICE pointer, caller owned, so that the caller can
- * SUM-reduce it across ranks as mpi_explicit_schur_complement.py:343 does).
+ * SUM-reduce it across ranks as mpi_explicit_schur_complement.py:343 does).  The buffer holds
+ * m_c*m_c + PP_SCHUR_TAIL doubles: the tail carries {1 if a local block is singular, 0, n_pos, n_neg,
+ * n_zero, 0, 0, 0} of this rank's blocks, so the same all-reduce also agrees the status and sums the
+ * inertia across ranks (roles of mpi_explicit_schur_complement.py:21 and :427-429).
  * Returns 0, 2 (a local block is singular) or 3.
  */
+#define PP_SCHUR_TAIL 8
 int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
                      void *stream);
 

@@ -767,6 +767,10 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
   CK(cudaGetLastError());
   const int bad = read_flag(h, 0, h->n_local, st);
   *sparse_bad = h->n_local > 0 ? h->pin_flag.p[1] : 0;
+  if (schur_local_dev) {  // stream-ordered after collect_info / inertia kernels; flag[0] is current
+    pack_tail_kernel<<<1, 32, 0, st>>>(schur_local_dev + (size_t)h->m_c * h->m_c, h->flag.p, h->inertia.p);
+    h->launches++;
+  }
   return bad;
 }
 
@@ -774,7 +778,7 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
                      void *stream) {
   if (!h || !h->have_symbolic) return fail("pp_numeric_local: symbolic factorization required first");
   if (h->nvals > 0 && !values) return fail("pp_numeric_local: null values");
-  if (h->m_c > 0 && !schur_local_dev) return fail("pp_numeric_local: null schur buffer");
+  if (!schur_local_dev) return fail("pp_numeric_local: null schur buffer");
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;

@@ -43,6 +43,21 @@ __global__ void collect_info_kernel(const Front *__restrict__ fronts, int count,
   if (threadIdx.x == 0) flag[0] = bad;
 }
 
+// Tail of the local Schur buffer: [blocks singular?, reserved, n_pos, n_neg, n_zero, 0, 0, 0] of this rank's
+// blocks, so that the ONE all-reduce of the Schur complement also agrees the status across ranks and sums the
+// inertia (the reference needs an allgather and three allreduces for that,
+// mpi_explicit_schur_complement.py:21,427-429).
+__global__ void pack_tail_kernel(double *__restrict__ tail, const int *__restrict__ flag,
+                                 const unsigned long long *__restrict__ inertia) {
+  const int t = threadIdx.x;
+  if (t < 8) {
+    double v = 0.0;
+    if (t == 0) v = flag[0] ? 1.0 : 0.0;
+    else if (t >= 2 && t <= 4) v = (double)inertia[t - 2];
+    tail[t] = v;
+  }
+}
+
 // ---- Schur gather ---------------------------------------------------------------------------
 // S_local(r,c) = sum over local fronts holding both coupling rows r and c of the front's trailing
 // block entry; sources are visited in front order, so the sum is reproducible.  Replaces the

@@ -24,6 +24,7 @@ from .comm import Communicator
 from .interface import LinearSolverInterface, LinearSolverResults, LinearSolverStatus
 
 _OK = (LinearSolverStatus.successful, LinearSolverStatus.warning)
+SCHUR_TAIL = 8  # PP_SCHUR_TAIL: status / inertia words appended to the Schur buffer
 
 
 class _NullTimer:
@@ -82,7 +83,7 @@ class CudaBackend:
         self._check(code, "pp_symbolic")
         mc = max(st.m_c, 1)
         with torch.cuda.device(self.device):
-            self.schur = torch.zeros(mc * mc, dtype=torch.float64, device=self.device)
+            self.schur = torch.zeros(mc * mc + SCHUR_TAIL, dtype=torch.float64, device=self.device)
             self.rc = torch.zeros(mc, dtype=torch.float64, device=self.device)
             self.ints = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.values_pin = torch.empty(max(st.nvals, 1), dtype=torch.float64, pin_memory=True)
@@ -207,6 +208,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.local_block_indices = []
         self._st = None
         self._status = None
+        self._tail = None
         self.logger = self.getLogger()
 
     @classmethod
@@ -214,6 +216,14 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         return "b200_schur"
 
     # ---------------------------------------------------------------------------------------
+    def _result(self, code, raise_on_error, what):
+        res = LinearSolverResults()
+        res.status = LinearSolverStatus(int(code))
+        self._status = res.status
+        if res.status not in _OK and raise_on_error:
+            raise RuntimeError(f"{what} unsuccessful; status: {res.status}")
+        return res
+
     def _finish(self, code, raise_on_error, what):
         """Agree on the worst status across ranks (``_gather_results``, ``mpi...:19-30``)."""
         if self.comm.size > 1:
@@ -261,18 +271,29 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         timer.start("factorize")
         code, schur_local = self.backend.numeric_local()
         timer.stop("factorize")
-        res = self._finish(code, raise_on_error, "Numeric factorization")
+        self._tail = None
+        if self.comm.size > 1:
+            # ONE collective per factorisation (mpi...:343): the tail of the buffer carries this rank's status
+            # and inertia, so no separate allgather / allreduce is needed (mpi...:21,427-429)
+            timer.start("communicate")
+            self.comm.allreduce_sum_(schur_local)
+            timer.stop("communicate")
+            mc2 = self._st.m_c * self._st.m_c
+            tail = schur_local[mc2:mc2 + SCHUR_TAIL].cpu().numpy()
+            self._tail = tail
+            if code == 0 and tail[0] > 0:
+                code = LinearSolverStatus.singular.value
+            if tail[1] > 0 or not np.all(np.isfinite(tail)):
+                code = LinearSolverStatus.error.value
+        res = self._result(code, raise_on_error, "Numeric factorization")
         if res.status not in _OK:
             timer.stop("form SC")
             return res
-        timer.start("communicate")
-        self.comm.allreduce_sum_(schur_local)
-        timer.stop("communicate")
         timer.stop("form SC")
         timer.start("factor SC")
-        code = self.backend.numeric_coupling(schur_local)
+        code = self.backend.numeric_coupling(schur_local)  # replicated: every rank gets the same status
         timer.stop("factor SC")
-        return self._finish(code, raise_on_error, "Numeric factorization")
+        return self._result(code, raise_on_error, "Numeric factorization")
 
     def do_back_solve(self, rhs, timer=None):
         """Three-phase block elimination (``explicit...:131-155``, ``mpi...:363-402``); returns a new
@@ -296,11 +317,10 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         (Haynsworth additivity; ``explicit...:157-172``, ``mpi...:404-436``).  Collective."""
         if self._status not in _OK or self.block_matrix is None:
             raise RuntimeError("The inertia is only available after a successful do_numeric_factorization.")
-        local = self.backend.inertia_local()
-        if self.comm.size > 1:
-            t = self.backend.int_tensor(local.tolist())
-            self.comm.allreduce_sum_(t)
-            local = t.cpu().numpy()
+        if self.comm.size > 1 and self._tail is not None:
+            local = np.rint(self._tail[2:5]).astype(np.int64)  # summed over ranks by the Schur all-reduce
+        else:
+            local = self.backend.inertia_local()
         tot = local + self.backend.inertia_coupling()
         return int(tot[0]), int(tot[1]), int(tot[2])
 

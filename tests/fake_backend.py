@@ -18,7 +18,7 @@ class FakeBackend:
     def symbolic(self, st):
         self.st = st
         mc = max(st.m_c, 1)
-        self.schur = torch.zeros(mc * mc, dtype=torch.float64)
+        self.schur = torch.zeros(mc * mc + 8, dtype=torch.float64)
         self.rc = torch.zeros(mc, dtype=torch.float64)
         self.ints = torch.zeros(4, dtype=torch.int64)
         self.values_pin = torch.zeros(max(st.nvals, 1), dtype=torch.float64)
@@ -57,12 +57,13 @@ class FakeBackend:
             if rows.size:
                 S[np.ix_(rows, rows)] -= A @ np.linalg.solve(K, A.T)
         self.Q = fronts[-1]
-        self.schur.copy_(torch.from_numpy(S.T.reshape(-1).copy()))
+        tail = np.array([1.0 if code == 2 else 0.0, 0.0, *self.inert.astype(float), 0.0, 0.0, 0.0])
+        self.schur.copy_(torch.from_numpy(np.concatenate([S.T.reshape(-1), tail])))
         return code, self.schur
 
     def numeric_coupling(self, schur_sum):
         mc = self.st.m_c
-        self.S = self.Q + schur_sum.numpy().reshape(mc, mc).T
+        self.S = self.Q + schur_sum.numpy()[: mc * mc].reshape(mc, mc).T
         if mc and np.linalg.matrix_rank(self.S) < mc:
             return 2
         self.inert_c = np.asarray(dense_inertia(self.S, "eigvalsh"), dtype=np.int64)
