@@ -74,10 +74,16 @@ int pp_set_option(pp_handle *h, const char *name, double value);
  *   dest_row/dest_col  position inside that front (row >= col).  A front is the symmetric matrix
  *                      [[K_i, .],[A_i(nonzero rows), 0]] of order n_i + m_i; border entry
  *                      (nonzero row a, column j) therefore has row = n_i + a, col = j.
+ *   values_hint        optional (may be NULL): representative numeric values of the nvals inputs (host).
+ *                      Only the ORDERING uses them: columns whose diagonal is numerically zero (constraint
+ *                      multipliers of a KKT block) are paired with a neighbour so that they can be
+ *                      eliminated as 2x2 pivots instead of being delayed.  The reference calls the symbolic
+ *                      phase with the real KKT matrix (algorithms/interior_point.py:542-552), so values are at
+ *                      hand; an all-zero hint (linalg/tests/test_linear_solvers.py:66-71) is equivalent to NULL.
  */
 int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
                 const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
-                const int32_t *dest_row, const int32_t *dest_col);
+                const int32_t *dest_row, const int32_t *dest_col, const double *values_hint);
 
 /*
  * Numeric phase, local part.  Replaces the per-block leaf factorisations and the Schur formation

@@ -99,6 +99,7 @@ struct pp_handle {
   // saved symbolic inputs (for the dense re-analysis after a sparse-path overflow)
   std::vector<int32_t> in_block_n, in_border_rows, in_dest_front, in_dest_row, in_dest_col;
   std::vector<int64_t> in_border_ptr;
+  std::vector<double> in_hint;    // representative values (ordering heuristics only)
   // multifrontal (subtree) part
   std::vector<PatternPlan> plans;
   std::vector<int> block_plan;
@@ -361,6 +362,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->no_fallback = value != 0.0;
   } else if (key == "sparse_dslot") {
     h->plan_opt.dslot = std::max(0, std::min((int)value, 32));
+  } else if (key == "pair_weak") {
+    h->plan_opt.pair_weak = value != 0.0;
   } else if (key == "ordering") {
     h->plan_opt.ordering = (int)value;
   } else if (key == "nd_leaf") {
@@ -406,6 +409,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
 
   // ---- per-block entry lists and pattern de-duplication ----
   std::vector<std::vector<int>> e_row(n_local), e_col(n_local), e_src(n_local);
+  std::vector<std::vector<double>> e_val(n_local);
+  const bool have_hint = (int64_t)h->in_hint.size() == nvals && nvals > 0;
   std::vector<int64_t> first_k(n_local, -1);
   std::vector<int64_t> coupling_k;
   for (int64_t k = 0; k < nvals; ++k) {
@@ -425,6 +430,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     e_row[f].push_back(r);
     e_col[f].push_back(c);
     e_src[f].push_back((int)(k - first_k[f]));
+    if (have_hint) e_val[f].push_back(h->in_hint[(size_t)k]);
   }
   h->plans.clear();
   h->block_plan.assign(n_local, -1);
@@ -442,7 +448,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
       if (it == seen.end()) {
         const int id = (int)h->plans.size();
         h->plans.push_back(build_plan(block_n[f], mloc[f], e_row[f], e_col[f], e_src[f], h->plan_opt,
-                                      force_dense || !h->use_sparse));
+                                      force_dense || !h->use_sparse, have_hint ? &e_val[f] : nullptr));
         seen.emplace(std::move(key), id);
         h->block_plan[f] = id;
       } else {
@@ -693,7 +699,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
 
 int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
                 const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
-                const int32_t *dest_row, const int32_t *dest_col) {
+                const int32_t *dest_row, const int32_t *dest_col, const double *values_hint) {
   if (!h) return fail("pp_symbolic: null handle");
   if (n_local < 0 || m_c < 0 || nvals < 0) return fail("pp_symbolic: negative size");
   if (n_local > 0 && (!block_n || !border_ptr)) return fail("pp_symbolic: null block description");
@@ -721,6 +727,7 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
     h->in_dest_front.assign(dest_front, dest_front + nvals);
     h->in_dest_row.assign(dest_row, dest_row + nvals);
     h->in_dest_col.assign(dest_col, dest_col + nvals);
+    if (values_hint) h->in_hint.assign(values_hint, values_hint + nvals); else h->in_hint.clear();
     h->sparse_failed = false;
     return do_symbolic(h, false);
   });

@@ -11,6 +11,7 @@
 // All index lists use ORIGINAL column numbers of the block.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <numeric>
 #include <set>
@@ -254,6 +255,8 @@ struct PlanOptions {
   int tiny_max_children = 8;  // fronts with more children are assembled by the whole CTA (staged fetch)
   int nd_leaf = 48;     // nested dissection stops at components of this many vertices
   int ordering = 0;     // 0 = pick the cheaper of minimum degree and nested dissection, 1 = MD, 2 = ND
+  int root_delay_max = 1024;  // cap on the root's delayed-pivot slots
+  bool pair_weak = true; // order zero-diagonal columns together with a partner (2x2 pivot pre-selection)
   int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front
   double max_density = 0.20; // ... as are blocks whose factor would fill more than this share of n^2/2
 };
@@ -263,7 +266,7 @@ struct PlanOptions {
 // entries with keep[k] == 0 are ignored.  src[k] = relative value index of entry k.
 inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
                                    const std::vector<int> &src, const PlanOptions &opt, bool force_dense,
-                                   bool dissect) {
+                                   bool dissect, const std::vector<double> *hint = nullptr) {
   PatternPlan P;
   P.n = n;
   P.m = m;
@@ -283,9 +286,106 @@ inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, c
   std::vector<int> order;
   std::vector<std::vector<int>> lstruct;
   if (!dense) {
-    std::vector<int> stage;
-    if (dissect) detail::nested_dissection_stages(n, adj, hold, opt.nd_leaf, stage);
-    detail::minimum_degree(n, adj, hold, stage, order, lstruct);
+    // ---- 2x2 pivot pre-selection for KKT structure ----
+    // A column whose diagonal is (numerically) zero -- constraint multipliers -- cannot be eliminated on its
+    // own: as a leaf of the tree it would be delayed to its parent.  Such a column is paired with a neighbour
+    // (the largest coupling entry, preferring columns with a usable diagonal) and the pair is ordered as ONE
+    // vertex, so both land in the same front and form a 2x2 pivot there (compressed-graph ordering in the
+    // manner of Duff & Pralet).  `hint` carries representative numeric values; without it only columns with
+    // no stored diagonal count as weak.
+    std::vector<double> dmag(n, 0.0), rmax(n, 0.0);
+    std::vector<char> has_diag(n, 0);
+    std::vector<std::vector<std::pair<int, double>>> inc(n);
+    for (size_t k = 0; k < ne; ++k) {
+      const int r = rows[k], c = cols[k];
+      if (r >= n) continue;
+      const double v = hint ? (*hint)[k] : 1.0;
+      if (r == c) { dmag[r] += v; has_diag[r] = 1; }
+      else { inc[r].push_back({c, fabs(v)}); inc[c].push_back({r, fabs(v)}); rmax[r] = std::max(rmax[r], fabs(v)); rmax[c] = std::max(rmax[c], fabs(v)); }
+    }
+    std::vector<char> weak(n, 0);
+    int nweak = 0;
+    for (int v = 0; v < n; ++v) {
+      weak[v] = !has_diag[v] || (hint && fabs(dmag[v]) <= 1e-8 * rmax[v]);
+      nweak += weak[v];
+    }
+    std::vector<int> mate(n, -1);
+    if (opt.pair_weak && nweak > 0) {
+      std::vector<int> wl;
+      for (int v = 0; v < n; ++v)
+        if (weak[v]) wl.push_back(v);
+      std::stable_sort(wl.begin(), wl.end(), [&](int a, int b) { return inc[a].size() < inc[b].size(); });
+      for (int v : wl) {
+        // border-touched columns stay in the dense root, where Bunch-Kaufman needs no help; pairing them
+        // would only drag their partner into the root as well
+        if (mate[v] >= 0 || hold[v]) continue;
+        int best = -1;
+        double bv = 0.0;
+        bool bstrong = false;
+        for (auto &e : inc[v]) {
+          const int w = e.first;
+          if (mate[w] >= 0 || w == v || hold[w] || e.second <= 0.0) continue;
+          const bool strong = !weak[w];
+          if (best < 0 || (strong && !bstrong) || (strong == bstrong && (e.second > bv || (e.second == bv && w < best)))) {
+            best = w; bv = e.second; bstrong = strong;
+          }
+        }
+        if (best >= 0) { mate[v] = best; mate[best] = v; }
+      }
+    }
+    // contracted graph: a pair is one vertex
+    std::vector<int> cid(n, -1);
+    std::vector<std::vector<int>> members;
+    for (int v = 0; v < n; ++v) {
+      if (cid[v] >= 0) continue;
+      cid[v] = (int)members.size();
+      if (mate[v] >= 0) {
+        cid[mate[v]] = cid[v];
+        // the member with the usable diagonal first
+        if (weak[v] && !weak[mate[v]]) members.push_back({mate[v], v}); else members.push_back({v, mate[v]});
+      } else {
+        members.push_back({v});
+      }
+    }
+    const int nc2 = (int)members.size();
+    std::vector<std::vector<int>> cadj(nc2);
+    std::vector<char> chold(nc2, 0);
+    for (int v = 0; v < n; ++v) {
+      if (hold[v]) chold[cid[v]] = 1;
+      for (int w : adj[v])
+        if (cid[w] != cid[v]) cadj[cid[v]].push_back(cid[w]);
+    }
+    for (auto &a : cadj) {
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+    }
+    for (int c = 0; c < nc2; ++c)
+      if (chold[c])
+        for (int v : members[c]) hold[v] = 1;  // a pair with a border-touched column stays in the root whole
+    std::vector<int> stage, corder;
+    std::vector<std::vector<int>> cstruct;
+    if (dissect) detail::nested_dissection_stages(nc2, cadj, chold, opt.nd_leaf, stage);
+    detail::minimum_degree(nc2, cadj, chold, stage, corder, cstruct);
+    order.clear();
+    lstruct.assign(n, {});
+    for (int c : corder) {
+      std::vector<int> reach;
+      for (int d : cstruct[c])
+        for (int v : members[d]) reach.push_back(v);
+      std::sort(reach.begin(), reach.end());
+      if (members[c].size() == 2) {
+        const int a = members[c][0], b = members[c][1];
+        order.push_back(a);
+        order.push_back(b);
+        lstruct[a] = reach;
+        lstruct[a].push_back(b);
+        std::sort(lstruct[a].begin(), lstruct[a].end());
+        lstruct[b] = reach;
+      } else {
+        order.push_back(members[c][0]);
+        lstruct[members[c][0]] = reach;
+      }
+    }
     double fill = 0;
     for (int p : order) fill += (double)lstruct[p].size() + 1;
     const double held = (double)(n - (int)order.size());
@@ -396,7 +496,9 @@ inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, c
     if (pos[v] < 0) { rootpos[v] = (int)P.rootcols.size(); P.rootcols.push_back(v); }
   P.nT = (int)P.rootcols.size();
   P.ns = (int)post.size();
-  P.DR = P.ns > 0 ? opt.dmax : 0;
+  // delayed columns from ALL children of the root meet here: capacity grows with the block (unused slots cost
+  // nothing in the factorisation, the root's pivot count is set on the device)
+  P.DR = P.ns > 0 ? std::max(opt.dmax, std::min(opt.root_delay_max, n / 32)) : 0;
 
   // ---- static per-supernode tables ----
   P.col_ptr.assign(1, 0);
@@ -581,10 +683,11 @@ inline double plan_schedule_cost(const PatternPlan &P) {
 // Minimum degree minimises fill, nested dissection the depth of the tree; build both, keep the one
 // with the shorter schedule unless it costs much more fill.
 inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
-                              const std::vector<int> &src, const PlanOptions &opt, bool force_dense) {
-  PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, false);
+                              const std::vector<int> &src, const PlanOptions &opt, bool force_dense,
+                              const std::vector<double> *hint = nullptr) {
+  PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, false, hint);
   if (force_dense || md.ns == 0 || opt.ordering == 1) return md;
-  PatternPlan nd = build_plan_with(n, m, rows, cols, src, opt, force_dense, true);
+  PatternPlan nd = build_plan_with(n, m, rows, cols, src, opt, force_dense, true, hint);
   if (opt.ordering == 2) return nd;
   if (nd.ns == 0) return md;
   const bool fill_ok = (double)nd.nnz_l <= 2.5 * (double)md.nnz_l + 1000.0 && nd.nT <= md.nT + 64;

@@ -25,7 +25,7 @@ SIGNATURES = {
     "pp_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "pp_destroy": (C.c_int, [_vp]),
     "pp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
-    "pp_symbolic": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp]),
+    "pp_symbolic": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp]),
     "pp_numeric_local": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "pp_numeric_coupling": (C.c_int, [_vp, _vp, _vp]),
     "pp_inertia_local": (C.c_int, [_vp, _i64p]),

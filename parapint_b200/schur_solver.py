@@ -73,13 +73,17 @@ class CudaBackend:
             pass
 
     # -- buffers -----------------------------------------------------------------------------
-    def symbolic(self, st: structure.Structure):
+    def symbolic(self, st: structure.Structure, values_hint=None):
         torch = self.torch
         self.st = st
+        hint = None
+        if values_hint is not None and values_hint.size == st.nvals and np.any(values_hint):
+            hint = np.ascontiguousarray(values_hint, dtype=np.float64)
         code = self.lib.pp_symbolic(
             self.handle, st.n_local, native.np_ptr(st.block_n), native.np_ptr(st.border_ptr),
             native.np_ptr(st.border_rows), st.m_c, st.nvals, native.np_ptr(st.dest_front),
-            native.np_ptr(st.dest_row), native.np_ptr(st.dest_col))
+            native.np_ptr(st.dest_row), native.np_ptr(st.dest_col),
+            native.np_ptr(hint) if hint is not None else None)
         self._check(code, "pp_symbolic")
         mc = max(st.m_c, 1)
         with torch.cuda.device(self.device):
@@ -245,7 +249,9 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         st = structure.analyse(matrix, self.comm.rank, self.comm.size)
         self.block_dim = st.n_blocks + 1
         self.local_block_indices = list(st.local_blocks)
-        self.backend.symbolic(st)
+        hint = np.zeros(st.nvals)
+        structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
+        self.backend.symbolic(st, hint)
         self._st = st
         self._status = None
         timer.stop("sc_structure")
@@ -264,7 +270,9 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             # regularisation): analyse again, as mumps_interface.py:82-83 does.
             self.logger.debug("nonzero pattern changed; repeating the symbolic phase")
             st = structure.analyse(matrix, self.comm.rank, self.comm.size)
-            self.backend.symbolic(st)
+            hint = np.zeros(st.nvals)
+            structure.gather_values(matrix, st, hint)
+            self.backend.symbolic(st, hint)
             self._st = st
             if not structure.gather_values(matrix, st, self.backend.values):
                 raise RuntimeError("could not gather the matrix values after re-analysis")
