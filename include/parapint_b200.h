@@ -134,6 +134,24 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
 int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_c, int on_device,
                       double *x_local, double *x_c, void *stream);
 
+/*
+ * Iterative refinement (no reference counterpart: the reference relies on its leaves' accuracy; here one
+ * refinement step with the ORIGINAL values restores ||Kx-b||/||b|| <= 1e-10 on ill-conditioned late-IPM
+ * systems).  The handle remembers the device copies of the last factorised values, right-hand side and
+ * solution.
+ *   pp_residual_local : r_loc = b_loc - (K x)_loc on this rank's rows; buf_dev (DEVICE, m_c + 2 doubles) receives
+ *                       -sum_i A_i x_i (partial coupling rows) and the partial sums |r_loc|^2, |b_loc|^2.
+ *                       The caller SUM-reduces buf_dev across ranks (nothing to do on one rank).
+ *   pp_residual_norms : r_c = b_c - Q x_c + buf_sum[0:m_c]; out = { |r|^2, |b|^2 } of the whole system.
+ *   pp_refine_forward / pp_refine_backward : solve K d = r exactly like pp_solve_forward/backward (the caller
+ *                       all-reduces rc in between) and add d to the solution (device; copied out if on_device = 0).
+ */
+int pp_residual_local(pp_handle *h, double *buf_dev, void *stream);
+int pp_residual_norms(pp_handle *h, const double *buf_sum_dev, double out[2], void *stream);
+int pp_refine_forward(pp_handle *h, double *rc_local_dev, void *stream);
+int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, double *x_local, double *x_c,
+                       void *stream);
+
 /* Sizes and introspection. */
 int64_t pp_factor_bytes(const pp_handle *h);  /* device bytes held by factors + workspaces */
 int64_t pp_local_dim(const pp_handle *h);     /* sum of n_i over local blocks */

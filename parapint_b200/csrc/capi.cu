@@ -113,6 +113,15 @@ struct pp_handle {
   DevBuf<long long> vec_off, root_off;
   int64_t root_total = 0;
   int max_leaves = 0;             // most level-0 small fronts in any local block
+  // iterative refinement: K applied from the input values (row lists), last solve's device vectors
+  DevBuf<long long> rl_ptr, rl_src, rb_ptr, rb_src, rq_ptr, rq_src;
+  DevBuf<int> rl_col, rb_col, rq_col;
+  DevBuf<double> res_loc, res_c, res_part, res_out, dx_tmp, dxc_tmp, bc_keep;
+  int res_blocks = 0;
+  const double *last_vals = nullptr, *last_rhs = nullptr;
+  double *last_x = nullptr, *last_xc = nullptr;
+  bool solved = false;
+  PinBuf<double> pin_out2;
   // device storage
   DevBuf<double> arenaA, arenaW, arenaZ, vals, rhs, x, xc, crhs;
   DevBuf<int> arenaI, flag;
@@ -685,6 +694,58 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->src_front.upload(sfront);
   h->src_pos.upload(spos);
 
+  // ---- row lists of K for the residual (iterative refinement) ----
+  {
+    const int64_t ldim = h->local_dim;
+    std::vector<std::vector<std::pair<int, long long>>> rl((size_t)ldim), rb((size_t)m_c), rq((size_t)m_c);
+    std::vector<int64_t> boff(n_local + 1, 0);
+    for (int f = 0; f < n_local; ++f) boff[f + 1] = boff[f] + block_n[f];
+    for (int64_t k = 0; k < nvals; ++k) {
+      const int f = dest_front[k];
+      if (f < 0) continue;
+      const int r = dest_row[k], c = dest_col[k];
+      if (f == n_local) {
+        rq[(size_t)r].push_back({c, k});
+        if (r != c) rq[(size_t)c].push_back({r, k});
+      } else if (r < block_n[f]) {
+        const int64_t a = boff[f] + r, b = boff[f] + c;
+        rl[(size_t)a].push_back({(int)b, k});
+        if (a != b) rl[(size_t)b].push_back({(int)a, k});
+      } else {
+        const int g = border_rows[border_ptr[f] + (r - block_n[f])];
+        const int64_t b = boff[f] + c;
+        rl[(size_t)b].push_back({(int)(ldim + g), k});
+        rb[(size_t)g].push_back({(int)b, k});
+      }
+    }
+    auto flat = [](const std::vector<std::vector<std::pair<int, long long>>> &rows, DevBuf<long long> &ptr,
+                   DevBuf<int> &col, DevBuf<long long> &src) {
+      std::vector<long long> hp(rows.size() + 1, 0), hs;
+      std::vector<int> hc;
+      for (size_t i = 0; i < rows.size(); ++i) {
+        for (auto &e : rows[i]) { hc.push_back(e.first); hs.push_back(e.second); }
+        hp[i + 1] = (long long)hc.size();
+      }
+      if (hc.empty()) { hc.push_back(0); hs.push_back(0); }
+      ptr.upload(hp);
+      col.upload(hc);
+      src.upload(hs);
+    };
+    if (ldim + m_c > 0x7fffffffLL) return fail("pp_symbolic: local dimension exceeds 2^31");
+    flat(rl, h->rl_ptr, h->rl_col, h->rl_src);
+    flat(rb, h->rb_ptr, h->rb_col, h->rb_src);
+    flat(rq, h->rq_ptr, h->rq_col, h->rq_src);
+    h->res_blocks = (int)((ldim + 255) / 256);
+    h->res_loc.alloc((size_t)std::max<int64_t>(ldim, 1));
+    h->dx_tmp.alloc((size_t)std::max<int64_t>(ldim, 1));
+    h->res_c.alloc((size_t)std::max(m_c, 1));
+    h->dxc_tmp.alloc((size_t)std::max(m_c, 1));
+    h->bc_keep.alloc((size_t)std::max(m_c, 1));
+    h->res_part.alloc((size_t)2 * std::max(h->res_blocks, 1));
+    h->res_out.alloc(2);
+    h->solved = false;
+  }
+
   // ---- solve buffers ----
   std::vector<int64_t> zero_off(nfronts + 1, 0);
   h->rhs_off.upload(zero_off);
@@ -801,6 +862,8 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
       dvals = h->vals.p;
     }
+    h->last_vals = dvals;
+    h->solved = false;
     int sparse_bad = 0;
     int bad = numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad);
     if (sparse_bad && h->no_fallback) return fail("pp_numeric_local: sparse path overflow (fallback disabled)");
@@ -865,6 +928,77 @@ int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
   return read_inertia(h, 1, out);
 }
 
+static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, cudaStream_t st) {
+  if (h->n_local > 0) {
+    ProfSpan sp(h, PP_PROF_FORWARD, st);
+    if (h->max_leaves > 0) {
+      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
+      subtree_leaf_forward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+                                                             h->ywork.p);
+      h->launches++;
+    }
+    subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+                                                              h->ywork.p, h->root_rhs.p, h->root_off.p);
+    const size_t sm = std::max(solve_smem(h->nfmax_local), solve_smem(h->m_c));
+    CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
+                                                                                  h->root_off64.p);
+    h->launches += 2;
+  }
+  if (h->m_c > 0) {
+    rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
+                                                          h->m_c, rc_local_dev);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+}
+
+// x_c = S^-1 (drc + rc_sum) into dxc, then the backward sweeps into dx (all device pointers)
+static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *drc, double *dx, double *dxc,
+                         cudaStream_t st) {
+  const int mc = h->m_c;
+  const size_t smax = std::max(solve_smem(h->nfmax_local), solve_smem(mc));
+  CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+  CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+  if (mc > 0) {
+    vec_add_kernel<<<(mc + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, mc, h->crhs.p);
+    const size_t sm = solve_smem(mc);
+    const Front *cf = h->fronts.p + h->n_local;
+    front_forward_kernel<512><<<1, 512, sm, st>>>(cf, h->crhs.p, h->rhs_off.p + h->n_local);
+    front_backward_kernel<512><<<1, 512, sm, st>>>(cf, nullptr, h->brow_ptr.p + h->n_local, h->brow.p, dxc,
+                                                  h->rhs_off.p + h->n_local);
+    h->launches += 3;
+  }
+  if (h->n_local > 0) {
+    ProfSpan sp(h, PP_PROF_BACKWARD, st);
+    front_backward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(
+        h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, h->root_x.p, h->root_off64.p);
+    subtree_backward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+                                                               h->vec_off.p, h->root_x.p, h->root_off.p, dx);
+    if (h->max_leaves > 0) {
+      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
+      subtree_leaf_backward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+                                                              h->vec_off.p, dx);
+      h->launches++;
+    }
+    h->launches += 2;
+  }
+  CK(cudaGetLastError());
+}
+
+static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *x_local, double *x_c,
+                     cudaStream_t st) {
+  const int mc = h->m_c;
+  h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
+  if (h->local_dim > 0)
+    CK(cudaMemcpyAsync(h->pin_vec.p, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (mc > 0)
+    CK(cudaMemcpyAsync(h->pin_vec.p + h->local_dim, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (h->local_dim > 0) std::memcpy(x_local, h->pin_vec.p, (size_t)h->local_dim * sizeof(double));
+  if (mc > 0) std::memcpy(x_c, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double));
+}
+
 int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, double *rc_local_dev,
                      void *stream) {
   if (!h || !h->local_factored) return fail("pp_solve_forward: numeric factorization required first");
@@ -873,6 +1007,7 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    h->solved = false;
     const double *drhs = rhs_local;
     if (!on_device && h->local_dim > 0) {
       h->pin_vec.ensure((size_t)h->local_dim + (size_t)h->m_c);
@@ -880,27 +1015,8 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
       CK(cudaMemcpyAsync(h->rhs.p, h->pin_vec.p, (size_t)h->local_dim * sizeof(double), cudaMemcpyHostToDevice, st));
       drhs = h->rhs.p;
     }
-    if (h->n_local > 0) {
-      ProfSpan sp(h, PP_PROF_FORWARD, st);
-      if (h->max_leaves > 0) {
-        dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-        subtree_leaf_forward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
-                                                               h->ywork.p);
-        h->launches++;
-      }
-      subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
-                                                                h->ywork.p, h->root_rhs.p, h->root_off.p);
-      const size_t sm = solve_smem(h->nfmax_local);
-      CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      front_forward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, h->root_rhs.p, h->root_off64.p);
-      h->launches += 2;
-    }
-    if (h->m_c > 0) {
-      rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p,
-                                                            h->src_pos.p, h->m_c, rc_local_dev);
-      h->launches++;
-    }
-    CK(cudaGetLastError());
+    h->last_rhs = drhs;
+    run_forward(h, drhs, rc_local_dev, st);
     h->forward_done = true;
     return (int)PP_SUCCESSFUL;
   });
@@ -918,53 +1034,92 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
     const int mc = h->m_c;
     double *dx = on_device ? x_local : h->x.p;
     double *dxc = on_device ? x_c : h->xc.p;
-    if (mc > 0) {
-      const double *drc = rhs_c;
-      if (!on_device) {
+    if (mc > 0) {  // keep b_c on the device for the residual
+      if (on_device) {
+        CK(cudaMemcpyAsync(h->bc_keep.p, rhs_c, (size_t)mc * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      } else {
         h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
         std::memcpy(h->pin_vec.p + h->local_dim, rhs_c, (size_t)mc * sizeof(double));
-        CK(cudaMemcpyAsync(h->xc.p, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double), cudaMemcpyHostToDevice, st));
-        drc = h->xc.p;
+        CK(cudaMemcpyAsync(h->bc_keep.p, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double), cudaMemcpyHostToDevice, st));
       }
-      vec_add_kernel<<<(mc + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, mc, h->crhs.p);
-      const size_t sm = solve_smem(mc);
-      CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)std::max(sm, solve_smem(h->nfmax_local))));
-      CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)std::max(sm, solve_smem(h->nfmax_local))));
-      const Front *cf = h->fronts.p + h->n_local;
-      front_forward_kernel<512><<<1, 512, sm, st>>>(cf, h->crhs.p, h->rhs_off.p + h->n_local);
-      front_backward_kernel<512><<<1, 512, sm, st>>>(cf, nullptr, h->brow_ptr.p + h->n_local, h->brow.p, dxc,
-                                                    h->rhs_off.p + h->n_local);
-      h->launches += 3;
     }
-    if (h->n_local > 0) {
-      ProfSpan sp(h, PP_PROF_BACKWARD, st);
-      const size_t sm = solve_smem(h->nfmax_local);
-      CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)std::max(sm, solve_smem(mc))));
-      front_backward_kernel<512><<<h->n_local, 512, sm, st>>>(h->fronts.p, dxc, h->brow_ptr.p, h->brow.p,
-                                                             h->root_x.p, h->root_off64.p);
-      subtree_backward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
-                                                                 h->vec_off.p, h->root_x.p, h->root_off.p, dx);
-      if (h->max_leaves > 0) {
-        dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-        subtree_leaf_backward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
-                                                                h->vec_off.p, dx);
-        h->launches++;
-      }
-      h->launches += 2;
+    run_backward(h, rc_sum_dev, h->bc_keep.p, dx, dxc, st);
+    h->last_x = dx;
+    h->last_xc = dxc;
+    h->solved = true;
+    if (!on_device) copy_out(h, dx, dxc, x_local, x_c, st);
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
+  if (!h || !h->solved || !h->last_vals) return fail("pp_residual_local: a completed solve is required first");
+  if (!buf_dev) return fail("pp_residual_local: null buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->res_blocks > 0) {
+      residual_rows_kernel<<<h->res_blocks, 256, 0, st>>>(h->rl_ptr.p, h->rl_col.p, h->rl_src.p, h->last_vals, h->last_x,
+                                                         h->last_xc, h->local_dim, h->last_rhs, h->res_loc.p,
+                                                         h->res_part.p, h->local_dim);
+      h->launches++;
+    }
+    residual_border_kernel<<<std::max(1, (h->m_c + 127) / 128), 128, 0, st>>>(
+        h->rb_ptr.p, h->rb_col.p, h->rb_src.p, h->last_vals, h->last_x, h->m_c, h->res_part.p, h->res_blocks, buf_dev);
+    h->launches++;
+    CK(cudaGetLastError());
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_residual_norms(pp_handle *h, const double *buf_sum_dev, double out[2], void *stream) {
+  if (!h || !h->solved) return fail("pp_residual_norms: a completed solve is required first");
+  if (!buf_sum_dev || !out) return fail("pp_residual_norms: null argument");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    residual_coupling_kernel<<<1, 256, 0, st>>>(h->rq_ptr.p, h->rq_col.p, h->rq_src.p, h->last_vals, h->last_xc,
+                                               h->bc_keep.p, buf_sum_dev, h->m_c, h->res_c.p, h->res_out.p);
+    h->launches++;
+    h->pin_out2.ensure(2);
+    CK(cudaMemcpyAsync(h->pin_out2.p, h->res_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out[0] = h->pin_out2.p[0];
+    out[1] = h->pin_out2.p[1];
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_refine_forward(pp_handle *h, double *rc_local_dev, void *stream) {
+  if (!h || !h->solved) return fail("pp_refine_forward: a completed solve and pp_residual_norms are required first");
+  if (h->m_c > 0 && !rc_local_dev) return fail("pp_refine_forward: null coupling buffer");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    run_forward(h, h->res_loc.p, rc_local_dev, (cudaStream_t)stream);
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, double *x_local, double *x_c,
+                       void *stream) {
+  if (!h || !h->solved) return fail("pp_refine_backward: a completed solve is required first");
+  if (h->m_c > 0 && !rc_sum_dev) return fail("pp_refine_backward: null coupling argument");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    run_backward(h, rc_sum_dev, h->res_c.p, h->dx_tmp.p, h->dxc_tmp.p, st);
+    if (h->local_dim > 0) {
+      axpy1_kernel<<<(unsigned)((h->local_dim + 255) / 256), 256, 0, st>>>(h->last_x, h->dx_tmp.p, h->local_dim);
+      h->launches++;
+    }
+    if (h->m_c > 0) {
+      axpy1_kernel<<<(h->m_c + 255) / 256, 256, 0, st>>>(h->last_xc, h->dxc_tmp.p, h->m_c);
+      h->launches++;
     }
     CK(cudaGetLastError());
     if (!on_device) {
-      h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
-      if (h->local_dim > 0)
-        CK(cudaMemcpyAsync(h->pin_vec.p, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
-      if (mc > 0)
-        CK(cudaMemcpyAsync(h->pin_vec.p + h->local_dim, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (h->local_dim > 0) std::memcpy(x_local, h->pin_vec.p, (size_t)h->local_dim * sizeof(double));
-      if (mc > 0) std::memcpy(x_c, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double));
+      if ((h->local_dim > 0 && !x_local) || (h->m_c > 0 && !x_c)) return fail("pp_refine_backward: null output");
+      copy_out(h, h->last_x, h->last_xc, x_local, x_c, st);
     }
     return (int)PP_SUCCESSFUL;
   });

@@ -111,6 +111,87 @@ __global__ void vec_add_kernel(const double *__restrict__ a, const double *__res
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// ---- residual r = b - K x for iterative refinement ---------------------------------------------
+// K is applied from the ORIGINAL input values through row-wise lists (col, source) built at symbolic time;
+// every sum runs in list order, block reductions are trees: the result is reproducible.
+// Columns < ldim index the local solution, the others the coupling solution.
+__global__ void residual_rows_kernel(const long long *__restrict__ ptr, const int *__restrict__ col,
+                                     const long long *__restrict__ src, const double *__restrict__ vals,
+                                     const double *__restrict__ x, const double *__restrict__ xc, long long ldim,
+                                     const double *__restrict__ b, double *__restrict__ r,
+                                     double *__restrict__ part, long long nrows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double ri = 0.0, bi = 0.0;
+  if (i < nrows) {
+    double s = 0.0;
+    for (long long p = ptr[i]; p < ptr[i + 1]; ++p) {
+      const int c = col[p];
+      s += vals[src[p]] * (c < ldim ? x[c] : xc[c - ldim]);
+    }
+    bi = b[i];
+    ri = bi - s;
+    r[i] = ri;
+  }
+  __shared__ double s1[256], s2[256];
+  s1[threadIdx.x] = ri * ri;
+  s2[threadIdx.x] = bi * bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = s1[0]; part[2 * blockIdx.x + 1] = s2[0]; }
+}
+
+// buf[g] = -(sum over local borders A x)(g) for g < m_c;  buf[m_c], buf[m_c+1] = sums of the row partials
+__global__ void residual_border_kernel(const long long *__restrict__ ptr, const int *__restrict__ col,
+                                       const long long *__restrict__ src, const double *__restrict__ vals,
+                                       const double *__restrict__ x, int m_c, const double *__restrict__ part,
+                                       int nparts, double *__restrict__ buf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < m_c) {
+    double s = 0.0;
+    for (long long p = ptr[g]; p < ptr[g + 1]; ++p) s += vals[src[p]] * x[col[p]];
+    buf[g] = -s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2) {
+    double s = 0.0;
+    for (int k = 0; k < nparts; ++k) s += part[2 * k + threadIdx.x];
+    buf[m_c + threadIdx.x] = s;
+  }
+}
+
+// r_c = b_c - Q x_c + bufsum[0:m_c]   (one block);  out2 = {bufsum[m_c] + |r_c|^2, bufsum[m_c+1] + |b_c|^2}
+__global__ void residual_coupling_kernel(const long long *__restrict__ ptr, const int *__restrict__ col,
+                                         const long long *__restrict__ src, const double *__restrict__ vals,
+                                         const double *__restrict__ xc, const double *__restrict__ bc,
+                                         const double *__restrict__ bufsum, int m_c, double *__restrict__ rc,
+                                         double *__restrict__ out2) {
+  __shared__ double s1[256], s2[256];
+  double a1 = 0.0, a2 = 0.0;
+  for (int g = threadIdx.x; g < m_c; g += blockDim.x) {
+    double s = 0.0;
+    for (long long p = ptr[g]; p < ptr[g + 1]; ++p) s += vals[src[p]] * xc[col[p]];
+    const double r = bc[g] - s + bufsum[g];
+    rc[g] = r;
+    a1 += r * r;
+    a2 += bc[g] * bc[g];
+  }
+  s1[threadIdx.x] = a1;
+  s2[threadIdx.x] = a2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = bufsum[m_c] + s1[0]; out2[1] = bufsum[m_c + 1] + s2[0]; }
+}
+
+__global__ void axpy1_kernel(double *__restrict__ x, const double *__restrict__ d, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] += d[i];
+}
+
 // ---- triangular solves ----------------------------------------------------------------------
 constexpr int SB = 32;         // columns per sweep block
 constexpr int SPITCH = SB + 1;

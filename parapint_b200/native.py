@@ -32,6 +32,10 @@ SIGNATURES = {
     "pp_inertia_coupling": (C.c_int, [_vp, _i64p]),
     "pp_solve_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "pp_solve_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "pp_residual_local": (C.c_int, [_vp, _vp, _vp]),
+    "pp_residual_norms": (C.c_int, [_vp, _vp, _f64p, _vp]),
+    "pp_refine_forward": (C.c_int, [_vp, _vp, _vp]),
+    "pp_refine_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),
     "pp_kernel_launches": (C.c_int64, [_vp]),

@@ -98,6 +98,56 @@ class FakeBackend:
             self.x_pin.numpy()[st.rhs_offsets[f]:st.rhs_offsets[f + 1]] = np.linalg.solve(self.K[f], r - corr)
         return self.x_pin.numpy(), self.xc_pin.numpy()
 
+    # -- iterative refinement --------------------------------------------------------------
+    def _matvec_parts(self):
+        st = self.st
+        x, xc = self.x_pin.numpy(), self.xc_pin.numpy()[: st.m_c]
+        b = self.rhs_pin.numpy()
+        r = np.zeros(max(st.local_dim, 1))
+        part = np.zeros(st.m_c)
+        for f in range(st.n_local):
+            sl = slice(st.rhs_offsets[f], st.rhs_offsets[f + 1])
+            r[sl] = b[sl] - self.K[f] @ x[sl]
+            if self.rows[f].size:
+                r[sl] -= self.A[f].T @ xc[self.rows[f]]
+                part[self.rows[f]] -= self.A[f] @ x[sl]
+        return r, part
+
+    def residual_local(self):
+        st = self.st
+        r, part = self._matvec_parts()
+        self.r_loc = r
+        b = self.rhs_pin.numpy()[: st.local_dim]
+        self.resbuf = torch.from_numpy(np.concatenate([part, [float(r[: st.local_dim] @ r[: st.local_dim]), float(b @ b)]]))
+        return self.resbuf
+
+    def residual_norms(self, buf_sum):
+        st = self.st
+        buf = buf_sum.numpy()
+        bc, xc = self.rhsc_pin.numpy()[: st.m_c], self.xc_pin.numpy()[: st.m_c]
+        self.r_c = bc - self.Q @ xc + buf[: st.m_c]
+        return float(buf[st.m_c] + self.r_c @ self.r_c), float(buf[st.m_c + 1] + bc @ bc)
+
+    def refine_forward(self):
+        st = self.st
+        rc = np.zeros(st.m_c)
+        for f in range(st.n_local):
+            y = np.linalg.solve(self.K[f], self.r_loc[st.rhs_offsets[f]:st.rhs_offsets[f + 1]])
+            if self.rows[f].size:
+                rc[self.rows[f]] -= self.A[f] @ y
+        self.rc[: st.m_c] = torch.from_numpy(rc)
+        return self.rc
+
+    def refine_backward(self, rc_sum, on_device=False):
+        st = self.st
+        dc = np.linalg.solve(self.S, self.r_c + rc_sum.numpy()[: st.m_c]) if st.m_c else np.zeros(0)
+        self.xc_pin.numpy()[: st.m_c] += dc
+        for f in range(st.n_local):
+            sl = slice(st.rhs_offsets[f], st.rhs_offsets[f + 1])
+            corr = self.A[f].T @ dc[self.rows[f]] if self.rows[f].size else 0.0
+            self.x_pin.numpy()[sl] += np.linalg.solve(self.K[f], self.r_loc[sl] - corr)
+        return self.x_pin.numpy(), self.xc_pin.numpy()
+
     def int_tensor(self, values):
         t = self.ints[: len(values)]
         t.copy_(torch.tensor(list(values), dtype=torch.int64))

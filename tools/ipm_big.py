@@ -28,6 +28,8 @@ for rep in range(3):
 print([ (s.backend.plan_stats(b)["delayed_to_root"], s.backend.plan_stats(b)["fell_back_dense"]) for b in range(min(nb, 4))])
 print({k: (round(v["ms"] / 3, 3), v["launches"] // 3) for k, v in s.backend.profile().items()})
 K = sym_full(kkt); b = rhs.flatten()
-print("rel residual", np.linalg.norm(K @ x.flatten() - b) / np.linalg.norm(b))
+print("rel residual", np.linalg.norm(K @ x.flatten() - b) / np.linalg.norm(b), "device estimate", s.last_residual, "refine steps", s.refine_steps)
+s.max_refine = 0; x0 = s.do_back_solve(rhs)
+print("rel residual without refinement", np.linalg.norm(K @ x0.flatten() - b) / np.linalg.norm(b))
 n_prim = nb * (n_x + n_in) + n_fs
 print("expected inertia if convex", (n_prim, sum(sizes) - n_prim, 0))
