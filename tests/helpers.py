@@ -46,7 +46,7 @@ def random_bordered(rng, n_blocks, n, m_c, density=0.05, border_nnz_rows=None, d
     return kkt
 
 
-def ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, barrier_span=(1e-4, 1e4), hess_shift=1.0):
+def ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, barrier_span=(1e-4, 1e4), hess_shift=1.0, pattern_rng=None):
     """Parapint-shaped primal-dual KKT of one scenario ("family P"):
     order [x, s, lam_eq, lam_in, lam_link]  (interfaces/interface.py:475-489 wrapped with the linking rows of
     interfaces/schur_complement/sc_ip_interface.py:1248-1266).  Returns (K sparse symmetric, n)."""
@@ -61,8 +61,12 @@ def ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, barrier_span=(1e-4, 1e4), hess_shi
     # full row rank by construction: the identity parts of L, J_eq and J_in sit on disjoint primal columns
     J_eq = (sp.eye(n_eq, n_x, k=n_fs) + sp.diags([rng.standard_normal(n_eq) * 0.5], [n_fs + 1], shape=(n_eq, n_x))
             + sp.diags([rng.standard_normal(n_eq) * 0.3], [n_fs - 1], shape=(n_eq, n_x))).tocsr()
-    J_in = (sp.random(n_in, n_x, density=2.0 / n_x, random_state=rng, data_rvs=rng.standard_normal) * 0.3
-            + sp.eye(n_in, n_x, k=n_x - n_in)).tocsr()
+    if pattern_rng is None:
+        R = sp.random(n_in, n_x, density=2.0 / n_x, random_state=rng, data_rvs=rng.standard_normal)
+    else:  # every scenario of one model shares the sparsity pattern; only the data differ
+        R = sp.random(n_in, n_x, density=2.0 / n_x, random_state=pattern_rng).tocoo()
+        R = sp.coo_matrix((rng.standard_normal(R.nnz), (R.row, R.col)), shape=R.shape)
+    J_in = (R * 0.3 + sp.eye(n_in, n_x, k=n_x - n_in)).tocsr()
     L = sp.eye(n_fs, n_x).tocsr()  # linking rows select the first n_fs primals
     Z = lambda a, b: sp.csr_matrix((a, b))
     I_in = sp.identity(n_in, format="csr")
@@ -76,13 +80,15 @@ def ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, barrier_span=(1e-4, 1e4), hess_shi
     return K, n_x + n_in + n_eq + n_in + n_fs
 
 
-def stochastic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_fs, **kw):
+def stochastic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_fs, same_pattern=False, **kw):
     """Block-bordered KKT of a two-stage stochastic NLP: border = [0 | -I] on the linking multipliers
     (sc_ip_interface.py:1275-1280), Q = 0 (:1282-1284)."""
     kkt = BlockMatrix(n_blocks + 1, n_blocks + 1)
     sizes = []
     for i in range(n_blocks):
         rng = np.random.default_rng(1000 * seed + i)
+        if same_pattern:
+            kw["pattern_rng"] = np.random.default_rng(77 + seed)
         K, n = ipm_kkt_block(rng, n_x, n_eq, n_in, n_fs, **kw)
         sizes.append(n)
         kkt.set_block(i, i, K)

@@ -191,3 +191,29 @@ def test_large_dense_fronts(cluster):
     assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
     assert _rel_residual(kkt, x, rhs) <= 1e-10
     assert s.get_inertia() == dense_inertia(dense, "ldl")
+
+
+def test_iterative_refinement():
+    """The device residual b - K x (computed from the values that were factorised) agrees with numpy's, and
+    refinement steps with a deliberately sloppy factorization (tiny pivot threshold => large element growth)
+    bring the residual back under the bar."""
+    from tests.helpers import stochastic_ipm_system
+    kkt, sizes = stochastic_ipm_system(5, 3, 400, 300, 40, 12)
+    rng = np.random.default_rng(5)
+    rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
+    s = B200SchurComplementLinearSolver(options={"pivot_threshold": 1e-9}, max_refine=0)
+    s.do_symbolic_factorization(kkt)
+    s.do_numeric_factorization(kkt)
+    raw = _rel_residual(kkt, s.do_back_solve(rhs), rhs)
+    assert s.refine_steps == 0 and s.last_residual is None
+    s.max_refine = 4
+    x = s.do_back_solve(rhs)
+    fin = _rel_residual(kkt, x, rhs)
+    assert fin <= 1e-10 and fin <= 2 * raw
+    assert s.last_residual is not None and 0.3 * fin <= s.last_residual <= 3 * fin + 1e-16
+    if raw > s.refine_tol:
+        assert s.refine_steps >= 1
+    # accurate factorization: the check costs no correction solve
+    s2, x2 = _solve(kkt, rhs)
+    assert s2.refine_steps == 0 and s2.last_residual <= s2.refine_tol
+    assert np.linalg.norm(x2.flatten() - x.flatten()) / np.linalg.norm(x2.flatten()) <= 1e-8
