@@ -50,7 +50,10 @@ int pp_destroy(pp_handle *h);
 /* Tunables: "pivot_tol" (absolute zero-pivot tolerance), "panel_width" (dense panel, <= 64),
  * "sparse" (0/1: multifrontal subtree path), "pivot_threshold" (u of the threshold test in subtree
  * fronts, default 0.01), "ordering" (0 auto, 1 minimum degree, 2 nested dissection), "nd_leaf",
- * "sparse_fmax", "sparse_dmax", "sparse_dslot", "sparse_min_n", "no_fallback", "profile". */
+ * "sparse_fmax", "sparse_dmax", "sparse_dslot", "sparse_min_n", "pair_weak" (0/1: 2x2 pivot pre-selection from
+ * the values hint), "cluster_panel" (0/1: thread-block-cluster panel kernel for tall fronts), "small_front"
+ * (0/1: whole-front shared-memory factorisation when every front of a batch has <= 164 rows), "no_fallback",
+ * "profile". */
 int pp_set_option(pp_handle *h, const char *name, double value);
 
 /*
@@ -156,6 +159,16 @@ int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, do
 int64_t pp_factor_bytes(const pp_handle *h);  /* device bytes held by factors + workspaces */
 int64_t pp_local_dim(const pp_handle *h);     /* sum of n_i over local blocks */
 int64_t pp_kernel_launches(const pp_handle *h); /* kernels launched by this handle so far */
+
+/*
+ * Host-side helper (no CUDA): copy `nseg` byte segments between scattered host arrays and one staging buffer
+ * (normally the pinned buffer handed to pp_numeric_local / pp_solve_forward) with up to `threads` worker threads.
+ * Segment k is len[k] bytes at ptr[k] <-> staging + off[k]; to_staging = 1 gathers, 0 scatters.  Replaces the
+ * per-block Python copies the reference does when it hands each K_i to its leaf (explicit_schur_complement.py:
+ * 96-101) -- here all blocks go to the device in one transfer.
+ */
+int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, void *staging,
+                 int to_staging, int threads);
 
 /*
  * Per-kernel-class device timing (measurement aid; enabled with pp_set_option(h, "profile", 1)).

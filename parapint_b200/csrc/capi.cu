@@ -16,7 +16,9 @@
 #include "front.cuh"
 #include "solve.cuh"
 #include "sparse.cuh"
+#include "small.cuh"
 #include "symbolic.hpp"
+#include "hostcopy.hpp"
 #include <map>
 
 using namespace ppb;
@@ -94,6 +96,7 @@ struct pp_handle {
   bool use_sparse = true;
   bool no_fallback = false;
   bool use_cluster = true;
+  bool use_small = true;          // whole-front shared-memory factorisation when every front of a batch fits
   bool sparse_failed = false;     // a block overflowed its delayed-pivot capacity: all blocks were redone dense
   PlanOptions plan_opt;
   // saved symbolic inputs (for the dense re-analysis after a sparse-path overflow)
@@ -219,6 +222,13 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
     nfmax = std::max(nfmax, h->nf[f]);
   }
   if (nmax == 0) return;
+  if (h->use_small && nfmax <= SM_CAP) {  // nf = static n + m bounds the active rows of every front
+    ProfSpan sp(h, PP_PROF_PANEL, st);
+    front_small_kernel<<<count, SF_NT, SM_SMEM, st>>>(fr, h->pivot_threshold, h->pivot_tol);
+    h->launches++;
+    CK(cudaGetLastError());
+    return;
+  }
   const bool small = nfmax <= 384;  // short columns: four warps per front keep the block reductions cheap
   // tall fronts: a cluster of CTAs per front, as many as fill the GPU once (8 is the portable maximum)
   int csize = 1;
@@ -327,6 +337,7 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaSetDevice(device));
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
+    CK(cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM));
     CK(cudaFuncSetAttribute(subtree_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
     CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
     CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
@@ -362,6 +373,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->panel_width = nb;
   } else if (key == "sparse") {
     h->use_sparse = value != 0.0;
+  } else if (key == "small_front") {
+    h->use_small = value != 0.0;
   } else if (key == "pivot_threshold") {
     if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
@@ -1128,6 +1141,20 @@ int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, do
 int64_t pp_factor_bytes(const pp_handle *h) { return h ? h->bytes : 0; }
 int64_t pp_local_dim(const pp_handle *h) { return h ? h->local_dim : 0; }
 int64_t pp_kernel_launches(const pp_handle *h) { return h ? h->launches : 0; }
+
+int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, void *staging,
+                 int to_staging, int threads) {
+  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len || !staging))) return fail("pp_host_copy: null argument");
+  for (int64_t k = 0; k < nseg; ++k)
+    if (len[k] < 0 || off[k] < 0 || (len[k] > 0 && !ptr[k])) return fail("pp_host_copy: bad segment");
+  try {
+    CopyPool::instance().run(nseg, ptr, off, len, static_cast<char *>(staging), to_staging != 0, threads);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return PP_ERROR;
+  }
+  return PP_SUCCESSFUL;
+}
 
 int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
   if (!h) return fail("pp_profile: null handle");

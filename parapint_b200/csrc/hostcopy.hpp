@@ -1,0 +1,153 @@
+// Host-side gather / scatter of many small arrays into / out of one staging buffer with a few worker threads.
+// The plugin's inputs are ~2 leaves per block (COO value arrays of K_i and A_i, right-hand-side blocks) scattered
+// over the Python heap; copying them one by one from Python costs more than the GPU spends factorising them.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <cstdlib>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace ppb {
+
+// Copy into the pinned staging buffer with non-temporal stores: the next reader is the GPU's DMA engine, and
+// lines left dirty in several cores' caches make that read slower than the whole factorisation step.
+inline void stream_copy(char *dst, const char *src, size_t n) {
+#if defined(__x86_64__)
+  static const bool nt = [] {
+    const char *e = std::getenv("PARAPINT_B200_NT_STORES");
+    return !(e && e[0] == '0');
+  }();
+  if (nt && n >= 256 && ((reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src)) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    while ((reinterpret_cast<uintptr_t>(dst) & 15) && n >= 8) {
+      std::memcpy(dst, src, 8);
+      dst += 8; src += 8; n -= 8;
+    }
+    size_t blocks = n / 64;
+    for (size_t b = 0; b < blocks; ++b) {
+      const __m128i a0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src));
+      const __m128i a1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 16));
+      const __m128i a2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 32));
+      const __m128i a3 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 48));
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst), a0);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 16), a1);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 32), a2);
+      _mm_stream_si128(reinterpret_cast<__m128i *>(dst + 48), a3);
+      src += 64; dst += 64;
+    }
+    n -= blocks * 64;
+    if (n) std::memcpy(dst, src, n);
+    _mm_sfence();
+    return;
+  }
+#endif
+  std::memcpy(dst, src, n);
+}
+
+class CopyPool {
+ public:
+  static CopyPool &instance() {
+    static CopyPool p;
+    return p;
+  }
+  // segs[k]: `len[k]` bytes at `ptr[k]` <-> staging offset `off[k]`; to_staging selects the direction
+  void run(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, char *staging, bool to_staging,
+           int threads) {
+    int64_t total = 0;
+    for (int64_t k = 0; k < nseg; ++k) total += len[k];
+    int T = (int)std::min<int64_t>(std::max(threads, 1), 1 + total / (256 << 10));  // >= 256 KB per thread
+    T = std::min(T, kMax);
+    if (T <= 1) {
+      copy_range(nseg, ptr, off, len, staging, to_staging, 0, total);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(api_);
+    ensure_workers(T - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = {nseg, ptr, off, len, staging, to_staging, total, T};
+      pending_ = T - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    copy_range(nseg, ptr, off, len, staging, to_staging, 0, total / T);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  static constexpr int kMax = 8;
+  struct Job {
+    int64_t nseg;
+    void *const *ptr;
+    const int64_t *off, *len;
+    char *staging;
+    bool to_staging;
+    int64_t total;
+    int T;
+  };
+  // copy the part of the concatenated byte stream [b0, b1) (segments in order)
+  static void copy_range(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, char *staging,
+                         bool to_staging, int64_t b0, int64_t b1) {
+    int64_t pos = 0;
+    for (int64_t k = 0; k < nseg && pos < b1; ++k) {
+      const int64_t lo = std::max(pos, b0), hi = std::min(pos + len[k], b1);
+      if (lo < hi) {
+        char *user = static_cast<char *>(ptr[k]) + (lo - pos);
+        char *st = staging + off[k] + (lo - pos);
+        if (to_staging) stream_copy(st, user, (size_t)(hi - lo));
+        else std::memcpy(user, st, (size_t)(hi - lo));
+      }
+      pos += len[k];
+    }
+  }
+  void ensure_workers(int n) {
+    while ((int)workers_.size() < n) {
+      const int id = (int)workers_.size() + 1;
+      workers_.emplace_back([this, id] { loop(id); });
+    }
+  }
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && id < job_.T); });
+        if (stop_) return;
+        seen = gen_;
+        j = job_;
+      }
+      copy_range(j.nseg, j.ptr, j.off, j.len, j.staging, j.to_staging, j.total * id / j.T, j.total * (id + 1) / j.T);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  CopyPool() = default;
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  std::mutex api_, mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  Job job_{};
+  uint64_t gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+}  // namespace ppb

@@ -70,18 +70,34 @@ __global__ void schur_gather_kernel(const Front *__restrict__ fronts, const int6
   const int c = blockIdx.y;
   if (r >= m_c || r < c) return;
   double s = 0.0;
-  for (int64_t p = src_ptr[r]; p < src_ptr[r + 1]; ++p) {
-    const int f = src_front[p], a = src_pos[p];
-    const int32_t *br = brow + brow_ptr[f];
-    int lo = 0, hi = a;  // c <= r  =>  position of c, if present, is <= a
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (br[mid] < c) lo = mid + 1; else hi = mid;
-    }
-    if (br[lo] == c) {
+  const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
+  // four sources in flight: the loads are independent, only the additions keep their order
+  for (int64_t pb = p0; pb < p1; pb += 4) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = 0.0;
+      const int64_t p = pb + q;
+      if (p >= p1) continue;
+      const int f = src_front[p], a = src_pos[p];
       const Front F = fronts[f];
-      s += F.A[(size_t)(F.nb + a) + (size_t)(F.nb + lo) * F.ld];
+      int lo = c;
+      if (F.m != m_c) {  // partial border: locate c among the front's border rows (c <= r => position <= a)
+        const int32_t *br = brow + brow_ptr[f];
+        int hi = a;
+        lo = 0;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (br[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (br[lo] != c) continue;
+      }
+      v[q] = F.A[(size_t)(F.nb + a) + (size_t)(F.nb + lo) * F.ld];
     }
+    s += v[0];
+    s += v[1];
+    s += v[2];
+    s += v[3];
   }
   S[(size_t)r + (size_t)c * m_c] = s;
   S[(size_t)c + (size_t)r * m_c] = s;

@@ -179,7 +179,8 @@ __device__ __forceinline__ void front_swap(const FrontBuf &B, int S, int a, int 
 // Partial factorisation of the S x S front; the first fs rows are fully summed.  Returns the number
 // of eliminated columns; inertia counts go to cnt[3] (shared, atomics on integers).
 template <int G>
-__device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double pivtol, int *cnt) {
+__device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double pivtol, int *cnt, int ntest = -1) {
+  if (ntest < 0) ntest = S;  // rows that take part in the threshold tests (a dense root excludes its border rows)
   const int tid = gtid<G>(), lane = tid & 31, gw = tid >> 5;
   constexpr int NW = G / 32;
   double *F = B.F;
@@ -193,11 +194,11 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       int kind = 0, pc = -1, pr = -1;
       for (int c = t; c < fs; ++c) {
         unsigned kmax = 0u, kbest = 0u;
-        for (int i = t + lane; i < S; i += 32) {
+        for (int i = t + lane; i < ntest; i += 32) {
           if (i == c) continue;
           const unsigned hi = (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu;
           kmax = max(kmax, hi);
-          if (i < fs) kbest = max(kbest, (hi & 0xffffff80u) | (unsigned)(127 - i));
+          if (i < fs) kbest = max(kbest, (hi & 0xffffff00u) | (unsigned)(255 - i));
         }
         kmax = __reduce_max_sync(0xffffffffu, kmax);
         kbest = __reduce_max_sync(0xffffffffu, kbest);
@@ -205,11 +206,11 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
         const double dcc = F[c + c * ld];
         if (fabs(dcc) > pivtol && fabs(dcc) >= u * cmax) { kind = 1; pc = c; break; }
         if (kbest != 0u) {
-          const int r = 127 - (int)(kbest & 127u);
+          const int r = 255 - (int)(kbest & 255u);  // fronts have at most 256 rows
           const double b = fent(F, ld, r, c);
           if (fabs(b) > pivtol) {
             unsigned kc = 0u, kr = 0u;
-            for (int i = t + lane; i < S; i += 32) {
+            for (int i = t + lane; i < ntest; i += 32) {
               if (i == c || i == r) continue;
               kc = max(kc, (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu);
               kr = max(kr, (unsigned)__double2hiint(fent(F, ld, i, r)) & 0x7fffffffu);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "pp_residual_norms": (C.c_int, [_vp, _vp, _f64p, _vp]),
     "pp_refine_forward": (C.c_int, [_vp, _vp, _vp]),
     "pp_refine_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),
     "pp_kernel_launches": (C.c_int64, [_vp]),
@@ -87,6 +88,49 @@ PLAN_ARRAYS = ("rootcols", "col_ptr", "cols", "row_ptr", "rows", "rel", "parent"
                "child_idx", "root_children", "tiny_ptr", "tiny_idx", "med_ptr", "med_idx", "big_ptr", "big_idx", "ent_ptr",
                "tgt_row", "tgt_col", "tgt_src_ptr", "tgt_src", "root_row", "root_col", "root_src")
 PLAN_SCALARS = ("n", "m", "nT", "DR", "ns", "nnz_l", "max_front", "l_total", "stack_cap", "nlevels")
+
+
+class HostCopier:
+    """Multi-threaded gather / scatter between many numpy arrays and one staging buffer (``pp_host_copy``).
+
+    The pointer table is cached while the caller keeps handing in the *same* array objects (the usual case:
+    an interior-point loop updates the KKT values in place); strong references are held so ids cannot be reused."""
+
+    def __init__(self, threads=None):
+        import os
+        self.lib = load()
+        self.threads = int(threads) if threads else max(1, min(8, (os.cpu_count() or 2) // 2))
+        self._keep = None
+        self._tables = None
+
+    def _table(self, arrays, offsets):
+        import numpy as np
+        keep = self._keep
+        if keep is not None and len(keep) == len(arrays) and all(a is b for a, b in zip(arrays, keep)):
+            return self._tables
+        for a in arrays:
+            if a.dtype != np.float64 or not a.flags.c_contiguous:
+                return None
+        ptr = np.array([a.__array_interface__["data"][0] for a in arrays], dtype=np.uintp)
+        off = np.asarray(offsets, dtype=np.int64) * 8
+        ln = np.array([a.size * 8 for a in arrays], dtype=np.int64)
+        self._keep = list(arrays)
+        self._tables = (ptr, off, ln, np_ptr(ptr), np_ptr(off), np_ptr(ln))
+        return self._tables
+
+    def copy(self, arrays, offsets, staging, to_staging=True):
+        """``arrays[k]`` (float64, contiguous) <-> ``staging[offsets[k] : offsets[k] + arrays[k].size]``.
+        Returns False when an array does not qualify (the caller falls back to numpy slicing)."""
+        if not arrays:
+            return True
+        t = self._table(arrays, offsets)
+        if t is None:
+            return False
+        code = self.lib.pp_host_copy(len(arrays), t[3], t[4], t[5], staging.ctypes.data, 1 if to_staging else 0,
+                                     self.threads)
+        if code != 0:
+            raise RuntimeError(f"pp_host_copy failed: {last_error()}")
+        return True
 
 
 def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1, ordering=0):

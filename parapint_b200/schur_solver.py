@@ -14,6 +14,7 @@ no CPU fallback: constructing the solver without the built library or without a 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import logging
 from typing import Optional
 
@@ -235,6 +236,9 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.max_refine = int(max_refine)
         self.last_residual = None
         self.refine_steps = 0
+        self._copiers = [None, None]
+        env = os.environ.get("PARAPINT_B200_HOST_THREADS")   # 0 disables the threaded host gather
+        self.host_threads = int(env) if env not in (None, "") else None
         self.schur_complement_solver = schur_complement_solver
         self.comm = comm if comm is not None else Communicator()
         self.backend = backend if backend is not None else CudaBackend(device, options)
@@ -296,7 +300,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         timer = timer or _NullTimer()
         self.block_matrix = matrix
         timer.start("form SC")
-        if not structure.gather_values(matrix, self._st, self.backend.values):
+        if not structure.gather_values(matrix, self._st, self.backend.values, self._copier(0)):
             # COO pattern / ordering changed since the symbolic phase (happens after the first
             # regularisation): analyse again, as mumps_interface.py:82-83 does.
             self.logger.debug("nonzero pattern changed; repeating the symbolic phase")
@@ -305,7 +309,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             structure.gather_values(matrix, st, hint)
             self.backend.symbolic(st, hint)
             self._st = st
-            if not structure.gather_values(matrix, st, self.backend.values):
+            if not structure.gather_values(matrix, st, self.backend.values, self._copier(0)):
                 raise RuntimeError("could not gather the matrix values after re-analysis")
         timer.start("factorize")
         code, schur_local = self.backend.numeric_local()
@@ -342,7 +346,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         timer = timer or _NullTimer()
         timer.start("back_solve")
         st = self._st
-        structure.pack_rhs(rhs, st, self.backend.rhs_pin.numpy())
+        structure.pack_rhs(rhs, st, self.backend.rhs_pin.numpy(), self._copier(1))
         self.backend.rhsc_pin.numpy()[: st.m_c] = structure.coupling_rhs(rhs, st)
         rc = self.backend.solve_forward()
         self.comm.allreduce_sum_(rc)
@@ -351,6 +355,14 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         out = structure.unpack_solution(rhs, st, x_local, x_c[: st.m_c])
         timer.stop("back_solve")
         return out
+
+    def _copier(self, which):
+        """Threaded host gather for the CUDA backend (values: slot 0, right-hand side: slot 1)."""
+        if not isinstance(self.backend, CudaBackend) or self.host_threads == 0:
+            return None
+        if self._copiers[which] is None:
+            self._copiers[which] = native.HostCopier(self.host_threads)
+        return self._copiers[which]
 
     def _refine(self, x_local, x_c):
         """Iterative refinement with the values that were factorised: while ||b - K x|| > refine_tol ||b||,

@@ -51,6 +51,13 @@ class Structure:
         return len(self.local_blocks)
 
     @property
+    def segment_starts(self):
+        starts = self.__dict__.get("_segment_starts")
+        if starts is None:
+            starts = self.__dict__["_segment_starts"] = [seg[2] for seg in self.segments]
+        return starts
+
+    @property
     def local_dim(self):
         return int(self.rhs_offsets[-1])
 
@@ -146,17 +153,31 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         segments=segments, patterns=patterns, rhs_offsets=offs)
 
 
-def gather_values(matrix, st: Structure, out: np.ndarray) -> bool:
+def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
     """Copy the numeric values of ``matrix`` into ``out`` in the order fixed by :func:`analyse`.
 
     Returns False when a block's COO pattern differs from the analysed one (the caller then
-    re-runs the symbolic phase, as ``mumps_interface.py:82-83`` does)."""
+    re-runs the symbolic phase, as ``mumps_interface.py:82-83`` does).  ``copier`` (a
+    ``native.HostCopier``) moves the leaves with a few threads instead of one numpy slice assignment each."""
     N = st.n_blocks
     get = matrix.get_block
-    for (kind, i, lo, hi), (prow, pcol) in zip(st.segments, st.patterns):
+    datas = [] if copier is not None else None
+    seen = st.__dict__.setdefault("_leaf_seen", [None] * len(st.segments))
+    for k, ((kind, i, lo, hi), (prow, pcol)) in enumerate(zip(st.segments, st.patterns)):
         blk = get(i, i) if kind != "A" else get(N, i)
         if blk is None:
             return False
+        # fastest path: the very leaf object validated last time, index tuple untouched (values updated in place)
+        last = seen[k]
+        if last is not None and last[0] is blk and getattr(blk, "coords", None) is last[1]:
+            data = blk.data
+            if data.size != hi - lo:
+                return False
+            if datas is None:
+                out[lo:hi] = data
+            else:
+                datas.append(data)
+            continue
         # fast path: a COO leaf that still carries the analysed index arrays (values updated in place)
         if getattr(blk, "format", None) == "coo" and blk.row is prow and blk.col is pcol:
             data = blk.data
@@ -167,11 +188,25 @@ def gather_values(matrix, st: Structure, out: np.ndarray) -> bool:
             data = c.data
         if data.size != hi - lo:
             return False
-        out[lo:hi] = data
+        coords = getattr(blk, "coords", None)
+        seen[k] = (blk, coords) if coords is not None and getattr(blk, "format", None) == "coo" \
+            and blk.row is prow and blk.col is pcol else None
+        if datas is None:
+            out[lo:hi] = data
+        else:
+            datas.append(data)
+    if datas is not None and not copier.copy(datas, st.segment_starts, out):
+        for (kind, i, lo, hi), data in zip(st.segments, datas):
+            out[lo:hi] = data
     return True
 
 
-def pack_rhs(rhs, st: Structure, out: np.ndarray):
+def pack_rhs(rhs, st: Structure, out: np.ndarray, copier=None):
+    if copier is not None:
+        blocks = [rhs.get_block(i) for i in st.local_blocks]
+        if all(type(b) is np.ndarray and b.ndim == 1 and b.size == st.rhs_offsets[f + 1] - st.rhs_offsets[f]
+               for f, b in enumerate(blocks)) and copier.copy(blocks, st.rhs_offsets[:-1], out):
+            return
     for f, i in enumerate(st.local_blocks):
         blk = rhs.get_block(i)
         flat = blk.flatten() if hasattr(blk, "nblocks") else np.asarray(blk, dtype=np.float64).ravel()

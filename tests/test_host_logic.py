@@ -231,3 +231,37 @@ def test_host_logic_generator_vs_oracle():
     o.symbolic(kkt); o.numeric(kkt)
     assert np.allclose(s.do_back_solve(rhs).flatten(), o.solve(rhs).flatten(), rtol=1e-9, atol=1e-9)
     assert s.get_inertia() == m.expected_inertia()
+
+
+def test_host_copier_matches_numpy():
+    """pp_host_copy (threaded gather / scatter used to stage the KKT values and the right-hand side) is a pure
+    host function: same bytes as numpy slice assignment, pointer table refreshed when the arrays change."""
+    from parapint_b200 import native, structure
+    from oracle.kkt_generator import EstimationModel
+    rng = np.random.default_rng(0)
+    arrays = [rng.standard_normal(int(k)) for k in rng.integers(0, 70000, size=40)]
+    offs = np.concatenate(([0], np.cumsum([a.size for a in arrays])))
+    for threads in (1, 3, 8):
+        cp = native.HostCopier(threads)
+        out = np.full(offs[-1], np.nan)
+        assert cp.copy(arrays, offs[:-1], out)
+        assert np.array_equal(out, np.concatenate(arrays))
+        back = [np.zeros_like(a) for a in arrays]
+        assert cp.copy(back, offs[:-1], out, to_staging=False)
+        assert all(np.array_equal(a, b) for a, b in zip(arrays, back))
+        arrays2 = [a * 2 for a in arrays]                       # new objects: the cached table must not be reused
+        assert cp.copy(arrays2, offs[:-1], out) and np.array_equal(out, 2 * np.concatenate(arrays))
+    assert not native.HostCopier(2).copy([np.zeros((4, 4))[:, 0]], [0], np.zeros(4))   # strided: caller falls back
+    m = EstimationModel(4, 20, 2, 5)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    st = structure.analyse(kkt, 0, 1)
+    a, b = np.zeros(st.nvals), np.zeros(st.nvals)
+    cp = native.HostCopier(4)
+    for _ in range(2):                                          # second pass takes the validated-leaf fast path
+        assert structure.gather_values(kkt, st, a) and structure.gather_values(kkt, st, b, cp)
+        assert np.array_equal(a, b)
+        kkt.get_block(1, 1).data[:] *= 1.5
+    ra, rb = np.zeros(st.local_dim), np.zeros(st.local_dim)
+    structure.pack_rhs(rhs, st, ra)
+    structure.pack_rhs(rhs, st, rb, native.HostCopier(4))
+    assert np.array_equal(ra, rb)
