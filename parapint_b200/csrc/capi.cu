@@ -1142,6 +1142,16 @@ int64_t pp_factor_bytes(const pp_handle *h) { return h ? h->bytes : 0; }
 int64_t pp_local_dim(const pp_handle *h) { return h ? h->local_dim : 0; }
 int64_t pp_kernel_launches(const pp_handle *h) { return h ? h->launches : 0; }
 
+#ifdef PP_TRACE
+extern "C" int pp_debug_trace_reset() {
+  int z = 0;
+  return cudaMemcpyToSymbol(ppb::g_tp, &z, sizeof(int)) == cudaSuccess ? 0 : 3;
+}
+extern "C" int pp_debug_trace(long long *out, int n) {
+  return cudaMemcpyFromSymbol(out, ppb::g_trace, sizeof(long long) * (size_t)std::min(n, 2048)) == cudaSuccess ? 0 : 3;
+}
+#endif
+
 int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, void *staging,
                  int to_staging, int threads) {
   if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len || !staging))) return fail("pp_host_copy: null argument");

@@ -14,6 +14,18 @@
 
 namespace ppb {
 
+#ifdef PP_TRACE
+// debugging aid (tools/trace_levels.py): cycle stamps of block 0, thread 0
+__device__ long long g_trace[2048];
+#define PP_TR(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (slot) < 2048) g_trace[(slot)] = clock64(); } while (0)
+__device__ int g_tp;
+// phase stamps inside process_front / forward_front (group 0 of block 0 only): (cycles << 4) | phase
+#define PP_TRP(ph) do { if (G == 128 && blockIdx.x == 0 && threadIdx.x == 0) { const int q_ = g_tp++; if (q_ < 760) g_trace[256 + q_] = (clock64() << 4) | (ph); } } while (0)
+#else
+#define PP_TR(slot) do { } while (0)
+#define PP_TRP(ph) do { } while (0)
+#endif
+
 // Static description of one supernode, fetched with a single 80-byte load.
 struct __align__(16) SnHead {
   int c0, nc, r0, ncb;            // own columns: cols[c0..c0+nc); contribution rows: rows[r0..r0+ncb)
@@ -289,6 +301,62 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
   return t;
 }
 
+// Offsets of a front's children in the staging area, computed by the first warp of the group: ndo[k] becomes the
+// exclusive prefix of the delayed-column counts, cnt[k] the exclusive prefix of the staged-entry counts
+// (cnt[nch] = total); children with a negative count are listed in big[] (index order).  Returns through
+// sh[4] = delayed columns in, sh[5] = number of big children, sh[7] = 1 if the staged entries exceed the
+// capacity (the caller then falls back to a serial first-fit pass).
+__device__ __forceinline__ void stage_prefix_warp(const Stage &stg, int nch, int *sh) {
+  const int lane = threadIdx.x & 31;
+  int offd = 0, ent = 0, nbig = 0;
+  for (int base = 0; base < nch; base += 32) {
+    const int k = base + lane;
+    const bool valid = k < nch;
+    const int d = valid ? stg.ndo[k] : 0, e = valid ? stg.cnt[k] : 0;
+    const bool isbig = valid && e < 0;
+    const int ep = e > 0 ? e : 0;
+    int ds = d, es = ep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t0 = __shfl_up_sync(0xffffffffu, ds, o), t1 = __shfl_up_sync(0xffffffffu, es, o);
+      if (lane >= o) { ds += t0; es += t1; }
+    }
+    const unsigned bm = __ballot_sync(0xffffffffu, isbig);
+    if (valid) { stg.ndo[k] = offd + ds - d; stg.cnt[k] = ent + es - ep; }
+    if (isbig) stg.big[nbig + __popc(bm & ((1u << lane) - 1u))] = k;
+    offd += __shfl_sync(0xffffffffu, ds, 31);
+    ent += __shfl_sync(0xffffffffu, es, 31);
+    nbig += __popc(bm);
+  }
+  if (lane == 0) { stg.cnt[nch] = ent; sh[4] = offd; sh[5] = nbig; sh[7] = ent > stg.cap ? 1 : 0; }
+}
+
+// dst[tgt[e]] += val[e] for e = 0..total-1 IN THAT ORDER, 32 entries per step on one warp: lanes that hit the same
+// target are found with match.any and their values are added in lane (= staged = child) order by every member of
+// the group; the lowest lane stores.  Same rounding as a serial walk, ~5x fewer dependent shared-memory round trips
+// when the children are tiny (a hub front of the generator family has 85 children of 6 entries each).
+__device__ __forceinline__ void apply_staged_warp(double *dst, const int *tgt, const double *val, int total) {
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < total; base += 32) {
+    const int e = base + lane;
+    const bool on = e < total;
+    const int t = on ? tgt[e] : -1 - lane;  // distinct dummies for idle lanes
+    const double v = on ? val[e] : 0.0;
+    const unsigned m = __match_any_sync(0xffffffffu, t);
+    const int mx = __reduce_max_sync(0xffffffffu, __popc(m));
+    double acc = on ? dst[t] : 0.0;
+    unsigned rest = m;
+    for (int it = 0; it < mx; ++it) {
+      const int src = rest ? __ffs(rest) - 1 : lane;
+      const double x = __shfl_sync(0xffffffffu, v, src);
+      if (rest) acc += x;
+      rest &= rest - 1;
+    }
+    if (on && lane == __ffs(m) - 1) dst[t] = acc;
+    __syncwarp();
+  }
+}
+
 enum { PF_OK = 0, PF_DEFER = 1, PF_FAIL = 2 };
 
 // Assemble, factor and store supernode s with group G.  PF_DEFER: the front (with its delayed
@@ -297,6 +365,7 @@ template <int G>
 __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const double *__restrict__ vals, int s,
                              const FrontBuf &B, double u, double pivtol, int *cnt, const Stage &stg) {
   const int tid = gtid<G>();
+  PP_TRP(0);
   const SnHead H = P.heads[s];
   const int nc = H.nc, ncb = H.ncb;
   const bool staged = G != 32 && H.nch >= 4 && H.nch <= stg.maxch;
@@ -310,24 +379,31 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       stg.cnt[k] = dim <= SF_CHDIM ? dim * (dim + 1) / 2 : -1;
     }
     gsync<G>();
-    if (tid == 0) {
-      int off = 0, ent = 0, nbig = 0;
-      for (int k = 0; k < H.nch; ++k) {
-        const int d = stg.ndo[k], e = stg.cnt[k];
-        stg.ndo[k] = off;
-        off += d;
-        if (e < 0 || ent + e > stg.cap) { stg.big[nbig++] = k; stg.cnt[k] = ent; }  // handled one by one
-        else { stg.cnt[k] = ent; ent += e; }
-        if (k + 1 == H.nch) stg.cnt[k + 1] = ent;
-      }
-      B.sh[4] = off;
-      B.sh[5] = nbig;
-    }
+    if (tid < 32) stage_prefix_warp(stg, H.nch, B.sh);
     gsync<G>();
+    if (B.sh[7]) {  // staging area too small for all of them (rare): serial first-fit from the source counts
+      if (tid == 0) {
+        int off = 0, ent = 0, nbig = 0;
+        for (int k = 0; k < H.nch; ++k) {
+          const int c = P.child_idx[H.ch0 + k];
+          const int dim = Bk.meta[3 * c + 1] - Bk.meta[3 * c];
+          const int e = dim <= SF_CHDIM ? dim * (dim + 1) / 2 : -1;
+          stg.ndo[k] = off;
+          off += Bk.meta[3 * c + 2];
+          if (e < 0 || ent + e > stg.cap) { stg.big[nbig++] = k; stg.cnt[k] = ent; }  // handled one by one
+          else { stg.cnt[k] = ent; ent += e; }
+          if (k + 1 == H.nch) stg.cnt[k + 1] = ent;
+        }
+        B.sh[4] = off;
+        B.sh[5] = nbig;
+      }
+      gsync<G>();
+    }
     nd_in = B.sh[4];
   } else {
     for (int k = 0; k < H.nch; ++k) nd_in += Bk.meta[3 * P.child_idx[H.ch0 + k] + 2];
   }
+  PP_TRP(1);
   const int fs = nc + nd_in, S = fs + ncb;
   if (S > B.cap) {
     if (G == SF_NT && tid == 0) { Bk.info[3] = 1; Bk.info[4] = s; Bk.info[5] = S; }
@@ -345,6 +421,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   for (int i = tid; i < ncb; i += G) B.fid[fs + i] = P.rows[H.r0 + i];
   for (int i = tid; i < fs; i += G) B.opos[i] = i;
   gsync<G>();
+  PP_TRP(2);
   // original entries: unique targets, sources summed in input order
   for (int e = tid; e < H.nent; e += G) {
     const int2 t = P.tgt[H.ent0 + e];
@@ -360,6 +437,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     F[r + ((t.x >> 8) & 255) * ld] = v;
   }
   gsync<G>();
+  PP_TRP(3);
   // children: fixed order (staged small ones in index order, then the others in index order)
   if (staged) {
     const int nbig = B.sh[5];
@@ -395,28 +473,13 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
           }
     }
     gsync<G>();
+    PP_TRP(4);
     {
       const int total = stg.cnt[H.nch];
-      if (S * (S + 1) / 2 <= G) {
-        // one thread per target entry sums its matches in staged (= child) order: parallel and reproducible
-        int a = 0, b = 0, left = tid;
-        while (b < S && left >= S - b) { left -= S - b; ++b; }
-        a = b + left;
-        if (b < S) {
-          const int mine = a + b * ld;
-          double acc = F[mine];
-          for (int e = 0; e < total; ++e)
-            if (stg.tgt[e] == mine) acc += stg.val[e];
-          F[mine] = acc;
-        }
-      } else if (tid < 32) {
-        for (int k = 0; k < H.nch; ++k) {
-          for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) F[stg.tgt[e]] += stg.val[e];
-          __syncwarp();
-        }
-      }
+      if (tid < 32) apply_staged_warp(F, stg.tgt, stg.val, total);
     }
     gsync<G>();
+    PP_TRP(5);
     for (int q = 0; q < nbig; ++q) {
       const int k = stg.big[q];
       const int c = P.child_idx[H.ch0 + k];
@@ -460,6 +523,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       off += ndo;
     }
   }
+  PP_TRP(6);
   int ne;
   if (G == SF_NT && S <= 48) {
     // small front assembled by the whole CTA: the pivot loop runs on four warps with a named barrier
@@ -473,6 +537,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   } else {
     ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
   }
+  PP_TRP(7);
   const int ndo = fs - ne, dim = S - ne;
   if (ndo > H.dslot) {
     if (tid == 0) {
@@ -495,6 +560,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     for (int i = j + tid; i < dim; i += G) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
   if (tid == 0) { Bk.meta[3 * s] = ne; Bk.meta[3 * s + 1] = S; Bk.meta[3 * s + 2] = ndo; }
   gsync<G>();
+  PP_TRP(8);
   return PF_OK;
 }
 
@@ -552,6 +618,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
   __syncthreads();
 
   for (int l = 0; l < P.nlevels; ++l) {
+    PP_TR(4 * l);
     // ---- small fronts: one warp each, all warps concurrently (the leaves were done by
     //      subtree_leaf_kernel, spread over the whole GPU) ----
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
@@ -565,6 +632,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
       }
     }
     __syncthreads();
+    PP_TR(4 * l + 1);
     // ---- medium fronts (up to 32 rows, any number of children): four warps each, four at a time ----
     for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
       const int s = P.med_idx[k];
@@ -577,6 +645,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
       }
     }
     __syncthreads();
+    PP_TR(4 * l + 2);
     // ---- larger fronts (and smaller ones that grew through delayed pivots): whole CTA, one by one ----
     const int ndef = min(cnt[4], 64);
     for (int k = 0; k < ndef; ++k) {
@@ -595,6 +664,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     }
     if (tid == 0) cnt[4] = 0;
     __syncthreads();
+    PP_TR(4 * l + 3);
     if (cnt[3]) break;
   }
   // ---- children of the root: add their contribution blocks into the dense root front ----
@@ -635,6 +705,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     Bk.info[0] = failed ? 1 : 0;
     Bk.info[1] = ndroot;
     Bk.info[2] = 0;  // leaf-failure flag consumed
+    PP_TR(4 * P.nlevels);
     fronts[Bk.root].n = P.nT + ndroot;  // pivot candidates of the dense root: static columns + delayed ones
     atomicAdd(&inertia[0], (unsigned long long)cnt[0]);
     atomicAdd(&inertia[1], (unsigned long long)cnt[1]);
@@ -708,17 +779,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
       stg.cnt[k] = Bk.meta[3 * c + 1] - Bk.meta[3 * c];
     }
     gsync<G>();
-    if (tid == 0) {
-      int off = 0, ent = 0;
-      for (int k = 0; k < H.nch; ++k) {
-        const int d = stg.ndo[k], e = stg.cnt[k];
-        stg.ndo[k] = off;
-        off += d;
-        stg.cnt[k] = ent;
-        ent += e;
-      }
-      stg.cnt[H.nch] = ent;
-    }
+    if (tid < 32) stage_prefix_warp(stg, H.nch, stg.big);  // no big children here: big[] doubles as scratch
     gsync<G>();
     const int total = stg.cnt[H.nch];
     if (total <= stg.cap) {
@@ -737,12 +798,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
         }
       }
       gsync<G>();
-      if (tid < 32) {
-        for (int k = 0; k < H.nch; ++k) {
-          for (int e = stg.cnt[k] + tid; e < stg.cnt[k + 1]; e += 32) B.v[stg.tgt[e]] += stg.val[e];
-          __syncwarp();
-        }
-      }
+      if (tid < 32) apply_staged_warp(B.v, stg.tgt, stg.val, total);
       gsync<G>();
     } else {
       for (int k = 0; k < H.nch; ++k) {
@@ -862,16 +918,19 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
   const double *r = rhs + vec_off[blockIdx.x];
   double *y = ywork + vec_off[blockIdx.x];
   for (int l = 0; l < P.nlevels; ++l) {
+    PP_TR(1024 + 4 * l);
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_TBUF) forward_front<32>(Bk, P, s, mine, r, y, mstg);
     }
     __syncthreads();
+    PP_TR(1024 + 4 * l + 1);
     for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
       const int s = P.med_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_MBUF) forward_front<128>(Bk, P, s, med, r, y, mstg);
     }
     __syncthreads();
+    PP_TR(1024 + 4 * l + 2);
     for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {  // fronts that outgrew their group
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] > SF_TBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
@@ -885,6 +944,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
       __syncthreads();
     }
     __syncthreads();
+    PP_TR(1024 + 4 * l + 3);
   }
   // root right-hand side: own entries + contributions of the root's children (fixed order)
   double *rr = root_rhs + root_off[blockIdx.x];
