@@ -116,6 +116,7 @@ struct pp_handle {
   DevBuf<long long> vec_off, root_off;
   int64_t root_total = 0;
   int max_leaves = 0;             // most level-0 small fronts in any local block
+  int leaf_cap = SF_TBUF;         // largest level-0 front (rows) over the local plans
   // iterative refinement: K applied from the input values (row lists), last solve's device vectors
   DevBuf<long long> rl_ptr, rl_src, rb_ptr, rb_src, rq_ptr, rq_src;
   DevBuf<int> rl_col, rb_col, rq_col;
@@ -649,6 +650,13 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     const PatternPlan &P = h->plans[h->block_plan[f]];
     if (P.nlevels > 0) h->max_leaves = std::max(h->max_leaves, P.tiny_ptr[1] - P.tiny_ptr[0]);
   }
+  h->leaf_cap = 4;
+  for (const PatternPlan &P : h->plans)
+    for (int k = P.nlevels > 0 ? P.tiny_ptr[0] : 0; P.nlevels > 0 && k < P.tiny_ptr[1]; ++k) {
+      const int s = P.tiny_idx[k];
+      h->leaf_cap = std::max(h->leaf_cap, (P.col_ptr[s + 1] - P.col_ptr[s]) + (P.row_ptr[s + 1] - P.row_ptr[s]));
+    }
+  h->leaf_cap = std::min(SF_TBUF, (h->leaf_cap + 3) & ~3);
   h->arenaL.alloc(std::max<size_t>(totL, 1));
   h->arenaStack.alloc(std::max<size_t>(totS, 1));
   h->arenaBI.alloc(std::max<size_t>(totBI, 1));
@@ -824,8 +832,9 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
     ProfSpan sp(h, PP_PROF_SUBTREE, st);
     if (h->max_leaves > 0) {
       dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      subtree_leaf_kernel<<<g, LF_NT, LF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold,
-                                                     h->pivot_tol, h->inertia.p);
+      const size_t lsm = LF_NW * align16(fb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      subtree_leaf_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold,
+                                                     h->pivot_tol, h->inertia.p, h->leaf_cap);
       h->launches++;
     }
     subtree_factor_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->fronts.p, dvals,
@@ -946,8 +955,9 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
     ProfSpan sp(h, PP_PROF_FORWARD, st);
     if (h->max_leaves > 0) {
       dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      subtree_leaf_forward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
-                                                             h->ywork.p);
+      const size_t lsm = LF_NW * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      subtree_leaf_forward_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
+                                                         h->ywork.p, h->leaf_cap);
       h->launches++;
     }
     subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
@@ -990,8 +1000,9 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
                                                                h->vec_off.p, h->root_x.p, h->root_off.p, dx);
     if (h->max_leaves > 0) {
       dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      subtree_leaf_backward_kernel<<<g, LF_NT, LS_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
-                                                              h->vec_off.p, dx);
+      const size_t lsm = LF_NW * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      subtree_leaf_backward_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
+                                                          h->vec_off.p, dx, h->leaf_cap);
       h->launches++;
     }
     h->launches += 2;

@@ -199,6 +199,32 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
   const int ld = B.ld;
   int t = 0;
   while (t < fs) {
+    {
+      // Fast path, decided redundantly (and identically) by every warp, so nothing has to be published: the
+      // diagonal of the leading column passes the threshold test as it is -- the first candidate the general
+      // search below would accept.  One barrier per eliminated column instead of four.
+      unsigned kmax = 0u;
+      for (int i = t + 1 + lane; i < ntest; i += 32)
+        kmax = max(kmax, (unsigned)__double2hiint(F[i + t * ld]) & 0x7fffffffu);
+      kmax = __reduce_max_sync(0xffffffffu, kmax);
+      const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
+      const double d = F[t + t * ld];
+      if (fabs(d) > pivtol && fabs(d) >= u * cmax) {
+        const double rd = 1.0 / d;
+        for (int j = t + 1 + gw; j < S; j += NW) {
+          const double wj = F[j + t * ld] * rd;
+          for (int i = j + lane; i < S; i += 32) F[i + j * ld] -= F[i + t * ld] * wj;
+        }
+        if (tid == 0) {
+          B.bsz[t] = 1;
+          atomicAdd(&cnt[d > 0.0 ? 0 : (d < 0.0 ? 1 : 2)], 1);
+        }
+        gsync<G>();
+        for (int i = t + 1 + tid; i < S; i += G) F[i + t * ld] *= rd;  // nobody reads column t any more
+        t += 1;
+        continue;
+      }
+    }
     if (gw == 0) {
       // Pivot search.  Column maxima only feed threshold tests, so they are reduced on the high 32
       // bits of |value| (monotone, one redux.sync each) and widened to an upper bound; the partner
@@ -241,6 +267,13 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
         }
       }
       if (lane == 0) { B.sh[0] = kind; B.sh[1] = pc; B.sh[2] = pr; }
+#ifdef PP_TRACE
+      if (G == 128 && blockIdx.x == 0 && threadIdx.x == 0) {
+        g_trace[2040 + kind] += 1;              // steps by kind (0 = no pivot, 1, 2)
+        g_trace[2043] += (pc >= 0 ? (kind == 2 ? min(pc, pr) : pc) - t + 1 : fs - t);  // candidates examined (approx.)
+        g_trace[2044] = clock64();
+      }
+#endif
     }
     gsync<G>();
     const int kind = B.sh[0];
@@ -415,8 +448,10 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   }
   double *F = B.F;
   const int ld = B.ld;
-  for (int j = 0; j < S; ++j)
-    for (int i = j + tid; i < S; i += G) F[i + j * ld] = 0.0;
+  constexpr int NWG = G / 32;  // columns dealt over the warps of the group, rows over the lanes
+  const int gwp = tid >> 5, lanep = tid & 31;
+  for (int j = gwp; j < S; j += NWG)
+    for (int i = j + lanep; i < S; i += 32) F[i + j * ld] = 0.0;
   for (int i = tid; i < nc; i += G) B.fid[i] = P.cols[H.c0 + i];
   for (int i = tid; i < ncb; i += G) B.fid[fs + i] = P.rows[H.r0 + i];
   for (int i = tid; i < fs; i += G) B.opos[i] = i;
@@ -494,9 +529,9 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
         else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
       }
       gsync<G>();
-      for (int j = 0; j < dim; ++j) {
+      for (int j = gwp; j < dim; j += NWG) {
         const int mj = B.map[j];
-        for (int i = j + tid; i < dim; i += G) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        for (int i = j + lanep; i < dim; i += 32) fent(F, ld, B.map[i], mj) += M[i + j * dim];
       }
       gsync<G>();
     }
@@ -515,9 +550,9 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
         else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
       }
       gsync<G>();
-      for (int j = 0; j < dim; ++j) {
+      for (int j = gwp; j < dim; j += NWG) {
         const int mj = B.map[j];
-        for (int i = j + tid; i < dim; i += G) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        for (int i = j + lanep; i < dim; i += 32) fent(F, ld, B.map[i], mj) += M[i + j * dim];
       }
       gsync<G>();
       off += ndo;
@@ -548,16 +583,16 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   }
   const int caprows = nc + H.dcap + ncb;
   double *Ls = Bk.L + H.l_off;
-  for (int j = 0; j < ne; ++j)
-    for (int i = j + tid; i < S; i += G) Ls[i + (long long)j * caprows] = F[i + j * ld];
+  for (int j = gwp; j < ne; j += NWG)
+    for (int i = j + lanep; i < S; i += 32) Ls[i + (long long)j * caprows] = F[i + j * ld];
   for (int i = tid; i < S; i += G) Bk.fid[H.fid_off + i] = B.fid[i];
   for (int i = tid; i < fs; i += G) {
     Bk.opos[H.fs_off + i] = B.opos[i];
     if (i < ne) Bk.pbz[H.fs_off + i] = B.bsz[i];
   }
   double *M = Bk.cb + H.cb_off;
-  for (int j = 0; j < dim; ++j)
-    for (int i = j + tid; i < dim; i += G) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
+  for (int j = gwp; j < dim; j += NWG)
+    for (int i = j + lanep; i < dim; i += 32) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
   if (tid == 0) { Bk.meta[3 * s] = ne; Bk.meta[3 * s + 1] = S; Bk.meta[3 * s + 2] = ndo; }
   gsync<G>();
   PP_TRP(8);
@@ -572,7 +607,9 @@ constexpr size_t LF_SMEM = LF_NW * SF_TINY_BYTES + 16;
 __global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *__restrict__ blocks,
                                                              const PlanDev *__restrict__ plans,
                                                              const double *__restrict__ vals, double u, double pivtol,
-                                                             unsigned long long *inertia) {
+                                                             unsigned long long *inertia, int cap) {
+  // cap = largest leaf front of any plan (leaves have no children, so their size is static): small per-warp
+  // buffers keep 64 warps resident per SM, which is what hides the chain of dependent loads of each leaf
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ int cnt[4];
   const SparseBlock Bk = blocks[blockIdx.y];
@@ -585,7 +622,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *
   __syncthreads();
   const int k = blockIdx.x * LF_NW + warp;
   if (k < nleaf) {
-    const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
+    const FrontBuf mine = carve(sm_raw + (size_t)warp * align16(fb_bytes(cap, cap | 1)), cap, cap | 1);
     Stage none;
     none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0; none.cap = 0; none.maxch = 0;
     const int rc = process_front<32>(Bk, P, vals, P.tiny_idx[P.tiny_ptr[0] + k], mine, u, pivtol, cnt, none);
@@ -750,8 +787,8 @@ __device__ void load_front(const SparseBlock &Bk, const SnHead &H, const SolveBu
   const int tid = gtid<G>();
   const int caprows = H.nc + H.dcap + H.ncb;
   const double *Lg = Bk.L + H.l_off;
-  for (int j = 0; j < ne; ++j)
-    for (int i = j + tid; i < S; i += G) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
+  for (int j = tid >> 5; j < ne; j += G / 32)
+    for (int i = j + (tid & 31); i < S; i += 32) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
   for (int i = tid; i < S; i += G) B.fid[i] = Bk.fid[H.fid_off + i];
   for (int i = tid; i < ne; i += G) B.bsz[i] = Bk.pbz[H.fs_off + i];
 }
@@ -1020,7 +1057,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const Spars
                                                                      const PlanDev *__restrict__ plans,
                                                                      const double *__restrict__ rhs,
                                                                      const long long *__restrict__ vec_off,
-                                                                     double *__restrict__ ywork) {
+                                                                     double *__restrict__ ywork, int cap) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.y];
   const PlanDev P = plans[Bk.plan];
@@ -1028,7 +1065,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const Spars
   if (P.nlevels == 0) return;
   const int k = blockIdx.x * LF_NW + warp;
   if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
-  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
   Stage none;
   none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0;
   forward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, rhs + vec_off[blockIdx.y], ywork + vec_off[blockIdx.y], none);
@@ -1038,7 +1075,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const Spar
                                                                       const PlanDev *__restrict__ plans,
                                                                       const double *__restrict__ ywork,
                                                                       const long long *__restrict__ vec_off,
-                                                                      double *__restrict__ xout) {
+                                                                      double *__restrict__ xout, int cap) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.y];
   const PlanDev P = plans[Bk.plan];
@@ -1046,7 +1083,7 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const Spar
   if (P.nlevels == 0) return;
   const int k = blockIdx.x * LF_NW + warp;
   if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
-  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
   backward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, ywork + vec_off[blockIdx.y], xout + vec_off[blockIdx.y]);
 }
 

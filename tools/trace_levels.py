@@ -42,3 +42,5 @@ for v in ph[:200]:
     if p == 0: print("  ---")
     if prev is not None and p != 0: print(f"    {names[p]:18s} {(cyc - prev) / mhz:7.2f}")
     prev = cyc
+
+print("factor_front<128> on block 0 / group 0 over 3 factorizations: no-pivot, 1x1, 2x2 steps:", t[2040:2043], "candidate columns examined:", t[2043])
