@@ -121,6 +121,49 @@ def ncu_traffic(kernel):
         return None
 
 
+def wide_border_leg(dev):
+    """Config-5 slice (BASELINE.json configs[4] is 128 x 20,000 x 2,000; 8 of its blocks here): the regime where the
+    work is the dense root fronts (2,082 pivots + 2,000 border rows each) and the FP64 tensor-core update kernel is
+    the dominant one -- reported next to the headline so that both rooflines of the path are on the line."""
+    import torch
+    from oracle.kkt_generator import EstimationModel
+    from parapint_b200 import B200SchurComplementLinearSolver
+    nb, nq, ym, nth = 8, 2000, 4, 2000
+    m = EstimationModel(nb, nq, ym, nth)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s = B200SchurComplementLinearSolver(options={"profile": 1})
+    t0 = time.perf_counter()
+    s.do_symbolic_factorization(kkt)
+    sym_s = time.perf_counter() - t0
+    reps, times = 4, []
+    for r in range(reps):
+        torch.cuda.synchronize(dev)
+        if r == 1:
+            s.backend.profile()
+        t0 = time.perf_counter()
+        s.do_numeric_factorization(kkt)
+        inertia = s.get_inertia()
+        x = s.do_back_solve(rhs)
+        torch.cuda.synchronize(dev)
+        times.append((time.perf_counter() - t0) * 1e3)
+    prof = s.backend.profile()
+    stats = s.backend.plan_stats(0)
+    per = {k: v["ms"] / (reps - 1) for k, v in prof.items()}
+    root_n = stats["root_cols"] + stats["delayed_to_root"]
+    flops_front, launches = update_flops(root_n, nth, 64)
+    peak64, src = fp64_peak()
+    ach = flops_front * nb / (per["update"] * 1e-3) / 1e12
+    ok = tuple(inertia) == tuple(m.expected_inertia())
+    del s
+    torch.cuda.empty_cache()
+    return {"workload": f"Model({nb},{nq},{ym},{nth}): {nb} blocks x {m.block_dim} rows, {nth} coupling vars (config-5 slice)",
+            "e2e_ms": float(np.median(times[1:])), "symbolic_s": sym_s, "kernels_ms_per_step": per,
+            "roofline": {"kernel": "front_update_kernel", "bound": "tensor", "achieved": ach, "peak": peak64,
+                         "unit": "TFLOP/s", "frac": ach / peak64, "peak_source": src,
+                         "algorithmic_flops_per_step": flops_front * nb, "launches_per_step": launches},
+            "check": {"inertia_matches_closed_form": bool(ok), "max_err": float(m.check_result(x))}}
+
+
 def build_model(n_gpus, rank):
     from oracle.kkt_generator import EstimationModel  # generator = input synthesis only
     n_blocks = BLOCKS_PER_GPU * n_gpus
@@ -175,6 +218,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the wide-border (config-5 slice) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -377,6 +421,10 @@ def main():
                                 "sample": f"full workload, median of {reps} runs of the serial reference algorithm "
                                           "(oracle port of SchurComplementLinearSolver + ScipyInterface/SuperLU leaves)"}
         line["check"]["rel_diff_vs_cpu_reference"] = rel
+    if not args.no_secondary and world == 1:
+        del solver, be
+        torch.cuda.empty_cache()
+        line["secondary"] = wide_border_leg(dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -339,9 +339,6 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
     CK(cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM));
-    CK(cudaFuncSetAttribute(subtree_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
-    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
-    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM));
     CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
     CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
     auto *h = new pp_handle();
@@ -831,10 +828,13 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_SUBTREE, st);
     if (h->max_leaves > 0) {
-      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      const size_t lsm = LF_NW * align16(fb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
-      subtree_leaf_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold,
-                                                     h->pivot_tol, h->inertia.p, h->leaf_cap);
+      const int lg = h->leaf_cap <= 8 ? 8 : (h->leaf_cap <= 16 ? 16 : 32), per = LF_NT / lg;
+      dim3 g((h->max_leaves + per - 1) / per, h->n_local);
+      const size_t lsm = per * align16(fb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      auto kern = lg == 8 ? subtree_leaf_kernel<8> : (lg == 16 ? subtree_leaf_kernel<16> : subtree_leaf_kernel<32>);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+      kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold, h->pivot_tol,
+                                  h->inertia.p, h->leaf_cap);
       h->launches++;
     }
     subtree_factor_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->fronts.p, dvals,
@@ -954,10 +954,13 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_FORWARD, st);
     if (h->max_leaves > 0) {
-      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      const size_t lsm = LF_NW * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
-      subtree_leaf_forward_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
-                                                         h->ywork.p, h->leaf_cap);
+      const int lg = h->leaf_cap <= 8 ? 8 : (h->leaf_cap <= 16 ? 16 : 32), per = LF_NT / lg;
+      dim3 g((h->max_leaves + per - 1) / per, h->n_local);
+      const size_t lsm = per * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      auto kern = lg == 8 ? subtree_leaf_forward_kernel<8>
+                          : (lg == 16 ? subtree_leaf_forward_kernel<16> : subtree_leaf_forward_kernel<32>);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+      kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p, h->ywork.p, h->leaf_cap);
       h->launches++;
     }
     subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
@@ -999,10 +1002,13 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
     subtree_backward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
                                                                h->vec_off.p, h->root_x.p, h->root_off.p, dx);
     if (h->max_leaves > 0) {
-      dim3 g((h->max_leaves + LF_NW - 1) / LF_NW, h->n_local);
-      const size_t lsm = LF_NW * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
-      subtree_leaf_backward_kernel<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
-                                                          h->vec_off.p, dx, h->leaf_cap);
+      const int lg = h->leaf_cap <= 8 ? 8 : (h->leaf_cap <= 16 ? 16 : 32), per = LF_NT / lg;
+      dim3 g((h->max_leaves + per - 1) / per, h->n_local);
+      const size_t lsm = per * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
+      auto kern = lg == 8 ? subtree_leaf_backward_kernel<8>
+                          : (lg == 16 ? subtree_leaf_backward_kernel<16> : subtree_leaf_backward_kernel<32>);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+      kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p, h->vec_off.p, dx, h->leaf_cap);
       h->launches++;
     }
     h->launches += 2;

@@ -135,12 +135,20 @@ __device__ __forceinline__ FrontBuf carve(unsigned char *base, int cap, int ld) 
   return b;
 }
 
-// groups: a warp (32), a quarter-CTA of four warps (128, named barrier 1 + group index) or the whole CTA
+// groups: part of a warp (8 or 16 lanes: several tiny leaf fronts share a warp), a warp (32), a quarter-CTA of
+// four warps (128, named barrier 1 + group index) or the whole CTA
+template <int G> struct Grp {
+  static constexpr int LW = G < 32 ? G : 32;       // lanes that walk a column together
+  static constexpr int NW = G < 32 ? 1 : G / 32;   // warps of the group
+};
+template <int G> __device__ __forceinline__ unsigned gmask() {  // lanes of this thread's group within its warp
+  return G < 32 ? (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1))) : 0xffffffffu;
+}
 template <int G> __device__ __forceinline__ int gtid() {
-  return G == 32 ? (int)(threadIdx.x & 31) : (G == 128 ? (int)(threadIdx.x & 127) : (int)threadIdx.x);
+  return G <= 32 ? (int)(threadIdx.x & (G - 1)) : (G == 128 ? (int)(threadIdx.x & 127) : (int)threadIdx.x);
 }
 template <int G> __device__ __forceinline__ void gsync() {
-  if (G == 32) __syncwarp();
+  if (G <= 32) __syncwarp(gmask<G>());
   else if (G == 128) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
   else __syncthreads();
 }
@@ -193,8 +201,9 @@ __device__ __forceinline__ void front_swap(const FrontBuf &B, int S, int a, int 
 template <int G>
 __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double pivtol, int *cnt, int ntest = -1) {
   if (ntest < 0) ntest = S;  // rows that take part in the threshold tests (a dense root excludes its border rows)
-  const int tid = gtid<G>(), lane = tid & 31, gw = tid >> 5;
-  constexpr int NW = G / 32;
+  constexpr int LW = Grp<G>::LW, NW = Grp<G>::NW;
+  const int tid = gtid<G>(), lane = tid & (LW - 1), gw = G < 32 ? 0 : tid >> 5;
+  const unsigned wmask = gmask<G>();
   double *F = B.F;
   const int ld = B.ld;
   int t = 0;
@@ -204,16 +213,16 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       // diagonal of the leading column passes the threshold test as it is -- the first candidate the general
       // search below would accept.  One barrier per eliminated column instead of four.
       unsigned kmax = 0u;
-      for (int i = t + 1 + lane; i < ntest; i += 32)
+      for (int i = t + 1 + lane; i < ntest; i += LW)
         kmax = max(kmax, (unsigned)__double2hiint(F[i + t * ld]) & 0x7fffffffu);
-      kmax = __reduce_max_sync(0xffffffffu, kmax);
+      kmax = __reduce_max_sync(wmask, kmax);
       const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
       const double d = F[t + t * ld];
       if (fabs(d) > pivtol && fabs(d) >= u * cmax) {
         const double rd = 1.0 / d;
         for (int j = t + 1 + gw; j < S; j += NW) {
           const double wj = F[j + t * ld] * rd;
-          for (int i = j + lane; i < S; i += 32) F[i + j * ld] -= F[i + t * ld] * wj;
+          for (int i = j + lane; i < S; i += LW) F[i + j * ld] -= F[i + t * ld] * wj;
         }
         if (tid == 0) {
           B.bsz[t] = 1;
@@ -232,14 +241,14 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       int kind = 0, pc = -1, pr = -1;
       for (int c = t; c < fs; ++c) {
         unsigned kmax = 0u, kbest = 0u;
-        for (int i = t + lane; i < ntest; i += 32) {
+        for (int i = t + lane; i < ntest; i += LW) {
           if (i == c) continue;
           const unsigned hi = (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu;
           kmax = max(kmax, hi);
           if (i < fs) kbest = max(kbest, (hi & 0xffffff00u) | (unsigned)(255 - i));
         }
-        kmax = __reduce_max_sync(0xffffffffu, kmax);
-        kbest = __reduce_max_sync(0xffffffffu, kbest);
+        kmax = __reduce_max_sync(wmask, kmax);
+        kbest = __reduce_max_sync(wmask, kbest);
         const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
         const double dcc = F[c + c * ld];
         if (fabs(dcc) > pivtol && fabs(dcc) >= u * cmax) { kind = 1; pc = c; break; }
@@ -248,13 +257,13 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
           const double b = fent(F, ld, r, c);
           if (fabs(b) > pivtol) {
             unsigned kc = 0u, kr = 0u;
-            for (int i = t + lane; i < ntest; i += 32) {
+            for (int i = t + lane; i < ntest; i += LW) {
               if (i == c || i == r) continue;
               kc = max(kc, (unsigned)__double2hiint(fent(F, ld, i, c)) & 0x7fffffffu);
               kr = max(kr, (unsigned)__double2hiint(fent(F, ld, i, r)) & 0x7fffffffu);
             }
-            kc = __reduce_max_sync(0xffffffffu, kc);
-            kr = __reduce_max_sync(0xffffffffu, kr);
+            kc = __reduce_max_sync(wmask, kc);
+            kr = __reduce_max_sync(wmask, kr);
             const double cm_c = kc ? __hiloint2double((int)kc, -1) : 0.0;
             const double cm_r = kr ? __hiloint2double((int)kr, -1) : 0.0;
             const double drr = F[r + r * ld];
@@ -289,7 +298,7 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       const double rd = 1.0 / d;
       for (int j = t + 1 + gw; j < S; j += NW) {
         const double wj = B.w0[j] * rd;
-        for (int i = j + lane; i < S; i += 32) F[i + j * ld] -= B.w0[i] * wj;
+        for (int i = j + lane; i < S; i += LW) F[i + j * ld] -= B.w0[i] * wj;
       }
       for (int i = t + 1 + tid; i < S; i += G) F[i + t * ld] = B.w0[i] * rd;
       if (tid == 0) {
@@ -310,7 +319,7 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       const double sc = (1.0 / (d11 * d22 - 1.0)) / e21;
       for (int j = t + 2 + gw; j < S; j += NW) {
         const double a0 = B.w0[j], a1 = B.w1[j];
-        for (int i = j + lane; i < S; i += 32) {
+        for (int i = j + lane; i < S; i += LW) {
           const double l0 = sc * (d11 * B.w0[i] - B.w1[i]), l1 = sc * (d22 * B.w1[i] - B.w0[i]);
           F[i + j * ld] -= l0 * a0 + l1 * a1;
         }
@@ -401,7 +410,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   PP_TRP(0);
   const SnHead H = P.heads[s];
   const int nc = H.nc, ncb = H.ncb;
-  const bool staged = G != 32 && H.nch >= 4 && H.nch <= stg.maxch;
+  const bool staged = G >= 128 && H.nch >= 4 && H.nch <= stg.maxch;
   int nd_in = 0;
   if (staged) {
     // one child per thread: delayed count and staged-entry count; serial prefix by thread 0
@@ -448,10 +457,10 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   }
   double *F = B.F;
   const int ld = B.ld;
-  constexpr int NWG = G / 32;  // columns dealt over the warps of the group, rows over the lanes
-  const int gwp = tid >> 5, lanep = tid & 31;
+  constexpr int NWG = Grp<G>::NW, LWG = Grp<G>::LW;  // columns dealt over the warps of the group, rows over the lanes
+  const int gwp = G < 32 ? 0 : tid >> 5, lanep = tid & (LWG - 1);
   for (int j = gwp; j < S; j += NWG)
-    for (int i = j + lanep; i < S; i += 32) F[i + j * ld] = 0.0;
+    for (int i = j + lanep; i < S; i += LWG) F[i + j * ld] = 0.0;
   for (int i = tid; i < nc; i += G) B.fid[i] = P.cols[H.c0 + i];
   for (int i = tid; i < ncb; i += G) B.fid[fs + i] = P.rows[H.r0 + i];
   for (int i = tid; i < fs; i += G) B.opos[i] = i;
@@ -531,7 +540,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       gsync<G>();
       for (int j = gwp; j < dim; j += NWG) {
         const int mj = B.map[j];
-        for (int i = j + lanep; i < dim; i += 32) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
       }
       gsync<G>();
     }
@@ -552,7 +561,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       gsync<G>();
       for (int j = gwp; j < dim; j += NWG) {
         const int mj = B.map[j];
-        for (int i = j + lanep; i < dim; i += 32) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
       }
       gsync<G>();
       off += ndo;
@@ -584,7 +593,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   const int caprows = nc + H.dcap + ncb;
   double *Ls = Bk.L + H.l_off;
   for (int j = gwp; j < ne; j += NWG)
-    for (int i = j + lanep; i < S; i += 32) Ls[i + (long long)j * caprows] = F[i + j * ld];
+    for (int i = j + lanep; i < S; i += LWG) Ls[i + (long long)j * caprows] = F[i + j * ld];
   for (int i = tid; i < S; i += G) Bk.fid[H.fid_off + i] = B.fid[i];
   for (int i = tid; i < fs; i += G) {
     Bk.opos[H.fs_off + i] = B.opos[i];
@@ -592,7 +601,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   }
   double *M = Bk.cb + H.cb_off;
   for (int j = gwp; j < dim; j += NWG)
-    for (int i = j + lanep; i < dim; i += 32) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
+    for (int i = j + lanep; i < dim; i += LWG) M[i + j * dim] = F[(ne + i) + (ne + j) * ld];
   if (tid == 0) { Bk.meta[3 * s] = ne; Bk.meta[3 * s + 1] = S; Bk.meta[3 * s + 2] = ndo; }
   gsync<G>();
   PP_TRP(8);
@@ -602,31 +611,33 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
 // Level-0 small fronts have no children, hence no dependencies at all: one warp per (block, leaf),
 // spread over the whole GPU.  grid = (ceil(max leaves / LF_NW), blocks).
 constexpr int LF_NT = 256, LF_NW = LF_NT / 32;
-constexpr size_t LF_SMEM = LF_NW * SF_TINY_BYTES + 16;
 
+template <int LG>
 __global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *__restrict__ blocks,
                                                              const PlanDev *__restrict__ plans,
                                                              const double *__restrict__ vals, double u, double pivtol,
                                                              unsigned long long *inertia, int cap) {
-  // cap = largest leaf front of any plan (leaves have no children, so their size is static): small per-warp
-  // buffers keep 64 warps resident per SM, which is what hides the chain of dependent loads of each leaf
+  // cap = largest leaf front of any plan (leaves have no children, so their size is static).  LG lanes per leaf:
+  // fronts of up to 8 (16) rows share a warp four (two) at a time, which divides the instruction count per leaf --
+  // the leaf kernels are issue-bound -- and small per-leaf buffers keep 64 warps resident per SM.
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ int cnt[4];
   const SparseBlock Bk = blocks[blockIdx.y];
   const PlanDev P = plans[Bk.plan];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PER_CTA = LF_NT / LG;
+  const int slot = threadIdx.x / LG;
   if (P.nlevels == 0) return;
   const int nleaf = P.tiny_ptr[1] - P.tiny_ptr[0];
-  if ((int)blockIdx.x * LF_NW >= nleaf) return;
+  if ((int)blockIdx.x * PER_CTA >= nleaf) return;
   if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int k = blockIdx.x * LF_NW + warp;
+  const int k = blockIdx.x * PER_CTA + slot;
   if (k < nleaf) {
-    const FrontBuf mine = carve(sm_raw + (size_t)warp * align16(fb_bytes(cap, cap | 1)), cap, cap | 1);
+    const FrontBuf mine = carve(sm_raw + (size_t)slot * align16(fb_bytes(cap, cap | 1)), cap, cap | 1);
     Stage none;
-    none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0; none.cap = 0; none.maxch = 0;
-    const int rc = process_front<32>(Bk, P, vals, P.tiny_idx[P.tiny_ptr[0] + k], mine, u, pivtol, cnt, none);
-    if (rc != PF_OK && lane == 0) Bk.info[2] = 1;
+    none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0;
+    const int rc = process_front<LG>(Bk, P, vals, P.tiny_idx[P.tiny_ptr[0] + k], mine, u, pivtol, cnt, none);
+    if (rc != PF_OK && gtid<LG>() == 0) Bk.info[2] = 1;
   }
   __syncthreads();
   if (threadIdx.x < 3 && cnt[threadIdx.x]) atomicAdd(&inertia[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
@@ -787,8 +798,8 @@ __device__ void load_front(const SparseBlock &Bk, const SnHead &H, const SolveBu
   const int tid = gtid<G>();
   const int caprows = H.nc + H.dcap + H.ncb;
   const double *Lg = Bk.L + H.l_off;
-  for (int j = tid >> 5; j < ne; j += G / 32)
-    for (int i = j + (tid & 31); i < S; i += 32) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
+  for (int j = G < 32 ? 0 : tid >> 5; j < ne; j += Grp<G>::NW)
+    for (int i = j + (tid & (Grp<G>::LW - 1)); i < S; i += Grp<G>::LW) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
   for (int i = tid; i < S; i += G) B.fid[i] = Bk.fid[H.fid_off + i];
   for (int i = tid; i < ne; i += G) B.bsz[i] = Bk.pbz[H.fs_off + i];
 }
@@ -796,7 +807,8 @@ __device__ void load_front(const SparseBlock &Bk, const SnHead &H, const SolveBu
 template <int G>
 __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, const SolveBuf &B,
                               const double *__restrict__ rhs, double *__restrict__ y, const Stage &stg) {
-  const int tid = gtid<G>(), lane = tid & 31;
+  constexpr int LW = Grp<G>::LW;
+  const int tid = gtid<G>(), lane = tid & (LW - 1);
   const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], fs = ne + Bk.meta[3 * s + 2];
   if (S == 0) return;
   const SnHead H = P.heads[s];
@@ -808,7 +820,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
   for (int i = tid; i < S; i += G)
     B.v[i] = (i < fs && Bk.opos[H.fs_off + i] < nc) ? rhs[B.fid[i]] : 0.0;
   gsync<G>();
-  if (G != 32 && H.nch >= 4 && H.nch <= stg.maxch) {
+  if (G >= 128 && H.nch >= 4 && H.nch <= stg.maxch) {
     // many children: fetch their vectors concurrently (one child per thread), apply in child order
     for (int k = tid; k < H.nch; k += G) {
       const int c = P.child_idx[H.ch0 + k];
@@ -876,9 +888,9 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
     for (int c = 0; c < ne; ++c) {
       const double zc = B.v[c];
       const int skip = B.bsz[c] == 2 ? c + 1 : -1;
-      for (int i = c + 1 + lane; i < ne; i += 32)
+      for (int i = c + 1 + lane; i < ne; i += LW)
         if (i != skip) B.v[i] -= B.Ls[i + c * B.ld] * zc;
-      __syncwarp();
+      __syncwarp(gmask<G>());
     }
   }
   gsync<G>();
@@ -895,7 +907,8 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
 template <int G>
 __device__ void backward_front(const SparseBlock &Bk, const PlanDev &P, int s, const SolveBuf &B,
                                const double *__restrict__ y, double *__restrict__ x) {
-  const int tid = gtid<G>(), lane = tid & 31;
+  constexpr int LW = Grp<G>::LW;
+  const int tid = gtid<G>(), lane = tid & (LW - 1);
   const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1];
   if (ne == 0) return;
   const SnHead H = P.heads[s];
@@ -926,9 +939,9 @@ __device__ void backward_front(const SparseBlock &Bk, const PlanDev &P, int s, c
   if (tid < 32) {
     for (int rr = ne - 1; rr > 0; --rr) {
       const double xv = B.z[rr];
-      for (int c = lane; c < rr; c += 32)
+      for (int c = lane; c < rr; c += LW)
         if (!(B.bsz[c] == 2 && rr == c + 1)) B.z[c] -= B.Ls[rr + c * B.ld] * xv;
-      __syncwarp();
+      __syncwarp(gmask<G>());
     }
   }
   gsync<G>();
@@ -1051,8 +1064,8 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
 }
 
 // leaves of the solves: one warp per (block, leaf) over the whole GPU
-constexpr size_t LS_SMEM = LF_NW * SV_TINY_BYTES + 16;
 
+template <int LG>
 __global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const SparseBlock *__restrict__ blocks,
                                                                      const PlanDev *__restrict__ plans,
                                                                      const double *__restrict__ rhs,
@@ -1061,16 +1074,17 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_forward_kernel(const Spars
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.y];
   const PlanDev P = plans[Bk.plan];
-  const int warp = threadIdx.x >> 5;
+  const int slot = threadIdx.x / LG;
   if (P.nlevels == 0) return;
-  const int k = blockIdx.x * LF_NW + warp;
+  const int k = blockIdx.x * (LF_NT / LG) + slot;
   if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
-  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)slot * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
   Stage none;
   none.val = nullptr; none.tgt = nullptr; none.cnt = nullptr; none.ndo = nullptr; none.big = nullptr; none.cap = 0; none.maxch = 0;
-  forward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, rhs + vec_off[blockIdx.y], ywork + vec_off[blockIdx.y], none);
+  forward_front<LG>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, rhs + vec_off[blockIdx.y], ywork + vec_off[blockIdx.y], none);
 }
 
+template <int LG>
 __global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const SparseBlock *__restrict__ blocks,
                                                                       const PlanDev *__restrict__ plans,
                                                                       const double *__restrict__ ywork,
@@ -1079,12 +1093,12 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const Spar
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.y];
   const PlanDev P = plans[Bk.plan];
-  const int warp = threadIdx.x >> 5;
+  const int slot = threadIdx.x / LG;
   if (P.nlevels == 0) return;
-  const int k = blockIdx.x * LF_NW + warp;
+  const int k = blockIdx.x * (LF_NT / LG) + slot;
   if (k >= P.tiny_ptr[1] - P.tiny_ptr[0]) return;
-  const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
-  backward_front<32>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, ywork + vec_off[blockIdx.y], xout + vec_off[blockIdx.y]);
+  const SolveBuf mine = carve_solve(sm_raw + (size_t)slot * align16(sb_bytes(cap, cap | 1)), cap, cap | 1);
+  backward_front<LG>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, ywork + vec_off[blockIdx.y], xout + vec_off[blockIdx.y]);
 }
 
 // worst failure flag over the sparse blocks -> flag[1]

@@ -7,7 +7,11 @@ from parapint_b200 import B200SchurComplementLinearSolver
 args = [int(a) for a in sys.argv[1:5]]
 check_oracle = len(sys.argv) > 5 and sys.argv[5] == "oracle"
 t0 = time.perf_counter(); m = EstimationModel(*args); kkt, rhs = m.build_kkt(), m.build_rhs(); print("build model s", time.perf_counter() - t0, "block n", m.block_dim)
-s = B200SchurComplementLinearSolver(options={"profile": 1})
+opts = {"profile": 1}
+for a in sys.argv[5:]:
+    if "=" in a:
+        k, v = a.split("="); opts[k] = float(v)
+s = B200SchurComplementLinearSolver(options=opts)
 t0 = time.perf_counter(); s.do_symbolic_factorization(kkt); torch.cuda.synchronize(); print("symbolic s", time.perf_counter() - t0)
 print(s.backend.plan_stats(0), "factor GB", s.backend.factor_bytes() / 1e9)
 for rep in range(3):
