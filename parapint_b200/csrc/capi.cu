@@ -96,6 +96,10 @@ struct pp_handle {
   bool use_sparse = true;
   bool no_fallback = false;
   bool use_cluster = true;
+  bool defer_status = false;      // single rank: one host sync per factorisation (status + inertia read together)
+  bool status_pending = false, inertia_cached = false;
+  unsigned long long inertia_cache[6] = {0, 0, 0, 0, 0, 0};
+  double *last_schur = nullptr;
   bool use_small = true;          // whole-front shared-memory factorisation when every front of a batch fits
   bool sparse_failed = false;     // a block overflowed its delayed-pivot capacity: all blocks were redone dense
   PlanOptions plan_opt;
@@ -285,11 +289,29 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   CK(cudaGetLastError());
 }
 
+// flag[slot] = any front of [first, first+count) reported a zero pivot (stream-ordered, no host sync)
+void post_flag(pp_handle *h, int first, int count, int slot, cudaStream_t st) {
+  if (count == 0) {
+    CK(cudaMemsetAsync(h->flag.p + slot, 0, sizeof(int), st));
+    return;
+  }
+  collect_info_kernel<<<1, 256, 0, st>>>(h->fronts.p + first, count, h->flag.p + slot);
+  h->launches++;
+}
+
+// flags (8 ints) and inertia (6 counters) to the host with one synchronisation
+void fetch_status(pp_handle *h, cudaStream_t st) {
+  h->pin_flag.ensure(8);
+  h->pin_inertia.ensure(8);
+  CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->pin_inertia.p, h->inertia.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+}
+
 int read_flag(pp_handle *h, int first, int count, cudaStream_t st) {
   if (count == 0) return 0;
-  collect_info_kernel<<<1, 256, 0, st>>>(h->fronts.p + first, count, h->flag.p);
-  h->launches++;
-  h->pin_flag.ensure(4);
+  post_flag(h, first, count, 0, st);
+  h->pin_flag.ensure(8);
   CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return h->pin_flag.p[0];
@@ -343,10 +365,10 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
     auto *h = new pp_handle();
     h->device = device;
-    h->flag.alloc(4);
+    h->flag.alloc(8);
     h->inertia.alloc(8);
     CK(cudaMemset(h->inertia.p, 0, 8 * sizeof(unsigned long long)));
-    CK(cudaMemset(h->flag.p, 0, 4 * sizeof(int)));
+    CK(cudaMemset(h->flag.p, 0, 8 * sizeof(int)));
     *out = h;
     return (int)PP_SUCCESSFUL;
   });
@@ -373,6 +395,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->use_sparse = value != 0.0;
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
+  } else if (key == "defer_status") {
+    h->defer_status = value != 0.0;
   } else if (key == "pivot_threshold") {
     if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
@@ -813,7 +837,7 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
 }
 
 static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_local_dev, cudaStream_t st,
-                              int *sparse_bad) {
+                              int *sparse_bad, bool defer = false) {
   {
     ProfSpan sp(h, PP_PROF_ASSEMBLE, st);
     CK(cudaMemsetAsync(h->arenaA.p, 0, h->arenaA_elems * sizeof(double), st));
@@ -855,8 +879,14 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
     h->launches += 2;
   }
   CK(cudaGetLastError());
-  const int bad = read_flag(h, 0, h->n_local, st);
-  *sparse_bad = h->n_local > 0 ? h->pin_flag.p[1] : 0;
+  int bad = 0;
+  if (defer) {
+    post_flag(h, 0, h->n_local, 0, st);  // read later, together with the coupling status and the inertia
+    *sparse_bad = 0;
+  } else {
+    bad = read_flag(h, 0, h->n_local, st);
+    *sparse_bad = h->n_local > 0 ? h->pin_flag.p[1] : 0;
+  }
   if (schur_local_dev) {  // stream-ordered after collect_info / inertia kernels; flag[0] is current
     pack_tail_kernel<<<1, 32, 0, st>>>(schur_local_dev + (size_t)h->m_c * h->m_c, h->flag.p, h->inertia.p);
     h->launches++;
@@ -886,7 +916,16 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
     }
     h->last_vals = dvals;
     h->solved = false;
+    h->inertia_cached = false;
+    h->status_pending = false;
+    h->last_schur = schur_local_dev;
     int sparse_bad = 0;
+    if (h->defer_status) {
+      numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad, true);
+      h->status_pending = true;
+      h->local_factored = true;
+      return (int)PP_SUCCESSFUL;  // provisional: pp_numeric_coupling reports the final status
+    }
     int bad = numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad);
     if (sparse_bad && h->no_fallback) return fail("pp_numeric_local: sparse path overflow (fallback disabled)");
     if (sparse_bad) {
@@ -911,16 +950,45 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     h->coupling_factored = h->forward_done = false;
     const int mc = h->m_c;
-    if (mc > 0) {
-      const Front C = h->hfronts[h->n_local];
-      dim3 g((mc + 127) / 128, mc);
-      coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
-      h->launches++;
-      factor_fronts(h, h->n_local, 1, st);
-      CK(cudaMemsetAsync(h->inertia.p + 3, 0, 3 * sizeof(unsigned long long), st));
-      front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
-      h->launches++;
-      CK(cudaGetLastError());
+    auto enqueue = [&]() {
+      if (mc > 0) {
+        const Front C = h->hfronts[h->n_local];
+        dim3 g((mc + 127) / 128, mc);
+        coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
+        h->launches++;
+        factor_fronts(h, h->n_local, 1, st);
+        CK(cudaMemsetAsync(h->inertia.p + 3, 0, 3 * sizeof(unsigned long long), st));
+        front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
+        h->launches++;
+        CK(cudaGetLastError());
+      }
+    };
+    enqueue();
+    if (h->status_pending) {
+      // single-rank fast path: the local status, the coupling status and both inertias in ONE synchronisation
+      if (schur_sum_dev != h->last_schur) return fail("pp_numeric_coupling: defer_status needs the local Schur buffer");
+      h->status_pending = false;
+      post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+      fetch_status(h, st);
+      if (h->n_local > 0 && h->pin_flag.p[1]) {  // sparse path overflow: redo with dense blocks, synchronously
+        if (h->no_fallback) return fail("pp_numeric_local: sparse path overflow (fallback disabled)");
+        h->sparse_failed = true;
+        const int rc = do_symbolic(h, true);
+        if (rc != PP_SUCCESSFUL) return rc;
+        int sparse_bad = 0;
+        const int bad_local = numeric_local_once(h, h->last_vals, h->last_schur, st, &sparse_bad);
+        if (sparse_bad) return fail("pp_numeric_local: internal error in the dense re-factorisation");
+        h->local_factored = true;
+        if (bad_local) return (int)PP_SINGULAR;
+        enqueue();
+        post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+        fetch_status(h, st);
+      }
+      for (int k = 0; k < 6; ++k) h->inertia_cache[k] = h->pin_inertia.p[k];
+      h->inertia_cached = true;
+      if (h->pin_flag.p[0]) return (int)PP_SINGULAR;
+      h->coupling_factored = true;
+      return h->pin_flag.p[4] ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
     }
     const int bad = mc > 0 ? read_flag(h, h->n_local, 1, st) : 0;
     h->coupling_factored = true;
@@ -930,6 +998,10 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
 
 static int read_inertia(pp_handle *h, int which, int64_t out[3]) {
   return guarded([&]() {
+    if (h->inertia_cached) {
+      for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->inertia_cache[which * 3 + k];
+      return (int)PP_SUCCESSFUL;
+    }
     CK(cudaSetDevice(h->device));
     h->pin_inertia.ensure(8);
     CK(cudaMemcpy(h->pin_inertia.p, h->inertia.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

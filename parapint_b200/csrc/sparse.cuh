@@ -496,25 +496,54 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       const int *crel = P.rel + C.r0;
       const double *M = Bk.cb + C.cb_off;
       const int off = stg.ndo[k];
+      // all global loads of a batch are issued before the first shared-memory store (the compiler cannot prove that
+      // the staging area does not alias the contribution block, so interleaved loads would each pay a full round trip)
       int mp[SF_CHDIM];
+#pragma unroll
+      for (int i = 0; i < SF_CHDIM; ++i) mp[i] = (i < dim && i >= ndo) ? crel[i - ndo] : -1;
 #pragma unroll
       for (int i = 0; i < SF_CHDIM; ++i) {
         if (i < dim) {
           if (i < ndo) { mp[i] = nc + off + i; B.fid[nc + off + i] = ids[i]; }
-          else { const int rr = crel[i - ndo]; mp[i] = rr < nc ? rr : rr + nd_in; }
+          else { const int rr = mp[i]; mp[i] = rr < nc ? rr : rr + nd_in; }
         }
       }
       int e = e0;
+      if (dim <= 4) {
+        double mv[10];
+        int q = 0;
 #pragma unroll
-      for (int j = 0; j < SF_CHDIM; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = j; i < SF_CHDIM; ++i)
-          if (i < dim) {
-            const int a = mp[i] >= mp[j] ? mp[i] : mp[j], b = mp[i] >= mp[j] ? mp[j] : mp[i];
-            stg.tgt[e] = a + b * ld;
-            stg.val[e] = M[i + j * dim];
-            ++e;
-          }
+          for (int i = j; i < 4; ++i, ++q) mv[q] = i < dim ? M[i + j * dim] : 0.0;
+        q = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = j; i < 4; ++i, ++q)
+            if (i < dim) {
+              const int a = mp[i] >= mp[j] ? mp[i] : mp[j], b = mp[i] >= mp[j] ? mp[j] : mp[i];
+              stg.tgt[e] = a + b * ld;
+              stg.val[e] = mv[q];
+              ++e;
+            }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SF_CHDIM; ++j) {
+          if (j >= dim) break;
+          double col[SF_CHDIM];
+#pragma unroll
+          for (int i = j; i < SF_CHDIM; ++i) col[i] = i < dim ? M[i + j * dim] : 0.0;
+#pragma unroll
+          for (int i = j; i < SF_CHDIM; ++i)
+            if (i < dim) {
+              const int a = mp[i] >= mp[j] ? mp[i] : mp[j], b = mp[i] >= mp[j] ? mp[j] : mp[i];
+              stg.tgt[e] = a + b * ld;
+              stg.val[e] = col[i];
+              ++e;
+            }
+        }
+      }
     }
     gsync<G>();
     PP_TRP(4);
@@ -838,12 +867,27 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
         const int ndo = Bk.meta[3 * c + 2], dim = stg.cnt[k + 1] - stg.cnt[k], off = stg.ndo[k];
         const int *crel = P.rel + C.r0;
         const double *uc = Bk.vec + C.vec_off;
-        for (int i = 0; i < dim; ++i) {
-          int q;
-          if (i < ndo) q = nc + off + i;
-          else { const int rr = crel[i - ndo]; q = rr < nc ? rr : rr + nd_in; }
-          stg.tgt[stg.cnt[k] + i] = q < fs ? B.inv[q] : q;
-          stg.val[stg.cnt[k] + i] = uc[i];
+        const int e0 = stg.cnt[k];
+        for (int i0 = 0; i0 < dim; i0 += 8) {  // loads of a batch first, then the shared-memory stores
+          int rl[8];
+          double uv[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int i = i0 + r;
+            rl[r] = (i < dim && i >= ndo) ? crel[i - ndo] : 0;
+            uv[r] = i < dim ? uc[i] : 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int i = i0 + r;
+            if (i < dim) {
+              int q;
+              if (i < ndo) q = nc + off + i;
+              else q = rl[r] < nc ? rl[r] : rl[r] + nd_in;
+              stg.tgt[e0 + i] = q < fs ? B.inv[q] : q;
+              stg.val[e0 + i] = uv[r];
+            }
+          }
         }
       }
       gsync<G>();

@@ -242,6 +242,9 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.schur_complement_solver = schur_complement_solver
         self.comm = comm if comm is not None else Communicator()
         self.backend = backend if backend is not None else CudaBackend(device, options)
+        if isinstance(self.backend, CudaBackend) and self.comm.size == 1 and "defer_status" not in (options or {}):
+            # no collective between the local and the coupling phase: read status + inertia with one host sync
+            self.backend.set_option("defer_status", 1)
         self.block_dim = 0
         self.block_matrix = None
         self.local_block_indices = []
