@@ -96,7 +96,9 @@ struct pp_handle {
   bool use_sparse = true;
   bool no_fallback = false;
   bool use_cluster = true;
-  bool defer_status = false;      // single rank: one host sync per factorisation (status + inertia read together)
+  int defer_status = 0;           // 1 single rank: one host sync per factorisation (status + inertia read together);
+                                  // 2 several ranks: pp_numeric_local does not synchronise, its status and overflow
+                                  //   flag travel in the tail of the Schur buffer the caller all-reduces
   bool status_pending = false, inertia_cached = false;
   unsigned long long inertia_cache[6] = {0, 0, 0, 0, 0, 0};
   double *last_schur = nullptr;
@@ -396,7 +398,7 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
   } else if (key == "defer_status") {
-    h->defer_status = value != 0.0;
+    h->defer_status = (int)value;
   } else if (key == "pivot_threshold") {
     if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
@@ -922,7 +924,7 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
     int sparse_bad = 0;
     if (h->defer_status) {
       numeric_local_once(h, dvals, schur_local_dev, st, &sparse_bad, true);
-      h->status_pending = true;
+      h->status_pending = h->defer_status == 1;
       h->local_factored = true;
       return (int)PP_SUCCESSFUL;  // provisional: pp_numeric_coupling reports the final status
     }

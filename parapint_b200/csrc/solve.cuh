@@ -43,7 +43,7 @@ __global__ void collect_info_kernel(const Front *__restrict__ fronts, int count,
   if (threadIdx.x == 0) flag[0] = bad;
 }
 
-// Tail of the local Schur buffer: [blocks singular?, reserved, n_pos, n_neg, n_zero, 0, 0, 0] of this rank's
+// Tail of the local Schur buffer: [blocks singular?, sparse overflow?, n_pos, n_neg, n_zero, 0, 0, 0] of this rank's
 // blocks, so that the ONE all-reduce of the Schur complement also agrees the status across ranks and sums the
 // inertia (the reference needs an allgather and three allreduces for that,
 // mpi_explicit_schur_complement.py:21,427-429).
@@ -53,6 +53,7 @@ __global__ void pack_tail_kernel(double *__restrict__ tail, const int *__restric
   if (t < 8) {
     double v = 0.0;
     if (t == 0) v = flag[0] ? 1.0 : 0.0;
+    else if (t == 1) v = flag[1] ? 1.0 : 0.0;  // sparse path ran out of delayed-pivot capacity (redo densely)
     else if (t >= 2 && t <= 4) v = (double)inertia[t - 2];
     tail[t] = v;
   }

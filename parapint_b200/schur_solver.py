@@ -242,9 +242,13 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.schur_complement_solver = schur_complement_solver
         self.comm = comm if comm is not None else Communicator()
         self.backend = backend if backend is not None else CudaBackend(device, options)
-        if isinstance(self.backend, CudaBackend) and self.comm.size == 1 and "defer_status" not in (options or {}):
-            # no collective between the local and the coupling phase: read status + inertia with one host sync
-            self.backend.set_option("defer_status", 1)
+        self._defer = 0
+        if isinstance(self.backend, CudaBackend) and "defer_status" not in (options or {}):
+            # one rank: no collective between the local and the coupling phase, status + inertia are read with one
+            # host sync.  Several ranks: the local phase is not synchronised at all, its status and overflow flag
+            # travel in the tail of the Schur all-reduce.
+            self._defer = 1 if self.comm.size == 1 else 2
+            self.backend.set_option("defer_status", self._defer)
         self.block_dim = 0
         self.block_matrix = None
         self.local_block_indices = []
@@ -327,6 +331,18 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             mc2 = self._st.m_c * self._st.m_c
             tail = schur_local[mc2:mc2 + SCHUR_TAIL].cpu().numpy()
             self._tail = tail
+            if tail[1] > 0 and self._defer == 2:
+                # some rank's sparse path ran out of delayed-pivot capacity (every rank sees it in the reduced
+                # tail): repeat the local phase synchronously -- the overflowing rank re-analyses densely -- and
+                # reduce again
+                self.backend.set_option("defer_status", 0)
+                try:
+                    code, schur_local = self.backend.numeric_local()
+                finally:
+                    self.backend.set_option("defer_status", 2)
+                self.comm.allreduce_sum_(schur_local)
+                tail = schur_local[mc2:mc2 + SCHUR_TAIL].cpu().numpy()
+                self._tail = tail
             if code == 0 and tail[0] > 0:
                 code = LinearSolverStatus.singular.value
             if tail[1] > 0 or not np.all(np.isfinite(tail)):
