@@ -132,6 +132,9 @@ struct pp_handle {
   double *last_x = nullptr, *last_xc = nullptr;
   bool solved = false;
   PinBuf<double> pin_out2;
+  bool auto_residual = false;     // single rank: pp_solve_backward also forms the residual norms (same sync as the copy-out)
+  bool norms_valid = false;
+  DevBuf<double> res_buf;
   // device storage
   DevBuf<double> arenaA, arenaW, arenaZ, vals, rhs, x, xc, crhs;
   DevBuf<int> arenaI, flag;
@@ -397,6 +400,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->use_sparse = value != 0.0;
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
+  } else if (key == "auto_residual") {
+    h->auto_residual = value != 0.0;
   } else if (key == "defer_status") {
     h->defer_status = (int)value;
   } else if (key == "pivot_threshold") {
@@ -1024,6 +1029,9 @@ int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
   return read_inertia(h, 1, out);
 }
 
+static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t st);
+static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cudaStream_t st);
+
 static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, cudaStream_t st) {
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_FORWARD, st);
@@ -1093,6 +1101,15 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
 static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *x_local, double *x_c,
                      cudaStream_t st) {
   const int mc = h->m_c;
+  // pinned caller buffers receive the device data directly; pageable ones go through the handle's staging buffer
+  const bool direct = (h->local_dim == 0 || is_pinned_host(x_local)) && (mc == 0 || is_pinned_host(x_c));
+  if (direct) {
+    if (h->local_dim > 0)
+      CK(cudaMemcpyAsync(x_local, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mc > 0) CK(cudaMemcpyAsync(x_c, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return;
+  }
   h->pin_vec.ensure((size_t)h->local_dim + (size_t)mc);
   if (h->local_dim > 0)
     CK(cudaMemcpyAsync(h->pin_vec.p, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1114,9 +1131,13 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
     h->solved = false;
     const double *drhs = rhs_local;
     if (!on_device && h->local_dim > 0) {
-      h->pin_vec.ensure((size_t)h->local_dim + (size_t)h->m_c);
-      std::memcpy(h->pin_vec.p, rhs_local, (size_t)h->local_dim * sizeof(double));
-      CK(cudaMemcpyAsync(h->rhs.p, h->pin_vec.p, (size_t)h->local_dim * sizeof(double), cudaMemcpyHostToDevice, st));
+      const double *src = rhs_local;
+      if (!is_pinned_host(rhs_local)) {  // pageable caller memory: stage through the handle's pinned buffer
+        h->pin_vec.ensure((size_t)h->local_dim + (size_t)h->m_c);
+        std::memcpy(h->pin_vec.p, rhs_local, (size_t)h->local_dim * sizeof(double));
+        src = h->pin_vec.p;
+      }
+      CK(cudaMemcpyAsync(h->rhs.p, src, (size_t)h->local_dim * sizeof(double), cudaMemcpyHostToDevice, st));
       drhs = h->rhs.p;
     }
     h->last_rhs = drhs;
@@ -1151,9 +1172,40 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
     h->last_x = dx;
     h->last_xc = dxc;
     h->solved = true;
-    if (!on_device) copy_out(h, dx, dxc, x_local, x_c, st);
+    h->norms_valid = false;
+    if (!on_device && h->auto_residual) {
+      // single rank: nothing to reduce, so the residual norms ride on the synchronisation of the copy-out
+      if (h->res_buf.n < (size_t)mc + 2) h->res_buf.alloc((size_t)mc + 2);
+      enqueue_residual_local(h, h->res_buf.p, st);
+      enqueue_residual_norms(h, h->res_buf.p, st);
+      CK(cudaGetLastError());
+    }
+    if (!on_device) {
+      copy_out(h, dx, dxc, x_local, x_c, st);
+      h->norms_valid = h->auto_residual;
+    }
     return (int)PP_SUCCESSFUL;
   });
+}
+
+static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t st) {
+  if (h->res_blocks > 0) {
+    residual_rows_kernel<<<h->res_blocks, 256, 0, st>>>(h->rl_ptr.p, h->rl_col.p, h->rl_src.p, h->last_vals, h->last_x,
+                                                       h->last_xc, h->local_dim, h->last_rhs, h->res_loc.p,
+                                                       h->res_part.p, h->local_dim);
+    h->launches++;
+  }
+  residual_border_kernel<<<std::max(1, (h->m_c + 127) / 128), 128, 0, st>>>(
+      h->rb_ptr.p, h->rb_col.p, h->rb_src.p, h->last_vals, h->last_x, h->m_c, h->res_part.p, h->res_blocks, buf_dev);
+  h->launches++;
+}
+
+static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cudaStream_t st) {
+  residual_coupling_kernel<<<1, 256, 0, st>>>(h->rq_ptr.p, h->rq_col.p, h->rq_src.p, h->last_vals, h->last_xc,
+                                             h->bc_keep.p, buf_sum_dev, h->m_c, h->res_c.p, h->res_out.p);
+  h->launches++;
+  h->pin_out2.ensure(2);
+  CK(cudaMemcpyAsync(h->pin_out2.p, h->res_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
 }
 
 int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
@@ -1161,16 +1213,8 @@ int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
   if (!buf_dev) return fail("pp_residual_local: null buffer");
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (h->res_blocks > 0) {
-      residual_rows_kernel<<<h->res_blocks, 256, 0, st>>>(h->rl_ptr.p, h->rl_col.p, h->rl_src.p, h->last_vals, h->last_x,
-                                                         h->last_xc, h->local_dim, h->last_rhs, h->res_loc.p,
-                                                         h->res_part.p, h->local_dim);
-      h->launches++;
-    }
-    residual_border_kernel<<<std::max(1, (h->m_c + 127) / 128), 128, 0, st>>>(
-        h->rb_ptr.p, h->rb_col.p, h->rb_src.p, h->last_vals, h->last_x, h->m_c, h->res_part.p, h->res_blocks, buf_dev);
-    h->launches++;
+    h->norms_valid = false;
+    enqueue_residual_local(h, buf_dev, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return (int)PP_SUCCESSFUL;
   });
@@ -1178,15 +1222,17 @@ int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
 
 int pp_residual_norms(pp_handle *h, const double *buf_sum_dev, double out[2], void *stream) {
   if (!h || !h->solved) return fail("pp_residual_norms: a completed solve is required first");
-  if (!buf_sum_dev || !out) return fail("pp_residual_norms: null argument");
+  if (!out) return fail("pp_residual_norms: null argument");
+  if (h->norms_valid) {  // formed by pp_solve_backward (option "auto_residual"): nothing to launch or wait for
+    out[0] = h->pin_out2.p[0];
+    out[1] = h->pin_out2.p[1];
+    return PP_SUCCESSFUL;
+  }
+  if (!buf_sum_dev) return fail("pp_residual_norms: null argument");
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    residual_coupling_kernel<<<1, 256, 0, st>>>(h->rq_ptr.p, h->rq_col.p, h->rq_src.p, h->last_vals, h->last_xc,
-                                               h->bc_keep.p, buf_sum_dev, h->m_c, h->res_c.p, h->res_out.p);
-    h->launches++;
-    h->pin_out2.ensure(2);
-    CK(cudaMemcpyAsync(h->pin_out2.p, h->res_out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    enqueue_residual_norms(h, buf_sum_dev, st);
     CK(cudaStreamSynchronize(st));
     out[0] = h->pin_out2.p[0];
     out[1] = h->pin_out2.p[1];
@@ -1211,6 +1257,7 @@ int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, do
   return guarded([&]() {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    h->norms_valid = false;
     run_backward(h, rc_sum_dev, h->res_c.p, h->dx_tmp.p, h->dxc_tmp.p, st);
     if (h->local_dim > 0) {
       axpy1_kernel<<<(unsigned)((h->local_dim + 255) / 256), 256, 0, st>>>(h->last_x, h->dx_tmp.p, h->local_dim);

@@ -53,6 +53,7 @@ class CudaBackend:
         for key, val in (options or {}).items():
             self._check(self.lib.pp_set_option(self.handle, key.encode(), float(val)), "pp_set_option")
         self.st = None
+        self._auto_residual = False
 
     def _check(self, code, what):
         if code == 3:
@@ -145,10 +146,13 @@ class CudaBackend:
                     "pp_residual_local")
         return self.resbuf
 
+    def norms_ready(self):
+        return self._auto_residual
+
     def residual_norms(self, buf_sum):
         out = (C.c_double * 2)()
-        self._check(self.lib.pp_residual_norms(self.handle, C.c_void_p(buf_sum.data_ptr()), out, self._stream()),
-                    "pp_residual_norms")
+        ptr = C.c_void_p(buf_sum.data_ptr()) if buf_sum is not None else None
+        self._check(self.lib.pp_residual_norms(self.handle, ptr, out, self._stream()), "pp_residual_norms")
         return float(out[0]), float(out[1])
 
     def refine_forward(self):
@@ -180,6 +184,8 @@ class CudaBackend:
 
     def set_option(self, name, value):
         self._check(self.lib.pp_set_option(self.handle, name.encode(), float(value)), "pp_set_option")
+        if name == "auto_residual":
+            self._auto_residual = bool(value)
 
     def profile(self, reset=True):
         """Accumulated device milliseconds and launch counts per kernel class (see pp_profile)."""
@@ -249,6 +255,9 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             # travel in the tail of the Schur all-reduce.
             self._defer = 1 if self.comm.size == 1 else 2
             self.backend.set_option("defer_status", self._defer)
+            if self.comm.size == 1 and refine_tol > 0 and max_refine > 0:
+                # nothing to reduce: the residual norms of the first solve ride on the copy-out's synchronisation
+                self.backend.set_option("auto_residual", 1)
         self.block_dim = 0
         self.block_matrix = None
         self.local_block_indices = []
@@ -393,9 +402,12 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             return x_local, x_c
         be = self.backend
         for step in range(self.max_refine + 1):
-            buf = be.residual_local()
-            self.comm.allreduce_sum_(buf)
-            r2, b2 = be.residual_norms(buf)
+            if step == 0 and getattr(be, "norms_ready", lambda: False)():
+                r2, b2 = be.residual_norms(None)            # formed by pp_solve_backward ("auto_residual")
+            else:
+                buf = be.residual_local()
+                self.comm.allreduce_sum_(buf)
+                r2, b2 = be.residual_norms(buf)
             rel = float(np.sqrt(r2 / b2)) if b2 > 0 else float(np.sqrt(r2))
             stalled = self.last_residual is not None and not rel < 0.25 * self.last_residual
             self.last_residual = rel if self.last_residual is None else min(rel, self.last_residual)
