@@ -207,8 +207,47 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
   double *F = B.F;
   const int ld = B.ld;
   int t = 0;
+  int npos = 0, nneg = 0, nzero = 0;  // inertia of the 1x1 fast paths, kept by thread 0 and flushed once
   while (t < fs) {
-    {
+    if (NW == 1 && S <= LW) {
+      // One row per lane (front no taller than the group): the pivot column lives in a register, its entries reach
+      // the other lanes by shuffle, and every lane updates only its own row -- one warp-level barrier per column.
+      // Same test and same arithmetic as the general 1x1 step below.
+      const bool mine = lane > t && lane < S;
+      const double d = F[t + t * ld];
+      const double rd = 1.0 / d;  // issued ahead of the column reduction it does not depend on
+      const double w = mine ? F[lane + t * ld] : 0.0;
+      unsigned kmax = (mine && lane < ntest) ? ((unsigned)__double2hiint(w) & 0x7fffffffu) : 0u;
+      kmax = __reduce_max_sync(wmask, kmax);
+      const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
+      if (fabs(d) > pivtol && fabs(d) >= u * cmax) {
+        const double ws = w * rd;
+        // eight columns per batch: shuffles and loads of a batch are issued together, then the FMAs, then the
+        // stores (a column-at-a-time loop would serialise one shuffle + one shared-memory round trip per column)
+        for (int j0 = t + 1; j0 < S; j0 += 8) {
+          double wj[8], f[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            wj[q] = __shfl_sync(wmask, ws, j < S ? j : t, LW);
+            f[q] = (j < S && lane >= j && lane < S) ? F[lane + j * ld] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q;
+            if (j < S && lane >= j && lane < S) F[lane + j * ld] = f[q] - w * wj[q];
+          }
+        }
+        if (mine) F[lane + t * ld] = ws;
+        if (tid == 0) {
+          B.bsz[t] = 1;
+          if (d > 0.0) ++npos; else if (d < 0.0) ++nneg; else ++nzero;
+        }
+        gsync<G>();
+        t += 1;
+        continue;
+      }
+    } else {
       // Fast path, decided redundantly (and identically) by every warp, so nothing has to be published: the
       // diagonal of the leading column passes the threshold test as it is -- the first candidate the general
       // search below would accept.  One barrier per eliminated column instead of four.
@@ -226,7 +265,7 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
         }
         if (tid == 0) {
           B.bsz[t] = 1;
-          atomicAdd(&cnt[d > 0.0 ? 0 : (d < 0.0 ? 1 : 2)], 1);
+          if (d > 0.0) ++npos; else if (d < 0.0) ++nneg; else ++nzero;
         }
         gsync<G>();
         for (int i = t + 1 + tid; i < S; i += G) F[i + t * ld] *= rd;  // nobody reads column t any more
@@ -340,6 +379,11 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       t += 2;
     }
   }
+  if (tid == 0) {
+    if (npos) atomicAdd(&cnt[0], npos);
+    if (nneg) atomicAdd(&cnt[1], nneg);
+    if (nzero) atomicAdd(&cnt[2], nzero);
+  }
   return t;
 }
 
@@ -373,29 +417,38 @@ __device__ __forceinline__ void stage_prefix_warp(const Stage &stg, int nch, int
   if (lane == 0) { stg.cnt[nch] = ent; sh[4] = offd; sh[5] = nbig; sh[7] = ent > stg.cap ? 1 : 0; }
 }
 
-// dst[tgt[e]] += val[e] for e = 0..total-1 IN THAT ORDER, 32 entries per step on one warp: lanes that hit the same
-// target are found with match.any and their values are added in lane (= staged = child) order by every member of
-// the group; the lowest lane stores.  Same rounding as a serial walk, ~5x fewer dependent shared-memory round trips
-// when the children are tiny (a hub front of the generator family has 85 children of 6 entries each).
-__device__ __forceinline__ void apply_staged_warp(double *dst, const int *tgt, const double *val, int total) {
-  const int lane = threadIdx.x & 31;
-  for (int base = 0; base < total; base += 32) {
-    const int e = base + lane;
-    const bool on = e < total;
+// dst[tgt[e]] += val[e] over the staged entries e = 0..total-1, reproducibly: the entries are cut into rounds of 32;
+// inside a round, lanes that hit the same target are found with match.any and their values are summed in lane
+// (= staged = child) order; the rounds' partial sums are committed to dst in round order.  The warps of the group
+// prepare NW rounds concurrently (that is the expensive part: match, shuffles) and then take turns committing, so a
+// hub front with 85 tiny children costs a handful of barriers instead of 85 dependent shared-memory round trips.
+template <int G>
+__device__ __forceinline__ void apply_staged(double *dst, const int *tgt, const double *val, int total) {
+  constexpr int NW = Grp<G>::NW;
+  const int tid = gtid<G>(), lane = tid & 31, gw = tid >> 5;
+  const int rounds = (total + 31) >> 5;
+  for (int r0 = 0; r0 < rounds; r0 += NW) {
+    const int r = r0 + gw;
+    const int e = (r << 5) + lane;
+    const bool on = r < rounds && e < total;
     const int t = on ? tgt[e] : -1 - lane;  // distinct dummies for idle lanes
     const double v = on ? val[e] : 0.0;
     const unsigned m = __match_any_sync(0xffffffffu, t);
     const int mx = __reduce_max_sync(0xffffffffu, __popc(m));
-    double acc = on ? dst[t] : 0.0;
+    double part = 0.0;
     unsigned rest = m;
     for (int it = 0; it < mx; ++it) {
       const int src = rest ? __ffs(rest) - 1 : lane;
       const double x = __shfl_sync(0xffffffffu, v, src);
-      if (rest) acc += x;
+      if (rest) part += x;
       rest &= rest - 1;
     }
-    if (on && lane == __ffs(m) - 1) dst[t] = acc;
-    __syncwarp();
+    const bool leader = on && lane == __ffs(m) - 1;
+    const int live = min(NW, rounds - r0);
+    for (int q = 0; q < live; ++q) {
+      if (gw == q && leader) dst[t] += part;
+      if (NW > 1) gsync<G>(); else __syncwarp();
+    }
   }
 }
 
@@ -549,7 +602,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     PP_TRP(4);
     {
       const int total = stg.cnt[H.nch];
-      if (tid < 32) apply_staged_warp(F, stg.tgt, stg.val, total);
+      apply_staged<G>(F, stg.tgt, stg.val, total);
     }
     gsync<G>();
     PP_TRP(5);
@@ -606,6 +659,14 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       if (tid == 0) B.sh[6] = ne;
     }
     __syncthreads();
+    ne = B.sh[6];
+  } else if (G == 128 && S <= 32) {
+    // assembled by four warps, but a front this small pivots fastest on one (row-per-lane steps, warp barriers)
+    if (tid < 32) {
+      ne = factor_front<32>(B, S, fs, u, pivtol, cnt);
+      if (tid == 0) B.sh[6] = ne;
+    }
+    gsync<G>();
     ne = B.sh[6];
   } else {
     ne = factor_front<G>(B, S, fs, u, pivtol, cnt);
@@ -827,8 +888,27 @@ __device__ void load_front(const SparseBlock &Bk, const SnHead &H, const SolveBu
   const int tid = gtid<G>();
   const int caprows = H.nc + H.dcap + H.ncb;
   const double *Lg = Bk.L + H.l_off;
-  for (int j = G < 32 ? 0 : tid >> 5; j < ne; j += Grp<G>::NW)
-    for (int i = j + (tid & (Grp<G>::LW - 1)); i < S; i += Grp<G>::LW) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
+  constexpr int NWL = Grp<G>::NW, LWL = Grp<G>::LW;
+  const int wl = G < 32 ? 0 : tid >> 5, ll = tid & (LWL - 1);
+  if (S <= LWL) {
+    // short columns: four columns of global loads in flight before the first shared-memory store
+    for (int j0 = wl; j0 < ne; j0 += 4 * NWL) {
+      double v4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q * NWL;
+        v4[q] = (j < ne && ll >= j && ll < S) ? Lg[ll + (long long)j * caprows] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q * NWL;
+        if (j < ne && ll >= j && ll < S) B.Ls[ll + j * B.ld] = v4[q];
+      }
+    }
+  } else {
+    for (int j = wl; j < ne; j += NWL)
+      for (int i = j + ll; i < S; i += LWL) B.Ls[i + j * B.ld] = Lg[i + (long long)j * caprows];
+  }
   for (int i = tid; i < S; i += G) B.fid[i] = Bk.fid[H.fid_off + i];
   for (int i = tid; i < ne; i += G) B.bsz[i] = Bk.pbz[H.fs_off + i];
 }
@@ -838,6 +918,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
                               const double *__restrict__ rhs, double *__restrict__ y, const Stage &stg) {
   constexpr int LW = Grp<G>::LW;
   const int tid = gtid<G>(), lane = tid & (LW - 1);
+  PP_TRP(0);
   const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], fs = ne + Bk.meta[3 * s + 2];
   if (S == 0) return;
   const SnHead H = P.heads[s];
@@ -846,9 +927,11 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
   load_front<G>(Bk, H, B, ne, S);
   for (int i = tid; i < fs; i += G) B.inv[Bk.opos[H.fs_off + i]] = i;  // pre-pivot -> stored position
   gsync<G>();
+  PP_TRP(1);
   for (int i = tid; i < S; i += G)
     B.v[i] = (i < fs && Bk.opos[H.fs_off + i] < nc) ? rhs[B.fid[i]] : 0.0;
   gsync<G>();
+  PP_TRP(2);
   if (G >= 128 && H.nch >= 4 && H.nch <= stg.maxch) {
     // many children: fetch their vectors concurrently (one child per thread), apply in child order
     for (int k = tid; k < H.nch; k += G) {
@@ -860,6 +943,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
     if (tid < 32) stage_prefix_warp(stg, H.nch, stg.big);  // no big children here: big[] doubles as scratch
     gsync<G>();
     const int total = stg.cnt[H.nch];
+    PP_TRP(3);
     if (total <= stg.cap) {
       for (int k = tid; k < H.nch; k += G) {
         const int c = P.child_idx[H.ch0 + k];
@@ -891,8 +975,10 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
         }
       }
       gsync<G>();
-      if (tid < 32) apply_staged_warp(B.v, stg.tgt, stg.val, total);
+      PP_TRP(4);
+      apply_staged<G>(B.v, stg.tgt, stg.val, total);
       gsync<G>();
+      PP_TRP(5);
     } else {
       for (int k = 0; k < H.nch; ++k) {
         const int c = P.child_idx[H.ch0 + k];
@@ -929,15 +1015,30 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
     }
   }
   if (tid < 32) {
-    for (int c = 0; c < ne; ++c) {
-      const double zc = B.v[c];
-      const int skip = B.bsz[c] == 2 ? c + 1 : -1;
-      for (int i = c + 1 + lane; i < ne; i += LW)
-        if (i != skip) B.v[i] -= B.Ls[i + c * B.ld] * zc;
-      __syncwarp(gmask<G>());
+    if (ne <= LW) {
+      // one row per lane: the solved entries travel by shuffle, the L entries are independent loads that pipeline
+      // (the loop over shared memory below costs a load-FMA-store-barrier chain per column)
+      const unsigned wm = gmask<G>();
+      double x = lane < ne ? B.v[lane] : 0.0;
+      const int flag = lane < ne ? B.bsz[lane] : 1;
+      for (int c = 0; c < ne; ++c) {
+        const double zc = __shfl_sync(wm, x, c, LW);
+        const int fc = __shfl_sync(wm, flag, c, LW);
+        if (lane > c && lane < ne && !(fc == 2 && lane == c + 1)) x -= B.Ls[lane + c * B.ld] * zc;
+      }
+      if (lane < ne) B.v[lane] = x;
+    } else {
+      for (int c = 0; c < ne; ++c) {
+        const double zc = B.v[c];
+        const int skip = B.bsz[c] == 2 ? c + 1 : -1;
+        for (int i = c + 1 + lane; i < ne; i += LW)
+          if (i != skip) B.v[i] -= B.Ls[i + c * B.ld] * zc;
+        __syncwarp(gmask<G>());
+      }
     }
   }
   gsync<G>();
+  PP_TRP(6);
   double *out = Bk.vec + H.vec_off;
   for (int i = ne + tid; i < S; i += G) {
     double acc = 0.0;
@@ -946,6 +1047,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
   }
   for (int i = tid; i < ne; i += G) y[B.fid[i]] = B.v[i];
   gsync<G>();
+  PP_TRP(7);
 }
 
 template <int G>
@@ -981,11 +1083,22 @@ __device__ void backward_front(const SparseBlock &Bk, const PlanDev &P, int s, c
   }
   gsync<G>();
   if (tid < 32) {
-    for (int rr = ne - 1; rr > 0; --rr) {
-      const double xv = B.z[rr];
-      for (int c = lane; c < rr; c += LW)
-        if (!(B.bsz[c] == 2 && rr == c + 1)) B.z[c] -= B.Ls[rr + c * B.ld] * xv;
-      __syncwarp(gmask<G>());
+    if (ne <= LW) {
+      const unsigned wm = gmask<G>();
+      double x = lane < ne ? B.z[lane] : 0.0;
+      const bool pair = lane < ne && B.bsz[lane] == 2;  // (lane, lane + 1) is a 2x2 pivot: no L entry between them
+      for (int rr = ne - 1; rr > 0; --rr) {
+        const double xv = __shfl_sync(wm, x, rr, LW);
+        if (lane < rr && !(pair && rr == lane + 1)) x -= B.Ls[rr + lane * B.ld] * xv;
+      }
+      if (lane < ne) B.z[lane] = x;
+    } else {
+      for (int rr = ne - 1; rr > 0; --rr) {
+        const double xv = B.z[rr];
+        for (int c = lane; c < rr; c += LW)
+          if (!(B.bsz[c] == 2 && rr == c + 1)) B.z[c] -= B.Ls[rr + c * B.ld] * xv;
+        __syncwarp(gmask<G>());
+      }
     }
   }
   gsync<G>();

@@ -15,7 +15,9 @@ s.do_symbolic_factorization(kkt)
 lib = native.load()
 for _ in range(3):
     torch.cuda.synchronize(); lib.pp_debug_trace_reset()
-    s.do_numeric_factorization(kkt); torch.cuda.synchronize(); x = s.do_back_solve(rhs)
+    s.do_numeric_factorization(kkt); torch.cuda.synchronize()
+    if os.environ.get("TRACE_SOLVE"): lib.pp_debug_trace_reset()
+    x = s.do_back_solve(rhs)
 torch.cuda.synchronize()
 buf = (C.c_longlong * 2048)()
 lib.pp_debug_trace.argtypes = [C.c_void_p, C.c_int]
@@ -34,7 +36,10 @@ for base, name in ((0, "factor"), (1024, "forward")):
         print(f"  root extend-add: {(tt[4 * nlev] - tt[4 * nlev - 1]) / mhz:7.2f} us")
 
 ph = t[256:1016]; ph = ph[ph != 0]
-names = ["start", "children counted", "zero+ids", "orig entries", "children fetched", "children applied", "big children", "factor", "stored"]
+if os.environ.get("TRACE_SOLVE"):
+    names = ["start", "L loaded + inv", "v init", "children counted", "children fetched", "children applied", "tri solve", "out stored", "-"]
+else:
+    names = ["start", "children counted", "zero+ids", "orig entries", "children fetched", "children applied", "big children", "factor", "stored"]
 print("process_front<128> phases (group 0 of block 0), us since previous stamp:")
 prev = None
 for v in ph[:200]:
