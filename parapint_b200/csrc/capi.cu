@@ -1069,13 +1069,10 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
   CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
   CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
   if (mc > 0) {
-    vec_add_kernel<<<(mc + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, mc, h->crhs.p);
     const size_t sm = solve_smem(mc);
-    const Front *cf = h->fronts.p + h->n_local;
-    front_forward_kernel<512><<<1, 512, sm, st>>>(cf, h->crhs.p, h->rhs_off.p + h->n_local);
-    front_backward_kernel<512><<<1, 512, sm, st>>>(cf, nullptr, h->brow_ptr.p + h->n_local, h->brow.p, dxc,
-                                                  h->rhs_off.p + h->n_local);
-    h->launches += 3;
+    CK(cudaFuncSetAttribute(coupling_solve_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    coupling_solve_kernel<512><<<1, 512, sm, st>>>(h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
+    h->launches++;
   }
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_BACKWARD, st);

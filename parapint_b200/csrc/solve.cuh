@@ -118,7 +118,16 @@ __global__ void rc_gather_kernel(const Front *__restrict__ fronts, const int64_t
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m_c) return;
   double s = 0.0;
-  for (int64_t p = src_ptr[r]; p < src_ptr[r + 1]; ++p) s += fronts[src_front[p]].bvec[src_pos[p]];
+  const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
+  for (int64_t pb = p0; pb < p1; pb += 4) {  // four sources in flight; the additions keep their order
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = pb + q < p1 ? fronts[src_front[pb + q]].bvec[src_pos[pb + q]] : 0.0;
+    s += v[0];
+    s += v[1];
+    s += v[2];
+    s += v[3];
+  }
   rc[r] = s;
 }
 
@@ -223,17 +232,21 @@ __device__ __forceinline__ void load_tri(const Front &F, int kb, int bw, double 
 }
 
 // v lives in dynamic shared memory (nf doubles) followed by the SB x SPITCH diagonal block.
+// forward sweep of one dense front; `r` (and `r2`, optional second addend) indexed by original row
 template <int NT>
-__global__ void __launch_bounds__(NT) front_forward_kernel(const Front *__restrict__ fronts,
-                                                           const double *__restrict__ rhs,
-                                                           const int64_t *__restrict__ rhs_off) {
-  extern __shared__ double sm[];
-  const Front F = fronts[blockIdx.x];
+__device__ __forceinline__ void front_forward_body(const Front &F, double *sm, const double *__restrict__ r,
+                                                   const double *__restrict__ r2) {
   const int n = F.n, nf = F.nf, ld = F.ld, tid = threadIdx.x;
   double *v = sm;
   double *tri = sm + ((nf + 1) & ~1);
-  const double *r = rhs + rhs_off[blockIdx.x];
-  for (int i = tid; i < nf; i += NT) v[i] = i < n ? r[F.perm[i]] : 0.0;
+  for (int i = tid; i < nf; i += NT) {
+    double val = 0.0;
+    if (i < n) {
+      const int o = F.perm[i];
+      val = r2 ? r[o] + r2[o] : r[o];
+    }
+    v[i] = val;
+  }
   __syncthreads();
   for (int kb = 0; kb < n; kb += SB) {
     const int bw = min(SB, n - kb);
@@ -278,23 +291,25 @@ __global__ void __launch_bounds__(NT) front_forward_kernel(const Front *__restri
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) front_backward_kernel(const Front *__restrict__ fronts,
-                                                            const double *__restrict__ xc,
-                                                            const int64_t *__restrict__ brow_ptr,
-                                                            const int32_t *__restrict__ brow,
-                                                            double *__restrict__ x,
-                                                            const int64_t *__restrict__ x_off) {
+__global__ void __launch_bounds__(NT) front_forward_kernel(const Front *__restrict__ fronts,
+                                                           const double *__restrict__ rhs,
+                                                           const int64_t *__restrict__ rhs_off) {
   extern __shared__ double sm[];
   const Front F = fronts[blockIdx.x];
+  front_forward_body<NT>(F, sm, rhs + rhs_off[blockIdx.x], nullptr);
+}
+
+// backward sweep of one dense front; border values from xc[br[a]], result scattered to out[perm[i]]
+template <int NT>
+__device__ __forceinline__ void front_backward_body(const Front &F, double *sm, const double *__restrict__ xc,
+                                                    const int32_t *__restrict__ br, double *__restrict__ out) {
   const int n = F.n, nf = F.nf, ld = F.ld, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   double *v = sm;
   double *tri = sm + ((nf + 1) & ~1);
   for (int i = tid; i < F.nb; i += NT) v[i] = i < n ? F.zbuf[i] : 0.0;
-  if (F.m > 0) {
-    const int32_t *br = brow + brow_ptr[blockIdx.x];
+  if (F.m > 0)
     for (int a = tid; a < F.m; a += NT) v[F.nb + a] = xc[br[a]];
-  }
   __syncthreads();
   for (int kb = ((n - 1) / SB) * SB; kb >= 0; kb -= SB) {
     const int bw = min(SB, n - kb);
@@ -321,8 +336,33 @@ __global__ void __launch_bounds__(NT) front_backward_kernel(const Front *__restr
     }
     __syncthreads();
   }
-  double *out = x + x_off[blockIdx.x];
   for (int i = tid; i < n; i += NT) out[F.perm[i]] = v[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) front_backward_kernel(const Front *__restrict__ fronts,
+                                                            const double *__restrict__ xc,
+                                                            const int64_t *__restrict__ brow_ptr,
+                                                            const int32_t *__restrict__ brow,
+                                                            double *__restrict__ x,
+                                                            const int64_t *__restrict__ x_off) {
+  extern __shared__ double sm[];
+  const Front F = fronts[blockIdx.x];
+  front_backward_body<NT>(F, sm, xc, brow + brow_ptr[blockIdx.x], x + x_off[blockIdx.x]);
+}
+
+// The coupling system S x_c = r_c + sum_i rc_i in ONE launch (one CTA): right-hand side formed on the fly, forward
+// sweep, D^-1, backward sweep.  The coupling front has no border rows.
+template <int NT>
+__global__ void __launch_bounds__(NT) coupling_solve_kernel(const Front *__restrict__ front,
+                                                            const double *__restrict__ rhs_c,
+                                                            const double *__restrict__ rc_sum,
+                                                            double *__restrict__ x_c) {
+  extern __shared__ double sm[];
+  const Front F = *front;
+  front_forward_body<NT>(F, sm, rhs_c, rc_sum);
+  __syncthreads();  // zbuf written above is read below by other threads of this CTA
+  front_backward_body<NT>(F, sm, nullptr, nullptr, x_c);
 }
 
 }  // namespace ppb
