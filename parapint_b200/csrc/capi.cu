@@ -143,6 +143,7 @@ struct pp_handle {
   DevBuf<unsigned long long> inertia;  // [0..2] local, [3..5] coupling
   DevBuf<int64_t> asm_dst, asm_ptr, asm_src, src_ptr, brow_ptr, rhs_off, root_off64;
   DevBuf<int32_t> src_front, src_pos, brow;
+  DevBuf<int64_t> src_boff;       // per Schur source: offset of the front's bvec entry in arenaZ (rc_gather)
   PinBuf<double> pin_vals, pin_vec;
   PinBuf<int> pin_flag;
   PinBuf<unsigned long long> pin_inertia;
@@ -742,6 +743,12 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->src_ptr.upload(sptr);
   h->src_front.upload(sfront);
   h->src_pos.upload(spos);
+  {
+    std::vector<int64_t> boff(spos.size());
+    for (size_t p = 0; p < spos.size(); ++p)
+      boff[p] = (int64_t)offZ[(size_t)sfront[p]] + h->n[(size_t)sfront[p]] + spos[p];
+    h->src_boff.upload(boff);
+  }
 
   // ---- row lists of K for the residual (iterative refinement) ----
   {
@@ -1054,8 +1061,8 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
     h->launches += 2;
   }
   if (h->m_c > 0) {
-    rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
-                                                          h->m_c, rc_local_dev);
+    rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->arenaZ.p, h->src_ptr.p, h->src_boff.p, h->m_c,
+                                                          rc_local_dev);
     h->launches++;
   }
   CK(cudaGetLastError());

@@ -112,21 +112,18 @@ __global__ void coupling_add_kernel(Front F, const double *__restrict__ Ssum, in
   F.A[(size_t)r + (size_t)c * F.ld] += Ssum[(size_t)r + (size_t)c * m_c];
 }
 
-__global__ void rc_gather_kernel(const Front *__restrict__ fronts, const int64_t *__restrict__ src_ptr,
-                                 const int32_t *__restrict__ src_front, const int32_t *__restrict__ src_pos,
-                                 int m_c, double *__restrict__ rc) {
+__global__ void rc_gather_kernel(const double *__restrict__ zarena, const int64_t *__restrict__ src_ptr,
+                                 const int64_t *__restrict__ src_boff, int m_c, double *__restrict__ rc) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m_c) return;
   double s = 0.0;
   const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
-  for (int64_t pb = p0; pb < p1; pb += 4) {  // four sources in flight; the additions keep their order
-    double v[4];
+  for (int64_t pb = p0; pb < p1; pb += 8) {  // eight sources in flight; the additions keep their (front) order
+    double v[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = pb + q < p1 ? fronts[src_front[pb + q]].bvec[src_pos[pb + q]] : 0.0;
-    s += v[0];
-    s += v[1];
-    s += v[2];
-    s += v[3];
+    for (int q = 0; q < 8; ++q) v[q] = pb + q < p1 ? zarena[src_boff[pb + q]] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
   }
   rc[r] = s;
 }
@@ -177,13 +174,24 @@ __global__ void residual_border_kernel(const long long *__restrict__ ptr, const 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < m_c) {
     double s = 0.0;
-    for (long long p = ptr[g]; p < ptr[g + 1]; ++p) s += vals[src[p]] * x[col[p]];
+    const long long p0 = ptr[g], p1 = ptr[g + 1];
+    for (long long pb = p0; pb < p1; pb += 8) {  // eight products in flight; the additions keep their order
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = pb + q < p1 ? vals[src[pb + q]] * x[col[pb + q]] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += t[q];
+    }
     buf[g] = -s;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 2) {
+  if (blockIdx.x == 0 && threadIdx.x < 64) {
+    // the two norms: warp w sums the partials of component w, each lane a strided subset, then a fixed tree
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int k = 0; k < nparts; ++k) s += part[2 * k + threadIdx.x];
-    buf[m_c + threadIdx.x] = s;
+    for (int k = lane; k < nparts; k += 32) s += part[2 * k + w];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) buf[m_c + w] = s;
   }
 }
 
