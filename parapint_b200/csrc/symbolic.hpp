@@ -687,6 +687,9 @@ inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const 
                               const std::vector<double> *hint = nullptr) {
   PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, false, hint);
   if (force_dense || md.ns == 0 || opt.ordering == 1) return md;
+  // nested dissection only pays when minimum degree left a deep tree (its staged ordering costs 5-10x the time of
+  // plain minimum degree on 20 000-row blocks, and it is rejected below whenever it inflates the root)
+  if (opt.ordering == 0 && md.nlevels <= 24) return md;
   PatternPlan nd = build_plan_with(n, m, rows, cols, src, opt, force_dense, true, hint);
   if (opt.ordering == 2) return nd;
   if (nd.ns == 0) return md;

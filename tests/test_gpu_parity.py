@@ -237,3 +237,27 @@ def test_wide_border_sparse_blocks(shape, cluster):
     assert o.numeric(kkt) == 0
     x_ref = o.solve(rhs).flatten()
     assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+
+
+@pytest.mark.parametrize("options", [{"defer_status": 0, "auto_residual": 0}, {"small_front": 0}, {"sparse": 0}])
+def test_alternative_control_paths(options):
+    """The synchronous status path several ranks fall back to (every phase reports its own status), the dense
+    panel / interchange / update launch sequence for small fronts, and whole blocks as dense fronts must give the
+    same answers as the default single-rank fast paths."""
+    m = EstimationModel(6, 40, 3, 8)
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s0, x0 = _solve(kkt, rhs)
+    s1, x1 = _solve(kkt, rhs, options=options)
+    assert s1.get_inertia() == s0.get_inertia() == m.expected_inertia()
+    assert _rel_residual(kkt, x1, rhs) <= 1e-10
+    assert np.linalg.norm(x1.flatten() - x0.flatten()) / np.linalg.norm(x0.flatten()) <= 1e-10
+    # a singular block is reported by both status paths
+    dense = np.zeros((5, 5))
+    dense[:2, :2] = [[1.0, 2.0], [2.0, 4.0]]  # rank 1
+    dense[2:4, 2:4] = np.eye(2)
+    dense[4, 4] = 1.0
+    dense[4, 0] = dense[0, 4] = 1.0
+    bad = bordered_from_dense(dense, [2, 2, 1])
+    s = B200SchurComplementLinearSolver(options=options)
+    s.do_symbolic_factorization(bad)
+    assert s.do_numeric_factorization(bad, raise_on_error=False).status == LinearSolverStatus.singular
