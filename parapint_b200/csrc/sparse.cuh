@@ -464,6 +464,9 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   const SnHead H = P.heads[s];
   const int nc = H.nc, ncb = H.ncb;
   const bool staged = G >= 128 && H.nch >= 4 && H.nch <= stg.maxch;
+  const bool pref = G <= 32 && H.nch > 0 && H.nch <= Grp<G>::LW;
+  int pc = 0, pcne = 0, pdim = 0, pndo = 0, pfid = 0, pr0 = 0;  // this lane's child (pref)
+  long long pcb = 0;
   int nd_in = 0;
   if (staged) {
     // one child per thread: delayed count and staged-entry count; serial prefix by thread 0
@@ -495,6 +498,23 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
       gsync<G>();
     }
     nd_in = B.sh[4];
+  } else if (pref) {
+    // (sub-)warp groups: lane k fetches everything about child k at once -- two dependent round trips for all the
+    // children instead of four per child; the loop below reads the fields by shuffle
+    if (tid < H.nch) {
+      pc = P.child_idx[H.ch0 + tid];
+      pcne = Bk.meta[3 * pc];
+      pdim = Bk.meta[3 * pc + 1] - pcne;
+      pndo = Bk.meta[3 * pc + 2];
+      const SnHead *C = P.heads + pc;
+      pfid = C->fid_off;
+      pr0 = C->r0;
+      pcb = C->cb_off;
+    }
+    int v = tid < H.nch ? pndo : 0;
+#pragma unroll
+    for (int o = Grp<G>::LW / 2; o; o >>= 1) v += __shfl_xor_sync(gmask<G>(), v, o, Grp<G>::LW);
+    nd_in = v;
   } else {
     for (int k = 0; k < H.nch; ++k) nd_in += Bk.meta[3 * P.child_idx[H.ch0 + k] + 2];
   }
@@ -620,30 +640,83 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
         else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
       }
       gsync<G>();
-      for (int j = gwp; j < dim; j += NWG) {
-        const int mj = B.map[j];
-        for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+      if (dim <= LWG) {
+        // one contribution row per lane: four columns of global loads in flight before the first update
+        const int mi = lanep < dim ? B.map[lanep] : 0;
+        for (int j0 = gwp; j0 < dim; j0 += 4 * NWG) {
+          double mv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q * NWG;
+            mv[q] = (j < dim && lanep >= j && lanep < dim) ? M[lanep + j * dim] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q * NWG;
+            if (j < dim && lanep >= j && lanep < dim) fent(F, ld, mi, B.map[j]) += mv[q];
+          }
+        }
+      } else {
+        for (int j = gwp; j < dim; j += NWG) {
+          const int mj = B.map[j];
+          for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        }
       }
       gsync<G>();
     }
   } else {
     int off = 0;
     for (int k = 0; k < H.nch; ++k) {
-      const int c = P.child_idx[H.ch0 + k];
-      const SnHead C = P.heads[c];
-      const int cne = Bk.meta[3 * c], cS = Bk.meta[3 * c + 1], ndo = Bk.meta[3 * c + 2];
-      const int dim = cS - cne;
-      const int *ids = Bk.fid + C.fid_off + cne;
-      const int *crel = P.rel + C.r0;
-      const double *M = Bk.cb + C.cb_off;
+      int cne, dim, ndo, c_fid, c_r0;
+      long long c_cb;
+      if (pref) {
+        const unsigned gm = gmask<G>();
+        constexpr int LWP = Grp<G>::LW;
+        cne = __shfl_sync(gm, pcne, k, LWP);
+        dim = __shfl_sync(gm, pdim, k, LWP);
+        ndo = __shfl_sync(gm, pndo, k, LWP);
+        c_fid = __shfl_sync(gm, pfid, k, LWP);
+        c_r0 = __shfl_sync(gm, pr0, k, LWP);
+        c_cb = __shfl_sync(gm, pcb, k, LWP);
+      } else {
+        const int c = P.child_idx[H.ch0 + k];
+        const SnHead C = P.heads[c];
+        cne = Bk.meta[3 * c];
+        dim = Bk.meta[3 * c + 1] - cne;
+        ndo = Bk.meta[3 * c + 2];
+        c_fid = C.fid_off;
+        c_r0 = C.r0;
+        c_cb = C.cb_off;
+      }
+      const int *ids = Bk.fid + c_fid + cne;
+      const int *crel = P.rel + c_r0;
+      const double *M = Bk.cb + c_cb;
       for (int i = tid; i < dim; i += G) {
         if (i < ndo) { B.map[i] = nc + off + i; B.fid[nc + off + i] = ids[i]; }
         else { const int rr = crel[i - ndo]; B.map[i] = rr < nc ? rr : rr + nd_in; }
       }
       gsync<G>();
-      for (int j = gwp; j < dim; j += NWG) {
-        const int mj = B.map[j];
-        for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+      if (dim <= LWG) {
+        // one contribution row per lane: four columns of global loads in flight before the first update
+        const int mi = lanep < dim ? B.map[lanep] : 0;
+        for (int j0 = gwp; j0 < dim; j0 += 4 * NWG) {
+          double mv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q * NWG;
+            mv[q] = (j < dim && lanep >= j && lanep < dim) ? M[lanep + j * dim] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q * NWG;
+            if (j < dim && lanep >= j && lanep < dim) fent(F, ld, mi, B.map[j]) += mv[q];
+          }
+        }
+      } else {
+        for (int j = gwp; j < dim; j += NWG) {
+          const int mj = B.map[j];
+          for (int i = j + lanep; i < dim; i += LWG) fent(F, ld, B.map[i], mj) += M[i + j * dim];
+        }
       }
       gsync<G>();
       off += ndo;
