@@ -20,7 +20,7 @@ __device__ long long g_trace[2048];
 #define PP_TR(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (slot) < 2048) g_trace[(slot)] = clock64(); } while (0)
 __device__ int g_tp;
 // phase stamps inside process_front / forward_front (group 0 of block 0 only): (cycles << 4) | phase
-#define PP_TRP(ph) do { if (G == 128 && blockIdx.x == 0 && threadIdx.x == 0) { const int q_ = g_tp++; if (q_ < 760) g_trace[256 + q_] = (clock64() << 4) | (ph); } } while (0)
+#define PP_TRP(ph) do { if (G == SF_MG && blockIdx.x == 0 && threadIdx.x == 0) { const int q_ = g_tp++; if (q_ < 760) g_trace[256 + q_] = (clock64() << 4) | (ph); } } while (0)
 #else
 #define PP_TR(slot) do { } while (0)
 #define PP_TRP(ph) do { } while (0)
@@ -84,8 +84,9 @@ constexpr size_t SF_TINY_BYTES = (fb_bytes(SF_TBUF, SF_TLD) + 15) / 16 * 16;
 constexpr int SF_STG = 2048;     // staged entries
 constexpr int SF_MAXCH = 512;    // children per staging batch
 constexpr int SF_CHDIM = 12;     // largest child contribution block that is staged
-// quarter-CTA groups: fronts of up to SF_MBUF rows, each group with its own staging area
-constexpr int SF_MBUF = 32, SF_MLD = SF_MBUF + 1, SF_MSTG = 1024, SF_MMAXCH = 256, SF_NG = 4;
+// two-warp groups: fronts of up to SF_MBUF rows, each group with its own staging area
+constexpr int SF_MBUF = 32, SF_MLD = SF_MBUF + 1, SF_MSTG = 1024, SF_MMAXCH = 256;
+constexpr int SF_MG = 64, SF_NG = 512 / SF_MG;  // medium fronts: eight groups of two warps (named barriers 1..8)
 
 
 struct Stage {
@@ -135,8 +136,8 @@ __device__ __forceinline__ FrontBuf carve(unsigned char *base, int cap, int ld) 
   return b;
 }
 
-// groups: part of a warp (8 or 16 lanes: several tiny leaf fronts share a warp), a warp (32), a quarter-CTA of
-// four warps (128, named barrier 1 + group index) or the whole CTA
+// groups: part of a warp (8 or 16 lanes: several tiny leaf fronts share a warp), a warp (32), two or four warps
+// (64 / 128 threads, named barrier 1 + group index) or the whole CTA
 template <int G> struct Grp {
   static constexpr int LW = G < 32 ? G : 32;       // lanes that walk a column together
   static constexpr int NW = G < 32 ? 1 : G / 32;   // warps of the group
@@ -145,11 +146,12 @@ template <int G> __device__ __forceinline__ unsigned gmask() {  // lanes of this
   return G < 32 ? (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1))) : 0xffffffffu;
 }
 template <int G> __device__ __forceinline__ int gtid() {
-  return G <= 32 ? (int)(threadIdx.x & (G - 1)) : (G == 128 ? (int)(threadIdx.x & 127) : (int)threadIdx.x);
+  return G <= 128 ? (int)(threadIdx.x & (G - 1)) : (int)threadIdx.x;
 }
 template <int G> __device__ __forceinline__ void gsync() {
   if (G <= 32) __syncwarp(gmask<G>());
   else if (G == 128) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
+  else if (G == 64) asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");
   else __syncthreads();
 }
 
@@ -316,7 +318,7 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       }
       if (lane == 0) { B.sh[0] = kind; B.sh[1] = pc; B.sh[2] = pr; }
 #ifdef PP_TRACE
-      if (G == 128 && blockIdx.x == 0 && threadIdx.x == 0) {
+      if (G == SF_MG && blockIdx.x == 0 && threadIdx.x == 0) {
         g_trace[2040 + kind] += 1;              // steps by kind (0 = no pivot, 1, 2)
         g_trace[2043] += (pc >= 0 ? (kind == 2 ? min(pc, pr) : pc) - t + 1 : fs - t);  // candidates examined (approx.)
         g_trace[2044] = clock64();
@@ -463,7 +465,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
   PP_TRP(0);
   const SnHead H = P.heads[s];
   const int nc = H.nc, ncb = H.ncb;
-  const bool staged = G >= 128 && H.nch >= 4 && H.nch <= stg.maxch;
+  const bool staged = G >= SF_MG && H.nch >= 4 && H.nch <= stg.maxch;
   const bool pref = G <= 32 && H.nch > 0 && H.nch <= Grp<G>::LW;
   int pc = 0, pcne = 0, pdim = 0, pndo = 0, pfid = 0, pr0 = 0;  // this lane's child (pref)
   long long pcb = 0;
@@ -733,8 +735,8 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     }
     __syncthreads();
     ne = B.sh[6];
-  } else if (G == 128 && S <= 32) {
-    // assembled by four warps, but a front this small pivots fastest on one (row-per-lane steps, warp barriers)
+  } else if (G == SF_MG && S <= 32) {
+    // assembled by two warps, but a front this small pivots fastest on one (row-per-lane steps, warp barriers)
     if (tid < 32) {
       ne = factor_front<32>(B, S, fs, u, pivtol, cnt);
       if (tid == 0) B.sh[6] = ne;
@@ -817,7 +819,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
   const Front R = fronts[Bk.root];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = tid / SF_MG;
   // the three work areas alias each other: the passes of a level are separated by block barriers
   const FrontBuf big = carve(sm_raw, SF_SBUF, SF_LDF);
   const Stage stg = carve_stage(sm_raw + SF_BIG_FB, SF_STG, SF_MAXCH);
@@ -844,11 +846,11 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     }
     __syncthreads();
     PP_TR(4 * l + 1);
-    // ---- medium fronts (up to 32 rows, any number of children): four warps each, four at a time ----
+    // ---- medium fronts (up to 32 rows, any number of children): two warps each, eight at a time ----
     for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
       const int s = P.med_idx[k];
-      const int rc = process_front<128>(Bk, P, vals, s, med, u, pivtol, cnt, mstg);
-      if ((tid & 127) == 0) {
+      const int rc = process_front<SF_MG>(Bk, P, vals, s, med, u, pivtol, cnt, mstg);
+      if ((tid & (SF_MG - 1)) == 0) {
         if (rc == PF_DEFER) {
           const int pos = atomicAdd(&cnt[4], 1);
           if (pos < 64) deferred[pos] = s; else cnt[3] = 1;
@@ -1005,7 +1007,7 @@ __device__ void forward_front(const SparseBlock &Bk, const PlanDev &P, int s, co
     B.v[i] = (i < fs && Bk.opos[H.fs_off + i] < nc) ? rhs[B.fid[i]] : 0.0;
   gsync<G>();
   PP_TRP(2);
-  if (G >= 128 && H.nch >= 4 && H.nch <= stg.maxch) {
+  if (G >= SF_MG && H.nch >= 4 && H.nch <= stg.maxch) {
     // many children: fetch their vectors concurrently (one child per thread), apply in child order
     for (int k = tid; k < H.nch; k += G) {
       const int c = P.child_idx[H.ch0 + k];
@@ -1189,7 +1191,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
-  const int tid = threadIdx.x, warp = tid >> 5, grp = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, grp = tid / SF_MG;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
   const Stage stg = carve_stage(sm_raw + SV_BIG_SB, SF_STG, SF_MAXCH);
   const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
@@ -1207,7 +1209,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
     PP_TR(1024 + 4 * l + 1);
     for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
       const int s = P.med_idx[k];
-      if (Bk.meta[3 * s + 1] <= SF_MBUF) forward_front<128>(Bk, P, s, med, r, y, mstg);
+      if (Bk.meta[3 * s + 1] <= SF_MBUF) forward_front<SF_MG>(Bk, P, s, med, r, y, mstg);
     }
     __syncthreads();
     PP_TR(1024 + 4 * l + 2);
@@ -1254,7 +1256,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const SparseBlock Bk = blocks[blockIdx.x];
   const PlanDev P = plans[Bk.plan];
-  const int tid = threadIdx.x, warp = tid >> 5, grp = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, grp = tid / SF_MG;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
   const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
@@ -1282,7 +1284,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
     __syncthreads();
     for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
       const int s = P.med_idx[k];
-      if (Bk.meta[3 * s + 1] <= SF_MBUF) backward_front<128>(Bk, P, s, med, y, x);
+      if (Bk.meta[3 * s + 1] <= SF_MBUF) backward_front<SF_MG>(Bk, P, s, med, y, x);
     }
     __syncthreads();
     for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {

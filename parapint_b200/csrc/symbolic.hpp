@@ -42,7 +42,7 @@ struct PatternPlan {
   int vec_total = 0;
   int nlevels = 0;                         // height classes: level 0 = leaves
   std::vector<int> tiny_ptr, tiny_idx;     // per level: fronts small enough for one warp
-  std::vector<int> med_ptr, med_idx;       // per level: fronts for a quarter-CTA (<= medium rows, any children)
+  std::vector<int> med_ptr, med_idx;       // per level: fronts for a two-warp group (<= medium rows, any children)
   std::vector<int> big_ptr, big_idx;       // per level: fronts factored by the whole CTA
   int max_front = 0;                  // largest subtree front incl. delayed capacity actually allowed
   int64_t nnz_l = 0;                  // static entries of L in the subtree part (statistics)
@@ -251,10 +251,12 @@ struct PlanOptions {
   int merge_max = 16;   // largest front produced by a merge that introduces explicit zeros
   int dslot = 16;       // delayed columns one front may hand to its parent
   int tiny = 16;        // largest static front handled by a single warp
-  int medium = 24;      // largest static front handled by four warps
+  int medium = 24;      // largest static front handled by a two-warp group
   int tiny_max_children = 8;  // fronts with more children are assembled by the whole CTA (staged fetch)
   int nd_leaf = 48;     // nested dissection stops at components of this many vertices
-  int ordering = 0;     // 0 = pick the cheaper of minimum degree and nested dissection, 1 = MD, 2 = ND
+  int int_leaf = 16;    // interior dissection: pieces of at most this many (paired) columns -- one medium front each
+  int int_max = 4096;   // ... attempted only on interiors up to this size (the staged ordering is slower)
+  int ordering = 0;     // 0 = cheapest schedule of the three, 1 = minimum degree, 2 = nested dissection, 3 = interior dissection
   int root_delay_max = 1024;  // cap on the root's delayed-pivot slots
   bool pair_weak = true; // order zero-diagonal columns together with a partner (2x2 pivot pre-selection)
   int min_sparse_n = 192;   // blocks smaller than this are kept as one dense front
@@ -266,7 +268,7 @@ struct PlanOptions {
 // entries with keep[k] == 0 are ignored.  src[k] = relative value index of entry k.
 inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
                                    const std::vector<int> &src, const PlanOptions &opt, bool force_dense,
-                                   bool dissect, const std::vector<double> *hint = nullptr) {
+                                   int dissect, const std::vector<double> *hint = nullptr) {
   PatternPlan P;
   P.n = n;
   P.m = m;
@@ -364,7 +366,58 @@ inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, c
         for (int v : members[c]) hold[v] = 1;  // a pair with a border-touched column stays in the root whole
     std::vector<int> stage, corder;
     std::vector<std::vector<int>> cstruct;
-    if (dissect) detail::nested_dissection_stages(nc2, cadj, chold, opt.nd_leaf, stage);
+    if (dissect == 1) {
+      detail::nested_dissection_stages(nc2, cadj, chold, opt.nd_leaf, stage);
+    } else if (dissect == 2) {
+      // Interior dissection.  Minimum degree peels a banded or path-like remainder from its ends, which leaves a
+      // chain of fronts -- one per level of the kernels' level loop.  Here the lowest two generations of the
+      // elimination tree keep their minimum-degree order, and only the graph of what remains (the interior, with
+      // the fill of the eliminated generations as cliques) is dissected, so that the chain becomes a shallow tree
+      // of independent pieces joined by small separators.
+      std::vector<int> o1;
+      std::vector<std::vector<int>> s1;
+      detail::minimum_degree(nc2, cadj, chold, std::vector<int>(), o1, s1);
+      std::vector<int> pos1(nc2, -1), height(nc2, 0);
+      for (size_t k = 0; k < o1.size(); ++k) pos1[o1[k]] = (int)k;
+      for (int c : o1) {
+        int par = -1;
+        for (int w : s1[c])
+          if (pos1[w] >= 0 && (par < 0 || pos1[w] < pos1[par])) par = w;
+        if (par >= 0) height[par] = std::max(height[par], height[c] + 1);
+      }
+      std::vector<int> iid(nc2, -1), ivert;
+      for (int c : o1)
+        if (height[c] >= 2) { iid[c] = (int)ivert.size(); ivert.push_back(c); }
+      const int ni = (int)ivert.size();
+      stage.assign(nc2, 0);
+      if (ni > opt.int_leaf && ni <= opt.int_max) {
+        std::vector<std::vector<int>> iadj(ni);
+        for (int c = 0; c < nc2; ++c) {
+          if (pos1[c] < 0) continue;  // held
+          if (iid[c] >= 0) {
+            for (int w : cadj[c])
+              if (iid[w] >= 0) iadj[iid[c]].push_back(iid[w]);
+          } else {
+            // fill left by an eliminated lower-generation vertex: a clique on its interior neighbours
+            std::vector<int> t;
+            for (int w : s1[c])
+              if (iid[w] >= 0) t.push_back(iid[w]);
+            for (size_t a = 0; a < t.size(); ++a)
+              for (size_t b = 0; b < t.size(); ++b)
+                if (a != b) iadj[t[a]].push_back(t[b]);
+          }
+        }
+        for (auto &a : iadj) {
+          std::sort(a.begin(), a.end());
+          a.erase(std::unique(a.begin(), a.end()), a.end());
+        }
+        std::vector<int> istage;
+        detail::nested_dissection_stages(ni, iadj, std::vector<char>(ni, 0), opt.int_leaf, istage);
+        for (int k = 0; k < ni; ++k) stage[ivert[k]] = 1 + std::max(istage[k], 0);
+      } else {
+        stage.clear();  // nothing to dissect: plain minimum degree
+      }
+    }
     detail::minimum_degree(nc2, cadj, chold, stage, corder, cstruct);
     order.clear();
     lstruct.assign(n, {});
@@ -666,7 +719,7 @@ namespace ppb {
 // Estimated time of the level-scheduled numeric kernels, in "front latencies": every level costs a
 // fixed front overhead plus the pivots of its widest front (fronts of a level run concurrently).
 inline double plan_schedule_cost(const PatternPlan &P) {
-  // per level: warps share the tiny fronts 16 at a time, quarter-CTAs the medium ones 4 at a time,
+  // per level: warps share the tiny fronts 16 at a time, two-warp groups the medium ones 8 at a time,
   // big fronts run one after the other; a front costs a fixed overhead plus its pivots
   double cost = 0;
   auto width = [&](int s) { return (double)(P.col_ptr[s + 1] - P.col_ptr[s]); };
@@ -675,7 +728,7 @@ inline double plan_schedule_cost(const PatternPlan &P) {
     for (int k = P.tiny_ptr[l]; k < P.tiny_ptr[l + 1]; ++k) { t += 6.0 + width(P.tiny_idx[k]); tmax = std::max(tmax, 6.0 + width(P.tiny_idx[k])); }
     for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) { m += 8.0 + width(P.med_idx[k]); mmax = std::max(mmax, 8.0 + width(P.med_idx[k])); }
     for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) b += 10.0 + 2.0 * width(P.big_idx[k]);
-    cost += std::max(t / 16.0, tmax) + std::max(m / 4.0, mmax) + b + 2.0;
+    cost += std::max(t / 16.0, tmax) + std::max(m / 8.0, mmax) + b + 2.0;
   }
   return cost + 0.02 * (double)(P.nT + P.DR) * (P.nT + P.DR) / 64.0;  // dense root panel steps
 }
@@ -685,16 +738,24 @@ inline double plan_schedule_cost(const PatternPlan &P) {
 inline PatternPlan build_plan(int n, int m, const std::vector<int> &rows, const std::vector<int> &cols,
                               const std::vector<int> &src, const PlanOptions &opt, bool force_dense,
                               const std::vector<double> *hint = nullptr) {
-  PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, false, hint);
+  PatternPlan md = build_plan_with(n, m, rows, cols, src, opt, force_dense, 0, hint);
   if (force_dense || md.ns == 0 || opt.ordering == 1) return md;
-  // nested dissection only pays when minimum degree left a deep tree (its staged ordering costs 5-10x the time of
-  // plain minimum degree on 20 000-row blocks, and it is rejected below whenever it inflates the root)
-  if (opt.ordering == 0 && md.nlevels <= 24) return md;
-  PatternPlan nd = build_plan_with(n, m, rows, cols, src, opt, force_dense, true, hint);
-  if (opt.ordering == 2) return nd;
-  if (nd.ns == 0) return md;
-  const bool fill_ok = (double)nd.nnz_l <= 2.5 * (double)md.nnz_l + 1000.0 && nd.nT <= md.nT + 64;
-  return (fill_ok && plan_schedule_cost(nd) < 0.8 * plan_schedule_cost(md)) ? nd : md;
+  if (opt.ordering == 2) return build_plan_with(n, m, rows, cols, src, opt, force_dense, 1, hint);
+  if (opt.ordering == 3) return build_plan_with(n, m, rows, cols, src, opt, force_dense, 2, hint);
+  PatternPlan best = md;
+  double best_cost = plan_schedule_cost(md);
+  auto consider = [&](PatternPlan &&cand, double fill_factor, int root_slack, double gain) {
+    if (cand.ns == 0) return;
+    const bool fill_ok = (double)cand.nnz_l <= fill_factor * (double)md.nnz_l + 1000.0 && cand.nT <= md.nT + root_slack;
+    const double c = plan_schedule_cost(cand);
+    if (fill_ok && c < gain * best_cost) { best = std::move(cand); best_cost = c; }
+  };
+  // a chain of fronts in the upper tree (more than a handful of levels): dissect the interior only
+  if (md.nlevels > 6) consider(build_plan_with(n, m, rows, cols, src, opt, force_dense, 2, hint), 1.5, 16, 0.9);
+  // nested dissection of the whole graph only pays when minimum degree left a deep tree (its staged ordering costs
+  // 5-10x the time of plain minimum degree on 20 000-row blocks, and it is rejected whenever it inflates the root)
+  if (md.nlevels > 24) consider(build_plan_with(n, m, rows, cols, src, opt, force_dense, 1, hint), 2.5, 64, 0.8);
+  return best;
 }
 
 }  // namespace ppb
