@@ -496,8 +496,18 @@ inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, c
       const long zeros = (long)nc * (pc + pcb - ncb);
       const int size = nc + pc + pcb;
       bool ok = size <= opt.fmax;
-      if (ok && zeros > 0)
-        ok = size <= opt.merge_max && (zeros <= opt.relax_zeros || zeros * 4 <= (long)(nc + pc) * size);
+      if (ok && zeros > 0) {
+        const bool small_ok = size <= opt.merge_max && (zeros <= opt.relax_zeros || zeros * 4 <= (long)(nc + pc) * size);
+        // an only child (or the only child that is not a leaf) is a link of a chain: no parallelism is lost by merging it, one level of the schedule is
+        // saved, and a third of the merged columns' area in explicit zeros costs less than that level
+        int inner = 0;  // children that are not leaves of the tree
+        for (int g : ch[p2]) inner += height[g] > 0;
+        // (not when the merge would push a warp- or group-sized parent into the whole-CTA class: those run many
+        // at a time, whole-CTA fronts one after the other)
+        const bool chain_ok = (ch[p2].size() == 1 || (inner == 1 && height[c] > 0)) && zeros <= 2L * size &&
+                              zeros * 3 <= (long)(nc + pc) * size && (size <= opt.medium || pc + pcb > opt.medium);
+        ok = small_ok || chain_ok;
+      }
       if (!ok) break;
       std::vector<int> merged(sn[c].cols);
       merged.insert(merged.end(), sn[p2].cols.begin(), sn[p2].cols.end());
