@@ -188,7 +188,13 @@ __global__ void residual_border_kernel(const long long *__restrict__ ptr, const 
     // the two norms: warp w sums the partials of component w, each lane a strided subset, then a fixed tree
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int k = lane; k < nparts; k += 32) s += part[2 * k + w];
+    for (int k0 = lane; k0 < nparts; k0 += 256) {  // eight loads in flight per lane
+      double t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = k0 + 32 * q < nparts ? part[2 * (k0 + 32 * q) + w] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += t[q];
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) buf[m_c + w] = s;

@@ -40,8 +40,11 @@ def _check_plan_invariants(plan, n):
             assert np.all(rel < plan["nT"])
 
 
+@pytest.mark.parametrize("ordering", [0, 1, 2, 3])
 @pytest.mark.parametrize("seed,n,m,density", [(0, 300, 7, 0.01), (1, 500, 20, 0.006), (2, 400, 0, 0.005)])
-def test_plan_reproduces_schur_complement(seed, n, m, density):
+def test_plan_reproduces_schur_complement(seed, n, m, density, ordering):
+    """Every ordering (0 = cheapest schedule, 1 = minimum degree, 2 = nested dissection, 3 = interior
+    dissection) must yield a plan whose emulated elimination reproduces -A K^-1 A^T."""
     rng = np.random.default_rng(seed)
     M = sp.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal)
     K = (M + M.T).tolil()
@@ -55,7 +58,10 @@ def test_plan_reproduces_schur_complement(seed, n, m, density):
         A = np.zeros((0, n))
     rows, cols, vals, mm = _lower_entries(K, A)
     assert mm == m
-    plan = native.build_plan(n, m, rows, cols, min_sparse_n=64)
+    plan = native.build_plan(n, m, rows, cols, min_sparse_n=64, ordering=ordering)
+    if ordering in (2, 3) and plan["ns"] == 0:
+        assert plan["nT"] == n  # a forced dissection may fill past the density cut-off on an expander-like graph: one dense front
+        return
     assert plan["ns"] > 0 and plan["nT"] < n
     _check_plan_invariants(plan, n)
     root, pivots = emulate(plan, vals, n, m)
@@ -94,3 +100,28 @@ def test_small_or_dense_blocks_stay_dense():
     rows, cols, vals, mm = _lower_entries(sp.csr_matrix(D + D.T), np.zeros((0, n)))
     plan = native.build_plan(n, 0, rows, cols)
     assert plan["ns"] == 0  # fill would exceed the density cut-off
+
+
+def test_interior_dissection_shortens_a_chain():
+    """A banded block (pentadiagonal, the shape the q-columns of the generator family leave behind): minimum
+    degree peels it from the ends into a chain of fronts; the interior dissection must give a shallower level
+    schedule, no more root columns, and the same Schur complement."""
+    n, m = 600, 4
+    rng = np.random.default_rng(5)
+    K = sp.diags([np.full(n - 2, 0.3), np.full(n - 1, -0.7), np.full(n, 4.0), np.full(n - 1, -0.7), np.full(n - 2, 0.3)],
+                 [-2, -1, 0, 1, 2]).tocsr()
+    A = np.zeros((m, n))
+    A[np.arange(m), rng.choice(n, size=m, replace=False)] = 1.0
+    rows, cols, vals, mm = _lower_entries(K, A)
+    md = native.build_plan(n, m, rows, cols, min_sparse_n=64, ordering=1)
+    it = native.build_plan(n, m, rows, cols, min_sparse_n=64, ordering=3)
+    auto = native.build_plan(n, m, rows, cols, min_sparse_n=64, ordering=0)
+    assert it["nlevels"] < md["nlevels"] and it["nT"] <= md["nT"] + 16
+    assert auto["nlevels"] <= md["nlevels"]
+    for plan in (md, it, auto):
+        _check_plan_invariants(plan, n)
+        root, pivots = emulate(plan, vals, n, m)
+        nr = plan["nT"] + plan["DR"]
+        R = np.tril(root) + np.tril(root, -1).T
+        schur = R[nr:, nr:] - R[nr:, :nr] @ np.linalg.solve(R[:nr, :nr], R[:nr, nr:])
+        assert np.allclose(schur, -A @ np.linalg.solve(K.toarray(), A.T), rtol=1e-9, atol=1e-11)
