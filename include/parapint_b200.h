@@ -175,6 +175,15 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
                  int to_staging, int threads);
 
 /*
+ * pp_host_copy + the host-to-device transfer of the values, pipelined: the segments (which must tile the `nvals`
+ * doubles of the analysed pattern in order) are gathered into the pinned `staging` buffer in `chunks` shares and
+ * every share is sent to the device as soon as it is complete, so the transfer of one overlaps the gather of the
+ * next.  A following pp_numeric_local(h, staging, 0, ...) finds the values already on their way and copies nothing.
+ */
+int pp_stage_values(pp_handle *h, int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len,
+                    void *staging, int threads, int chunks, void *stream);
+
+/*
  * Per-kernel-class device timing (measurement aid; enabled with pp_set_option(h, "profile", 1)).
  * CUDA events are recorded on the launching stream around every launch of each class; this call
  * waits for them and returns accumulated milliseconds and launch counts per class.

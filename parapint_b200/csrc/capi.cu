@@ -132,6 +132,7 @@ struct pp_handle {
   double *last_x = nullptr, *last_xc = nullptr;
   bool solved = false;
   PinBuf<double> pin_out2;
+  const void *staged_from = nullptr;  // pinned buffer whose contents pp_stage_values already sent to h->vals
   bool auto_residual = false;     // single rank: pp_solve_backward also forms the residual norms (same sync as the copy-out)
   bool norms_valid = false;
   DevBuf<double> res_buf;
@@ -800,6 +801,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     h->res_part.alloc((size_t)2 * std::max(h->res_blocks, 1));
     h->res_out.alloc(2);
     h->solved = false;
+    h->staged_from = nullptr;
   }
 
   // ---- solve buffers ----
@@ -887,23 +889,28 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
                                            h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
     h->launches++;
   }
-  if (h->n_local > 0) {
-    front_inertia_kernel<<<h->n_local, 256, 0, st>>>(h->fronts.p, h->inertia.p);
-    collect_sparse_info_kernel<<<1, 256, 0, st>>>(h->blocks_dev.p, h->n_local, h->flag.p);
-    h->launches += 2;
-  }
-  CK(cudaGetLastError());
+  double *tail = schur_local_dev ? schur_local_dev + (size_t)h->m_c * h->m_c : nullptr;
   int bad = 0;
-  if (defer) {
-    post_flag(h, 0, h->n_local, 0, st);  // read later, together with the coupling status and the inertia
-    *sparse_bad = 0;
-  } else {
-    bad = read_flag(h, 0, h->n_local, st);
-    *sparse_bad = h->n_local > 0 ? h->pin_flag.p[1] : 0;
-  }
-  if (schur_local_dev) {  // stream-ordered after collect_info / inertia kernels; flag[0] is current
-    pack_tail_kernel<<<1, 32, 0, st>>>(schur_local_dev + (size_t)h->m_c * h->m_c, h->flag.p, h->inertia.p);
+  *sparse_bad = 0;
+  if (h->n_local > 0) {
+    // inertia of the roots, status flags and the Schur tail in one launch (the last CTA to finish packs them)
+    local_finalize_kernel<<<h->n_local, 256, 0, st>>>(h->fronts.p, h->blocks_dev.p, h->n_local, h->inertia.p, h->flag.p,
+                                                      tail);
     h->launches++;
+    CK(cudaGetLastError());
+    if (!defer) {
+      h->pin_flag.ensure(8);
+      CK(cudaMemcpyAsync(h->pin_flag.p, h->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      bad = h->pin_flag.p[0];
+      *sparse_bad = h->pin_flag.p[1];
+    }
+  } else {
+    CK(cudaMemsetAsync(h->flag.p, 0, 2 * sizeof(int), st));
+    if (tail) {
+      pack_tail_kernel<<<1, 32, 0, st>>>(tail, h->flag.p, h->inertia.p);
+      h->launches++;
+    }
   }
   return bad;
 }
@@ -918,7 +925,9 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
     cudaStream_t st = (cudaStream_t)stream;
     h->local_factored = h->coupling_factored = h->forward_done = false;
     const double *dvals = values;
-    if (!on_device && h->nvals > 0) {
+    if (!on_device && h->nvals > 0 && h->staged_from == (const void *)values) {
+      dvals = h->vals.p;  // pp_stage_values gathered these values and already queued their transfer
+    } else if (!on_device && h->nvals > 0) {
       const double *src = values;
       if (!is_pinned_host(values)) {  // pageable caller memory: stage through the handle's pinned buffer
         h->pin_vals.ensure((size_t)h->nvals);
@@ -928,6 +937,7 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
       dvals = h->vals.p;
     }
+    h->staged_from = nullptr;
     h->last_vals = dvals;
     h->solved = false;
     h->inertia_cached = false;
@@ -1293,6 +1303,40 @@ extern "C" int pp_debug_trace(long long *out, int n) {
   return cudaMemcpyFromSymbol(out, ppb::g_trace, sizeof(long long) * (size_t)std::min(n, 2048)) == cudaSuccess ? 0 : 3;
 }
 #endif
+
+int pp_stage_values(pp_handle *h, int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len,
+                    void *staging, int threads, int chunks, void *stream) {
+  if (!h || !h->have_symbolic) return fail("pp_stage_values: symbolic factorization required first");
+  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len)) || !staging) return fail("pp_stage_values: null argument");
+  int64_t total = 0;
+  for (int64_t k = 0; k < nseg; ++k) {
+    if (len[k] < 0 || off[k] != total || (len[k] > 0 && !ptr[k])) return fail("pp_stage_values: segments must tile the buffer in order");
+    total += len[k];
+  }
+  if (total != (int64_t)h->nvals * (int64_t)sizeof(double)) return fail("pp_stage_values: size does not match the analysed pattern");
+  if (!is_pinned_host(staging)) return fail("pp_stage_values: the staging buffer must be pinned host memory");
+  return guarded([&]() {
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    h->staged_from = nullptr;
+    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(chunks, total / (512 << 10)));
+    int64_t k0 = 0;
+    for (int c = 0; c < nch; ++c) {
+      // segments [k0, k1): up to the c-th share of the bytes; their transfer overlaps the gather of the next share
+      const int64_t goal = total * (c + 1) / nch;
+      int64_t k1 = k0, hi = k0 < nseg ? off[k0] : total;
+      while (k1 < nseg && (off[k1] + len[k1] <= goal || c == nch - 1)) { hi = off[k1] + len[k1]; ++k1; }
+      if (k1 == k0) continue;
+      const int64_t lo = off[k0];
+      CopyPool::instance().run(k1 - k0, ptr + k0, off + k0, len + k0, static_cast<char *>(staging), true, threads);
+      CK(cudaMemcpyAsync(reinterpret_cast<char *>(h->vals.p) + lo, static_cast<char *>(staging) + lo, (size_t)(hi - lo),
+                         cudaMemcpyHostToDevice, st));
+      k0 = k1;
+    }
+    h->staged_from = staging;
+    return (int)PP_SUCCESSFUL;
+  });
+}
 
 int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, void *staging,
                  int to_staging, int threads) {

@@ -31,7 +31,7 @@ __global__ void reset_fronts_kernel(const Front *__restrict__ fronts, unsigned l
     F.bsz[i] = 1;
   }
   if (threadIdx.x < 4) F.state[threadIdx.x] = 0;
-  if (blockIdx.x == 0 && threadIdx.x < 6 && inertia) inertia[threadIdx.x] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x < 8 && threadIdx.x != 6 && inertia) inertia[threadIdx.x] = 0ull;  // [7] = finalize ticket
 }
 
 // Worst info over a range of fronts -> flag[0] (0 = all fine).

@@ -1333,6 +1333,64 @@ __global__ void __launch_bounds__(LF_NT) subtree_leaf_backward_kernel(const Spar
   backward_front<LG>(Bk, P, P.tiny_idx[P.tiny_ptr[0] + k], mine, ywork + vec_off[blockIdx.y], xout + vec_off[blockIdx.y]);
 }
 
+// End of the local phase in ONE launch (one CTA per block): the inertia of every dense root front is added to the
+// counters, and the CTA that finishes last (ticket in inertia[7]; no waiting) reduces the status flags of all fronts
+// and sparse blocks -- flag[0] = a root reported a zero pivot, flag[1] = a sparse block ran out of delayed-pivot
+// capacity -- and packs the tail of the Schur buffer (status + inertia) that the caller all-reduces.
+__global__ void local_finalize_kernel(const Front *__restrict__ fronts, const SparseBlock *__restrict__ blocks,
+                                      int count, unsigned long long *inertia, int *flag, double *tail) {
+  const Front F = fronts[blockIdx.x];
+  int pos = 0, neg = 0, zero = 0;
+  for (int k = threadIdx.x; k < F.n; k += blockDim.x) {
+    const int b = F.bsz[k];
+    if (b == 1) {
+      const double d = F.A[k + (size_t)k * F.ld];
+      pos += d > 0.0;
+      neg += d < 0.0;
+      zero += !(d > 0.0) && !(d < 0.0);
+    } else if (b == 2) {
+      const double a = F.A[k + (size_t)k * F.ld], o = F.A[k + 1 + (size_t)k * F.ld],
+                   c = F.A[k + 1 + (size_t)(k + 1) * F.ld];
+      const double det = (a / o) * (c / o) - 1.0;  // sign of a*c - o^2, scaled as in the factorisation
+      if (det < 0.0) { pos += 1; neg += 1; }
+      else if (det > 0.0) { if (a + c > 0.0) pos += 2; else neg += 2; }
+      else { zero += 1; if (a + c > 0.0) pos += 1; else if (a + c < 0.0) neg += 1; else zero += 1; }
+    }
+  }
+  __shared__ int s[3];
+  __shared__ int last;
+  if (threadIdx.x < 3) s[threadIdx.x] = 0;
+  __syncthreads();
+  atomicAdd(&s[0], pos);
+  atomicAdd(&s[1], neg);
+  atomicAdd(&s[2], zero);
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(&inertia[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&inertia[7], 1ull) == (unsigned long long)(gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  int bad = 0, sbad = 0;
+  for (int f = threadIdx.x; f < count; f += blockDim.x) {
+    if (fronts[f].state[ST_INFO] != 0) bad = 1;
+    if (blocks[f].info[0] != 0) sbad = 1;
+  }
+  bad = __syncthreads_or(bad);
+  sbad = __syncthreads_or(sbad);
+  if (threadIdx.x == 0) {
+    flag[0] = bad;
+    flag[1] = sbad;
+    if (tail) {
+      tail[0] = bad ? 1.0 : 0.0;
+      tail[1] = sbad ? 1.0 : 0.0;
+      for (int k = 0; k < 3; ++k) tail[2 + k] = (double)*((volatile unsigned long long *)&inertia[k]);
+      tail[5] = tail[6] = tail[7] = 0.0;
+    }
+  }
+}
+
 // worst failure flag over the sparse blocks -> flag[1]
 __global__ void collect_sparse_info_kernel(const SparseBlock *__restrict__ blocks, int count, int *flag) {
   int bad = 0;

@@ -37,6 +37,7 @@ SIGNATURES = {
     "pp_refine_forward": (C.c_int, [_vp, _vp, _vp]),
     "pp_refine_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "pp_stage_values": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),
     "pp_kernel_launches": (C.c_int64, [_vp]),
@@ -107,6 +108,7 @@ class HostCopier:
             self.threads = max(1, min(4, (os.cpu_count() or 2) // (2 * ranks)))
         self._keep = None
         self._tables = None
+        self.stage = None   # (handle, stream getter): gather straight into a transfer (see copy)
 
     def _table(self, arrays, offsets):
         import numpy as np
@@ -131,6 +133,14 @@ class HostCopier:
         t = self._table(arrays, offsets)
         if t is None:
             return False
+        if self.stage is not None and to_staging:
+            # values of a factorisation: gather + host-to-device transfer pipelined by the library
+            handle, stream = self.stage
+            code = self.lib.pp_stage_values(handle, len(arrays), t[3], t[4], t[5], staging.ctypes.data, self.threads,
+                                            4, stream())
+            if code == 0:
+                return True
+            self.stage = None  # e.g. pattern with gaps: fall back to the plain gather below
         code = self.lib.pp_host_copy(len(arrays), t[3], t[4], t[5], staging.ctypes.data, 1 if to_staging else 0,
                                      self.threads)
         if code != 0:

@@ -390,6 +390,8 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             return None
         if self._copiers[which] is None:
             self._copiers[which] = native.HostCopier(self.host_threads)
+            if which == 0:
+                self._copiers[0].stage = (self.backend.handle, self.backend._stream)
         return self._copiers[which]
 
     def _refine(self, x_local, x_c):
