@@ -778,7 +778,7 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
 constexpr int LF_NT = 256, LF_NW = LF_NT / 32;
 
 template <int LG>
-__global__ void __launch_bounds__(LF_NT) subtree_leaf_kernel(const SparseBlock *__restrict__ blocks,
+__global__ void __launch_bounds__(LF_NT, 4) subtree_leaf_kernel(const SparseBlock *__restrict__ blocks,
                                                              const PlanDev *__restrict__ plans,
                                                              const double *__restrict__ vals, double u, double pivtol,
                                                              unsigned long long *inertia, int cap) {
