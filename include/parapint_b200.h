@@ -159,6 +159,16 @@ int pp_refine_forward(pp_handle *h, double *rc_local_dev, void *stream);
 int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, double *x_local, double *x_c,
                        void *stream);
 
+/*
+ * With defer_status = 2 pp_numeric_coupling reads the reduced tail of the Schur buffer itself and returns
+ * PP_SINGULAR if any rank's local phase was singular, PP_NOT_ENOUGH_MEMORY if any rank's sparse path ran out of
+ * delayed-pivot capacity (every rank then repeats pp_numeric_local with defer_status = 0 -- the overflowing rank
+ * re-analyses densely -- reduces again and calls pp_numeric_coupling again; the reference's contract for that status
+ * is the same: enlarge and retry, interior_point.py:645-651).  pp_schur_tail returns that tail:
+ * [singular?, overflow?, n_pos, n_neg, n_zero of all ranks' blocks, 0, 0, 0].
+ */
+int pp_schur_tail(pp_handle *h, double out[8]);
+
 /* Sizes and introspection. */
 int64_t pp_factor_bytes(const pp_handle *h);  /* device bytes held by factors + workspaces */
 int64_t pp_local_dim(const pp_handle *h);     /* sum of n_i over local blocks */

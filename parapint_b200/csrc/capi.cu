@@ -132,6 +132,8 @@ struct pp_handle {
   double *last_x = nullptr, *last_xc = nullptr;
   bool solved = false;
   PinBuf<double> pin_out2;
+  PinBuf<double> pin_tail;
+  bool tail_valid = false;
   const void *staged_from = nullptr;  // pinned buffer whose contents pp_stage_values already sent to h->vals
   bool auto_residual = false;     // single rank: pp_solve_backward also forms the residual norms (same sync as the copy-out)
   bool norms_valid = false;
@@ -938,6 +940,7 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       dvals = h->vals.p;
     }
     h->staged_from = nullptr;
+    h->tail_valid = false;
     h->last_vals = dvals;
     h->solved = false;
     h->inertia_cached = false;
@@ -1014,10 +1017,35 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
       h->coupling_factored = true;
       return h->pin_flag.p[4] ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
     }
+    if (h->defer_status == 2 && schur_sum_dev) {
+      // several ranks: the reduced tail of the Schur buffer (status of every rank's local phase, summed inertia),
+      // this rank's coupling status and its inertia counters come back with ONE synchronisation
+      post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+      h->pin_tail.ensure(PP_SCHUR_TAIL);
+      CK(cudaMemcpyAsync(h->pin_tail.p, schur_sum_dev + (size_t)mc * mc, PP_SCHUR_TAIL * sizeof(double),
+                         cudaMemcpyDeviceToHost, st));
+      fetch_status(h, st);
+      h->tail_valid = true;
+      for (int k = 0; k < 6; ++k) h->inertia_cache[k] = h->pin_inertia.p[k];
+      h->inertia_cached = true;
+      for (int k = 0; k < PP_SCHUR_TAIL; ++k)
+        if (!std::isfinite(h->pin_tail.p[k])) return fail("pp_numeric_coupling: non-finite status tail in the Schur buffer");
+      if (h->pin_tail.p[1] > 0.0) return (int)PP_NOT_ENOUGH_MEMORY;  // some rank's sparse path overflowed: redo densely
+      if (h->pin_tail.p[0] > 0.0) return (int)PP_SINGULAR;
+      h->coupling_factored = true;
+      return h->pin_flag.p[4] ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+    }
     const int bad = mc > 0 ? read_flag(h, h->n_local, 1, st) : 0;
     h->coupling_factored = true;
     return bad ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
   });
+}
+
+int pp_schur_tail(pp_handle *h, double out[8]) {
+  if (!h || !out) return fail("pp_schur_tail: null argument");
+  if (!h->tail_valid) return fail("pp_schur_tail: available after pp_numeric_coupling with defer_status = 2");
+  for (int k = 0; k < PP_SCHUR_TAIL; ++k) out[k] = h->pin_tail.p[k];
+  return PP_SUCCESSFUL;
 }
 
 static int read_inertia(pp_handle *h, int which, int64_t out[3]) {

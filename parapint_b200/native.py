@@ -36,6 +36,7 @@ SIGNATURES = {
     "pp_residual_norms": (C.c_int, [_vp, _vp, _f64p, _vp]),
     "pp_refine_forward": (C.c_int, [_vp, _vp, _vp]),
     "pp_refine_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "pp_schur_tail": (C.c_int, [_vp, _f64p]),
     "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "pp_stage_values": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),

@@ -108,6 +108,11 @@ class CudaBackend:
                                          C.c_void_p(self.schur.data_ptr()), self._stream())
         return self._check(code, "pp_numeric_local"), self.schur
 
+    def schur_tail(self):
+        out = (C.c_double * SCHUR_TAIL)()
+        self._check(self.lib.pp_schur_tail(self.handle, out), "pp_schur_tail")
+        return np.array(out[:], dtype=np.float64)
+
     def numeric_coupling(self, schur_sum):
         code = self.lib.pp_numeric_coupling(self.handle, C.c_void_p(schur_sum.data_ptr()), self._stream())
         return self._check(code, "pp_numeric_coupling")
@@ -331,6 +336,30 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         code, schur_local = self.backend.numeric_local()
         timer.stop("factorize")
         self._tail = None
+        if self.comm.size > 1 and self._defer == 2:
+            # ONE collective and ONE host synchronisation per factorisation: the tail of the reduced buffer carries
+            # every rank's status and the summed inertia (mpi...:21,343,427-429), and the coupling phase reads it
+            timer.start("communicate")
+            self.comm.allreduce_sum_(schur_local)
+            timer.stop("communicate")
+            timer.stop("form SC")
+            timer.start("factor SC")
+            code = self.backend.numeric_coupling(schur_local)
+            if code == LinearSolverStatus.not_enough_memory.value:
+                # some rank's sparse path ran out of delayed-pivot capacity (every rank sees it in the reduced
+                # tail): repeat the local phase synchronously -- the overflowing rank re-analyses densely
+                self.backend.set_option("defer_status", 0)
+                try:
+                    code, schur_local = self.backend.numeric_local()
+                finally:
+                    self.backend.set_option("defer_status", 2)
+                self.comm.allreduce_sum_(schur_local)
+                code = self.backend.numeric_coupling(schur_local)
+                if code == LinearSolverStatus.not_enough_memory.value:
+                    code = LinearSolverStatus.error.value
+            self._tail = self.backend.schur_tail()
+            timer.stop("factor SC")
+            return self._result(code, raise_on_error, "Numeric factorization")
         if self.comm.size > 1:
             # ONE collective per factorisation (mpi...:343): the tail of the buffer carries this rank's status
             # and inertia, so no separate allgather / allreduce is needed (mpi...:21,427-429)
