@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restr
     if (tid == 0 && F.state[ST_INFO] == 0) F.state[ST_INFO] = 1;
     return;
   }
+  PP_TR(1999 + (gridDim.x > 1 ? 0 : 8) * 0);
   const FrontBuf B = carve(sm_raw, SM_CAP, SM_LD);
   const int ldA = F.ld;
   double *__restrict__ A = F.A;
@@ -42,9 +43,122 @@ __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restr
     B.map[i] = i < n ? F.perm[i] : 0;
   }
   if (tid < 3) cnt[tid] = 0;
+  PP_TR(2000 + (gridDim.x > 1 ? 0 : 8));
   __syncthreads();
-  const int t = factor_front<SF_NT>(B, S, n, u, pivtol, cnt, n);
+  PP_TR(2001 + (gridDim.x > 1 ? 0 : 8));
+  // Pivots are chosen and tested among the first n rows only, so the n x n pivot block can be factorised on its own
+  // (a quarter of the per-column update work when the border is as wide as the block) and the border rows brought
+  // up afterwards without any per-column barrier: one warp per border row carries the row in registers through the
+  // forward substitution, then one pass forms the trailing block.  Needs n <= 64 (two columns per lane) and
+  // scratch for W = L_B D behind the front in shared memory; otherwise everything is done in one sweep.
+  const bool two_phase = m > 0 && n <= 64 && (long)m * n <= (long)(SM_CAP - S) * SM_LD;
+  const int t = factor_front<SF_NT>(B, two_phase ? n : S, n, u, pivtol, cnt, n);
   __syncthreads();
+  PP_TR(2002 + (gridDim.x > 1 ? 0 : 8));
+  if (two_phase) {
+    double *W = B.F + (size_t)S * SM_LD;  // m x n, column-major: W[r + k * m]
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWS = SF_NT / 32, RW = 4;  // RW border rows per warp at a time: independent chains overlap
+    const int k0 = lane, k1 = lane + 32;
+    // pivot kinds as two 32-bit masks (uniform tests instead of a dependent shared-memory load per step)
+    const unsigned two_lo = __ballot_sync(0xffffffffu, k0 < t && B.bsz[k0] == 2);
+    const unsigned two_hi = __ballot_sync(0xffffffffu, k1 < t && B.bsz[k1] == 2);
+    const int f0 = k0 < n ? B.fid[k0] : 0, f1 = k1 < n ? B.fid[k1] : 0;
+    for (int rb = warp; rb < m; rb += NWS * RW) {
+      double x0[RW], x1[RW];
+#pragma unroll
+      for (int q = 0; q < RW; ++q) {
+        const int r = rb + q * NWS;
+        // the row in pivot order (the pivot block's interchanges did not touch the border rows)
+        x0[q] = (r < m && k0 < n) ? B.F[(n + r) + f0 * SM_LD] : 0.0;
+        x1[q] = (r < m && k1 < n) ? B.F[(n + r) + f1 * SM_LD] : 0.0;
+      }
+      for (int j = 0; j < t;) {
+        const bool pair = j < 32 ? (two_lo >> j) & 1u : (two_hi >> (j - 32)) & 1u;
+        if (pair) {
+          const int j1 = j + 1;
+          const double la0 = (k0 > j1 && k0 < n) ? B.F[k0 + j * SM_LD] : 0.0, lb0 = (k0 > j1 && k0 < n) ? B.F[k0 + j1 * SM_LD] : 0.0;
+          const double la1 = (k1 > j1 && k1 < n) ? B.F[k1 + j * SM_LD] : 0.0, lb1 = (k1 > j1 && k1 < n) ? B.F[k1 + j1 * SM_LD] : 0.0;
+#pragma unroll
+          for (int q = 0; q < RW; ++q) {
+            const double w0 = __shfl_sync(0xffffffffu, j < 32 ? x0[q] : x1[q], j & 31);
+            const double w1 = __shfl_sync(0xffffffffu, j1 < 32 ? x0[q] : x1[q], j1 & 31);
+            x0[q] -= w0 * la0 + w1 * lb0;
+            x1[q] -= w0 * la1 + w1 * lb1;
+          }
+          j += 2;
+        } else {
+          const double l0 = (k0 > j && k0 < n) ? B.F[k0 + j * SM_LD] : 0.0;
+          const double l1 = (k1 > j && k1 < n) ? B.F[k1 + j * SM_LD] : 0.0;
+#pragma unroll
+          for (int q = 0; q < RW; ++q) {
+            const double w0 = __shfl_sync(0xffffffffu, j < 32 ? x0[q] : x1[q], j & 31);
+            x0[q] -= w0 * l0;
+            x1[q] -= w0 * l1;
+          }
+          j += 1;
+        }
+      }
+      __syncwarp();  // every lane has read its original entries of the rows before any is overwritten
+      // x = W (rows of L_B D); L_B = W D^-1, pivot by pivot
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = h ? k1 : k0;
+        const int bk = k < t ? B.bsz[k] : 1;
+        // partner of a 2x2 pivot: the next column for its first member, the previous one for its second
+        const int kp = bk == 2 ? k + 1 : (bk == 0 ? k - 1 : k);
+        double s1 = 1.0, s2 = 0.0;  // l = s1 * x + s2 * partner
+        if (k < t) {
+          if (bk == 1) {
+            s1 = 1.0 / B.F[k + k * SM_LD];
+          } else {
+            const int a = bk == 2 ? k : k - 1;  // first column of the pair
+            const double e11 = B.F[a + a * SM_LD], e21 = B.F[a + 1 + a * SM_LD], e22 = B.F[a + 1 + (a + 1) * SM_LD];
+            const double d11 = e22 / e21, d22 = e11 / e21;
+            const double sc = (1.0 / (d11 * d22 - 1.0)) / e21;
+            s1 = sc * (bk == 2 ? d11 : d22);
+            s2 = -sc;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < RW; ++q) {
+          const int r = rb + q * NWS;
+          const double xv = h ? x1[q] : x0[q];
+          const double p0 = __shfl_sync(0xffffffffu, x0[q], kp & 31), p1 = __shfl_sync(0xffffffffu, x1[q], kp & 31);
+          const double xp = (kp & 32) ? p1 : p0;
+          if (r < m && k < n) {
+            W[r + k * m] = k < t ? xv : 0.0;
+            B.F[(n + r) + k * SM_LD] = k < t ? s1 * xv + s2 * xp : xv;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    PP_TR(2003);
+    // trailing block: T -= L_B W^T (lower triangle), 2 x 2 outputs per thread
+    const int mh = (m + 1) / 2;
+    for (int idx = tid; idx < mh * mh; idx += SF_NT) {
+      const int cb = idx / mh, rbk = idx - cb * mh;
+      if (rbk < cb) continue;
+      const int r = 2 * rbk, c = 2 * cb;
+      const bool r1 = r + 1 < m, c1 = c + 1 < m;
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+      for (int k = 0; k < t; ++k) {
+        const double l0 = B.F[(n + r) + k * SM_LD], l1 = r1 ? B.F[(n + r + 1) + k * SM_LD] : 0.0;
+        const double w0 = W[c + k * m], w1 = c1 ? W[c + 1 + k * m] : 0.0;
+        a00 += l0 * w0;
+        a01 += l0 * w1;
+        a10 += l1 * w0;
+        a11 += l1 * w1;
+      }
+      B.F[(n + r) + (n + c) * SM_LD] -= a00;
+      if (r1) B.F[(n + r + 1) + (n + c) * SM_LD] -= a10;
+      if (c1 && r >= c + 1) B.F[(n + r) + (n + c + 1) * SM_LD] -= a01;
+      if (r1 && c1) B.F[(n + r + 1) + (n + c + 1) * SM_LD] -= a11;
+    }
+    __syncthreads();
+    PP_TR(2004);
+  }
   // columns that found no pivot: the remaining fully-summed block is (numerically) null -> singular
   for (int k = t + tid; k < n; k += SF_NT) {
     B.bsz[k] = 1;
@@ -61,6 +175,7 @@ __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restr
     F.bsz[k] = B.bsz[k];
     F.perm[k] = B.map[B.fid[k]];
   }
+  PP_TR(2005 + (gridDim.x > 1 ? 0 : 8));
   if (tid == 0) {
     F.state[ST_KPREV] = n;
     F.state[ST_KCUR] = n;

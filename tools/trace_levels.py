@@ -49,3 +49,7 @@ for v in ph[:200]:
     prev = cyc
 
 print("factor_front<128> on block 0 / group 0 over 3 factorizations: no-pivot, 1x1, 2x2 steps:", t[2040:2043], "candidate columns examined:", t[2043])
+
+sm = t[1999:2016]
+print("front_small_kernel, block 0: roots  load %.2f  sync %.2f  pivot block %.2f  border rows %.2f  trailing %.2f  store %.2f us" % tuple((sm[i + 1] - sm[i]) / mhz for i in range(6)))
+print("front_small_kernel, coupling: pivot block %.2f  store %.2f us" % ((sm[11] - sm[10]) / mhz, (sm[14] - sm[11]) / mhz))
