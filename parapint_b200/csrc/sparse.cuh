@@ -253,14 +253,14 @@ __device__ int factor_front(const FrontBuf &B, int S, int fs, double u, double p
       // Fast path, decided redundantly (and identically) by every warp, so nothing has to be published: the
       // diagonal of the leading column passes the threshold test as it is -- the first candidate the general
       // search below would accept.  One barrier per eliminated column instead of four.
+      const double d = F[t + t * ld];
+      const double rd = 1.0 / d;  // issued ahead of the column scan it does not depend on
       unsigned kmax = 0u;
       for (int i = t + 1 + lane; i < ntest; i += LW)
         kmax = max(kmax, (unsigned)__double2hiint(F[i + t * ld]) & 0x7fffffffu);
       kmax = __reduce_max_sync(wmask, kmax);
       const double cmax = kmax ? __hiloint2double((int)kmax, -1) : 0.0;
-      const double d = F[t + t * ld];
       if (fabs(d) > pivtol && fabs(d) >= u * cmax) {
-        const double rd = 1.0 / d;
         for (int j = t + 1 + gw; j < S; j += NW) {
           const double wj = F[j + t * ld] * rd;
           for (int i = j + lane; i < S; i += LW) F[i + j * ld] -= F[i + t * ld] * wj;
