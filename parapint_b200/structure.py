@@ -27,6 +27,49 @@ def _coo(block):
     return c.row, c.col, np.asarray(c.data, dtype=np.float64), c.shape
 
 
+def _is_nested(block) -> bool:
+    return hasattr(block, "bshape") and hasattr(block, "get_block")
+
+
+def _walk_leaves(block, path=()):
+    """COO sub-leaves of a nested block matrix in row-major block order (the order ``tocoo()`` concatenates them):
+    list of (path, leaf); None when a sub-block is neither nested nor a COO matrix."""
+    out = []
+    nbr, nbc = block.bshape
+    get = block.get_block
+    for i in range(nbr):
+        for j in range(nbc):
+            sub = get(i, j)
+            if sub is None:
+                continue
+            if _is_nested(sub):
+                inner = _walk_leaves(sub, path + ((i, j),))
+                if inner is None:
+                    return None
+                out.extend(inner)
+            elif getattr(sub, "format", None) == "coo":
+                out.append((path + ((i, j),), sub))
+            else:
+                return None
+    return out
+
+
+def _flatten_recipe(block, data):
+    """How to gather the values of a nested leaf without flattening it every iteration (parapint builds a new
+    nested 4x4 BlockMatrix per scenario and iteration, ``interface.py:432-491``; its ``tocoo()`` costs far more
+    than the factorisation): the COO sub-leaves in concatenation order with their index arrays.  The recipe is
+    only kept when concatenating the sub-leaves' values reproduces ``tocoo().data`` exactly."""
+    if not _is_nested(block):
+        return None
+    leaves = _walk_leaves(block)
+    if not leaves:
+        return None
+    parts = [np.asarray(leaf.data, dtype=np.float64) for _, leaf in leaves]
+    if sum(p.size for p in parts) != data.size or not np.array_equal(np.concatenate(parts), data):
+        return None
+    return [(path, leaf.row, leaf.col) for path, leaf in leaves]
+
+
 @dataclass
 class Structure:
     n_blocks: int                      # N (number of diagonal blocks, all ranks)
@@ -40,6 +83,7 @@ class Structure:
     dest_col: np.ndarray               # int32[nvals]
     segments: list = field(default_factory=list)   # (kind, block index, start, stop) per gathered COO array
     patterns: list = field(default_factory=list)   # (row, col) arrays per segment, to detect pattern changes
+    recipes: list = field(default_factory=list)    # per segment: sub-leaf recipe of a nested block, or None
     rhs_offsets: np.ndarray = None     # int64[n_local + 1] offsets of local blocks in the packed rhs
 
     @property
@@ -92,13 +136,13 @@ def analyse(matrix, rank=0, size=1) -> Structure:
 
     block_n, border_ptr, border_rows = [], [0], []
     dfront, drow, dcol = [], [], []
-    segments, patterns = [], []
+    segments, patterns, recipes = [], [], []
     pos = 0
     for f, i in enumerate(local):
         K = matrix.get_block(i, i)
         if K is None:
             raise ValueError(f"diagonal block {i} is missing on its owner")
-        kr, kc, _, kshape = _coo(K)
+        kr, kc, kdata, kshape = _coo(K)
         if kshape[0] != kshape[1]:
             raise ValueError(f"diagonal block {i} is not square")
         n_i = int(kshape[0])
@@ -109,13 +153,14 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         dcol.append(np.where(keep, kc, 0))
         segments.append(("K", i, pos, pos + kr.size))
         patterns.append((kr, kc))
+        recipes.append(_flatten_recipe(K, kdata))
         pos += kr.size
 
         A = matrix.get_block(N, i)
         if A is None:
             border_ptr.append(border_ptr[-1])
             continue
-        ar, ac, _, ashape = _coo(A)
+        ar, ac, adata, ashape = _coo(A)
         if ashape != (m_c, n_i):
             raise ValueError(f"border block ({N},{i}) has shape {ashape}, expected {(m_c, n_i)}")
         nz_rows = np.unique(ar)  # rows with stored entries (explicit zeros count, as in _BorderMatrix)
@@ -128,6 +173,7 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         dcol.append(ac)
         segments.append(("A", i, pos, pos + ar.size))
         patterns.append((ar, ac))
+        recipes.append(_flatten_recipe(A, adata))
         pos += ar.size
 
     n_local = len(local)
@@ -138,6 +184,7 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         dcol.append(np.where(keep, q_col, 0))
         segments.append(("Q", N, pos, pos + q_row.size))
         patterns.append((q_row, q_col))
+        recipes.append(None)
         pos += q_row.size
 
     def cat(parts, dtype):
@@ -150,7 +197,11 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         border_ptr=np.asarray(border_ptr, dtype=np.int64),
         border_rows=cat(border_rows, np.int32),
         dest_front=cat(dfront, np.int32), dest_row=cat(drow, np.int32), dest_col=cat(dcol, np.int32),
-        segments=segments, patterns=patterns, rhs_offsets=offs)
+        segments=segments, patterns=patterns, recipes=recipes, rhs_offsets=offs)
+
+
+def _same_index(a, b) -> bool:
+    return a is b or (a.size == b.size and np.array_equal(a, b))
 
 
 def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
@@ -158,11 +209,16 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
 
     Returns False when a block's COO pattern differs from the analysed one (the caller then
     re-runs the symbolic phase, as ``mumps_interface.py:82-83`` does).  ``copier`` (a
-    ``native.HostCopier``) moves the leaves with a few threads instead of one numpy slice assignment each."""
+    ``native.HostCopier``) moves the leaves with a few threads instead of one numpy slice assignment each.
+
+    Three paths per leaf, fastest first: the very object validated last time (values updated in place); a nested
+    block matrix walked sub-leaf by sub-leaf against the recipe recorded by :func:`analyse` (index arrays compared,
+    nothing concatenated); ``tocoo()`` and a comparison of the flattened index arrays."""
     N = st.n_blocks
     get = matrix.get_block
-    datas = [] if copier is not None else None
+    datas, starts = [], []
     seen = st.__dict__.setdefault("_leaf_seen", [None] * len(st.segments))
+    recipes = st.recipes if st.recipes else [None] * len(st.segments)
     for k, ((kind, i, lo, hi), (prow, pcol)) in enumerate(zip(st.segments, st.patterns)):
         blk = get(i, i) if kind != "A" else get(N, i)
         if blk is None:
@@ -173,17 +229,30 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             data = blk.data
             if data.size != hi - lo:
                 return False
-            if datas is None:
-                out[lo:hi] = data
-            else:
-                datas.append(data)
+            datas.append(data)
+            starts.append(lo)
             continue
-        # fast path: a COO leaf that still carries the analysed index arrays (values updated in place)
+        recipe = recipes[k]
+        if recipe is not None and _is_nested(blk):
+            leaves = _walk_leaves(blk)
+            if leaves is None or len(leaves) != len(recipe):
+                return False
+            pos = lo
+            for (path, leaf), (rpath, rrow, rcol) in zip(leaves, recipe):
+                if path != rpath or not _same_index(leaf.row, rrow) or not _same_index(leaf.col, rcol):
+                    return False
+                datas.append(leaf.data)
+                starts.append(pos)
+                pos += leaf.data.size
+            if pos != hi:
+                return False
+            continue
+        # a COO leaf that still carries the analysed index arrays (values updated in place)
         if getattr(blk, "format", None) == "coo" and blk.row is prow and blk.col is pcol:
             data = blk.data
         else:
             c = blk.tocoo()
-            if not ((c.row is prow or np.array_equal(c.row, prow)) and (c.col is pcol or np.array_equal(c.col, pcol))):
+            if not (_same_index(c.row, prow) and _same_index(c.col, pcol)):
                 return False
             data = c.data
         if data.size != hi - lo:
@@ -191,13 +260,11 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
         coords = getattr(blk, "coords", None)
         seen[k] = (blk, coords) if coords is not None and getattr(blk, "format", None) == "coo" \
             and blk.row is prow and blk.col is pcol else None
-        if datas is None:
-            out[lo:hi] = data
-        else:
-            datas.append(data)
-    if datas is not None and not copier.copy(datas, st.segment_starts, out):
-        for (kind, i, lo, hi), data in zip(st.segments, datas):
-            out[lo:hi] = data
+        datas.append(data)
+        starts.append(lo)
+    if copier is None or not copier.copy(datas, starts, out):
+        for lo, data in zip(starts, datas):
+            out[lo:lo + data.size] = data
     return True
 
 

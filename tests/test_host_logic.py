@@ -265,3 +265,49 @@ def test_host_copier_matches_numpy():
     structure.pack_rhs(rhs, st, ra)
     structure.pack_rhs(rhs, st, rb, native.HostCopier(4))
     assert np.array_equal(ra, rb)
+
+
+def test_nested_blocks_are_gathered_by_recipe():
+    """parapint hands over a freshly built nested 4x4 BlockMatrix per scenario and iteration (interface.py:432-491).
+    The values must come out exactly as a flattening with tocoo() gives them, without calling it, and any change of
+    the nested pattern (a sub-leaf's indices, an extra sub-block) must be reported so that the symbolic phase is
+    repeated."""
+    from parapint_b200 import structure
+    from parapint_b200.carriers import BlockMatrix
+    rng = np.random.default_rng(3)
+
+    def scenario(seed, extra=False, shift=False):
+        r = np.random.default_rng(seed)
+        H = sp.random(6, 6, density=0.4, random_state=np.random.default_rng(11)).tocoo()
+        H = sp.coo_matrix((r.standard_normal(H.nnz), (H.row, H.col)), shape=H.shape)
+        J = sp.coo_matrix((r.standard_normal(4), ([0, 1, 2, 2], [0, 2, 3, 5 if not shift else 4])), shape=(3, 6))
+        K = BlockMatrix(2, 2)
+        K.set_block(0, 0, H)
+        K.set_block(1, 0, J)
+        K.set_block(0, 1, J.transpose().tocoo())
+        if extra:
+            K.set_block(1, 1, sp.identity(3, format="coo") * 1e-8)
+        else:
+            K.set_row_size(1, 3) if hasattr(K, "set_row_size") else None
+        return K
+
+    def system(seeds, **kw):
+        kkt = BlockMatrix(len(seeds) + 1, len(seeds) + 1)
+        for i, sd in enumerate(seeds):
+            kkt.set_block(i, i, scenario(sd, **kw))
+            kkt.set_block(len(seeds), i, sp.coo_matrix(([-1.0, -1.0], ([0, 1], [0, 1])), shape=(2, 9)))
+        kkt.set_block(len(seeds), len(seeds), sp.coo_matrix((2, 2)))
+        return kkt
+
+    kkt = system([1, 2, 3])
+    st = structure.analyse(kkt, 0, 1)
+    assert all(rec is not None for (kind, *_), rec in zip(st.segments, st.recipes) if kind == "K")
+    fresh = system([4, 5, 6])                       # new objects, same pattern, new values
+    out = np.zeros(st.nvals)
+    assert structure.gather_values(fresh, st, out)
+    expect = np.concatenate([fresh.get_block(i, i).tocoo().data if kind == "K" else
+                             (fresh.get_block(3, i).tocoo().data if kind == "A" else fresh.get_block(3, 3).tocoo().data)
+                             for (kind, i, lo, hi) in st.segments])
+    assert np.array_equal(out, expect)
+    assert not structure.gather_values(system([4, 5, 6], shift=True), st, out)   # a sub-leaf's column index moved
+    assert not structure.gather_values(system([4, 5, 6], extra=True), st, out)   # an extra sub-block appeared
