@@ -96,6 +96,7 @@ struct pp_handle {
   bool use_sparse = true;
   bool no_fallback = false;
   bool use_cluster = true;
+  int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
   int defer_status = 0;           // 1 single rank: one host sync per factorisation (status + inertia read together);
                                   // 2 several ranks: pp_numeric_local does not synchronise, its status and overflow
                                   //   flag travel in the tail of the Schur buffer the caller all-reduces
@@ -248,6 +249,7 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   int csize = 1;
   if (h->use_cluster && nfmax >= 1024)
     while (csize < 8 && count * csize * 2 <= 128 && PC_NT * csize * 2 <= nfmax + PC_NT) csize *= 2;
+  if (h->use_cluster && h->cluster_size > 0 && nfmax >= 1024) csize = h->cluster_size;
   const int iters = (nmax + (NB - 2)) / (NB - 1);
   for (int it = 0; it < iters; ++it) {
     {
@@ -402,6 +404,10 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->panel_width = nb;
   } else if (key == "sparse") {
     h->use_sparse = value != 0.0;
+  } else if (key == "cluster_size") {
+    const int c = (int)value;
+    if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return fail("cluster_size must be 0, 1, 2, 4 or 8");
+    h->cluster_size = c;
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
   } else if (key == "auto_residual") {

@@ -292,12 +292,13 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
     const double absakk = fabs(akk);
 
     int kstep = 1, kp = k;
-    bool zero_pivot = false;
+    bool zero_pivot = false, copied = false, second = false;
     if (!(fmax(absakk, colmax) > pivtol)) {
       zero_pivot = true;
     } else if (absakk >= BK_ALPHA * colmax) {
       kp = k;
     } else {
+      second = true;
       double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
       for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[imax + (size_t)j * ld];
       __syncthreads();
@@ -323,12 +324,15 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
       } else if (fabs(wimax) >= BK_ALPHA * rowmax) {
         kp = imax;
         for (int i = k + gtid; i < nf; i += GT) Wk[i] = Wk1[i];
+        copied = true;
       } else {
         kp = imax;
         kstep = 2;
       }
     }
-    cl.sync();
+    // everything the interchange below reads was written before the barrier inside the last cluster_argmax --
+    // except the copy above, whose rows belong to other CTAs (the decision is the same in every CTA)
+    if (copied) cl.sync(); else __syncthreads();
 
     const int kk = k + kstep - 1;
     if (kp != kk) {
@@ -388,7 +392,11 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
         if (!isfinite(sc) && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
       }
     }
-    cl.sync();
+    // A column accepted at once (no second sweep, no interchange) leaves nothing that another CTA could still be
+    // reading or about to overwrite: the L entries a thread reads in the next sweep are the ones it just wrote,
+    // and W(:, kw) was published by the barrier inside cluster_argmax.  Otherwise W(:, kw + 1) (the candidate
+    // column) is reused by the next step and rows were exchanged across CTAs: full cluster barrier.
+    if (second || kp != kk) cl.sync(); else __syncthreads();
     k += kstep;
   }
   if (gtid == 0) {
