@@ -147,6 +147,8 @@ struct pp_handle {
   DevBuf<unsigned long long> inertia;  // [0..2] local, [3..5] coupling
   DevBuf<int64_t> asm_dst, asm_ptr, asm_src, src_ptr, brow_ptr, rhs_off, root_off64;
   DevBuf<int32_t> src_front, src_pos, brow;
+  DevBuf<int64_t> src_aoff;       // per Schur source: arena offset of (its border row, first border column) in the front
+  DevBuf<int32_t> src_ld;         // ... and the front's leading dimension (negative: partial border)
   DevBuf<int64_t> src_boff;       // per Schur source: offset of the front's bvec entry in arenaZ (rc_gather)
   PinBuf<double> pin_vals, pin_vec;
   PinBuf<int> pin_flag;
@@ -753,6 +755,18 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->src_front.upload(sfront);
   h->src_pos.upload(spos);
   {
+    std::vector<int64_t> aoff(spos.size());
+    std::vector<int32_t> sld(spos.size());
+    for (size_t p = 0; p < spos.size(); ++p) {
+      const int f = sfront[p];
+      const int nbf = h->n[(size_t)f];  // first border row of the front (static)
+      aoff[p] = (int64_t)offA[(size_t)f] + nbf + spos[p] + (int64_t)nbf * h->ld[(size_t)f];
+      sld[p] = h->m[(size_t)f] == m_c ? h->ld[(size_t)f] : -h->ld[(size_t)f];
+    }
+    h->src_aoff.upload(aoff);
+    h->src_ld.upload(sld);
+  }
+  {
     std::vector<int64_t> boff(spos.size());
     for (size_t p = 0; p < spos.size(); ++p)
       boff[p] = (int64_t)offZ[(size_t)sfront[p]] + h->n[(size_t)sfront[p]] + spos[p];
@@ -893,8 +907,9 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
   if (h->m_c > 0) {
     ProfSpan sp(h, PP_PROF_SCHUR, st);
     dim3 g((h->m_c + 127) / 128, h->m_c);
-    schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
-                                           h->brow_ptr.p, h->brow.p, h->m_c, schur_local_dev);
+    schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->arenaA.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
+                                           h->src_aoff.p, h->src_ld.p, h->brow_ptr.p, h->brow.p, h->m_c,
+                                           schur_local_dev);
     h->launches++;
   }
   double *tail = schur_local_dev ? schur_local_dev + (size_t)h->m_c * h->m_c : nullptr;

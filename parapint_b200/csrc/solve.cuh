@@ -63,27 +63,30 @@ __global__ void pack_tail_kernel(double *__restrict__ tail, const int *__restric
 // S_local(r,c) = sum over local fronts holding both coupling rows r and c of the front's trailing
 // block entry; sources are visited in front order, so the sum is reproducible.  Replaces the
 // scatter through sc_data_slices of mpi_explicit_schur_complement.py:249-254,329.
-__global__ void schur_gather_kernel(const Front *__restrict__ fronts, const int64_t *__restrict__ src_ptr,
-                                    const int32_t *__restrict__ src_front, const int32_t *__restrict__ src_pos,
-                                    const int64_t *__restrict__ brow_ptr, const int32_t *__restrict__ brow,
-                                    int m_c, double *__restrict__ S) {
+__global__ void schur_gather_kernel(const Front *__restrict__ fronts, const double *__restrict__ arenaA,
+                                    const int64_t *__restrict__ src_ptr, const int32_t *__restrict__ src_front,
+                                    const int32_t *__restrict__ src_pos, const int64_t *__restrict__ src_aoff,
+                                    const int32_t *__restrict__ src_ld, const int64_t *__restrict__ brow_ptr,
+                                    const int32_t *__restrict__ brow, int m_c, double *__restrict__ S) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (r >= m_c || r < c) return;
   double s = 0.0;
   const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
-  // four sources in flight: the loads are independent, only the additions keep their order
-  for (int64_t pb = p0; pb < p1; pb += 4) {
-    double v[4];
+  // eight sources in flight: the loads are independent, only the additions keep their order.  src_aoff[p] is
+  // the arena offset of (row of r, first border column) in the source front and src_ld[p] its leading dimension
+  // -- negated when the front carries only part of the coupling rows and c has to be located first.
+  for (int64_t pb = p0; pb < p1; pb += 8) {
+    double v[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       v[q] = 0.0;
       const int64_t p = pb + q;
       if (p >= p1) continue;
-      const int f = src_front[p], a = src_pos[p];
-      const Front F = fronts[f];
+      const int ldf = src_ld[p];
       int lo = c;
-      if (F.m != m_c) {  // partial border: locate c among the front's border rows (c <= r => position <= a)
+      if (ldf < 0) {  // partial border: locate c among the front's border rows (c <= r => position <= a)
+        const int f = src_front[p], a = src_pos[p];
         const int32_t *br = brow + brow_ptr[f];
         int hi = a;
         lo = 0;
@@ -93,12 +96,10 @@ __global__ void schur_gather_kernel(const Front *__restrict__ fronts, const int6
         }
         if (br[lo] != c) continue;
       }
-      v[q] = F.A[(size_t)(F.nb + a) + (size_t)(F.nb + lo) * F.ld];
+      v[q] = arenaA[src_aoff[p] + (int64_t)lo * (ldf < 0 ? -ldf : ldf)];
     }
-    s += v[0];
-    s += v[1];
-    s += v[2];
-    s += v[3];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
   }
   S[(size_t)r + (size_t)c * m_c] = s;
   S[(size_t)c + (size_t)r * m_c] = s;
