@@ -67,7 +67,9 @@ def _flatten_recipe(block, data):
     parts = [np.asarray(leaf.data, dtype=np.float64) for _, leaf in leaves]
     if sum(p.size for p in parts) != data.size or not np.array_equal(np.concatenate(parts), data):
         return None
-    return [(path, leaf.row, leaf.col) for path, leaf in leaves]
+    # the index arrays are kept both as arrays and as bytes: comparing bytes is 4x cheaper than np.array_equal on the
+    # few-thousand-entry leaves this is for, and it is done ~30 times per scenario and iteration
+    return [(path, leaf.row, leaf.col, leaf.row.tobytes(), leaf.col.tobytes()) for path, leaf in leaves]
 
 
 @dataclass
@@ -238,8 +240,13 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             if leaves is None or len(leaves) != len(recipe):
                 return False
             pos = lo
-            for (path, leaf), (rpath, rrow, rcol) in zip(leaves, recipe):
-                if path != rpath or not _same_index(leaf.row, rrow) or not _same_index(leaf.col, rcol):
+            for (path, leaf), (rpath, rrow, rcol, rrow_b, rcol_b) in zip(leaves, recipe):
+                lrow, lcol = leaf.row, leaf.col
+                if path != rpath:
+                    return False
+                if not (lrow is rrow or lrow.tobytes() == rrow_b or _same_index(lrow, rrow)):
+                    return False
+                if not (lcol is rcol or lcol.tobytes() == rcol_b or _same_index(lcol, rcol)):
                     return False
                 datas.append(leaf.data)
                 starts.append(pos)
