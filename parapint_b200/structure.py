@@ -298,6 +298,32 @@ def coupling_rhs(rhs, st: Structure) -> np.ndarray:
     return np.ascontiguousarray(flat, dtype=np.float64)
 
 
+def _views_like(template, seg):
+    """A vector with the (nested) block structure of ``template`` whose leaves are views of ``seg`` -- one pass, no
+    zero-filled intermediate as ``copy_structure()`` + ``copyfrom()`` would need."""
+    if not hasattr(template, "nblocks"):
+        return seg
+    out = type(template)(template.nblocks)
+    pos = 0
+    for k in range(template.nblocks):
+        sub = template.get_block(k)
+        n = int(sub.size)
+        out.set_block(k, _views_like(sub, seg[pos:pos + n]))
+        pos += n
+    if pos != seg.size:
+        raise ValueError("block sizes do not add up")
+    return out
+
+
+def _nested_like(template, values):
+    try:
+        return _views_like(template, np.array(values, dtype=np.float64))
+    except Exception:  # noqa: BLE001 - an unusual vector class: go through its own copy_structure / copyfrom
+        blk = template.copy_structure()
+        blk.copyfrom(values)
+        return blk
+
+
 def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray):
     """New vector with the block structure of ``rhs`` (``mpi_explicit_schur_complement.py:390``;
     nested blocks keep their structure as the SciPy leaf does, ``scipy_interface.py:57-60``).
@@ -310,16 +336,17 @@ def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray):
         template = get(i)
         seg = flat[offs[f]:offs[f + 1]]
         if hasattr(template, "nblocks"):
-            blk = template.copy_structure()
-            blk.copyfrom(seg)
-            put(i, blk)
+            try:
+                put(i, _views_like(template, seg))
+            except Exception:  # noqa: BLE001 - an unusual vector class
+                blk = template.copy_structure()
+                blk.copyfrom(seg)
+                put(i, blk)
         else:
             put(i, seg)
     template = get(st.n_blocks)
     if hasattr(template, "nblocks"):
-        blk = template.copy_structure()
-        blk.copyfrom(x_c)
-        put(st.n_blocks, blk)
+        put(st.n_blocks, _nested_like(template, x_c))
     else:
         put(st.n_blocks, np.array(x_c, dtype=np.float64))
     return out
