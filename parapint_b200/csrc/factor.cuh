@@ -208,15 +208,18 @@ __global__ void __launch_bounds__(NT) front_panel_kernel(const Front *__restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int PC_NT = 512;
 
+// `extra` travels with the result: the value held by thread 0 of rank 0, or -- when s_extra is given -- the value some
+// thread of rank `extra_rank` deposited in its CTA's shared slot *s_extra before the call.
 __device__ __forceinline__ void cluster_argmax(cooperative_groups::cluster_group &cl, double &val, int &idx,
                                                double &extra, double *sval, int *sidx, double *xval, int *xidx,
-                                               double *xextra, int &parity) {
+                                               double *xextra, int &parity, const double *s_extra = nullptr,
+                                               int extra_rank = 0) {
   // block-level reduce, then every CTA reads every CTA's result over DSMEM (one lane per remote CTA).
   // The exchange slots are double-buffered, so one cluster barrier per call suffices.
   block_argmax<PC_NT>(val, idx, sval, sidx);
   const int p = parity;
   parity ^= 1;
-  if (threadIdx.x == 0) { xval[p] = val; xidx[p] = idx; xextra[p] = extra; }
+  if (threadIdx.x == 0) { xval[p] = val; xidx[p] = idx; xextra[p] = s_extra ? *s_extra : extra; }
   cl.sync();
   if (threadIdx.x < 32) {
     const unsigned nb = cl.num_blocks();
@@ -225,7 +228,7 @@ __device__ __forceinline__ void cluster_argmax(cooperative_groups::cluster_group
     if (threadIdx.x < nb) {
       v = *cl.map_shared_rank(xval + p, threadIdx.x);
       i = *cl.map_shared_rank(xidx + p, threadIdx.x);
-      if (threadIdx.x == 0) e = *cl.map_shared_rank(xextra + p, 0);
+      if (threadIdx.x == 0) e = *cl.map_shared_rank(xextra + p, extra_rank);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
   __shared__ double sval[32];
   __shared__ int sidx[32];
   __shared__ double xval[2], xextra[2];
+  __shared__ double s_wimax;
   __shared__ int xidx[2];
   int parity = 0;
 
@@ -292,13 +296,12 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
     const double absakk = fabs(akk);
 
     int kstep = 1, kp = k;
-    bool zero_pivot = false, copied = false, second = false;
+    bool zero_pivot = false, copied = false;
     if (!(fmax(absakk, colmax) > pivtol)) {
       zero_pivot = true;
     } else if (absakk >= BK_ALPHA * colmax) {
       kp = k;
     } else {
-      second = true;
       double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
       for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[imax + (size_t)j * ld];
       __syncthreads();
@@ -314,10 +317,10 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
           const double a = fabs(acc);
           if (a > rbest) { rbest = a; rbesti = i; }
         }
+        if (i == imax) s_wimax = acc;  // travels with the arg-max exchange: no CTA reads W(imax, kw+1) afterwards
       }
-      double dummy = 0.0;
-      cluster_argmax(cl, rbest, rbesti, dummy, sval, sidx, xval, xidx, xextra, parity);
-      wimax = Wk1[imax];  // written before the cluster barrier inside cluster_argmax
+      cluster_argmax(cl, rbest, rbesti, wimax, sval, sidx, xval, xidx, xextra, parity, &s_wimax,
+                     ((imax - k) % GT) / PC_NT);
       const double rowmax = rbesti >= 0 ? rbest : 0.0;
       if (absakk >= BK_ALPHA * colmax * (colmax / rowmax)) {
         kp = k;
@@ -392,11 +395,11 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
         if (!isfinite(sc) && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
       }
     }
-    // A column accepted at once (no second sweep, no interchange) leaves nothing that another CTA could still be
-    // reading or about to overwrite: the L entries a thread reads in the next sweep are the ones it just wrote,
-    // and W(:, kw) was published by the barrier inside cluster_argmax.  Otherwise W(:, kw + 1) (the candidate
-    // column) is reused by the next step and rows were exchanged across CTAs: full cluster barrier.
-    if (second || kp != kk) cl.sync(); else __syncthreads();
+    // No cluster barrier at the end of a column: the L entries a thread reads in the next sweep are the ones it just
+    // wrote (same row mapping), W(:, kw) and W(:, kw + 1) were published by the barriers inside cluster_argmax, the
+    // candidate's diagonal entry travelled with the exchange, and a copy or an interchange is followed by its own
+    // cluster barrier above.
+    __syncthreads();
     k += kstep;
   }
   if (gtid == 0) {
