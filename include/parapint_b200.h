@@ -52,7 +52,8 @@ int pp_destroy(pp_handle *h);
  * fronts, default 0.01), "ordering" (0 auto, 1 minimum degree, 2 nested dissection), "nd_leaf",
  * "sparse_fmax", "sparse_dmax", "sparse_dslot", "sparse_min_n", "pair_weak" (0/1: 2x2 pivot pre-selection from
  * the values hint), "cluster_panel" (0/1: thread-block-cluster panel kernel for tall fronts), "cluster_size" (0 = automatic, or 1/2/4/8
- * CTAs per front), "small_front"
+ * CTAs per front), "panel_onchip" (0/1: cluster panel kernel that keeps the panel's rows of L in registers / shared
+ * memory), "small_front"
  * (0/1: whole-front shared-memory factorisation when every front of a batch has <= 164 rows), "defer_status"
  * (0/1, single-rank use: pp_numeric_local returns a provisional PP_SUCCESSFUL without synchronising and
  * pp_numeric_coupling -- which must then be given the local Schur buffer -- reports the status of both phases and

@@ -96,6 +96,7 @@ struct pp_handle {
   bool use_sparse = true;
   bool no_fallback = false;
   bool use_cluster = true;
+  bool panel_onchip = true;       // cluster panel kernel with the panel's rows of L in registers / shared memory
   int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
   int defer_status = 0;           // 1 single rank: one host sync per factorisation (status + inertia read together);
                                   // 2 several ranks: pp_numeric_local does not synchronise, its status and overflow
@@ -251,6 +252,12 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
   int csize = 1;
   if (h->use_cluster && nfmax >= 1024)
     while (csize < 8 && count * csize * 2 <= 128 && PC_NT * csize * 2 <= nfmax + PC_NT) csize *= 2;
+  if (h->use_cluster && h->panel_onchip && nfmax >= 1024) {
+    // on-chip panel: one CTA per SM (196 KB of shared memory), about one row per thread (more CTAs per front than
+    // rows to fill them only lengthen the cluster barriers)
+    csize = 1;
+    while (csize < 8 && count * csize * 2 <= 148 && PC_NT * csize * 2 <= nfmax + PC_NT / 2) csize *= 2;
+  }
   if (h->use_cluster && h->cluster_size > 0 && nfmax >= 1024) csize = h->cluster_size;
   const int iters = (nmax + (NB - 2)) / (NB - 1);
   for (int it = 0; it < iters; ++it) {
@@ -271,7 +278,12 @@ void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_kernel, fr, NB, h->pivot_tol));
+        if (h->panel_onchip) {
+          cfg.dynamicSmemBytes = OC_SMEM;
+          CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_oc_kernel, fr, NB, h->pivot_tol));
+        } else {
+          CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_kernel, fr, NB, h->pivot_tol));
+        }
       } else {
         front_panel_kernel<512><<<count, 512, 0, st>>>(fr, NB, h->pivot_tol);
       }
@@ -372,6 +384,7 @@ int pp_create(int device, pp_handle **out) {
     if (device < 0 || device >= count) return fail("pp_create: no such CUDA device");
     CK(cudaSetDevice(device));
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
+    CK(cudaFuncSetAttribute(front_panel_cluster_oc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
     CK(cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM));
     CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
@@ -406,6 +419,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->panel_width = nb;
   } else if (key == "sparse") {
     h->use_sparse = value != 0.0;
+  } else if (key == "panel_onchip") {
+    h->panel_onchip = value != 0.0;
   } else if (key == "cluster_size") {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return fail("cluster_size must be 0, 1, 2, 4 or 8");

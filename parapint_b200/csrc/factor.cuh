@@ -427,6 +427,221 @@ __global__ void front_swaps_left_kernel(const Front *__restrict__ fronts) {
   }
 }
 
+// The same panel factorisation with the panel's rows of L kept on chip (see inside).  Used when fronts are tall and few.
+constexpr int OC_REG = 16, OC_SM = NBMAX - OC_REG;
+constexpr size_t OC_SMEM = (size_t)OC_SM * PC_NT * sizeof(double);
+
+__global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Front *__restrict__ fronts, int NB,
+                                                                    double pivtol) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  const Front F = fronts[blockIdx.x / C];
+  const int tid = threadIdx.x;
+  const int gtid = rank * PC_NT + tid, GT = C * PC_NT;
+  const int n = F.n, nf = F.nf, ld = F.ld;
+  double *__restrict__ A = F.A;
+  double *__restrict__ W = F.W;
+  const int k0 = F.state[ST_KCUR];
+  if (k0 >= n) {
+    if (gtid == 0) F.state[ST_KPREV] = k0;
+    return;  // uniform over the cluster
+  }
+  __shared__ double wrow[NBMAX];
+  __shared__ double sval[32];
+  __shared__ int sidx[32];
+  __shared__ double xval[2], xextra[2];
+  __shared__ double s_wimax, s_akk;
+  __shared__ int xidx[2];
+  int parity = 0;
+  // The thread's row of the current panel stays on chip: columns [0, OC_REG) in registers, the rest in shared memory
+  // ([column][thread]: conflict-free).  Rows are dealt once per panel (row0 = k0 + gtid), not per column, so the
+  // lazy sweep of a column is kw fused multiply-adds from registers / shared memory instead of kw loads from L2
+  // (130 kB per CTA and column at 4 000 rows).  Rows beyond the first GT of a very tall front use the L2 path.
+  extern __shared__ double Ls[];  // [OC_SM][PC_NT]
+  double Lr[OC_REG];
+#pragma unroll
+  for (int j = 0; j < OC_REG; ++j) Lr[j] = 0.0;
+  const int row0 = k0 + gtid;
+  auto dot_onchip = [&](int kw) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < OC_REG; ++j)
+      if (j < kw) acc += Lr[j] * wrow[j];
+    for (int j = OC_REG; j < kw; ++j) acc += Ls[(j - OC_REG) * PC_NT + tid] * wrow[j];
+    return acc;
+  };
+  auto store_onchip = [&](int slot, double v) {
+    if (slot < OC_REG) {
+#pragma unroll
+      for (int j = 0; j < OC_REG; ++j)
+        if (j == slot) Lr[j] = v;
+    } else {
+      Ls[(slot - OC_REG) * PC_NT + tid] = v;
+    }
+  };
+
+  const bool last_panel = (n - k0 <= NB);
+  int k = k0;
+  while (k < n && (last_panel || (k - k0) < NB - 1)) {
+    const int kw = k - k0;
+    double *__restrict__ Wk = W + (size_t)kw * ld;
+    for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[k + (size_t)j * ld];
+    __syncthreads();
+    double best = -1.0, akk = 0.0;
+    int besti = -1;
+    for (int i = row0; i < nf; i += GT) {
+      if (i < k) continue;  // a row of this panel that is already a pivot row
+      double acc = A[i + (size_t)k * ld];
+      if (i == row0) {
+        acc -= dot_onchip(kw);
+      } else {
+        const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 8
+        for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+      }
+      Wk[i] = acc;
+      if (i > k && i < n) {
+        const double a = fabs(acc);
+        if (a > best) { best = a; besti = i; }
+      }
+      if (i == k) s_akk = acc;  // travels with the exchange from the CTA that owns row k
+    }
+    cluster_argmax(cl, best, besti, akk, sval, sidx, xval, xidx, xextra, parity, &s_akk, ((k - k0) % GT) / PC_NT);
+    const double colmax = besti >= 0 ? best : 0.0;
+    const int imax = besti;
+    const double absakk = fabs(akk);
+
+    int kstep = 1, kp = k;
+    bool zero_pivot = false, copied = false;
+    if (!(fmax(absakk, colmax) > pivtol)) {
+      zero_pivot = true;
+    } else if (absakk >= BK_ALPHA * colmax) {
+      kp = k;
+    } else {
+      double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[imax + (size_t)j * ld];
+      __syncthreads();
+      double rbest = -1.0, wimax = 0.0;
+      int rbesti = -1;
+      for (int i = row0; i < nf; i += GT) {
+        if (i < k) continue;
+        double acc = (i < imax) ? A[imax + (size_t)i * ld] : A[i + (size_t)imax * ld];
+        if (i == row0) {
+          acc -= dot_onchip(kw);
+        } else {
+          const double *__restrict__ Li = A + i + (size_t)k0 * ld;
+#pragma unroll 8
+          for (int j = 0; j < kw; ++j) acc -= Li[(size_t)j * ld] * wrow[j];
+        }
+        Wk1[i] = acc;
+        if (i < n && i != imax) {
+          const double a = fabs(acc);
+          if (a > rbest) { rbest = a; rbesti = i; }
+        }
+        if (i == imax) s_wimax = acc;  // travels with the arg-max exchange: no CTA reads W(imax, kw+1) afterwards
+      }
+      cluster_argmax(cl, rbest, rbesti, wimax, sval, sidx, xval, xidx, xextra, parity, &s_wimax,
+                     ((imax - k0) % GT) / PC_NT);
+      const double rowmax = rbesti >= 0 ? rbest : 0.0;
+      if (absakk >= BK_ALPHA * colmax * (colmax / rowmax)) {
+        kp = k;
+      } else if (fabs(wimax) >= BK_ALPHA * rowmax) {
+        kp = imax;
+        for (int i = row0; i < nf; i += GT)
+          if (i >= k) Wk[i] = Wk1[i];
+        copied = true;
+      } else {
+        kp = imax;
+        kstep = 2;
+      }
+    }
+    // everything the interchange below reads was written before the barrier inside the last cluster_argmax --
+    // except the copy above, whose rows belong to other CTAs (the decision is the same in every CTA)
+    if (copied) cl.sync(); else __syncthreads();
+
+    const int kk = k + kstep - 1;
+    if (kp != kk) {
+      if (gtid == 0) {
+        A[kp + (size_t)kp * ld] = A[kk + (size_t)kk * ld];
+        const int t = F.perm[kk];
+        F.perm[kk] = F.perm[kp];
+        F.perm[kp] = t;
+      }
+      for (int j = kk + 1 + gtid; j < kp; j += GT) A[kp + (size_t)j * ld] = A[j + (size_t)kk * ld];
+      for (int i = kp + 1 + gtid; i < nf; i += GT) A[i + (size_t)kp * ld] = A[i + (size_t)kk * ld];
+      for (int j = gtid; j < kw; j += GT) {
+        double *c = A + (size_t)(k0 + j) * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      for (int j = gtid; j < kw + kstep; j += GT) {
+        double *c = W + (size_t)j * ld;
+        const double t = c[kk];
+        c[kk] = c[kp];
+        c[kp] = t;
+      }
+      cl.sync();
+      // the two exchanged rows changed owners' contents: their on-chip copies are read back
+      if (row0 == kk || row0 == kp)
+        for (int j = 0; j < kw; ++j) store_onchip(j, A[row0 + (size_t)(k0 + j) * ld]);
+    }
+
+    if (kstep == 1) {
+      const double d = Wk[k];
+      const bool bad = zero_pivot || !(fabs(d) > pivtol) || !isfinite(d);
+      const double rd = bad ? 0.0 : 1.0 / d;
+      for (int i = row0; i < nf; i += GT) {
+        if (i <= k) continue;
+        const double v = Wk[i] * rd;
+        A[i + (size_t)k * ld] = v;
+        if (i == row0) store_onchip(kw, v);
+      }
+      if (gtid == 0) {
+        A[k + (size_t)k * ld] = bad ? 0.0 : d;
+        F.ipiv[k] = kp;
+        F.bsz[k] = 1;
+        if (bad && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    } else {
+      const double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      const double e11 = Wk[k], e21 = Wk[k + 1], e22 = Wk1[k + 1];
+      const double d11 = e22 / e21, d22 = e11 / e21;
+      const double t = 1.0 / (d11 * d22 - 1.0);
+      const double sc = t / e21;
+      for (int i = row0; i < nf; i += GT) {
+        if (i <= k + 1) continue;
+        const double w0 = Wk[i], w1 = Wk1[i];
+        const double l0 = sc * (d11 * w0 - w1), l1 = sc * (d22 * w1 - w0);
+        A[i + (size_t)k * ld] = l0;
+        A[i + (size_t)(k + 1) * ld] = l1;
+        if (i == row0) { store_onchip(kw, l0); store_onchip(kw + 1, l1); }
+      }
+      if (gtid == 0) {
+        A[k + (size_t)k * ld] = e11;
+        A[k + 1 + (size_t)k * ld] = e21;
+        A[k + 1 + (size_t)(k + 1) * ld] = e22;
+        F.ipiv[k] = kp;
+        F.ipiv[k + 1] = kp;
+        F.bsz[k] = 2;
+        F.bsz[k + 1] = 0;
+        if (!isfinite(sc) && F.state[ST_INFO] == 0) F.state[ST_INFO] = k + 1;
+      }
+    }
+    // No cluster barrier at the end of a column: the L entries a thread reads in the next sweep are its own (rows are
+    // dealt once per panel), W(:, kw) and W(:, kw + 1) were published by the barriers inside cluster_argmax, the
+    // candidate's diagonal entry travelled with the exchange, and a copy or an interchange is followed by its own
+    // cluster barrier above.
+    __syncthreads();
+    k += kstep;
+  }
+  if (gtid == 0) {
+    F.state[ST_KPREV] = k0;
+    F.state[ST_KCUR] = k;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Trailing update  A(i,j) -= sum_k L(i,k) * W(j,k)   (i >= j >= kcur), FP64 DMMA m8n8k4.
 // 128 x 128 output tile per CTA, 16 warps of 32 x 32, whole panel (K <= NBMAX) staged in smem.

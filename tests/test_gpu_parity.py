@@ -175,8 +175,8 @@ def test_delayed_pivot_overflow_falls_back_to_dense():
     assert st["fell_back_dense"] == 1 or st["delayed_to_root"] == 0
 
 
-@pytest.mark.parametrize("cluster", [1, 0])
-def test_large_dense_fronts(cluster):
+@pytest.mark.parametrize("options", [{}, {"panel_onchip": 0}, {"cluster_panel": 0}])
+def test_large_dense_fronts(options):
     """Dense blocks tall enough for the cluster panel kernel (and, with cluster_panel=0, the single-CTA one):
     both must make the same pivot choices, so inertia and solution agree with LAPACK."""
     rng = np.random.default_rng(11)
@@ -184,7 +184,7 @@ def test_large_dense_fronts(cluster):
     kkt = random_bordered(rng, nb, n, m_c, density=0.6, border_nnz_rows=25)
     sizes = [n] * nb + [m_c]
     rhs = block_vector(rng.standard_normal(sum(sizes)), sizes)
-    s, x = _solve(kkt, rhs, options={"cluster_panel": cluster})
+    s, x = _solve(kkt, rhs, options=options)
     assert s.backend.plan_stats(0)["supernodes"] == 0  # dense plan
     dense = sym_full(kkt).toarray()
     x_ref = np.linalg.solve(dense, rhs.flatten())
@@ -219,15 +219,17 @@ def test_iterative_refinement():
     assert np.linalg.norm(x2.flatten() - x.flatten()) / np.linalg.norm(x2.flatten()) <= 1e-8
 
 
-@pytest.mark.parametrize("shape,cluster", [((2, 300, 4, 200), 1), ((2, 800, 3, 800), 1), ((2, 800, 3, 800), 0)])
-def test_wide_border_sparse_blocks(shape, cluster):
+@pytest.mark.parametrize("shape,options", [((2, 300, 4, 200), {}), ((2, 800, 3, 800), {}),
+                                           ((2, 800, 3, 800), {"panel_onchip": 0}),
+                                           ((2, 800, 3, 800), {"cluster_panel": 0})])
+def test_wide_border_sparse_blocks(shape, options):
     """Config-5-shaped blocks (family G with a wide border): sparse subtree + a dense root front of
     `root columns + border rows` factorised by the panel kernel (single-CTA and, for the taller one, thread-block
-    clusters) and the DMMA update, with the root's pivot count set on the device.  Checked against the closed-form
+    clusters with the panel's rows of L on chip or re-read from L2) and the DMMA update, with the root's pivot count set on the device.  Checked against the closed-form
     inertia, the residual bar, and the reference algorithm (oracle) on the same system."""
     m = EstimationModel(*shape)
     kkt, rhs = m.build_kkt(), m.build_rhs()
-    s, x = _solve(kkt, rhs, options={"cluster_panel": cluster})
+    s, x = _solve(kkt, rhs, options=options)
     st = s.backend.plan_stats(0)
     assert st["supernodes"] > 0 and not st["fell_back_dense"] and st["root_cols"] + shape[3] > 164
     assert s.get_inertia() == m.expected_inertia()
