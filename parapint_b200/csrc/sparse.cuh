@@ -1,14 +1,15 @@
 // Multifrontal factorisation / solves of the SUBTREE part of every diagonal block (one CTA per block).
 //
 // The block's assembly tree is processed level by level (level 0 = leaves).  Fronts of one level
-// are independent: small ones are taken by single warps concurrently, larger ones by the whole CTA.
+// are independent: tiny ones are taken by single warps concurrently (leaves even by parts of a warp, GPU-wide),
+// medium ones by two-warp groups eight at a time, larger ones by the whole CTA.
 // A front is assembled in shared memory (original entries + the contribution blocks of its
 // children, read from per-front slots in HBM), partially factorised with threshold pivoting among
 // its fully-summed rows (1x1 and 2x2 pivots; columns that find no acceptable pivot are DELAYED to the
 // parent, MA57-style), its L/D columns go to the block's factor arena and its contribution block to
-// its slot.  Children of the root are finally added into the block's dense root front, which the
-// batched Bunch-Kaufman kernels of factor.cuh finish (they also see the delayed columns, so no pivot
-// is ever forced: the inertia stays exact).  All sums run in a fixed order: results are reproducible.
+// its slot.  Children of the root are finally added into the block's dense root front, which
+// front_small_kernel (small.cuh) or the batched Bunch-Kaufman kernels of factor.cuh finish (they also see the
+// delayed columns, so no pivot is ever forced: the inertia stays exact).  All sums run in a fixed order: results are reproducible.
 #pragma once
 #include "front.cuh"
 
