@@ -1,0 +1,91 @@
+"""GPU, world_size 2 on ONE device: the real CUDA backend under the multi-rank control flow.
+
+Two processes share cuda:0 and all-reduce their device buffers through gloo (NCCL refuses two ranks on one GPU),
+so the path several GPUs take -- no host synchronisation in the local phase, status / overflow flag / inertia in
+the tail of the Schur all-reduce, the coupling phase reading that tail, the residual exchange -- is exercised
+by the GPU test tier on a single B200.  Mirrors reference test_mpi_explicit_schur_complement.py:19-115.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.kkt_generator import EstimationModel
+        from oracle.schur_oracle import dense_inertia, solve_partitioned, sym_full
+        from parapint_b200 import B200SchurComplementLinearSolver, Communicator, LinearSolverStatus
+        from tests.helpers import block_vector, bordered_from_dense, stochastic_ipm_system
+
+        comm = Communicator()
+        if case == "generator":
+            full = EstimationModel(6, 40, 3, 8)
+            local = EstimationModel(6, 40, 3, 8, local_blocks=[i for i in range(6) if i % world == rank])
+            kkt, rhs = local.build_kkt(), local.build_rhs()
+            solver = B200SchurComplementLinearSolver(comm=comm)
+            assert solver._defer == 2
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            for _ in range(2):
+                assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+                x = solver.do_back_solve(rhs)
+            _, x_ref, _ = solve_partitioned(full.build_kkt(), full.build_rhs(), world)
+            for i in local.local_blocks:
+                assert np.allclose(x.get_block(i), x_ref.get_block(i), rtol=1e-9, atol=1e-9)
+            assert np.allclose(x.get_block(6), x_ref.get_block(6), rtol=1e-9, atol=1e-9)
+            assert solver.get_inertia() == full.expected_inertia()
+            assert solver.last_residual is not None and solver.last_residual <= 1e-10
+        elif case == "overflow":
+            # no delayed-pivot capacity: the sparse path of some rank overflows, every rank learns it from the reduced
+            # tail and repeats its local phase (the overflowing one densely)
+            kkt, sizes = stochastic_ipm_system(3, 4, 300, 240, 30, 10)
+            rhs = block_vector(np.random.default_rng(3).standard_normal(sum(sizes)), sizes)
+            solver = B200SchurComplementLinearSolver(comm=comm, options={"sparse_dmax": 0})
+            solver.do_symbolic_factorization(kkt)
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+            x = solver.do_back_solve(rhs)
+            dense = sym_full(kkt).toarray()
+            x_ref = np.linalg.solve(dense, rhs.flatten())
+            off = np.concatenate(([0], np.cumsum(sizes)))
+            for i in list(solver.local_block_indices) + [len(sizes) - 1]:
+                assert np.allclose(np.asarray(x.get_block(i)).ravel(), x_ref[off[i]:off[i + 1]], rtol=1e-7, atol=1e-9)
+            assert solver.get_inertia() == dense_inertia(dense, "ldl")
+        elif case == "singular":
+            dense = np.zeros((5, 5))
+            dense[:2, :2] = [[1.0, 2.0], [2.0, 4.0]]  # block 0 (rank 0) is singular
+            dense[2:4, 2:4] = np.eye(2)
+            dense[4, 4] = 1.0
+            dense[4, 0] = dense[0, 4] = 1.0
+            kkt = bordered_from_dense(dense, [2, 2, 1])
+            solver = B200SchurComplementLinearSolver(comm=comm)
+            solver.do_symbolic_factorization(kkt)
+            res = solver.do_numeric_factorization(kkt, raise_on_error=False)
+            assert res.status == LinearSolverStatus.singular  # every rank agrees (mpi...:19-30)
+        open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["generator", "overflow", "singular"])
+def test_two_ranks_on_one_gpu(tmp_path, case):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"ok_{case}_0", f"ok_{case}_1"]
