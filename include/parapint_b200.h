@@ -10,7 +10,7 @@
  *  - plain pointers and sizes only; no C++/torch types.  One handle per process / per GPU.
  *  - every function returns a status code equal to parapint's LinearSolverStatus value
  *    (parapint/linalg/results.py:4-9): 0 successful, 1 not_enough_memory, 2 singular, 3 error,
- *    4 warning.  Nothing throws.  pp_last_error() gives a message for code 3.
+ *    4 warning.  Nothing throws.  pp_last_error() gives a message for code 3 and for PP_MISUSE (-1, see below).
  *  - "local blocks" are the diagonal blocks K_i owned by this rank
  *    (parapint/linalg/schur_complement/mpi_explicit_schur_complement.py:198-203); the coupling
  *    matrix Q / S is replicated on every rank (:142-144, :352-360).
@@ -35,7 +35,11 @@ enum {
   PP_NOT_ENOUGH_MEMORY = 1,
   PP_SINGULAR = 2,
   PP_ERROR = 3,
-  PP_WARNING = 4
+  PP_WARNING = 4,
+  /* not a LinearSolverStatus: the CALL was wrong (null pointer, call order, malformed description).  Nothing was
+   * enqueued; pp_last_error() says what.  A binding raises on it at once -- the same call is wrong on every rank --
+   * whereas PP_ERROR (a run-time failure of this rank, e.g. a CUDA error) is a status the ranks must first agree on. */
+  PP_MISUSE = -1
 };
 
 /* Library / build identification (ABI version, compiled arch). */

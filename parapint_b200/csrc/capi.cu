@@ -68,8 +68,9 @@ struct PinBuf {
     if (count <= n) return;
     if (p) cudaFreeHost(p);
     p = nullptr;
-    n = count;
+    n = 0;
     CK(cudaMallocHost(&p, count * sizeof(T)));
+    n = count;  // only after the allocation succeeded
   }
   ~PinBuf() {
     if (p) cudaFreeHost(p);
@@ -77,6 +78,19 @@ struct PinBuf {
 };
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) CK(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 }  // namespace
 
@@ -365,6 +379,12 @@ int fail(const std::string &msg) {
   return PP_ERROR;
 }
 
+// API misuse (null pointer, wrong call order, malformed description): not a LinearSolverStatus
+int misuse(const std::string &msg) {
+  g_error = msg;
+  return PP_MISUSE;
+}
+
 }  // namespace
 
 extern "C" {
@@ -376,13 +396,13 @@ const char *pp_build_info(void) { return "parapint_b200 sm_100a fp64 dmma-m8n8k4
 const char *pp_last_error(void) { return g_error.c_str(); }
 
 int pp_create(int device, pp_handle **out) {
-  if (!out) return fail("pp_create: null out pointer");
+  if (!out) return misuse("pp_create: null out pointer");
   *out = nullptr;
   return guarded([&]() {
     int count = 0;
     CK(cudaGetDeviceCount(&count));
-    if (device < 0 || device >= count) return fail("pp_create: no such CUDA device");
-    CK(cudaSetDevice(device));
+    if (device < 0 || device >= count) return misuse("pp_create: no such CUDA device");
+    DeviceGuard dev_guard(device);
     CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
     CK(cudaFuncSetAttribute(front_panel_cluster_oc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
@@ -402,20 +422,23 @@ int pp_create(int device, pp_handle **out) {
 
 int pp_destroy(pp_handle *h) {
   if (!h) return PP_SUCCESSFUL;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   delete h;
+  if (prev >= 0) cudaSetDevice(prev);
   return PP_SUCCESSFUL;
 }
 
 int pp_set_option(pp_handle *h, const char *name, double value) {
-  if (!h || !name) return fail("pp_set_option: null argument");
+  if (!h || !name) return misuse("pp_set_option: null argument");
   const std::string key(name);
   if (key == "pivot_tol") {
-    if (value < 0) return fail("pivot_tol must be >= 0");
+    if (value < 0) return misuse("pivot_tol must be >= 0");
     h->pivot_tol = value;
   } else if (key == "panel_width") {
     const int nb = (int)value;
-    if (nb < 4 || nb > NBMAX) return fail("panel_width must be in [4, 64]");
+    if (nb < 4 || nb > NBMAX) return misuse("panel_width must be in [4, 64]");
     h->panel_width = nb;
   } else if (key == "sparse") {
     h->use_sparse = value != 0.0;
@@ -423,7 +446,7 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->panel_onchip = value != 0.0;
   } else if (key == "cluster_size") {
     const int c = (int)value;
-    if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return fail("cluster_size must be 0, 1, 2, 4 or 8");
+    if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("cluster_size must be 0, 1, 2, 4 or 8");
     h->cluster_size = c;
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
@@ -432,7 +455,7 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   } else if (key == "defer_status") {
     h->defer_status = (int)value;
   } else if (key == "pivot_threshold") {
-    if (!(value > 0.0 && value <= 0.5)) return fail("pivot_threshold must be in (0, 0.5]");
+    if (!(value > 0.0 && value <= 0.5)) return misuse("pivot_threshold must be in (0, 0.5]");
     h->pivot_threshold = value;
   } else if (key == "cluster_panel") {
     h->use_cluster = value != 0.0;
@@ -457,7 +480,7 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
   } else if (key == "use_graph" || key == "refine_steps") {
     // accepted for forward compatibility; no effect in this build
   } else {
-    return fail("pp_set_option: unknown option " + key);
+    return misuse("pp_set_option: unknown option " + key);
   }
   return PP_SUCCESSFUL;
 }
@@ -494,15 +517,15 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   for (int64_t k = 0; k < nvals; ++k) {
     const int f = dest_front[k];
     if (f < 0) continue;
-    if (f > n_local) return fail("pp_symbolic: dest_front out of range");
+    if (f > n_local) return misuse("pp_symbolic: dest_front out of range");
     const int r = dest_row[k], c = dest_col[k];
     if (f == n_local) {
-      if (r < 0 || c < 0 || r >= m_c || c > r) return fail("pp_symbolic: coupling entry outside the lower triangle");
+      if (r < 0 || c < 0 || r >= m_c || c > r) return misuse("pp_symbolic: coupling entry outside the lower triangle");
       coupling_k.push_back(k);
       continue;
     }
     if (r < 0 || c < 0 || r >= block_n[f] + mloc[f] || c > r || c >= block_n[f])
-      return fail("pp_symbolic: destination outside the lower triangle of its front");
+      return misuse("pp_symbolic: destination outside the lower triangle of its front");
     if (first_k[f] < 0) first_k[f] = k;
     if (k - first_k[f] > 0x7fffffff) return fail("pp_symbolic: block values span more than 2^31 entries");
     e_row[f].push_back(r);
@@ -856,21 +879,21 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
 int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
                 const int32_t *border_rows, int32_t m_c, int64_t nvals, const int32_t *dest_front,
                 const int32_t *dest_row, const int32_t *dest_col, const double *values_hint) {
-  if (!h) return fail("pp_symbolic: null handle");
-  if (n_local < 0 || m_c < 0 || nvals < 0) return fail("pp_symbolic: negative size");
-  if (n_local > 0 && (!block_n || !border_ptr)) return fail("pp_symbolic: null block description");
-  if (nvals > 0 && (!dest_front || !dest_row || !dest_col)) return fail("pp_symbolic: null destination arrays");
+  if (!h) return misuse("pp_symbolic: null handle");
+  if (n_local < 0 || m_c < 0 || nvals < 0) return misuse("pp_symbolic: negative size");
+  if (n_local > 0 && (!block_n || !border_ptr)) return misuse("pp_symbolic: null block description");
+  if (nvals > 0 && (!dest_front || !dest_row || !dest_col)) return misuse("pp_symbolic: null destination arrays");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     h->have_symbolic = false;
     for (int f = 0; f < n_local; ++f) {
-      if (block_n[f] < 0) return fail("pp_symbolic: negative block order");
+      if (block_n[f] < 0) return misuse("pp_symbolic: negative block order");
       const int64_t mi = border_ptr[f + 1] - border_ptr[f];
-      if (mi < 0 || mi > m_c) return fail("pp_symbolic: bad border_ptr");
+      if (mi < 0 || mi > m_c) return misuse("pp_symbolic: bad border_ptr");
       for (int64_t p = border_ptr[f]; p < border_ptr[f + 1]; ++p) {
-        if (border_rows[p] < 0 || border_rows[p] >= m_c) return fail("pp_symbolic: border row out of range");
+        if (border_rows[p] < 0 || border_rows[p] >= m_c) return misuse("pp_symbolic: border row out of range");
         if (p > border_ptr[f] && border_rows[p] <= border_rows[p - 1])
-          return fail("pp_symbolic: border rows must be strictly ascending");
+          return misuse("pp_symbolic: border rows must be strictly ascending");
       }
     }
     h->n_local = n_local;
@@ -955,11 +978,11 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
 
 int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
                      void *stream) {
-  if (!h || !h->have_symbolic) return fail("pp_numeric_local: symbolic factorization required first");
-  if (h->nvals > 0 && !values) return fail("pp_numeric_local: null values");
-  if (!schur_local_dev) return fail("pp_numeric_local: null schur buffer");
+  if (!h || !h->have_symbolic) return misuse("pp_numeric_local: symbolic factorization required first");
+  if (h->nvals > 0 && !values) return misuse("pp_numeric_local: null values");
+  if (!schur_local_dev) return misuse("pp_numeric_local: null schur buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->local_factored = h->coupling_factored = h->forward_done = false;
     const double *dvals = values;
@@ -1006,10 +1029,10 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
 }
 
 int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream) {
-  if (!h || !h->local_factored) return fail("pp_numeric_coupling: pp_numeric_local required first");
-  if (h->m_c > 0 && !schur_sum_dev) return fail("pp_numeric_coupling: null schur buffer");
+  if (!h || !h->local_factored) return misuse("pp_numeric_coupling: pp_numeric_local required first");
+  if (h->m_c > 0 && !schur_sum_dev) return misuse("pp_numeric_coupling: null schur buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->coupling_factored = h->forward_done = false;
     const int mc = h->m_c;
@@ -1029,7 +1052,7 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
     enqueue();
     if (h->status_pending) {
       // single-rank fast path: the local status, the coupling status and both inertias in ONE synchronisation
-      if (schur_sum_dev != h->last_schur) return fail("pp_numeric_coupling: defer_status needs the local Schur buffer");
+      if (schur_sum_dev != h->last_schur) return misuse("pp_numeric_coupling: defer_status needs the local Schur buffer");
       h->status_pending = false;
       post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
       fetch_status(h, st);
@@ -1078,8 +1101,8 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
 }
 
 int pp_schur_tail(pp_handle *h, double out[8]) {
-  if (!h || !out) return fail("pp_schur_tail: null argument");
-  if (!h->tail_valid) return fail("pp_schur_tail: available after pp_numeric_coupling with defer_status = 2");
+  if (!h || !out) return misuse("pp_schur_tail: null argument");
+  if (!h->tail_valid) return misuse("pp_schur_tail: available after pp_numeric_coupling with defer_status = 2");
   for (int k = 0; k < PP_SCHUR_TAIL; ++k) out[k] = h->pin_tail.p[k];
   return PP_SUCCESSFUL;
 }
@@ -1090,7 +1113,7 @@ static int read_inertia(pp_handle *h, int which, int64_t out[3]) {
       for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->inertia_cache[which * 3 + k];
       return (int)PP_SUCCESSFUL;
     }
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     h->pin_inertia.ensure(8);
     CK(cudaMemcpy(h->pin_inertia.p, h->inertia.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->pin_inertia.p[which * 3 + k];
@@ -1099,14 +1122,14 @@ static int read_inertia(pp_handle *h, int which, int64_t out[3]) {
 }
 
 int pp_inertia_local(pp_handle *h, int64_t out[3]) {
-  if (!h || !out) return fail("pp_inertia_local: null argument");
-  if (!h->local_factored) return fail("pp_inertia_local: numeric factorization required first");
+  if (!h || !out) return misuse("pp_inertia_local: null argument");
+  if (!h->local_factored) return misuse("pp_inertia_local: numeric factorization required first");
   return read_inertia(h, 0, out);
 }
 
 int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
-  if (!h || !out) return fail("pp_inertia_coupling: null argument");
-  if (!h->coupling_factored) return fail("pp_inertia_coupling: numeric factorization required first");
+  if (!h || !out) return misuse("pp_inertia_coupling: null argument");
+  if (!h->coupling_factored) return misuse("pp_inertia_coupling: numeric factorization required first");
   return read_inertia(h, 1, out);
 }
 
@@ -1200,11 +1223,11 @@ static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *
 
 int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, double *rc_local_dev,
                      void *stream) {
-  if (!h || !h->local_factored) return fail("pp_solve_forward: numeric factorization required first");
-  if (h->local_dim > 0 && !rhs_local) return fail("pp_solve_forward: null rhs");
-  if (h->m_c > 0 && !rc_local_dev) return fail("pp_solve_forward: null coupling buffer");
+  if (!h || !h->local_factored) return misuse("pp_solve_forward: numeric factorization required first");
+  if (h->local_dim > 0 && !rhs_local) return misuse("pp_solve_forward: null rhs");
+  if (h->m_c > 0 && !rc_local_dev) return misuse("pp_solve_forward: null coupling buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->solved = false;
     const double *drhs = rhs_local;
@@ -1228,11 +1251,11 @@ int pp_solve_forward(pp_handle *h, const double *rhs_local, int on_device, doubl
 int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_c, int on_device,
                       double *x_local, double *x_c, void *stream) {
   if (!h || !h->coupling_factored || !h->forward_done)
-    return fail("pp_solve_backward: numeric factorization and pp_solve_forward required first");
-  if (h->m_c > 0 && (!rc_sum_dev || !rhs_c || !x_c)) return fail("pp_solve_backward: null coupling argument");
-  if (h->local_dim > 0 && !x_local) return fail("pp_solve_backward: null solution buffer");
+    return misuse("pp_solve_backward: numeric factorization and pp_solve_forward required first");
+  if (h->m_c > 0 && (!rc_sum_dev || !rhs_c || !x_c)) return misuse("pp_solve_backward: null coupling argument");
+  if (h->local_dim > 0 && !x_local) return misuse("pp_solve_backward: null solution buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int mc = h->m_c;
     double *dx = on_device ? x_local : h->x.p;
@@ -1287,10 +1310,10 @@ static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cuda
 }
 
 int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
-  if (!h || !h->solved || !h->last_vals) return fail("pp_residual_local: a completed solve is required first");
-  if (!buf_dev) return fail("pp_residual_local: null buffer");
+  if (!h || !h->solved || !h->last_vals) return misuse("pp_residual_local: a completed solve is required first");
+  if (!buf_dev) return misuse("pp_residual_local: null buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     h->norms_valid = false;
     enqueue_residual_local(h, buf_dev, (cudaStream_t)stream);
     CK(cudaGetLastError());
@@ -1299,16 +1322,16 @@ int pp_residual_local(pp_handle *h, double *buf_dev, void *stream) {
 }
 
 int pp_residual_norms(pp_handle *h, const double *buf_sum_dev, double out[2], void *stream) {
-  if (!h || !h->solved) return fail("pp_residual_norms: a completed solve is required first");
-  if (!out) return fail("pp_residual_norms: null argument");
+  if (!h || !h->solved) return misuse("pp_residual_norms: a completed solve is required first");
+  if (!out) return misuse("pp_residual_norms: null argument");
   if (h->norms_valid) {  // formed by pp_solve_backward (option "auto_residual"): nothing to launch or wait for
     out[0] = h->pin_out2.p[0];
     out[1] = h->pin_out2.p[1];
     return PP_SUCCESSFUL;
   }
-  if (!buf_sum_dev) return fail("pp_residual_norms: null argument");
+  if (!buf_sum_dev) return misuse("pp_residual_norms: null argument");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     enqueue_residual_norms(h, buf_sum_dev, st);
     CK(cudaStreamSynchronize(st));
@@ -1319,10 +1342,10 @@ int pp_residual_norms(pp_handle *h, const double *buf_sum_dev, double out[2], vo
 }
 
 int pp_refine_forward(pp_handle *h, double *rc_local_dev, void *stream) {
-  if (!h || !h->solved) return fail("pp_refine_forward: a completed solve and pp_residual_norms are required first");
-  if (h->m_c > 0 && !rc_local_dev) return fail("pp_refine_forward: null coupling buffer");
+  if (!h || !h->solved) return misuse("pp_refine_forward: a completed solve and pp_residual_norms are required first");
+  if (h->m_c > 0 && !rc_local_dev) return misuse("pp_refine_forward: null coupling buffer");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     run_forward(h, h->res_loc.p, rc_local_dev, (cudaStream_t)stream);
     return (int)PP_SUCCESSFUL;
   });
@@ -1330,10 +1353,10 @@ int pp_refine_forward(pp_handle *h, double *rc_local_dev, void *stream) {
 
 int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, double *x_local, double *x_c,
                        void *stream) {
-  if (!h || !h->solved) return fail("pp_refine_backward: a completed solve is required first");
-  if (h->m_c > 0 && !rc_sum_dev) return fail("pp_refine_backward: null coupling argument");
+  if (!h || !h->solved) return misuse("pp_refine_backward: a completed solve is required first");
+  if (h->m_c > 0 && !rc_sum_dev) return misuse("pp_refine_backward: null coupling argument");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->norms_valid = false;
     run_backward(h, rc_sum_dev, h->res_c.p, h->dx_tmp.p, h->dxc_tmp.p, st);
@@ -1347,7 +1370,7 @@ int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, do
     }
     CK(cudaGetLastError());
     if (!on_device) {
-      if ((h->local_dim > 0 && !x_local) || (h->m_c > 0 && !x_c)) return fail("pp_refine_backward: null output");
+      if ((h->local_dim > 0 && !x_local) || (h->m_c > 0 && !x_c)) return misuse("pp_refine_backward: null output");
       copy_out(h, h->last_x, h->last_xc, x_local, x_c, st);
     }
     return (int)PP_SUCCESSFUL;
@@ -1370,17 +1393,17 @@ extern "C" int pp_debug_trace(long long *out, int n) {
 
 int pp_stage_values(pp_handle *h, int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len,
                     void *staging, int threads, int chunks, void *stream) {
-  if (!h || !h->have_symbolic) return fail("pp_stage_values: symbolic factorization required first");
-  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len)) || !staging) return fail("pp_stage_values: null argument");
+  if (!h || !h->have_symbolic) return misuse("pp_stage_values: symbolic factorization required first");
+  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len)) || !staging) return misuse("pp_stage_values: null argument");
   int64_t total = 0;
   for (int64_t k = 0; k < nseg; ++k) {
-    if (len[k] < 0 || off[k] != total || (len[k] > 0 && !ptr[k])) return fail("pp_stage_values: segments must tile the buffer in order");
+    if (len[k] < 0 || off[k] != total || (len[k] > 0 && !ptr[k])) return misuse("pp_stage_values: segments must tile the buffer in order");
     total += len[k];
   }
-  if (total != (int64_t)h->nvals * (int64_t)sizeof(double)) return fail("pp_stage_values: size does not match the analysed pattern");
-  if (!is_pinned_host(staging)) return fail("pp_stage_values: the staging buffer must be pinned host memory");
+  if (total != (int64_t)h->nvals * (int64_t)sizeof(double)) return misuse("pp_stage_values: size does not match the analysed pattern");
+  if (!is_pinned_host(staging)) return misuse("pp_stage_values: the staging buffer must be pinned host memory");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->staged_from = nullptr;
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(chunks, total / (512 << 10)));
@@ -1404,9 +1427,9 @@ int pp_stage_values(pp_handle *h, int64_t nseg, void *const *ptr, const int64_t 
 
 int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, void *staging,
                  int to_staging, int threads) {
-  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len || !staging))) return fail("pp_host_copy: null argument");
+  if (nseg < 0 || (nseg > 0 && (!ptr || !off || !len || !staging))) return misuse("pp_host_copy: null argument");
   for (int64_t k = 0; k < nseg; ++k)
-    if (len[k] < 0 || off[k] < 0 || (len[k] > 0 && !ptr[k])) return fail("pp_host_copy: bad segment");
+    if (len[k] < 0 || off[k] < 0 || (len[k] > 0 && !ptr[k])) return misuse("pp_host_copy: bad segment");
   try {
     CopyPool::instance().run(nseg, ptr, off, len, static_cast<char *>(staging), to_staging != 0, threads);
   } catch (const std::exception &e) {
@@ -1417,9 +1440,9 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
 }
 
 int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
-  if (!h) return fail("pp_profile: null handle");
+  if (!h) return misuse("pp_profile: null handle");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     resolve_profile(h);
     for (int c = 0; c < PP_PROF_CLASSES; ++c) {
       if (ms) ms[c] = h->prof_ms[c];
@@ -1431,7 +1454,7 @@ int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
 }
 
 int pp_plan_stats(pp_handle *h, int32_t block, int64_t out[12]) {
-  if (!h || !h->have_symbolic || block < 0 || block >= h->n_local || !out) return fail("pp_plan_stats: bad argument");
+  if (!h || !h->have_symbolic || block < 0 || block >= h->n_local || !out) return misuse("pp_plan_stats: bad argument");
   const PatternPlan &P = h->plans[h->block_plan[block]];
   out[0] = h->block_plan[block];
   out[1] = P.ns;
@@ -1470,13 +1493,13 @@ int pp_plan_set_ordering(int32_t ordering) {
 
 int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols, int32_t fmax,
                    int32_t dmax, int32_t min_sparse_n, pp_plan **out) {
-  if (!out || n < 0 || m < 0 || nent < 0 || (nent > 0 && (!rows || !cols))) return fail("pp_plan_create: bad argument");
+  if (!out || n < 0 || m < 0 || nent < 0 || (nent > 0 && (!rows || !cols))) return misuse("pp_plan_create: bad argument");
   *out = nullptr;
   return guarded([&]() {
     std::vector<int> r(rows, rows + nent), c(cols, cols + nent), src((size_t)nent);
     std::iota(src.begin(), src.end(), 0);
     for (int64_t k = 0; k < nent; ++k)
-      if (r[k] < c[k] || c[k] < 0 || c[k] >= n || r[k] >= n + m) return fail("pp_plan_create: entry outside the lower triangle");
+      if (r[k] < c[k] || c[k] < 0 || c[k] >= n || r[k] >= n + m) return misuse("pp_plan_create: entry outside the lower triangle");
     PlanOptions opt;
     if (fmax > 0) opt.fmax = std::max(8, std::min((int)fmax, SF_SBUF - 8));
     if (dmax >= 0) opt.dmax = std::max(0, std::min((int)dmax, SF_SBUF / 2));
@@ -1490,7 +1513,7 @@ int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, cons
 }
 
 int pp_plan_get(const pp_plan *pl, const char *name, const int32_t **data, int64_t *len) {
-  if (!pl || !name || !data || !len) return fail("pp_plan_get: null argument");
+  if (!pl || !name || !data || !len) return misuse("pp_plan_get: null argument");
   const PatternPlan &P = pl->P;
   const std::string k(name);
   const std::vector<int> *v = nullptr;
@@ -1521,14 +1544,14 @@ int pp_plan_get(const pp_plan *pl, const char *name, const int32_t **data, int64
   else if (k == "root_row") v = &P.root_row;
   else if (k == "root_col") v = &P.root_col;
   else if (k == "root_src") v = &P.root_src;
-  else return fail("pp_plan_get: unknown array " + k);
+  else return misuse("pp_plan_get: unknown array " + k);
   *data = v->data();
   *len = (int64_t)v->size();
   return PP_SUCCESSFUL;
 }
 
 int pp_plan_scalar(const pp_plan *pl, const char *name, int64_t *value) {
-  if (!pl || !name || !value) return fail("pp_plan_scalar: null argument");
+  if (!pl || !name || !value) return misuse("pp_plan_scalar: null argument");
   const PatternPlan &P = pl->P;
   const std::string k(name);
   if (k == "n") *value = P.n;
@@ -1541,7 +1564,7 @@ int pp_plan_scalar(const pp_plan *pl, const char *name, int64_t *value) {
   else if (k == "l_total") *value = P.l_total;
   else if (k == "stack_cap") *value = P.stack_cap;
   else if (k == "nlevels") *value = P.nlevels;
-  else return fail("pp_plan_scalar: unknown scalar " + k);
+  else return misuse("pp_plan_scalar: unknown scalar " + k);
   return PP_SUCCESSFUL;
 }
 
@@ -1552,16 +1575,16 @@ int pp_plan_destroy(pp_plan *pl) {
 
 int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,
                    int32_t *bsz) {
-  if (!h || !h->have_symbolic || f < 0 || f > h->n_local) return fail("pp_debug_front: bad front index");
+  if (!h || !h->have_symbolic || f < 0 || f > h->n_local) return misuse("pp_debug_front: bad front index");
   return guarded([&]() {
-    CK(cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     CK(cudaDeviceSynchronize());
     Front F;
     CK(cudaMemcpy(&F, h->fronts.p + f, sizeof(Front), cudaMemcpyDeviceToHost));
     const int64_t need = (int64_t)F.ld * F.nf;
     if (ld) *ld = F.ld;
     if (out) {
-      if (out_len < need) return fail("pp_debug_front: output buffer too small");
+      if (out_len < need) return misuse("pp_debug_front: output buffer too small");
       CK(cudaMemcpy(out, F.A, (size_t)need * sizeof(double), cudaMemcpyDeviceToHost));
     }
     if (piv) CK(cudaMemcpy(piv, F.ipiv, (size_t)F.n * sizeof(int), cudaMemcpyDeviceToHost));

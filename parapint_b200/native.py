@@ -114,13 +114,14 @@ class HostCopier:
     def _table(self, arrays, offsets):
         import numpy as np
         keep = self._keep
-        if keep is not None and len(keep) == len(arrays) and all(a is b for a, b in zip(arrays, keep)):
+        off = np.asarray(offsets, dtype=np.int64) * 8
+        if keep is not None and len(keep) == len(arrays) and all(a is b for a, b in zip(arrays, keep)) \
+                and np.array_equal(off, self._tables[1]):   # same arrays AND same destinations
             return self._tables
         for a in arrays:
             if a.dtype != np.float64 or not a.flags.c_contiguous:
                 return None
         ptr = np.array([a.__array_interface__["data"][0] for a in arrays], dtype=np.uintp)
-        off = np.asarray(offsets, dtype=np.int64) * 8
         ln = np.array([a.size * 8 for a in arrays], dtype=np.int64)
         self._keep = list(arrays)
         self._tables = (ptr, off, ln, np_ptr(ptr), np_ptr(off), np_ptr(ln))

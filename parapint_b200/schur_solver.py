@@ -25,6 +25,9 @@ from .comm import Communicator
 from .interface import LinearSolverInterface, LinearSolverResults, LinearSolverStatus
 
 _OK = (LinearSolverStatus.successful, LinearSolverStatus.warning)
+# severity order of the status values for cross-rank agreement
+_SEVERITY = {0: 0, 4: 1, 1: 2, 2: 3, 3: 4}
+_FROM_SEVERITY = {v: k for k, v in _SEVERITY.items()}
 SCHUR_TAIL = 8  # PP_SCHUR_TAIL: status / inertia words appended to the Schur buffer
 
 
@@ -54,10 +57,20 @@ class CudaBackend:
             self._check(self.lib.pp_set_option(self.handle, key.encode(), float(val)), "pp_set_option")
         self.st = None
         self._auto_residual = False
+        with torch.cuda.device(self.device):
+            self.ints = torch.zeros(4, dtype=torch.int64, device=self.device)   # status agreement across ranks
+        self.last_error = ""
+        self.failed = False
 
     def _check(self, code, what):
+        """Only API misuse (PP_MISUSE: wrong call order, null pointer -- the same mistake on every rank) raises
+        here.  Every other code, PP_ERROR included, is a *status* of this rank that the solver first agrees
+        across ranks (``_finish`` / the tail of the Schur all-reduce) and only then returns or raises on."""
+        if code < 0:
+            raise RuntimeError(f"{what}: {native.last_error()}")
         if code == 3:
-            raise RuntimeError(f"{what} failed: {native.last_error()}")
+            self.last_error = f"{what} failed: {native.last_error()}"
+            self.failed = True
         return code
 
     def _stream(self):
@@ -86,13 +99,14 @@ class CudaBackend:
             native.np_ptr(st.border_rows), st.m_c, st.nvals, native.np_ptr(st.dest_front),
             native.np_ptr(st.dest_row), native.np_ptr(st.dest_col),
             native.np_ptr(hint) if hint is not None else None)
-        self._check(code, "pp_symbolic")
+        if self._check(code, "pp_symbolic") != 0:
+            return code
         mc = max(st.m_c, 1)
+        self.schur_size = st.m_c * st.m_c
         with torch.cuda.device(self.device):
-            self.schur = torch.zeros(mc * mc + SCHUR_TAIL, dtype=torch.float64, device=self.device)
+            self.schur = torch.zeros(max(self.schur_size, 1) + SCHUR_TAIL, dtype=torch.float64, device=self.device)
             self.rc = torch.zeros(mc, dtype=torch.float64, device=self.device)
             self.resbuf = torch.zeros(mc + 2, dtype=torch.float64, device=self.device)
-            self.ints = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.values_pin = torch.empty(max(st.nvals, 1), dtype=torch.float64, pin_memory=True)
         self.rhs_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
         self.x_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
@@ -253,16 +267,25 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.schur_complement_solver = schur_complement_solver
         self.comm = comm if comm is not None else Communicator()
         self.backend = backend if backend is not None else CudaBackend(device, options)
-        self._defer = 0
-        if isinstance(self.backend, CudaBackend) and "defer_status" not in (options or {}):
-            # one rank: no collective between the local and the coupling phase, status + inertia are read with one
-            # host sync.  Several ranks: the local phase is not synchronised at all, its status and overflow flag
-            # travel in the tail of the Schur all-reduce.
-            self._defer = 1 if self.comm.size == 1 else 2
-            self.backend.set_option("defer_status", self._defer)
-            if self.comm.size == 1 and refine_tol > 0 and max_refine > 0:
-                # nothing to reduce: the residual norms of the first solve ride on the copy-out's synchronisation
-                self.backend.set_option("auto_residual", 1)
+        # one rank: no collective between the local and the coupling phase, status + inertia are read with one host
+        # sync (defer_status 1; 0 on request).  Several ranks: always 2 -- the local phase is not synchronised at all,
+        # its status and overflow flag travel in the tail of the Schur all-reduce (a per-rank status read would let
+        # ranks disagree and desynchronise the collectives).
+        want = (options or {}).get("defer_status")
+        if self.comm.size > 1:
+            if want not in (None, 2):
+                raise ValueError("defer_status must be 2 (or unset) when the communicator has more than one rank")
+            self._defer = 2
+        else:
+            self._defer = 1 if want is None else int(want)
+            if self._defer not in (0, 1):
+                raise ValueError("defer_status must be 0 or 1 on a single rank")
+        self.backend.set_option("defer_status", self._defer)
+        if self.comm.size == 1 and self._defer == 1 and refine_tol > 0 and max_refine > 0 \
+                and isinstance(self.backend, CudaBackend):
+            # nothing to reduce: the residual norms of the first solve ride on the copy-out's synchronisation
+            self.backend.set_option("auto_residual", 1)
+        self.symbolic_calls = 0
         self.block_dim = 0
         self.block_matrix = None
         self.local_block_indices = []
@@ -281,37 +304,42 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         res.status = LinearSolverStatus(int(code))
         self._status = res.status
         if res.status not in _OK and raise_on_error:
-            raise RuntimeError(f"{what} unsuccessful; status: {res.status}")
+            detail = getattr(self.backend, "last_error", "")
+            raise RuntimeError(f"{what} unsuccessful; status: {res.status}" + (f" ({detail})" if detail else ""))
         return res
 
     def _finish(self, code, raise_on_error, what):
-        """Agree on the worst status across ranks (``_gather_results``, ``mpi...:19-30``)."""
+        """Agree on the worst status across ranks (``_gather_results``, ``mpi...:19-30``): the codes are ranked
+        successful < warning < not_enough_memory < singular < error before the MAX reduction (the raw enum values do
+        not order that way), so one rank's error is never masked by another rank's warning."""
         if self.comm.size > 1:
-            t = self.backend.int_tensor([int(code)])
+            t = self.backend.int_tensor([_SEVERITY[int(code)]])
             self.comm.allreduce_max_(t)
-            code = int(t[0].item())
-        res = LinearSolverResults()
-        res.status = LinearSolverStatus(int(code))
-        self._status = res.status
-        if res.status not in _OK and raise_on_error:
-            raise RuntimeError(f"{what} unsuccessful; status: {res.status}")
-        return res
+            code = _FROM_SEVERITY[int(t[0].item())]
+        return self._result(code, raise_on_error, what)
+
+    def _analyse(self, matrix):
+        """Structure + native symbolic phase; returns this rank's status code (agreed by the caller)."""
+        st = structure.analyse(matrix, self.comm.rank, self.comm.size)
+        self.block_dim = st.n_blocks + 1
+        self.local_block_indices = list(st.local_blocks)
+        hint = np.zeros(st.nvals)
+        structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
+        self._copiers = [None, None]               # pointer tables of the old structure are stale
+        code = self.backend.symbolic(st, hint)
+        self._st = st
+        self._status = None
+        self.symbolic_calls += 1
+        return code
 
     def do_symbolic_factorization(self, matrix, raise_on_error=True, timer=None):
         """Analyse the block structure and allocate the fronts (``explicit...:44-78``,
         ``mpi...:165-255``).  Collective over the communicator."""
         timer = timer or _NullTimer()
         timer.start("sc_structure")
-        st = structure.analyse(matrix, self.comm.rank, self.comm.size)
-        self.block_dim = st.n_blocks + 1
-        self.local_block_indices = list(st.local_blocks)
-        hint = np.zeros(st.nvals)
-        structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
-        self.backend.symbolic(st, hint)
-        self._st = st
-        self._status = None
+        code = self._analyse(matrix)
         timer.stop("sc_structure")
-        return self._finish(0, raise_on_error, "Symbolic factorization")
+        return self._finish(code, raise_on_error, "Symbolic factorization")
 
     def do_numeric_factorization(self, matrix, raise_on_error=True, timer=None):
         """Factor every local front, all-reduce the Schur complement, factor it
@@ -320,79 +348,94 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             raise RuntimeError("do_symbolic_factorization must be called before do_numeric_factorization")
         timer = timer or _NullTimer()
         self.block_matrix = matrix
+        be = self.backend
         timer.start("form SC")
-        if not structure.gather_values(matrix, self._st, self.backend.values, self._copier(0)):
-            # COO pattern / ordering changed since the symbolic phase (happens after the first
-            # regularisation): analyse again, as mumps_interface.py:82-83 does.
-            self.logger.debug("nonzero pattern changed; repeating the symbolic phase")
-            st = structure.analyse(matrix, self.comm.rank, self.comm.size)
-            hint = np.zeros(st.nvals)
-            structure.gather_values(matrix, st, hint)
-            self.backend.symbolic(st, hint)
-            self._st = st
-            if not structure.gather_values(matrix, st, self.backend.values, self._copier(0)):
-                raise RuntimeError("could not gather the matrix values after re-analysis")
-        timer.start("factorize")
-        code, schur_local = self.backend.numeric_local()
-        timer.stop("factorize")
-        self._tail = None
-        if self.comm.size > 1 and self._defer == 2:
-            # ONE collective and ONE host synchronisation per factorisation: the tail of the reduced buffer carries
-            # every rank's status and the summed inertia (mpi...:21,343,427-429), and the coupling phase reads it
-            timer.start("communicate")
-            self.comm.allreduce_sum_(schur_local)
-            timer.stop("communicate")
+        changed = not structure.gather_values(matrix, self._st, be.values, self._copier(0))
+        if self.comm.size == 1:
+            if changed:
+                # COO pattern / ordering changed since the symbolic phase (happens after the first
+                # regularisation): analyse again, as mumps_interface.py:82-83 does.
+                self.logger.debug("nonzero pattern changed; repeating the symbolic phase")
+                code = self._analyse(matrix)
+                if code != 0:
+                    timer.stop("form SC")
+                    return self._result(code, raise_on_error, "Numeric factorization")
+                if not structure.gather_values(matrix, self._st, be.values, self._copier(0)):
+                    raise RuntimeError("could not gather the matrix values after re-analysis")
+            timer.start("factorize")
+            code, schur_local = be.numeric_local()
+            timer.stop("factorize")
+            self._tail = None
+            if code != 0:   # not deferred (or a run-time failure): nothing to factor in the coupling phase
+                timer.stop("form SC")
+                return self._result(code, raise_on_error, "Numeric factorization")
             timer.stop("form SC")
             timer.start("factor SC")
-            code = self.backend.numeric_coupling(schur_local)
-            if code == LinearSolverStatus.not_enough_memory.value:
-                # some rank's sparse path ran out of delayed-pivot capacity (every rank sees it in the reduced
-                # tail): repeat the local phase synchronously -- the overflowing rank re-analyses densely
-                self.backend.set_option("defer_status", 0)
-                try:
-                    code, schur_local = self.backend.numeric_local()
-                finally:
-                    self.backend.set_option("defer_status", 2)
-                self.comm.allreduce_sum_(schur_local)
-                code = self.backend.numeric_coupling(schur_local)
-                if code == LinearSolverStatus.not_enough_memory.value:
-                    code = LinearSolverStatus.error.value
-            self._tail = self.backend.schur_tail()
+            code = be.numeric_coupling(schur_local)
             timer.stop("factor SC")
             return self._result(code, raise_on_error, "Numeric factorization")
-        if self.comm.size > 1:
-            # ONE collective per factorisation (mpi...:343): the tail of the buffer carries this rank's status
-            # and inertia, so no separate allgather / allreduce is needed (mpi...:21,427-429)
+
+        # Several ranks.  ONE collective and ONE host synchronisation per factorisation in the common case: the local
+        # phase is not synchronised, the tail of the reduced Schur buffer carries every rank's status, the summed
+        # inertia (mpi...:21,343,427-429) and two "do it again" requests, and the coupling phase reads it:
+        #   tail[0] some block singular      tail[1] some rank's sparse path overflowed (redo synchronously, dense)
+        #   tail[2:5] inertia                tail[5] some rank's nonzero pattern changed (re-analyse, collectively)
+        #   NaN anywhere = some rank failed at run time (CUDA error, capacity): every rank returns `error`.
+        sync, reanalysed = False, False
+        code = LinearSolverStatus.error.value
+        for _ in range(4):
+            n_s = be.schur_size
+            if changed:
+                schur_local = be.schur
+                schur_local.zero_()
+                schur_local[n_s + 5] = 1.0
+                local_code = -1                       # this rank has nothing factorised
+            else:
+                timer.start("factorize")
+                if sync:
+                    be.set_option("defer_status", 0)
+                try:
+                    local_code, schur_local = be.numeric_local()
+                finally:
+                    if sync:
+                        be.set_option("defer_status", 2)
+                timer.stop("factorize")
+                if local_code in (LinearSolverStatus.error.value, LinearSolverStatus.not_enough_memory.value):
+                    schur_local[n_s:n_s + SCHUR_TAIL] = float("nan")   # seen by every rank after the reduction
             timer.start("communicate")
             self.comm.allreduce_sum_(schur_local)
             timer.stop("communicate")
-            mc2 = self._st.m_c * self._st.m_c
-            tail = schur_local[mc2:mc2 + SCHUR_TAIL].cpu().numpy()
-            self._tail = tail
-            if tail[1] > 0 and self._defer == 2:
-                # some rank's sparse path ran out of delayed-pivot capacity (every rank sees it in the reduced
-                # tail): repeat the local phase synchronously -- the overflowing rank re-analyses densely -- and
-                # reduce again
-                self.backend.set_option("defer_status", 0)
-                try:
-                    code, schur_local = self.backend.numeric_local()
-                finally:
-                    self.backend.set_option("defer_status", 2)
-                self.comm.allreduce_sum_(schur_local)
-                tail = schur_local[mc2:mc2 + SCHUR_TAIL].cpu().numpy()
-                self._tail = tail
-            if code == 0 and tail[0] > 0:
-                code = LinearSolverStatus.singular.value
-            if tail[1] > 0 or not np.all(np.isfinite(tail)):
+            if local_code in (0, LinearSolverStatus.singular.value):
+                code = be.numeric_coupling(schur_local)   # reads the reduced tail: same answer on every rank
+                tail = be.schur_tail()
+            else:
+                tail = schur_local[n_s:n_s + SCHUR_TAIL].cpu().numpy()
                 code = LinearSolverStatus.error.value
-        res = self._result(code, raise_on_error, "Numeric factorization")
-        if res.status not in _OK:
-            timer.stop("form SC")
-            return res
+            self._tail = tail
+            if not np.all(np.isfinite(tail)):
+                code = LinearSolverStatus.error.value
+                break
+            if tail[5] > 0:
+                if reanalysed:
+                    code = LinearSolverStatus.error.value
+                    break
+                self.logger.debug("nonzero pattern changed on some rank; repeating the symbolic phase on all")
+                reanalysed = True
+                sym = self._finish(self._analyse(matrix), False, "Symbolic factorization")
+                if sym.status not in _OK:
+                    code = sym.status.value
+                    break
+                be = self.backend
+                changed = not structure.gather_values(matrix, self._st, be.values, self._copier(0))
+                continue
+            if tail[1] > 0:
+                if sync:
+                    code = LinearSolverStatus.error.value
+                    break
+                sync = True                            # the overflowing rank re-analyses densely
+                continue
+            break
         timer.stop("form SC")
-        timer.start("factor SC")
-        code = self.backend.numeric_coupling(schur_local)  # replicated: every rank gets the same status
-        timer.stop("factor SC")
         return self._result(code, raise_on_error, "Numeric factorization")
 
     def do_back_solve(self, rhs, timer=None):
@@ -405,10 +448,16 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         st = self._st
         structure.pack_rhs(rhs, st, self.backend.rhs_pin.numpy(), self._copier(1))
         self.backend.rhsc_pin.numpy()[: st.m_c] = structure.coupling_rhs(rhs, st)
-        rc = self.backend.solve_forward()
+        be = self.backend
+        be.failed = False
+        rc = be.solve_forward()
+        if be.failed:
+            rc.fill_(float("nan"))      # a run-time failure on this rank: every rank sees it after the reduction
         self.comm.allreduce_sum_(rc)
-        x_local, x_c = self.backend.solve_backward(rc)
+        x_local, x_c = be.solve_backward(rc)
         x_local, x_c = self._refine(x_local, x_c)
+        if be.failed or not np.all(np.isfinite(x_c[: st.m_c])):
+            raise RuntimeError("back solve failed" + (f": {be.last_error}" if be.last_error else ""))
         out = structure.unpack_solution(rhs, st, x_local, x_c[: st.m_c])
         timer.stop("back_solve")
         return out

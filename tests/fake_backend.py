@@ -14,11 +14,22 @@ from oracle.schur_oracle import dense_inertia
 class FakeBackend:
     def __init__(self):
         self.launches = 0
+        self.last_error = ""
+        self.failed = False
+        self.fail_symbolic = self.fail_numeric = False   # test hooks: a run-time failure on this rank
+        self.ints = torch.zeros(4, dtype=torch.int64)
+
+    def set_option(self, name, value):
+        pass
 
     def symbolic(self, st, values_hint=None):
         self.st = st
+        if self.fail_symbolic:
+            self.last_error = "injected symbolic failure"
+            return 3
         mc = max(st.m_c, 1)
-        self.schur = torch.zeros(mc * mc + 8, dtype=torch.float64)
+        self.schur_size = st.m_c * st.m_c
+        self.schur = torch.zeros(max(self.schur_size, 1) + 8, dtype=torch.float64)
         self.rc = torch.zeros(mc, dtype=torch.float64)
         self.ints = torch.zeros(4, dtype=torch.int64)
         self.values_pin = torch.zeros(max(st.nvals, 1), dtype=torch.float64)
@@ -41,6 +52,9 @@ class FakeBackend:
 
     def numeric_local(self):
         st = self.st
+        if self.fail_numeric:
+            self.last_error = "injected numeric failure"
+            return 3, self.schur
         fronts = self._fronts()
         self.K, self.A, self.rows, self.inert = [], [], [], np.zeros(3, dtype=np.int64)
         S = np.zeros((st.m_c, st.m_c))
@@ -58,16 +72,29 @@ class FakeBackend:
                 S[np.ix_(rows, rows)] -= A @ np.linalg.solve(K, A.T)
         self.Q = fronts[-1]
         tail = np.array([1.0 if code == 2 else 0.0, 0.0, *self.inert.astype(float), 0.0, 0.0, 0.0])
-        self.schur.copy_(torch.from_numpy(np.concatenate([S.T.reshape(-1), tail])))
+        self.schur.zero_()
+        self.schur[: self.schur_size] = torch.from_numpy(S.T.reshape(-1).copy())
+        self.schur[self.schur_size: self.schur_size + 8] = torch.from_numpy(tail)
         return code, self.schur
 
     def numeric_coupling(self, schur_sum):
+        """Like pp_numeric_coupling with defer_status = 2: reads the (reduced) tail of the Schur buffer."""
         mc = self.st.m_c
+        self.tail = schur_sum.numpy()[self.schur_size: self.schur_size + 8].copy()
+        if not np.all(np.isfinite(self.tail)):
+            return 3
+        if self.tail[1] > 0:
+            return 1
+        if self.tail[0] > 0:
+            return 2
         self.S = self.Q + schur_sum.numpy()[: mc * mc].reshape(mc, mc).T
         if mc and np.linalg.matrix_rank(self.S) < mc:
             return 2
         self.inert_c = np.asarray(dense_inertia(self.S, "eigvalsh"), dtype=np.int64)
         return 0
+
+    def schur_tail(self):
+        return self.tail.copy()
 
     def inertia_local(self):
         return self.inert.copy()

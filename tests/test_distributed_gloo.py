@@ -67,12 +67,55 @@ def _worker(rank, world, port, case, out_dir):
                 raise AssertionError("expected RuntimeError on every rank")
             except RuntimeError:
                 pass
+        elif case == "rank_local_failure":
+            # a run-time failure on ONE rank must become the same status on EVERY rank (no hang, no
+            # exception on one rank only), in the symbolic phase and in the numeric phase.
+            local = EstimationModel(4, 8, 2, 3, local_blocks=[i for i in range(4) if i % world == rank])
+            kkt = local.build_kkt()
+            be = solver.backend
+            be.fail_symbolic = rank == 1
+            res = solver.do_symbolic_factorization(kkt, raise_on_error=False)
+            assert res.status == LinearSolverStatus.error
+            be.fail_symbolic = False
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            be.fail_numeric = rank == 0
+            res = solver.do_numeric_factorization(kkt, raise_on_error=False)
+            assert res.status == LinearSolverStatus.error
+            be.fail_numeric = False
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+            # warning (4) on one rank must not mask singular (2) on another: severity order, not enum order
+            t = solver._finish(4 if rank == 0 else 2, False, "x")
+            assert t.status == LinearSolverStatus.singular
+        elif case == "pattern_change_one_rank":
+            # the COO pattern of ONE rank's block changes between factorisations: every rank repeats the symbolic
+            # phase together (it is collective), then the factorisation succeeds
+            import scipy.sparse as sp
+            full = EstimationModel(4, 8, 2, 3)
+            local = EstimationModel(4, 8, 2, 3, local_blocks=[i for i in range(4) if i % world == rank])
+            kkt, rhs = local.build_kkt(), local.build_rhs()
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+            before = solver.symbolic_calls
+            if rank == 1:
+                i = local.local_blocks[0]
+                K = kkt.get_block(i, i).tocoo()
+                n = K.shape[0]
+                K2 = sp.coo_matrix((np.concatenate([K.data, np.zeros(n)]),
+                                    (np.concatenate([K.row, np.arange(n)]), np.concatenate([K.col, np.arange(n)]))), shape=K.shape)
+                kkt.set_block(i, i, K2)
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+            assert solver.symbolic_calls == before + 1          # on both ranks
+            x = solver.do_back_solve(rhs)
+            st, x_ref, _ = solve_partitioned(full.build_kkt(), full.build_rhs(), world)
+            for i in local.local_blocks:
+                assert np.allclose(x.get_block(i), x_ref.get_block(i), rtol=1e-9, atol=1e-9)
+            assert solver.get_inertia() == full.expected_inertia()
         open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["generator", "singular"])
+@pytest.mark.parametrize("case", ["generator", "singular", "rank_local_failure", "pattern_change_one_rank"])
 def test_world_size_2(tmp_path, case):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)

@@ -42,10 +42,13 @@ def test_status_codes_match_reference_enum():
 
 def test_null_handle_calls_fail_cleanly():
     lib = native.load()
-    assert lib.pp_numeric_local(None, None, 0, None, None) == 3
+    # API misuse is PP_MISUSE (-1), distinct from the run-time status PP_ERROR (3) that ranks must agree on
+    header = open(os.path.join(ROOT, "include", "parapint_b200.h")).read()
+    assert re.search(r"PP_MISUSE\s*=\s*-1\b", header)
+    assert lib.pp_numeric_local(None, None, 0, None, None) == -1
     assert b"symbolic" in lib.pp_last_error()
     assert lib.pp_destroy(None) == 0
-    assert lib.pp_set_option(None, b"pivot_tol", 0.0) == 3
+    assert lib.pp_set_option(None, b"pivot_tol", 0.0) == -1
 
 
 def test_solver_without_gpu_fails_loudly():
