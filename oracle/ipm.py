@@ -353,6 +353,184 @@ class StochasticInterface:
         return kkt
 
 
+class DynamicInterface(StochasticInterface):
+    """Restates ``DynamicSchurComplementInteriorPointInterface`` (``sc_ip_interface.py:22-1030``) on flat vectors:
+    ``N`` time blocks, ``n_s`` states shared by neighbouring blocks through ``n_s (N-1)`` coupling variables ``z``.
+
+    Per block ``i`` (``:143-177,359-475``): ``Lb_i`` selects the start states (``0 x n`` for block 0), ``Lf_i`` the end
+    states (``0 x n`` for the last block); ``Cb_i`` / ``Cf_i`` select the coupling variables of the interface before /
+    after the block.  Linking constraints ``Lb_i x_i - Cb_i z = 0`` and ``Lf_i x_i - Cf_i z = 0`` (``:716-739``).
+    Equality duals per block are ordered ``[eq_i, backward link, forward link]`` (``:634-647``).
+
+    KKT layout (``:274-357``): diagonal block ``[[KKT_i, Lb_i^T],[Lb_i, 0*I]]`` -- the *backward* multipliers live in
+    the block --; coupling part ``[forward multipliers of every block ; z]`` with
+    ``Q = [[0*I, -Cf],[-Cf^T, 0*I]]``; border of block ``i``: ``Lf_i`` into the rows of its forward multipliers
+    and ``-Cb_i^T`` from its backward-multiplier columns into the rows of ``z``.  ``Q != 0`` and the border is a
+    nested 2x2 block matrix: the structure BASELINE config 3 scales up."""
+
+    def __init__(self, blocks, start_states, end_states):
+        self.sc = [ScenarioInterface(b) for b in blocks]
+        self.N = N = len(self.sc)
+        self.n_s = n_s = len(start_states[0])
+        self.n_c = n_s * (N - 1)                                   # :477-478
+        self.nb = [0 if i == 0 else n_s for i in range(N)]        # backward-link rows per block
+        self.nf = [0 if i == N - 1 else n_s for i in range(N)]    # forward-link rows per block
+
+        def select(rows, idx, n):
+            idx = np.asarray(idx[:rows], dtype=int)
+            return sp.coo_matrix((np.ones(rows), (np.arange(rows), idx)), shape=(rows, n))
+
+        self.Lb = [select(self.nb[i], start_states[i], b.n) for i, b in enumerate(blocks)]      # :418-446
+        self.Lf = [select(self.nf[i], end_states[i], b.n) for i, b in enumerate(blocks)]        # :359-387
+        self.Cb = [select(self.nb[i], n_s * (i - 1) + np.arange(n_s), self.n_c) for i in range(N)]   # :448-475
+        self.Cf = [select(self.nf[i], n_s * i + np.arange(n_s), self.n_c) for i in range(N)]         # :389-416
+        self.z = np.zeros(self.n_c)
+        self.link_b = [np.zeros(k) for k in self.nb]
+        self.link_f = [np.zeros(k) for k in self.nf]
+        self.d_link_b = [np.zeros(k) for k in self.nb]
+        self.d_link_f = [np.zeros(k) for k in self.nf]
+        self.d_z = np.zeros(self.n_c)
+        self.x_off = np.concatenate(([0], np.cumsum([s.nlp.n for s in self.sc])))
+        self.s_off = np.concatenate(([0], np.cumsum([s.nlp.n_in for s in self.sc])))
+        self.e_off = np.concatenate(([0], np.cumsum([s.nlp.n_eq + self.nb[i] + self.nf[i] for i, s in enumerate(self.sc)])))
+        self.kkt_evals = 0
+
+    def set_duals_eq(self, v):                                     # :659-677
+        for i, s in enumerate(self.sc):
+            seg = v[self.e_off[i]:self.e_off[i + 1]]
+            ne = s.nlp.n_eq
+            s.duals_eq = seg[:ne].copy()
+            self.link_b[i] = seg[ne:ne + self.nb[i]].copy()
+            self.link_f[i] = seg[ne + self.nb[i]:].copy()
+
+    def get_duals_eq(self):
+        return np.concatenate([np.concatenate([s.duals_eq, self.link_b[i], self.link_f[i]]) for i, s in enumerate(self.sc)])
+
+    def evaluate_eq_constraints(self):                             # :716-739
+        return np.concatenate([np.concatenate([s.nlp.eq(), self.Lb[i] @ s.nlp.x - self.Cb[i] @ self.z,
+                                               self.Lf[i] @ s.nlp.x - self.Cf[i] @ self.z])
+                               for i, s in enumerate(self.sc)])
+
+    def evaluate_jacobian_eq(self):                                # :254-272,753-765
+        rows = []
+        for i, s in enumerate(self.sc):
+            row = [sp.coo_matrix((s.nlp.n_eq + self.nb[i] + self.nf[i], t.nlp.n)) for t in self.sc] + [None]
+            row[i] = sp.vstack([s.nlp.A_eq, self.Lb[i], self.Lf[i]])
+            row[self.N] = sp.vstack([sp.coo_matrix((s.nlp.n_eq, self.n_c)), -self.Cb[i], -self.Cf[i]])
+            rows.append(row)
+        return sp.bmat(rows).tocsr()
+
+    def evaluate_primal_dual_kkt_matrix(self, timer=None):
+        """:274-357 (structure) + :839-843 (values)."""
+        self.kkt_evals += 1
+        N, n_s = self.N, self.n_s
+        kkt = BlockMatrix(N + 1, N + 1)
+        for i, s in enumerate(self.sc):
+            n = s.nlp.n + s.nlp.n_eq + 2 * s.nlp.n_in
+            sizes = (s.nlp.n, s.nlp.n_in, s.nlp.n_eq, s.nlp.n_in)
+            sub = BlockMatrix(2, 2)
+            sub.set_row_size(0, n); sub.set_col_size(0, n)
+            sub.set_row_size(1, self.nb[i]); sub.set_col_size(1, self.nb[i])
+            ptb = sp.identity(self.nb[i], format="coo"); ptb.data.fill(0)
+            sub.set_block(1, 1, ptb)
+            row1 = BlockMatrix(1, 4)
+            row1.set_row_size(0, self.nb[i])
+            for k, sz in enumerate(sizes):
+                row1.set_col_size(k, sz)
+            row1.set_block(0, 0, self.Lb[i])
+            sub.set_block(1, 0, row1)
+            sub.set_block(0, 1, row1.transpose())
+            sub.set_block(0, 0, s.kkt())
+            kkt.set_block(i, i, sub)
+            # border (:318-333): [[forward-link rows of every block x KKT_i columns, .],[., -Cb_i^T]]
+            border = BlockMatrix(2, 2)
+            fwd = BlockMatrix(N, 4)
+            for k, sz in enumerate(sizes):
+                fwd.set_col_size(k, sz)
+            for j in range(N):
+                fwd.set_row_size(j, self.nf[j])
+            fwd.set_block(i, 0, self.Lf[i])
+            border.set_block(0, 0, fwd)
+            border.set_block(1, 1, (-self.Cb[i].transpose()).tocoo())
+            kkt.set_block(N, i, border)
+            kkt.set_block(i, N, border.transpose())
+        # bottom-right block (:335-357)
+        Q = BlockMatrix(2, 2)
+        sub = BlockMatrix(1, N)
+        for j in range(N):
+            sub.set_block(0, j, (-self.Cf[j].transpose()).tocoo())
+        Q.set_block(1, 0, sub)
+        Q.set_block(0, 1, sub.transpose())
+        ptb = sp.identity(n_s * (N - 1), format="coo"); ptb.data.fill(0)
+        Q.set_block(0, 0, ptb)
+        ptb = sp.identity(self.n_c, format="coo"); ptb.data.fill(0)
+        Q.set_block(1, 1, ptb)
+        kkt.set_block(N, N, Q)
+        return kkt
+
+    def evaluate_primal_dual_kkt_rhs(self, timer=None):
+        """:845-862."""
+        N = self.N
+        rhs = BlockVector(N + 1)
+        fwd = BlockVector(N)
+        last = np.zeros(self.n_c)
+        for i, s in enumerate(self.sc):
+            parts = s.rhs()
+            parts[0] = parts[0] - (self.Lb[i].T @ self.link_b[i] + self.Lf[i].T @ self.link_f[i])
+            inner = BlockVector(4)
+            for k, p in enumerate(parts):
+                inner.set_block(k, p)
+            outer = BlockVector(2)
+            outer.set_block(0, inner)
+            outer.set_block(1, self.Cb[i] @ self.z - self.Lb[i] @ s.nlp.x)
+            rhs.set_block(i, outer)
+            fwd.set_block(i, self.Cf[i] @ self.z - self.Lf[i] @ s.nlp.x)
+            last = last + self.Cb[i].T @ self.link_b[i] + self.Cf[i].T @ self.link_f[i]
+        tail = BlockVector(2)
+        tail.set_block(0, fwd)
+        tail.set_block(1, last)
+        rhs.set_block(N, tail)
+        return rhs
+
+    def set_primal_dual_kkt_solution(self, sol):
+        """:864-877 -- relies on the solver returning the nested structure of the right-hand side."""
+        for i, s in enumerate(self.sc):
+            inner = sol.get_block(i).get_block(0)
+            s.set_solution([inner.get_block(k) for k in range(4)])
+            self.d_link_b[i] = np.asarray(sol.get_block(i).get_block(1), dtype=float)
+            self.d_link_f[i] = np.asarray(sol.get_block(self.N).get_block(0).get_block(i), dtype=float)
+        self.d_z = np.asarray(sol.get_block(self.N).get_block(1), dtype=float)
+
+    def get_delta_duals_eq(self):
+        return np.concatenate([np.concatenate([s.d_eq, self.d_link_b[i], self.d_link_f[i]]) for i, s in enumerate(self.sc)])
+
+    def regularize_equality_gradient(self, kkt, coef, copy_kkt=True):
+        """:903-920."""
+        if copy_kkt:
+            kkt = kkt.copy()
+        for i, s in enumerate(self.sc):
+            inner = kkt.get_block(i, i).get_block(0, 0)
+            inner.set_block(2, 2, coef * sp.identity(s.nlp.n_eq, format="coo"))
+            inner.set_block(3, 3, coef * sp.identity(s.nlp.n_in, format="coo"))
+            kkt.get_block(i, i).set_block(1, 1, coef * sp.identity(self.nb[i], format="coo"))
+        block = kkt.get_block(self.N, self.N)
+        block.set_block(0, 0, coef * sp.identity(block.get_row_size(0), format="coo"))
+        kkt.set_block(self.N, self.N, block)
+        return kkt
+
+    def regularize_hessian(self, kkt, coef, copy_kkt=True):
+        """:922-933."""
+        if copy_kkt:
+            kkt = kkt.copy()
+        for i, s in enumerate(self.sc):
+            inner = kkt.get_block(i, i).get_block(0, 0)
+            inner.set_block(0, 0, inner.get_block(0, 0) + coef * sp.identity(s.nlp.n, format="coo"))
+        block = kkt.get_block(self.N, self.N)
+        block.set_block(1, 1, coef * sp.identity(block.get_row_size(1), format="coo"))
+        kkt.set_block(self.N, self.N, block)
+        return kkt
+
+
 # --------------------------------------------------------------------------------------------------
 class IPOptions:
     """Defaults of ``interior_point.py:57-60,86-88,159-171``."""
@@ -622,3 +800,59 @@ def random_stochastic_qp(seed, n_scen, n_x, n_eq, n_in, n_fs, negative_curvature
         scen.append(QuadraticScenario(c, np.full(n_x, -5.0), np.full(n_x, 5.0), A_in, g_mid - 2.0, g_mid + 3.0,
                                       A_eq=A_eq, b_eq=b_eq, H=H))
     return scen, [list(range(n_fs))] * n_scen
+
+
+def dynamics_time_blocks(t0=0, delta_t=1, num_finite_elements=90, constant_control_duration=10, time_scale=0.1,
+                         num_time_blocks=3):
+    """The dynamics example of ``parapint/examples/dynamics.py:37-100,103-143`` with closed-form data:
+
+        min  sum over finite elements of 0.5 dt [(x(t0) - sin(w t0) - 1)^2 + (x(t1) - sin(w t1) - 1)^2]   (trapezoid)
+        s.t. x(t1) - (x(t0) + dt (p(t_p) - x(t1))) = 0        (implicit Euler of dx/dt = p - x),   p <= 2
+
+    per time block; ``p`` is piecewise constant over ``constant_control_duration``.  Variable order per block:
+    ``x`` at the block's ``nfe + 1`` time points, then its ``p`` values.  Returns the blocks, the start / end state
+    indices and, per block, the times of its ``p`` variables (for the goldens of
+    ``examples/tests/test_examples.py:47-57``)."""
+    assert num_finite_elements % num_time_blocks == 0
+    nfe = num_finite_elements // num_time_blocks
+    assert constant_control_duration >= delta_t and constant_control_duration % delta_t == 0
+    assert (nfe * delta_t) % constant_control_duration == 0
+    blocks, starts, ends, p_times = [], [], [], []
+    for b in range(num_time_blocks):
+        bt0 = t0 + b * nfe * delta_t
+        tx = [bt0 + k * delta_t for k in range(nfe + 1)]
+        n_p = (nfe * delta_t) // constant_control_duration
+        tp = [bt0 + k * constant_control_duration for k in range(n_p)]
+        n = len(tx) + n_p
+        h = np.zeros(n)
+        c = np.zeros(n)
+        const = 0.0
+        for fe in range(nfe):                                  # dynamics.py:84-89
+            for k in (fe, fe + 1):
+                target = np.sin(time_scale * tx[k]) + 1.0
+                h[k] += delta_t                                # 0.5 dt (x - target)^2 -> Hessian dt, gradient -dt*target
+                c[k] += -delta_t * target
+                const += 0.5 * delta_t * target * target
+        rows, cols, vals = [], [], []
+        for fe in range(nfe):                                  # dynamics.py:94-98
+            ip = len(tx) + int(np.floor(fe / (constant_control_duration / delta_t)))
+            rows += [fe, fe, fe]
+            cols += [fe + 1, fe, ip]
+            vals += [1.0 + delta_t, -1.0, -float(delta_t)]
+        A_eq = sp.coo_matrix((vals, (rows, cols)), shape=(nfe, n))
+        ub = np.full(n, np.inf)
+        ub[len(tx):] = 2.0                                     # dynamics.py:80-81
+        blk = QuadraticScenario(c, np.full(n, -np.inf), ub, None, np.zeros(0), np.zeros(0), A_eq=A_eq,
+                                b_eq=np.zeros(nfe), H=sp.diags(h).tocoo())
+        blk.const = const
+        blocks.append(blk)
+        starts.append([0])
+        ends.append([len(tx) - 1])
+        p_times.append(tp)
+    return blocks, starts, ends, p_times
+
+
+#: ``parapint/examples/tests/test_examples.py:47-57``: optimal controls p(t) of the dynamics example (7 places)
+DYNAMICS_GOLDEN_P = {0: 1.6046242850486279, 10: 2.0, 20: 1.4792062911745605, 30: 0.5082444341496647,
+                     40: -0.009859487375413882, 50: 0.40043954978583834, 60: 1.3619861771562247,
+                     70: 1.99059057528143, 80: 1.7102013685364827}

@@ -189,14 +189,20 @@ class SchurOracle:
     def solve_coupling(self, rhs, r_c_sum):
         N = self.nblocks
         top = rhs.get_block(N)
-        top = top.flatten() if is_block_vector(top) else np.asarray(top, dtype=np.float64)
-        return self.coupling_leaf.solve(top + r_c_sum)
+        flat = top.flatten() if is_block_vector(top) else np.asarray(top, dtype=np.float64)
+        sol = self.coupling_leaf.solve(flat + r_c_sum)
+        if is_block_vector(top):   # the leaf keeps the nested structure of its right-hand side (scipy_interface.py:57-60)
+            out = top.copy_structure()
+            out.copyfrom(sol)
+            return out
+        return sol
 
     def local_backward(self, rhs, x_c, out):
         N = self.nblocks
         for i in self.local_blocks:
             At = self.kkt.get_block(N, i).tocsr().transpose()
-            out.set_block(i, self.leaves[i].solve(rhs.get_block(i) - At.dot(x_c)))
+            xc_flat = x_c.flatten() if is_block_vector(x_c) else x_c   # explicit...:153 `coupling.flatten()`
+            out.set_block(i, self.leaves[i].solve(rhs.get_block(i) - At.dot(xc_flat)))
         return out
 
     def solve(self, rhs):

@@ -263,3 +263,124 @@ def test_alternative_control_paths(options):
     s = B200SchurComplementLinearSolver(options=options)
     s.do_symbolic_factorization(bad)
     assert s.do_numeric_factorization(bad, raise_on_error=False).status == LinearSolverStatus.singular
+
+
+def test_config5_shape_vs_oracle():
+    """BASELINE config 5's block shape at full size -- 20 000 rows, 2 000 coupling columns (two of its 128 blocks):
+    dense root fronts of ~4 082 rows through the cluster panel kernel and the DMMA update.  Against the closed-form
+    inertia, the residual bar and the reference algorithm (oracle) on the same system."""
+    m = EstimationModel(2, 2000, 4, 2000)
+    assert m.block_dim == 20000
+    kkt, rhs = m.build_kkt(), m.build_rhs()
+    s, x = _solve(kkt, rhs)
+    st = s.backend.plan_stats(0)
+    assert st["supernodes"] > 0 and not st["fell_back_dense"]
+    assert s.get_inertia() == m.expected_inertia()
+    assert _rel_residual(kkt, x, rhs) <= 1e-10
+    o = SchurOracle()
+    o.symbolic(kkt)
+    assert o.numeric(kkt) == 0
+    x_ref = o.solve(rhs).flatten()
+    assert np.linalg.norm(x.flatten() - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+    assert abs(m.check_result(x) - m.check_result(o.solve(rhs))) <= 1e-8
+
+
+def _lapack_inertia(dense):
+    """Inertia from the pivots of LAPACK dsytrf (blocked Bunch-Kaufman)."""
+    from scipy.linalg import lapack
+    n = dense.shape[0]
+    lw, _ = lapack.dsytrf_lwork(n, lower=1)
+    ldu, ipiv, info = lapack.dsytrf(np.asfortranarray(dense), lower=1, lwork=int(lw), overwrite_a=1)
+    assert info == 0
+    pos = neg = zero = 0
+    k = 0
+    while k < n:
+        if ipiv[k] < 0:   # 2x2 pivot (LAPACK convention, lower: ipiv[k] = ipiv[k+1] < 0)
+            ev = np.linalg.eigvalsh(np.array([[ldu[k, k], ldu[k + 1, k]], [ldu[k + 1, k], ldu[k + 1, k + 1]]]))
+            k += 2
+        else:
+            ev = np.array([ldu[k, k]])
+            k += 1
+        pos += int((ev > 0).sum()); neg += int((ev < 0).sum()); zero += int((ev == 0).sum())
+    return pos, neg, zero
+
+
+def _family_p_case(nb, scale, seed=7):
+    from tests.helpers import stochastic_ipm_system
+    n_x, n_eq, n_in, n_fs = int(10000 * scale), int(8000 * scale), int(1000 * scale), int(200 * scale)
+    kkt, sizes = stochastic_ipm_system(seed, nb, n_x, n_eq, n_in, n_fs, same_pattern=True)
+    rng = np.random.default_rng(0)
+    return kkt, sizes, block_vector(rng.standard_normal(sum(sizes)), sizes)
+
+
+def _check_blocks_against_superlu(kkt, rhs, x, nb):
+    """Per block: residual <= max(1e-10, 2 x the reference SuperLU leaf's residual on the same block) and the two
+    solutions agree to 1e-8 or to the forward-error bound cond_1(K) * eps.  Returns (leaves, worst leaf residual)."""
+    import scipy.sparse.linalg as spl
+    xc = np.asarray(x.get_block(nb))
+    bnorm = np.linalg.norm(rhs.flatten())
+    eps = np.finfo(float).eps
+    leaves, worst_lu = [], 0.0
+    for i in range(nb):
+        K = kkt.get_block(i, i).tocsc()
+        A = kkt.get_block(nb, i).tocsr()
+        xi = np.asarray(x.get_block(i))
+        bi = np.asarray(rhs.get_block(i)) - A.T @ xc
+        lu = spl.splu(K)                                # the reference's leaf (scipy_interface.py:29,52) on this block
+        y = lu.solve(bi)
+        r_gpu = np.linalg.norm(K @ xi - bi) / bnorm
+        r_lu = np.linalg.norm(K @ y - bi) / bnorm
+        worst_lu = max(worst_lu, r_lu)
+        assert r_gpu <= max(1e-10, 2.0 * r_lu), (i, r_gpu, r_lu)
+        inv_norm = spl.onenormest(spl.LinearOperator(K.shape, matvec=lu.solve, rmatvec=lambda v: lu.solve(v, "T")))
+        cond = inv_norm * spl.norm(K, 1)
+        diff = np.linalg.norm(xi - y) / np.linalg.norm(y)
+        assert diff <= max(1e-8, 10.0 * cond * eps), (i, diff, cond)
+        leaves.append((K, A, lu))
+    return leaves, worst_lu
+
+
+def test_config4_shape_blocks_vs_superlu_leaf():
+    """BASELINE config 4's block shape at full size: family-P scenarios of 20 200 rows (n_x 10 000, n_eq 8 000,
+    n_in 1 000, 200 first-stage variables; two of the 1 024 scenarios).  Barrier diagonals over eight decades make
+    some of these blocks numerically singular (|x_i| ~ 1e10 for |b| ~ 1e2), where no FP64 solver reaches 1e-10: the
+    bar is "no worse than twice the reference's SuperLU leaf on the same block" (see the helper above).  The inertia
+    is cross-checked at this size against the same library's dense Bunch-Kaufman path (a different pivoting
+    algorithm on 20 400-row dense fronts; by Sylvester's law both must count the same signs) and, at a size LAPACK
+    can factor, against dsytrf in test_config4_shape_inertia_vs_lapack."""
+    nb = 2
+    kkt, sizes, rhs = _family_p_case(nb, 1.0)
+    assert sizes[0] == 20200
+    s, x = _solve(kkt, rhs)
+    st = s.backend.plan_stats(0)
+    assert st["supernodes"] > 0 and not st["fell_back_dense"]
+    _, worst_lu = _check_blocks_against_superlu(kkt, rhs, x, nb)
+    assert _rel_residual(kkt, x, rhs) <= max(1e-10, 2.0 * worst_lu)
+    inertia = s.get_inertia()
+    del s
+    d = B200SchurComplementLinearSolver(options={"sparse": 0})
+    assert d.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+    assert d.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+    assert d.backend.plan_stats(0)["supernodes"] == 0
+    assert d.get_inertia() == inertia
+    assert inertia[2] == 0 and sum(inertia) == sum(sizes)
+
+
+def test_config4_shape_inertia_vs_lapack():
+    """Family-P scenarios at 0.35 x the config-4 block size (7 070 rows: the multifrontal path with delayed pivots):
+    inertia = sum of LAPACK dsytrf pivot signs per block + the eigenvalue signs of S formed with the reference's
+    leaf (Haynsworth additivity, explicit_schur_complement.py:157-172)."""
+    nb = 2
+    kkt, sizes, rhs = _family_p_case(nb, 0.35)
+    s, x = _solve(kkt, rhs)
+    assert s.backend.plan_stats(0)["supernodes"] > 0 and not s.backend.plan_stats(0)["fell_back_dense"]
+    leaves, worst_lu = _check_blocks_against_superlu(kkt, rhs, x, nb)
+    assert _rel_residual(kkt, x, rhs) <= max(1e-10, 2.0 * worst_lu)
+    m_c = sizes[-1]
+    S = np.zeros((m_c, m_c))
+    tot = np.zeros(3, dtype=np.int64)
+    for K, A, lu in leaves:
+        tot += np.asarray(_lapack_inertia(K.toarray()), dtype=np.int64)
+        S -= A @ lu.solve(A.T.toarray())
+    tot += np.asarray(dense_inertia(0.5 * (S + S.T), "eigvalsh"), dtype=np.int64)
+    assert s.get_inertia() == tuple(int(v) for v in tot)
