@@ -99,13 +99,34 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
                 const int32_t *dest_row, const int32_t *dest_col, const double *values_hint);
 
 /*
+ * Sparse coupling systems.  When the pattern of S = Q - sum_i A_i K_i^-1 A_i^T -- the union over ALL blocks of
+ * nonzero_rows(A_i) x nonzero_rows(A_i) and of the pattern of Q, as MPISchurComplementLinearSolver._get_sc_structure
+ * builds it (mpi_explicit_schur_complement.py:88-125,228-255) -- is sparse and m_c is not small (the block-tridiagonal
+ * S of time-decomposed problems, interfaces/schur_complement/sc_ip_interface.py:274-357), pp_symbolic keeps S as the
+ * values of that pattern: the Schur buffers of pp_numeric_local / pp_numeric_coupling then hold pp_schur_size(h)
+ * doubles (+ PP_SCHUR_TAIL) instead of m_c * m_c, which is what the caller all-reduces (sc_nnz values, :343), and S
+ * is factorised level by level as a block-bordered matrix of its own (block cyclic reduction on a chain).
+ *
+ * pp_set_coupling_cliques: with several ranks the pattern of S depends on the borders of the blocks of EVERY rank
+ * (the reference all-gathers them, :244-247).  Call it before pp_symbolic with the nonzero border rows (ascending) of
+ * all blocks of all ranks, in any order that is the same on every rank; without it only the local blocks are used
+ * (correct on one rank).  n_cliques = 0 forgets a previous list.
+ * pp_coupling_stats: out = {child levels (0 = dense coupling front), pp_schur_size, m_c, order of the dense coupling
+ * front at the bottom of the chain, diagonal blocks over all levels, largest front of the levels, blocks of level 1, 0}.
+ * Options: "coupling_min_sparse" (smallest m_c held sparse, default 384), "coupling_max_density" (default 0.30).
+ */
+int pp_set_coupling_cliques(pp_handle *h, int32_t n_cliques, const int64_t *ptr, const int32_t *rows);
+int64_t pp_schur_size(const pp_handle *h);
+int pp_coupling_stats(pp_handle *h, int64_t out[8]);
+
+/*
  * Numeric phase, local part.  Replaces the per-block leaf factorisations and the Schur formation
  * loop (explicit_schur_complement.py:99-121; mpi_explicit_schur_complement.py:292-333): assembles
  * the fronts from `values`, runs the batched Bunch-Kaufman LDL^T of every local front and writes
- * this rank's dense contribution  -sum_i A_i K_i^{-1} A_i^T  (m_c x m_c, column-major, lower
- * triangle valid) to `schur_local_dev` (DEVICE pointer, caller owned, so that the caller can
- * SUM-reduce it across ranks as mpi_explicit_schur_complement.py:343 does).  The buffer holds
- * m_c*m_c + PP_SCHUR_TAIL doubles: the tail carries {1 if a local block is singular, 0, n_pos, n_neg,
+ * this rank's contribution  -sum_i A_i K_i^{-1} A_i^T  (dense: m_c x m_c, column-major, lower
+ * triangle valid; sparse coupling system: the values of the pattern) to `schur_local_dev` (DEVICE
+ * pointer, caller owned, so that the caller can SUM-reduce it across ranks as
+ * mpi_explicit_schur_complement.py:343 does).  The buffer holds pp_schur_size(h) + PP_SCHUR_TAIL doubles: the tail carries {1 if a local block is singular, 0, n_pos, n_neg,
  * n_zero, 0, 0, 0} of this rank's blocks, so the same all-reduce also agrees the status and sums the
  * inertia across ranks (roles of mpi_explicit_schur_complement.py:21 and :427-429).
  * Returns 0, 2 (a local block is singular) or 3.
@@ -240,6 +261,18 @@ int pp_plan_set_ordering(int32_t ordering); /* for pp_plan_create: 0 auto, 1 min
 int pp_plan_get(const pp_plan *plan, const char *name, const int32_t **data, int64_t *len);
 int pp_plan_scalar(const pp_plan *plan, const char *name, int64_t *value);
 int pp_plan_destroy(pp_plan *plan);
+
+/*
+ * Host-only access to one level of the sparse-coupling analysis (no GPU needed): pattern of S from the cliques and
+ * Q, and its view as a block-bordered matrix (blocks = an independent set of variable groups).  Arrays (as int64):
+ * scalars = {sparse?, n_blocks, m_next, nnz, m_c}, colptr, rowidx, block_n, border_ptr, border_rows, dest_front,
+ * dest_row, dest_col (one per pattern entry), perm_local, perm_c.  min_mc / max_density < 0: defaults.
+ */
+typedef struct pp_cplan pp_cplan;
+int pp_cplan_create(int32_t m_c, int32_t n_cliques, const int64_t *ptr, const int32_t *rows, int64_t nq,
+                    const int32_t *qrow, const int32_t *qcol, int32_t min_mc, double max_density, pp_cplan **out);
+int pp_cplan_get(const pp_cplan *plan, const char *name, int64_t *buf, int64_t cap, int64_t *len);
+int pp_cplan_destroy(pp_cplan *plan);
 
 /* Debug / test access: copy front `f` (0..n_local-1 local, n_local = coupling) to host,
  * column-major with leading dimension *ld; piv/bsz receive the pivot records (n entries). */

@@ -32,6 +32,15 @@ class Communicator:
             dist.all_reduce(tensor, op=dist.ReduceOp.MAX, group=self.group)
         return tensor
 
+    def allgather_object(self, obj):
+        """Every rank's ``obj`` in rank order (border structure of all blocks for the pattern of a sparse Schur
+        complement, ``:244-247``; symbolic phase only)."""
+        if self.size == 1:
+            return [obj]
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
     def barrier(self):
         if self.size > 1:
             dist.barrier(group=self.group)

@@ -19,6 +19,7 @@
 #include "small.cuh"
 #include "symbolic.hpp"
 #include "hostcopy.hpp"
+#include "coupling.hpp"
 #include <map>
 
 using namespace ppb;
@@ -172,6 +173,21 @@ struct pp_handle {
   size_t arenaA_elems = 0;
   int64_t launches = 0;
   int64_t bytes = 0;
+  // sparse coupling system (time-decomposed problems): S is kept as the values of its pattern and factorised by a
+  // CHILD handle that sees it as a block-bordered matrix once more (coupling.hpp); children are replicated per rank
+  CouplingOptions cpl_opt;
+  bool have_cliques = false;
+  std::vector<int64_t> clq_ptr;       // borders of the blocks of ALL ranks (pp_set_coupling_cliques); else the local ones
+  std::vector<int32_t> clq_rows;
+  pp_handle *child = nullptr;
+  int depth = 0;
+  int64_t schur_size = 0;             // doubles of the Schur payload: m_c^2 (dense) or the pattern size (sparse)
+  int64_t sc_nnz = 0;
+  DevBuf<int32_t> sp_row, sp_col, sp_perm_local, sp_perm_c;
+  DevBuf<int64_t> sp_qptr, sp_qsrc;
+  DevBuf<double> sp_vals, own_schur, own_rc;
+  unsigned long long chain_inertia[3] = {0, 0, 0};
+  bool chain_singular = false;
   // optional per-kernel-class timing (option "profile"): CUDA events around every launch
   bool profile = false;
   struct Span { cudaEvent_t a, b; int cls; };
@@ -182,6 +198,7 @@ struct pp_handle {
   ~pp_handle() {
     for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
+    delete child;
   }
 };
 
@@ -475,6 +492,11 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->plan_opt.dmax = std::max(0, std::min((int)value, SF_SBUF / 2));
   } else if (key == "sparse_min_n") {
     h->plan_opt.min_sparse_n = (int)value;
+  } else if (key == "coupling_min_sparse") {
+    h->cpl_opt.min_mc = std::max(2, (int)value);
+  } else if (key == "coupling_max_density") {
+    if (!(value >= 0.0 && value <= 1.0)) return misuse("coupling_max_density must be in [0, 1]");
+    h->cpl_opt.max_density = value;
   } else if (key == "profile") {
     h->profile = value != 0.0;
   } else if (key == "use_graph" || key == "refine_steps") {
@@ -571,8 +593,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     h->nmin[f] = P.nT;
     h->m[f] = mloc[f];
   }
-  h->n[n_local] = m_c;
-  h->nmin[n_local] = m_c;
+  h->n[n_local] = h->child ? 0 : m_c;  // sparse coupling system: no dense coupling front
+  h->nmin[n_local] = h->n[n_local];
   h->m[n_local] = 0;
   std::vector<size_t> offA(nfronts), offW(nfronts), offZ(nfronts), offI(nfronts);
   size_t totA = 0, totW = 0, totZ = 0, totI = 0;
@@ -632,7 +654,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
                          first_k[f] + P.root_src[i]);
   }
   for (int64_t k : coupling_k)
-    keyed.emplace_back((int64_t)(offA[n_local] + (size_t)dest_row[k] + (size_t)dest_col[k] * h->ld[n_local]), k);
+    if (!h->child) keyed.emplace_back((int64_t)(offA[n_local] + (size_t)dest_row[k] + (size_t)dest_col[k] * h->ld[n_local]), k);
   std::stable_sort(keyed.begin(), keyed.end(), [](const auto &a, const auto &b) {
     return a.first != b.first ? a.first < b.first : a.second < b.second;
   });
@@ -872,8 +894,86 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->xc.alloc((size_t)std::max(m_c, 1));
   h->crhs.alloc((size_t)std::max(m_c, 1));
   h->bytes = (int64_t)((totA + totW + totZ + totL + totS) * sizeof(double) + (totI + totBI) * sizeof(int));
+  h->schur_size = h->child ? h->sc_nnz : (int64_t)m_c * m_c;
+  if (h->depth > 0) {  // a child keeps its own Schur and coupling-rhs buffers (nothing is reduced across ranks)
+    h->own_schur.alloc((size_t)h->schur_size + PP_SCHUR_TAIL);
+    h->own_rc.alloc((size_t)std::max(m_c, 1));
+  }
   h->have_symbolic = true;
   return (int)PP_SUCCESSFUL;
+}
+
+// Decides how the coupling system is held -- one dense front, or (sparse pattern, e.g. the block-tridiagonal S of a
+// chain of time blocks) a child handle that factorises S as a block-bordered matrix of its own -- and, in the second
+// case, builds the pattern tables and runs the child's symbolic phase (which may recurse).
+// Every rank reaches the same decision: it only depends on m_c, the borders of ALL blocks and the pattern of Q.
+static int setup_coupling(pp_handle *h) {
+  delete h->child;
+  h->child = nullptr;
+  h->sc_nnz = 0;
+  const int m_c = h->m_c, n_local = h->n_local;
+  if (m_c == 0 || h->depth >= h->cpl_opt.max_levels) return PP_SUCCESSFUL;
+  std::vector<int32_t> qrow, qcol;
+  std::vector<int64_t> qk;
+  for (int64_t k = 0; k < h->nvals; ++k)
+    if (h->in_dest_front[(size_t)k] == n_local) {
+      const int r = h->in_dest_row[(size_t)k], c = h->in_dest_col[(size_t)k];
+      if (r < 0 || c < 0 || r >= m_c || c > r) return misuse("pp_symbolic: coupling entry outside the lower triangle");
+      qrow.push_back(r);
+      qcol.push_back(c);
+      qk.push_back(k);
+    }
+  const std::vector<int64_t> &cp = h->have_cliques ? h->clq_ptr : h->in_border_ptr;
+  const std::vector<int32_t> &cr = h->have_cliques ? h->clq_rows : h->in_border_rows;
+  for (int32_t r : cr)
+    if (r < 0 || r >= m_c) return misuse("pp_symbolic: clique row out of range");
+  CouplingLevel L = analyse_coupling(m_c, cp, cr, qrow, qcol, h->cpl_opt);
+  if (!L.sparse) return PP_SUCCESSFUL;
+  const int64_t nnz = L.nnz();
+  // pattern entries on the device, Q sources per entry
+  std::vector<int32_t> er((size_t)nnz), ec((size_t)nnz);
+  for (int c = 0; c < m_c; ++c)
+    for (int64_t p = L.colptr[(size_t)c]; p < L.colptr[(size_t)c + 1]; ++p) { er[(size_t)p] = L.rowidx[(size_t)p]; ec[(size_t)p] = c; }
+  std::vector<std::pair<int64_t, int64_t>> qs;  // (pattern slot, value index), input order inside a slot
+  qs.reserve(qk.size());
+  for (size_t i = 0; i < qk.size(); ++i) {
+    const int64_t a = L.colptr[(size_t)qcol[i]], b = L.colptr[(size_t)qcol[i] + 1];
+    const auto it = std::lower_bound(L.rowidx.begin() + a, L.rowidx.begin() + b, qrow[i]);
+    qs.emplace_back((int64_t)(it - L.rowidx.begin()), qk[i]);
+  }
+  std::stable_sort(qs.begin(), qs.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+  std::vector<int64_t> qptr((size_t)nnz + 1, 0), qsrc(qs.size());
+  for (size_t i = 0; i < qs.size(); ++i) { qptr[(size_t)qs[i].first + 1]++; qsrc[i] = qs[i].second; }
+  for (int64_t e = 0; e < nnz; ++e) qptr[(size_t)e + 1] += qptr[(size_t)e];
+  if (qsrc.empty()) qsrc.push_back(0);
+  h->sp_row.upload(er);
+  h->sp_col.upload(ec);
+  h->sp_qptr.upload(qptr);
+  h->sp_qsrc.upload(qsrc);
+  h->sp_perm_local.upload(L.perm_local);
+  if (L.perm_c.empty()) L.perm_c.push_back(0);
+  h->sp_perm_c.upload(L.perm_c);
+  h->sp_vals.alloc((size_t)nnz);
+  h->sc_nnz = nnz;
+  // the child: S as a block-bordered matrix (dense diagonal blocks, replicated on every rank)
+  pp_handle *c = nullptr;
+  int rc = pp_create(h->device, &c);
+  if (rc != PP_SUCCESSFUL) return rc;
+  h->child = c;
+  c->depth = h->depth + 1;
+  c->cpl_opt = h->cpl_opt;
+  c->pivot_tol = h->pivot_tol;
+  c->pivot_threshold = h->pivot_threshold;
+  c->panel_width = h->panel_width;
+  c->use_cluster = h->use_cluster;
+  c->panel_onchip = h->panel_onchip;
+  c->use_small = h->use_small;
+  c->use_sparse = false;     // the blocks of S are dense
+  c->defer_status = 1;
+  rc = pp_symbolic(c, L.n_blocks, L.block_n.data(), L.border_ptr.data(), L.border_rows.data(), L.m_next, nnz,
+                   L.dest_front.data(), L.dest_row.data(), L.dest_col.data(), nullptr);
+  if (rc == PP_MISUSE) return fail(std::string("internal error in the coupling analysis: ") + g_error);
+  return rc;
 }
 
 int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int64_t *border_ptr,
@@ -908,8 +1008,54 @@ int pp_symbolic(pp_handle *h, int32_t n_local, const int32_t *block_n, const int
     h->in_dest_col.assign(dest_col, dest_col + nvals);
     if (values_hint) h->in_hint.assign(values_hint, values_hint + nvals); else h->in_hint.clear();
     h->sparse_failed = false;
+    const int rc = setup_coupling(h);
+    if (rc != PP_SUCCESSFUL) return rc;
     return do_symbolic(h, false);
   });
+}
+
+int pp_set_coupling_cliques(pp_handle *h, int32_t n_cliques, const int64_t *ptr, const int32_t *rows) {
+  if (!h) return misuse("pp_set_coupling_cliques: null handle");
+  if (n_cliques < 0 || (n_cliques > 0 && (!ptr || (ptr[n_cliques] > 0 && !rows))))
+    return misuse("pp_set_coupling_cliques: null argument");
+  return guarded([&]() {
+    h->have_cliques = n_cliques > 0;
+    h->clq_ptr.clear();
+    h->clq_rows.clear();
+    if (n_cliques > 0) {
+      for (int k = 0; k < n_cliques; ++k) {
+        if (ptr[k + 1] < ptr[k]) return misuse("pp_set_coupling_cliques: bad ptr");
+        for (int64_t p = ptr[k] + 1; p < ptr[k + 1]; ++p)
+          if (rows[p] <= rows[p - 1]) return misuse("pp_set_coupling_cliques: rows must be strictly ascending");
+      }
+      h->clq_ptr.assign(ptr, ptr + n_cliques + 1);
+      h->clq_rows.assign(rows, rows + ptr[n_cliques]);
+    }
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int64_t pp_schur_size(const pp_handle *h) { return h ? h->schur_size : 0; }
+
+int pp_coupling_stats(pp_handle *h, int64_t out[8]) {
+  if (!h || !h->have_symbolic || !out) return misuse("pp_coupling_stats: bad argument");
+  int levels = 0;
+  int64_t last_mc = h->m_c, blocks = 0, maxfront = 0;
+  for (pp_handle *c = h->child; c; c = c->child) {
+    ++levels;
+    last_mc = c->m_c;
+    blocks += c->n_local;
+    maxfront = std::max<int64_t>(maxfront, c->nfmax_local);
+  }
+  out[0] = levels;          // child levels below this handle (0 = dense coupling front)
+  out[1] = h->schur_size;   // doubles of the Schur payload the caller all-reduces
+  out[2] = h->m_c;
+  out[3] = last_mc;         // order of the dense coupling front at the bottom of the chain
+  out[4] = blocks;          // diagonal blocks over all child levels
+  out[5] = maxfront;        // largest front of the child levels
+  out[6] = h->child ? h->child->n_local : 0;
+  out[7] = 0;
+  return PP_SUCCESSFUL;
 }
 
 static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_local_dev, cudaStream_t st,
@@ -942,7 +1088,13 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
     h->launches++;
   }
   factor_fronts(h, 0, h->n_local, st);
-  if (h->m_c > 0) {
+  if (h->m_c > 0 && h->child) {
+    ProfSpan sp(h, PP_PROF_SCHUR, st);
+    schur_gather_sparse_kernel<<<(unsigned)((h->sc_nnz + 255) / 256), 256, 0, st>>>(
+        h->arenaA.p, h->src_ptr.p, h->src_front.p, h->src_pos.p, h->src_aoff.p, h->src_ld.p, h->brow_ptr.p, h->brow.p,
+        h->sp_row.p, h->sp_col.p, h->sc_nnz, schur_local_dev);
+    h->launches++;
+  } else if (h->m_c > 0) {
     ProfSpan sp(h, PP_PROF_SCHUR, st);
     dim3 g((h->m_c + 127) / 128, h->m_c);
     schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->arenaA.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
@@ -950,7 +1102,7 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
                                            schur_local_dev);
     h->launches++;
   }
-  double *tail = schur_local_dev ? schur_local_dev + (size_t)h->m_c * h->m_c : nullptr;
+  double *tail = schur_local_dev ? schur_local_dev + (size_t)h->schur_size : nullptr;
   int bad = 0;
   *sparse_bad = 0;
   if (h->n_local > 0) {
@@ -1028,6 +1180,63 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
   });
 }
 
+// ---- coupling phase -----------------------------------------------------------------------------------
+static void enqueue_numeric_all(pp_handle *c, const double *dvals, cudaStream_t st);
+
+// S = Q + reduced Schur sum, factorised: a dense front, or (sparse pattern) the child handle, level by level.
+// Nothing is synchronised; the statuses are read afterwards (chain_status).
+static void enqueue_coupling(pp_handle *h, const double *schur_sum_dev, cudaStream_t st) {
+  const int mc = h->m_c;
+  if (mc == 0) return;
+  if (h->child) {
+    coupling_values_kernel<<<(unsigned)((h->sc_nnz + 255) / 256), 256, 0, st>>>(
+        schur_sum_dev, h->last_vals, h->sp_qptr.p, h->sp_qsrc.p, h->sc_nnz, h->sp_vals.p);
+    h->launches++;
+    CK(cudaGetLastError());
+    enqueue_numeric_all(h->child, h->sp_vals.p, st);
+    return;
+  }
+  const Front C = h->hfronts[h->n_local];
+  dim3 g((mc + 127) / 128, mc);
+  coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
+  h->launches++;
+  factor_fronts(h, h->n_local, 1, st);
+  CK(cudaMemsetAsync(h->inertia.p + 3, 0, 3 * sizeof(unsigned long long), st));
+  front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
+  h->launches++;
+  CK(cudaGetLastError());
+}
+
+// A child level: local blocks, its own Schur complement, its coupling system; flags and inertia counters are sent
+// to pinned memory on the same stream (the parent's one synchronisation completes them).
+static void enqueue_numeric_all(pp_handle *c, const double *dvals, cudaStream_t st) {
+  int sparse_bad = 0;
+  c->last_vals = dvals;
+  c->solved = false;
+  c->local_factored = c->coupling_factored = c->forward_done = false;
+  numeric_local_once(c, dvals, c->own_schur.p, st, &sparse_bad, true);
+  c->local_factored = true;
+  enqueue_coupling(c, c->own_schur.p, st);
+  post_flag(c, c->n_local, (c->m_c > 0 && !c->child) ? 1 : 0, 4, st);
+  c->pin_flag.ensure(8);
+  c->pin_inertia.ensure(8);
+  CK(cudaMemcpyAsync(c->pin_flag.p, c->flag.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(c->pin_inertia.p, c->inertia.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  c->coupling_factored = true;
+}
+
+// After the stream was synchronised: status and inertia of the whole chain below h (the factorisation of S).
+static void chain_status(pp_handle *h) {
+  h->chain_singular = false;
+  for (int k = 0; k < 3; ++k) h->chain_inertia[k] = 0;
+  for (pp_handle *c = h->child; c; c = c->child) {
+    if (c->pin_flag.p[0] || c->pin_flag.p[1] || c->pin_flag.p[4]) h->chain_singular = true;
+    for (int k = 0; k < 3; ++k) h->chain_inertia[k] += c->pin_inertia.p[k];
+    if (!c->child)
+      for (int k = 0; k < 3; ++k) h->chain_inertia[k] += c->pin_inertia.p[3 + k];
+  }
+}
+
 int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream) {
   if (!h || !h->local_factored) return misuse("pp_numeric_coupling: pp_numeric_local required first");
   if (h->m_c > 0 && !schur_sum_dev) return misuse("pp_numeric_coupling: null schur buffer");
@@ -1036,25 +1245,13 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     h->coupling_factored = h->forward_done = false;
     const int mc = h->m_c;
-    auto enqueue = [&]() {
-      if (mc > 0) {
-        const Front C = h->hfronts[h->n_local];
-        dim3 g((mc + 127) / 128, mc);
-        coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
-        h->launches++;
-        factor_fronts(h, h->n_local, 1, st);
-        CK(cudaMemsetAsync(h->inertia.p + 3, 0, 3 * sizeof(unsigned long long), st));
-        front_inertia_kernel<<<1, 256, 0, st>>>(h->fronts.p + h->n_local, h->inertia.p + 3);
-        h->launches++;
-        CK(cudaGetLastError());
-      }
-    };
-    enqueue();
+    const int dense_c = (mc > 0 && !h->child) ? 1 : 0;  // a dense coupling front reports through its own info word
+    enqueue_coupling(h, schur_sum_dev, st);
     if (h->status_pending) {
       // single-rank fast path: the local status, the coupling status and both inertias in ONE synchronisation
       if (schur_sum_dev != h->last_schur) return misuse("pp_numeric_coupling: defer_status needs the local Schur buffer");
       h->status_pending = false;
-      post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+      post_flag(h, h->n_local, dense_c, 4, st);
       fetch_status(h, st);
       if (h->n_local > 0 && h->pin_flag.p[1]) {  // sparse path overflow: redo with dense blocks, synchronously
         if (h->no_fallback) return fail("pp_numeric_local: sparse path overflow (fallback disabled)");
@@ -1066,24 +1263,26 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
         if (sparse_bad) return fail("pp_numeric_local: internal error in the dense re-factorisation");
         h->local_factored = true;
         if (bad_local) return (int)PP_SINGULAR;
-        enqueue();
-        post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+        enqueue_coupling(h, schur_sum_dev, st);
+        post_flag(h, h->n_local, dense_c, 4, st);
         fetch_status(h, st);
       }
+      chain_status(h);
       for (int k = 0; k < 6; ++k) h->inertia_cache[k] = h->pin_inertia.p[k];
       h->inertia_cached = true;
       if (h->pin_flag.p[0]) return (int)PP_SINGULAR;
       h->coupling_factored = true;
-      return h->pin_flag.p[4] ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+      return (h->pin_flag.p[4] || h->chain_singular) ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
     }
     if (h->defer_status == 2 && schur_sum_dev) {
       // several ranks: the reduced tail of the Schur buffer (status of every rank's local phase, summed inertia),
       // this rank's coupling status and its inertia counters come back with ONE synchronisation
-      post_flag(h, h->n_local, mc > 0 ? 1 : 0, 4, st);
+      post_flag(h, h->n_local, dense_c, 4, st);
       h->pin_tail.ensure(PP_SCHUR_TAIL);
-      CK(cudaMemcpyAsync(h->pin_tail.p, schur_sum_dev + (size_t)mc * mc, PP_SCHUR_TAIL * sizeof(double),
+      CK(cudaMemcpyAsync(h->pin_tail.p, schur_sum_dev + (size_t)h->schur_size, PP_SCHUR_TAIL * sizeof(double),
                          cudaMemcpyDeviceToHost, st));
       fetch_status(h, st);
+      chain_status(h);
       h->tail_valid = true;
       for (int k = 0; k < 6; ++k) h->inertia_cache[k] = h->pin_inertia.p[k];
       h->inertia_cached = true;
@@ -1092,11 +1291,13 @@ int pp_numeric_coupling(pp_handle *h, const double *schur_sum_dev, void *stream)
       if (h->pin_tail.p[1] > 0.0) return (int)PP_NOT_ENOUGH_MEMORY;  // some rank's sparse path overflowed: redo densely
       if (h->pin_tail.p[0] > 0.0) return (int)PP_SINGULAR;
       h->coupling_factored = true;
-      return h->pin_flag.p[4] ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+      return (h->pin_flag.p[4] || h->chain_singular) ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
     }
-    const int bad = mc > 0 ? read_flag(h, h->n_local, 1, st) : 0;
+    const int bad = read_flag(h, h->n_local, dense_c, st) | 0;
+    if (!dense_c) CK(cudaStreamSynchronize(st));
+    chain_status(h);
     h->coupling_factored = true;
-    return bad ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
+    return (bad || h->chain_singular) ? (int)PP_SINGULAR : (int)PP_SUCCESSFUL;
   });
 }
 
@@ -1109,6 +1310,10 @@ int pp_schur_tail(pp_handle *h, double out[8]) {
 
 static int read_inertia(pp_handle *h, int which, int64_t out[3]) {
   return guarded([&]() {
+    if (which == 1 && h->child) {  // sparse coupling system: the sum over the chain of child levels
+      for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->chain_inertia[k];
+      return (int)PP_SUCCESSFUL;
+    }
     if (h->inertia_cached) {
       for (int k = 0; k < 3; ++k) out[k] = (int64_t)h->inertia_cache[which * 3 + k];
       return (int)PP_SUCCESSFUL;
@@ -1136,6 +1341,8 @@ int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
 static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t st);
 static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cudaStream_t st);
 
+static size_t coupling_smem(const pp_handle *h) { return h->child ? 0 : solve_smem(h->m_c); }
+
 static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, cudaStream_t st) {
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_FORWARD, st);
@@ -1151,7 +1358,7 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
     }
     subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
                                                               h->ywork.p, h->root_rhs.p, h->root_off.p);
-    const size_t sm = std::max(solve_smem(h->nfmax_local), solve_smem(h->m_c));
+    const size_t sm = std::max(solve_smem(h->nfmax_local), coupling_smem(h));
     CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
                                                                                   h->root_off64.p);
@@ -1169,10 +1376,23 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
 static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *drc, double *dx, double *dxc,
                          cudaStream_t st) {
   const int mc = h->m_c;
-  const size_t smax = std::max(solve_smem(h->nfmax_local), solve_smem(mc));
+  const size_t smax = std::max(solve_smem(h->nfmax_local), coupling_smem(h));
   CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
   CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-  if (mc > 0) {
+  if (mc > 0 && h->child) {
+    // sparse coupling system: S x_c = r_c + rc_sum is solved by the child level (which recurses the same way);
+    // its local vector and its coupling vector are a permutation of this level's coupling variables
+    pp_handle *c = h->child;
+    const int nl = (int)c->local_dim, nc = c->m_c;
+    if (nl > 0) gather_perm_kernel<<<(nl + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, h->sp_perm_local.p, nl, c->rhs.p);
+    if (nc > 0) gather_perm_kernel<<<(nc + 255) / 256, 256, 0, st>>>(drc, rc_sum_dev, h->sp_perm_c.p, nc, c->crhs.p);
+    h->launches += 2;
+    run_forward(c, c->rhs.p, c->own_rc.p, st);
+    run_backward(c, c->own_rc.p, c->crhs.p, c->x.p, c->xc.p, st);
+    if (nl > 0) scatter_perm_kernel<<<(nl + 255) / 256, 256, 0, st>>>(c->x.p, h->sp_perm_local.p, nl, dxc);
+    if (nc > 0) scatter_perm_kernel<<<(nc + 255) / 256, 256, 0, st>>>(c->xc.p, h->sp_perm_c.p, nc, dxc);
+    h->launches += 2;
+  } else if (mc > 0) {
     const size_t sm = solve_smem(mc);
     CK(cudaFuncSetAttribute(coupling_solve_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     coupling_solve_kernel<512><<<1, 512, sm, st>>>(h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
@@ -1377,9 +1597,17 @@ int pp_refine_backward(pp_handle *h, const double *rc_sum_dev, int on_device, do
   });
 }
 
-int64_t pp_factor_bytes(const pp_handle *h) { return h ? h->bytes : 0; }
+int64_t pp_factor_bytes(const pp_handle *h) {
+  int64_t tot = 0;
+  for (; h; h = h->child) tot += h->bytes + (int64_t)h->sc_nnz * 32;
+  return tot;
+}
 int64_t pp_local_dim(const pp_handle *h) { return h ? h->local_dim : 0; }
-int64_t pp_kernel_launches(const pp_handle *h) { return h ? h->launches : 0; }
+int64_t pp_kernel_launches(const pp_handle *h) {
+  int64_t tot = 0;
+  for (; h; h = h->child) tot += h->launches;
+  return tot;
+}
 
 #ifdef PP_TRACE
 extern "C" int pp_debug_trace_reset() {
@@ -1569,6 +1797,66 @@ int pp_plan_scalar(const pp_plan *pl, const char *name, int64_t *value) {
 }
 
 int pp_plan_destroy(pp_plan *pl) {
+  delete pl;
+  return PP_SUCCESSFUL;
+}
+
+// ---- host-only access to the analysis of a sparse coupling system (tests; no GPU needed) ----
+struct pp_cplan {
+  CouplingLevel L;
+};
+
+int pp_cplan_create(int32_t m_c, int32_t n_cliques, const int64_t *ptr, const int32_t *rows, int64_t nq,
+                    const int32_t *qrow, const int32_t *qcol, int32_t min_mc, double max_density, pp_cplan **out) {
+  if (!out || m_c < 0 || n_cliques < 0 || nq < 0 || (n_cliques > 0 && !ptr) || (nq > 0 && (!qrow || !qcol)))
+    return misuse("pp_cplan_create: bad argument");
+  *out = nullptr;
+  return guarded([&]() {
+    std::vector<int64_t> cp(1, 0);
+    std::vector<int32_t> cr;
+    if (n_cliques > 0) {
+      cp.assign(ptr, ptr + n_cliques + 1);
+      cr.assign(rows, rows + ptr[n_cliques]);
+    }
+    for (int32_t r : cr)
+      if (r < 0 || r >= m_c) return misuse("pp_cplan_create: clique row out of range");
+    std::vector<int32_t> qr(qrow, qrow + nq), qc(qcol, qcol + nq);
+    for (int64_t k = 0; k < nq; ++k)
+      if (qc[(size_t)k] < 0 || qr[(size_t)k] < qc[(size_t)k] || qr[(size_t)k] >= m_c) return misuse("pp_cplan_create: Q entry outside the lower triangle");
+    CouplingOptions opt;
+    if (min_mc >= 0) opt.min_mc = min_mc;
+    if (max_density >= 0.0) opt.max_density = max_density;
+    auto *pl = new pp_cplan();
+    pl->L = analyse_coupling(m_c, cp, cr, qr, qc, opt);
+    *out = pl;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_cplan_get(const pp_cplan *pl, const char *name, int64_t *buf, int64_t cap, int64_t *len) {
+  if (!pl || !name || !len) return misuse("pp_cplan_get: null argument");
+  const CouplingLevel &L = pl->L;
+  const std::string k(name);
+  std::vector<int64_t> v;
+  auto widen = [&](const std::vector<int32_t> &a) { v.assign(a.begin(), a.end()); };
+  if (k == "scalars") v = {L.sparse ? 1 : 0, L.n_blocks, L.m_next, L.nnz(), L.m_c};
+  else if (k == "colptr") v = L.colptr;
+  else if (k == "border_ptr") v = L.border_ptr;
+  else if (k == "rowidx") widen(L.rowidx);
+  else if (k == "block_n") widen(L.block_n);
+  else if (k == "border_rows") widen(L.border_rows);
+  else if (k == "dest_front") widen(L.dest_front);
+  else if (k == "dest_row") widen(L.dest_row);
+  else if (k == "dest_col") widen(L.dest_col);
+  else if (k == "perm_local") widen(L.perm_local);
+  else if (k == "perm_c") widen(L.perm_c);
+  else return misuse("pp_cplan_get: unknown array " + k);
+  *len = (int64_t)v.size();
+  if (buf && cap >= (int64_t)v.size()) std::copy(v.begin(), v.end(), buf);
+  return PP_SUCCESSFUL;
+}
+
+int pp_cplan_destroy(pp_cplan *pl) {
   delete pl;
   return PP_SUCCESSFUL;
 }

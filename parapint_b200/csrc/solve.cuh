@@ -105,6 +105,61 @@ __global__ void schur_gather_kernel(const Front *__restrict__ fronts, const doub
   S[(size_t)c + (size_t)r * m_c] = s;
 }
 
+// The same gather for a SPARSE Schur complement (time-decomposed problems): one thread per pattern entry (r, c), the
+// result goes to slot p of the value array -- the role of sc_data_slices in mpi_explicit_schur_complement.py:249-254,
+// 326-331, where the all-reduce then moves sc_nnz values instead of m_c^2.
+__global__ void schur_gather_sparse_kernel(const double *__restrict__ arenaA, const int64_t *__restrict__ src_ptr,
+                                           const int32_t *__restrict__ src_front, const int32_t *__restrict__ src_pos,
+                                           const int64_t *__restrict__ src_aoff, const int32_t *__restrict__ src_ld,
+                                           const int64_t *__restrict__ brow_ptr, const int32_t *__restrict__ brow,
+                                           const int32_t *__restrict__ ent_row, const int32_t *__restrict__ ent_col,
+                                           int64_t nnz, double *__restrict__ S) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int r = ent_row[e], c = ent_col[e];
+  double s = 0.0;
+  for (int64_t p = src_ptr[r]; p < src_ptr[r + 1]; ++p) {  // fronts holding row r, in front order
+    const int ldf = src_ld[p];
+    int lo = c;
+    if (ldf < 0) {
+      const int f = src_front[p], a = src_pos[p];
+      const int32_t *br = brow + brow_ptr[f];
+      int hi = a;
+      lo = 0;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (br[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      if (br[lo] != c) continue;
+    }
+    s += arenaA[src_aoff[p] + (int64_t)lo * (ldf < 0 ? -ldf : ldf)];
+  }
+  S[e] = s;
+}
+
+// values of the next level: S(p) = reduced Schur sum + the entries of Q that fall on pattern slot p (input order)
+__global__ void coupling_values_kernel(const double *__restrict__ Ssum, const double *__restrict__ vals,
+                                       const int64_t *__restrict__ q_ptr, const int64_t *__restrict__ q_src,
+                                       int64_t nnz, double *__restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  double s = 0.0;
+  for (int64_t p = q_ptr[e]; p < q_ptr[e + 1]; ++p) s += vals[q_src[p]];
+  out[e] = Ssum[e] + s;
+}
+
+// out[j] = a[perm[j]] (+ b[perm[j]]);  out[perm[j]] = in[j]
+__global__ void gather_perm_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                   const int32_t *__restrict__ perm, int n, double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = b ? a[perm[j]] + b[perm[j]] : a[perm[j]];
+}
+__global__ void scatter_perm_kernel(const double *__restrict__ in, const int32_t *__restrict__ perm, int n,
+                                    double *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[perm[j]] = in[j];
+}
+
 // coupling front (lower) += reduced Schur sum; Q was assembled into it already.
 __global__ void coupling_add_kernel(Front F, const double *__restrict__ Ssum, int m_c) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -26,6 +26,12 @@ SIGNATURES = {
     "pp_destroy": (C.c_int, [_vp]),
     "pp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "pp_symbolic": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp]),
+    "pp_set_coupling_cliques": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "pp_schur_size": (C.c_int64, [_vp]),
+    "pp_coupling_stats": (C.c_int, [_vp, _i64p]),
+    "pp_cplan_create": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, C.c_double, C.POINTER(_vp)]),
+    "pp_cplan_get": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64, _i64p]),
+    "pp_cplan_destroy": (C.c_int, [_vp]),
     "pp_numeric_local": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "pp_numeric_coupling": (C.c_int, [_vp, _vp, _vp]),
     "pp_inertia_local": (C.c_int, [_vp, _i64p]),
@@ -175,3 +181,35 @@ def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1, ordering=0):
         return out
     finally:
         lib.pp_plan_destroy(plan)
+
+
+CPLAN_ARRAYS = ("scalars", "colptr", "rowidx", "block_n", "border_ptr", "border_rows", "dest_front", "dest_row",
+                "dest_col", "perm_local", "perm_c")
+
+
+def coupling_plan(m_c, clique_ptr, clique_rows, qrow, qcol, min_mc=-1, max_density=-1.0):
+    """One level of the host analysis of a sparse coupling system (``pp_cplan_*``) as a dict of numpy arrays."""
+    import numpy as np
+    lib = load()
+    cp = np.ascontiguousarray(clique_ptr, dtype=np.int64)
+    cr = np.ascontiguousarray(clique_rows, dtype=np.int32)
+    qr = np.ascontiguousarray(qrow, dtype=np.int32)
+    qc = np.ascontiguousarray(qcol, dtype=np.int32)
+    plan = _vp()
+    if lib.pp_cplan_create(int(m_c), cp.size - 1, np_ptr(cp), np_ptr(cr), qr.size, np_ptr(qr), np_ptr(qc), int(min_mc),
+                           float(max_density), C.byref(plan)) != 0:
+        raise RuntimeError(last_error())
+    try:
+        out = {}
+        for name in CPLAN_ARRAYS:
+            ln = C.c_int64()
+            if lib.pp_cplan_get(plan, name.encode(), None, 0, C.byref(ln)) != 0:
+                raise RuntimeError(last_error())
+            buf = np.zeros(max(ln.value, 1), dtype=np.int64)
+            lib.pp_cplan_get(plan, name.encode(), np_ptr(buf), buf.size, C.byref(ln))
+            out[name] = buf[: ln.value]
+        sc = out.pop("scalars")
+        out.update(sparse=bool(sc[0]), n_blocks=int(sc[1]), m_next=int(sc[2]), nnz=int(sc[3]), m_c=int(sc[4]))
+        return out
+    finally:
+        lib.pp_cplan_destroy(plan)

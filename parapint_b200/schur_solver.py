@@ -88,9 +88,17 @@ class CudaBackend:
             pass
 
     # -- buffers -----------------------------------------------------------------------------
-    def symbolic(self, st: structure.Structure, values_hint=None):
+    def symbolic(self, st: structure.Structure, values_hint=None, cliques=None):
+        """``cliques``: (ptr, rows) of the nonzero border rows of the blocks of ALL ranks (several ranks only)."""
         torch = self.torch
         self.st = st
+        if cliques is not None:
+            ptr = np.ascontiguousarray(cliques[0], dtype=np.int64)
+            rows = np.ascontiguousarray(cliques[1], dtype=np.int32)
+            self._check(self.lib.pp_set_coupling_cliques(self.handle, ptr.size - 1, native.np_ptr(ptr),
+                                                         native.np_ptr(rows)), "pp_set_coupling_cliques")
+        else:
+            self._check(self.lib.pp_set_coupling_cliques(self.handle, 0, None, None), "pp_set_coupling_cliques")
         hint = None
         if values_hint is not None and values_hint.size == st.nvals and np.any(values_hint):
             hint = np.ascontiguousarray(values_hint, dtype=np.float64)
@@ -102,7 +110,7 @@ class CudaBackend:
         if self._check(code, "pp_symbolic") != 0:
             return code
         mc = max(st.m_c, 1)
-        self.schur_size = st.m_c * st.m_c
+        self.schur_size = int(self.lib.pp_schur_size(self.handle))   # m_c^2, or the pattern size of a sparse S
         with torch.cuda.device(self.device):
             self.schur = torch.zeros(max(self.schur_size, 1) + SCHUR_TAIL, dtype=torch.float64, device=self.device)
             self.rc = torch.zeros(mc, dtype=torch.float64, device=self.device)
@@ -213,6 +221,12 @@ class CudaBackend:
         self._check(self.lib.pp_profile(self.handle, ms, cnt, 1 if reset else 0), "pp_profile")
         names = ("assemble", "panel", "swaps", "update", "schur", "forward", "backward", "subtree")
         return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(names)}
+
+    def coupling_stats(self):
+        out = (C.c_int64 * 8)()
+        self._check(self.lib.pp_coupling_stats(self.handle, out), "pp_coupling_stats")
+        keys = ("levels", "schur_size", "m_c", "bottom_m_c", "blocks", "max_front", "level1_blocks")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def plan_stats(self, block=0):
         out = (C.c_int64 * 12)()
@@ -326,7 +340,13 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         hint = np.zeros(st.nvals)
         structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
         self._copiers = [None, None]               # pointer tables of the old structure are stale
-        code = self.backend.symbolic(st, hint)
+        cliques = None
+        if self.comm.size > 1:
+            # the pattern of S is the union over the blocks of EVERY rank (mpi...:244-247 all-gathers the same lists)
+            parts = self.comm.allgather_object((np.diff(st.border_ptr), st.border_rows))
+            lens = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=np.int64)
+            cliques = (np.concatenate(([0], np.cumsum(lens))), np.concatenate([p[1] for p in parts]))
+        code = self.backend.symbolic(st, hint, cliques)
         self._st = st
         self._status = None
         self.symbolic_calls += 1

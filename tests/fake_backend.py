@@ -22,7 +22,7 @@ class FakeBackend:
     def set_option(self, name, value):
         pass
 
-    def symbolic(self, st, values_hint=None):
+    def symbolic(self, st, values_hint=None, cliques=None):
         self.st = st
         if self.fail_symbolic:
             self.last_error = "injected symbolic failure"

@@ -97,3 +97,52 @@ def stochastic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_fs, same_pattern=Fa
     kkt.set_block(n_blocks, n_blocks, sp.coo_matrix((n_fs, n_fs)))
     sizes.append(n_fs)
     return kkt, sizes
+
+
+def dynamic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_s, same_pattern=True, local_blocks=None, **kw):
+    """Block-bordered KKT of a time-decomposed NLP ("family P, dynamic"; layout of
+    interfaces/schur_complement/sc_ip_interface.py:274-357): time block i couples to its neighbours through n_s
+    states.  Diagonal block i = [[KKT_i, Lb_i^T],[Lb_i, 0]] (backward-link multipliers inside the block; none for
+    block 0); coupling part = [forward-link multipliers of blocks 0..N-2 ; coupling variables z (n_s per interface)];
+    border of block i: Lf_i (end states) into the rows of its forward multipliers, -I from its backward multipliers
+    into the rows of z_{i-1}; Q = [[0, -I],[-I, 0]].  m_c = 2 n_s (N - 1); S is block tridiagonal.
+    Blocks not in ``local_blocks`` are left empty (the other ranks' blocks).  Returns (kkt, sizes)."""
+    N = n_blocks
+    assert 2 * n_s + n_eq + n_in <= n_x
+    nf_tot = n_s * (N - 1)
+    m_c = 2 * nf_tot
+    kkt = BlockMatrix(N + 1, N + 1)
+    sizes = []
+    for i in range(N):
+        nb = 0 if i == 0 else n_s
+        n = n_x + 2 * n_in + n_eq + nb
+        sizes.append(n)
+        if local_blocks is not None and i not in local_blocks:
+            continue
+        rng = np.random.default_rng(1000 * seed + i)
+        if same_pattern:
+            kw["pattern_rng"] = np.random.default_rng(77 + seed)
+        K, n_chk = ipm_kkt_block(rng, n_x, n_eq, n_in, nb, **kw)
+        assert n_chk == n
+        kkt.set_block(i, i, K)
+        rows, cols, vals = [], [], []
+        if i < N - 1:   # Lf_i: end states = primals [c0, c0 + n_s), disjoint from the identity parts of Lb, J_eq, J_in
+            c0 = nb + n_eq
+            rows += list(n_s * i + np.arange(n_s))
+            cols += list(c0 + np.arange(n_s))
+            vals += [1.0] * n_s
+        if i > 0:       # -Cb_i^T: backward multipliers (last nb columns) against z_{i-1}
+            rows += list(nf_tot + n_s * (i - 1) + np.arange(n_s))
+            cols += list(n - nb + np.arange(nb))
+            vals += [-1.0] * n_s
+        kkt.set_block(N, i, sp.coo_matrix((vals, (rows, cols)), shape=(m_c, n)))
+    idx = np.arange(nf_tot)
+    Q = sp.coo_matrix((np.concatenate([np.zeros(m_c), -np.ones(nf_tot)]),
+                       (np.concatenate([np.arange(m_c), nf_tot + idx]), np.concatenate([np.arange(m_c), idx]))),
+                      shape=(m_c, m_c))
+    kkt.set_block(N, N, Q)
+    for i in range(N):
+        kkt.set_row_size(i, sizes[i])
+        kkt.set_col_size(i, sizes[i])
+    sizes.append(m_c)
+    return kkt, sizes
