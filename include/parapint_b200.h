@@ -120,6 +120,26 @@ int64_t pp_schur_size(const pp_handle *h);
 int pp_coupling_stats(pp_handle *h, int64_t out[8]);
 
 /*
+ * Device-side regularisation (inertia correction without re-uploading the matrix).  parapint's inertia-correction
+ * loop (algorithms/interior_point.py:369-395) refactorises up to ~17 times per iteration with diagonal shifts applied
+ * by the problem interface (interfaces/interface.py:590-619; sc_ip_interface.py:903-933,1736-1757): +delta added to
+ * the Hessian diagonal of every block (accumulating over the retries of one iteration), -delta SET on the
+ * (2,2)/(3,3)/linking-multiplier diagonals, +delta SET on the diagonal of the coupling variables.
+ * pp_set_diagonal_classes (before pp_symbolic) declares the class of every local row (concatenated blocks) and
+ * coupling row: 0 none, 1..PP_SHIFT_SLOTS the shift slot whose value is ADDED to that diagonal entry; the symbolic
+ * phase then reserves those diagonal entries (so a Hessian shift never changes the analysed pattern).
+ * pp_set_shifts sets the slot values used by the following factorisations (zero after the classes are set), and
+ * pp_numeric_local(h, NULL, PP_VALUES_REUSE, ...) factorises the values of the previous call again -- no gather,
+ * no host-to-device transfer, no symbolic phase.  pp_value_uploads counts the transfers of the value array.
+ */
+#define PP_SHIFT_SLOTS 3
+#define PP_VALUES_REUSE 2
+int pp_set_diagonal_classes(pp_handle *h, int64_t n_local_rows, const int8_t *cls_local, int32_t m_c,
+                            const int8_t *cls_c);
+int pp_set_shifts(pp_handle *h, const double *shifts);
+int64_t pp_value_uploads(const pp_handle *h);
+
+/*
  * Numeric phase, local part.  Replaces the per-block leaf factorisations and the Schur formation
  * loop (explicit_schur_complement.py:99-121; mpi_explicit_schur_complement.py:292-333): assembles
  * the fronts from `values`, runs the batched Bunch-Kaufman LDL^T of every local front and writes

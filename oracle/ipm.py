@@ -329,6 +329,10 @@ class StochasticInterface:
     def get_delta_duals_slacks_lb(self): return np.concatenate([s.d_sl() for s in self.sc])
     def get_delta_duals_slacks_ub(self): return np.concatenate([s.d_su() for s in self.sc])
 
+    def regularization_classes(self):
+        """(per block, coupling): first-stage variables are the coupling primals (``:1755``)."""
+        return {i: _block_classes(s, self.n_c) for i, s in enumerate(self.sc)}, np.full(self.n_c, 3, dtype=np.int8)
+
     def regularize_equality_gradient(self, kkt, coef, copy_kkt=True):
         """:1736-1745 with ``interface.py:590-608`` on every scenario."""
         if copy_kkt:
@@ -351,6 +355,13 @@ class StochasticInterface:
             inner.set_block(0, 0, hess)
         kkt.set_block(self.N, self.N, coef * sp.identity(self.n_c, format="coo"))
         return kkt
+
+
+def _block_classes(s, n_link):
+    """Diagonal classes of one diagonal block ``[x, s, lam_eq, lam_in, linking multipliers]`` for device-side
+    regularisation (``parapint_b200/regularization.py``): what ``regularize_hessian`` / ``regularize_equality_gradient``
+    touch (``interface.py:590-619``; linking rows ``sc_ip_interface.py:915-916,1744``)."""
+    return np.concatenate([np.full(s.nlp.n, 1), np.zeros(s.nlp.n_in), np.full(s.nlp.n_eq + s.nlp.n_in + n_link, 2)]).astype(np.int8)
 
 
 class DynamicInterface(StochasticInterface):
@@ -504,6 +515,11 @@ class DynamicInterface(StochasticInterface):
     def get_delta_duals_eq(self):
         return np.concatenate([np.concatenate([s.d_eq, self.d_link_b[i], self.d_link_f[i]]) for i, s in enumerate(self.sc)])
 
+    def regularization_classes(self):
+        """(per block, coupling): the coupling part is [forward multipliers (``:917-919``) ; z (``:929-931``)]."""
+        return ({i: _block_classes(s, self.nb[i]) for i, s in enumerate(self.sc)},
+                np.concatenate([np.full(self.n_s * (self.N - 1), 2), np.full(self.n_c, 3)]).astype(np.int8))
+
     def regularize_equality_gradient(self, kkt, coef, copy_kkt=True):
         """:903-920."""
         if copy_kkt:
@@ -529,6 +545,13 @@ class DynamicInterface(StochasticInterface):
         block.set_block(1, 1, coef * sp.identity(block.get_row_size(1), format="coo"))
         kkt.set_block(self.N, self.N, block)
         return kkt
+
+
+def device_regularized(cls):
+    """The same interface with the ``regularize_*`` methods replaced by the device-side variant
+    (``parapint_b200.regularization.DeviceRegularizationMixin``): what a parapint user adds to switch it on."""
+    from parapint_b200.regularization import DeviceRegularizationMixin
+    return type("DeviceRegularized" + cls.__name__, (DeviceRegularizationMixin, cls), {})
 
 
 # --------------------------------------------------------------------------------------------------

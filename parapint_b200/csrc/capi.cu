@@ -27,6 +27,7 @@ using namespace ppb;
 namespace {
 
 thread_local std::string g_error;
+size_t h_optin_smem = 227 * 1024;  // opt-in shared memory per block of the device (set by pp_create)
 
 struct CudaFail {
   std::string msg;
@@ -173,6 +174,13 @@ struct pp_handle {
   size_t arenaA_elems = 0;
   int64_t launches = 0;
   int64_t bytes = 0;
+  // device-side regularisation: class of every local / coupling diagonal entry (0 = none) and the shift slots, which
+  // live behind the nvals input values on the device so that a retry of the inertia-correction loop is a refactor only
+  std::vector<int8_t> cls_local, cls_c;
+  bool have_classes = false;
+  double shifts[PP_SHIFT_SLOTS] = {0.0, 0.0, 0.0};
+  PinBuf<double> pin_shifts;
+  int64_t value_uploads = 0;          // host-to-device transfers of the value array so far (statistics)
   // sparse coupling system (time-decomposed problems): S is kept as the values of its pattern and factorised by a
   // CHILD handle that sees it as a block-bordered matrix once more (coupling.hpp); children are replicated per rank
   CouplingOptions cpl_opt;
@@ -420,12 +428,31 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return misuse("pp_create: no such CUDA device");
     DeviceGuard dev_guard(device);
-    CK(cudaFuncSetAttribute(front_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
-    CK(cudaFuncSetAttribute(front_panel_cluster_oc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM));
-    CK(cudaFuncSetAttribute(subtree_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM));
-    CK(cudaFuncSetAttribute(front_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM));
-    CK(cudaFuncSetAttribute(subtree_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
-    CK(cudaFuncSetAttribute(subtree_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
+    // Every kernel that uses dynamic shared memory may use up to the device's opt-in limit (227 KB on B200); set
+    // once per device -- a per-launch setting would let a child level LOWER the limit its parent still needs.
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if ((size_t)optin < SM_SMEM) return fail("pp_create: the device offers too little shared memory per block");
+    const auto lim = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    CK(cudaFuncSetAttribute(front_update_kernel, lim, (int)UPD_SMEM));
+    CK(cudaFuncSetAttribute(front_panel_cluster_oc_kernel, lim, (int)OC_SMEM));
+    CK(cudaFuncSetAttribute(subtree_factor_kernel, lim, (int)SF_SMEM));
+    CK(cudaFuncSetAttribute(front_small_kernel, lim, (int)SM_SMEM));
+    CK(cudaFuncSetAttribute(subtree_forward_kernel, lim, (int)SV_SMEM));
+    CK(cudaFuncSetAttribute(subtree_backward_kernel, lim, (int)SV_SMEM));
+    CK(cudaFuncSetAttribute(front_forward_kernel<512>, lim, optin));
+    CK(cudaFuncSetAttribute(front_backward_kernel<512>, lim, optin));
+    CK(cudaFuncSetAttribute(coupling_solve_kernel<512>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_kernel<8>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_kernel<16>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_kernel<32>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<8>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<16>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<32>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<8>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<16>, lim, optin));
+    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<32>, lim, optin));
+    h_optin_smem = (size_t)optin;
     auto *h = new pp_handle();
     h->device = device;
     h->flag.alloc(8);
@@ -555,6 +582,25 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     e_src[f].push_back((int)(k - first_k[f]));
     if (have_hint) e_val[f].push_back(h->in_hint[(size_t)k]);
   }
+  // diagonal entries that can be shifted on the device: one more (duplicate) source per classified row, a negative
+  // source -c standing for shift slot c - 1 (the same encoding in every block, so equal patterns still share a plan)
+  if (h->have_classes) {
+    if ((int64_t)h->cls_local.size() != h->local_dim || (int)h->cls_c.size() != m_c)
+      return misuse("pp_symbolic: the diagonal classes do not match the block sizes (pp_set_diagonal_classes)");
+    int64_t off = 0;
+    for (int f = 0; f < n_local; ++f) {
+      for (int i = 0; i < block_n[f]; ++i) {
+        const int c = h->cls_local[(size_t)(off + i)];
+        if (c <= 0) continue;
+        if (first_k[f] < 0) first_k[f] = 0;
+        e_row[f].push_back(i);
+        e_col[f].push_back(i);
+        e_src[f].push_back(-c);
+        if (have_hint) e_val[f].push_back(0.0);
+      }
+      off += block_n[f];
+    }
+  }
   h->plans.clear();
   h->block_plan.assign(n_local, -1);
   {
@@ -613,7 +659,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
       h->nmax_local = std::max(h->nmax_local, h->n[f]);
       h->nfmax_local = std::max(h->nfmax_local, h->nf[f]);
     }
-    if (solve_smem(h->nf[f]) > 200 * 1024) return fail("pp_symbolic: dense front too large for the in-smem solve (nf > ~25000)");
+    if (solve_smem(h->nf[f]) > h_optin_smem) return fail("pp_symbolic: dense front too large for the in-smem solve (nf > ~28000)");
   }
   h->arenaA_elems = totA;
   h->arenaA.alloc(totA);
@@ -651,8 +697,12 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     const PatternPlan &P = h->plans[h->block_plan[f]];
     for (size_t i = 0; i < P.root_row.size(); ++i)
       keyed.emplace_back((int64_t)(offA[f] + (size_t)P.root_row[i] + (size_t)P.root_col[i] * h->ld[f]),
-                         first_k[f] + P.root_src[i]);
+                         P.root_src[i] >= 0 ? first_k[f] + P.root_src[i] : nvals + (-P.root_src[i] - 1));
   }
+  if (h->have_classes && !h->child)
+    for (int g = 0; g < m_c; ++g)
+      if (h->cls_c[(size_t)g] > 0)
+        keyed.emplace_back((int64_t)(offA[n_local] + (size_t)g + (size_t)g * h->ld[n_local]), nvals + (h->cls_c[(size_t)g] - 1));
   for (int64_t k : coupling_k)
     if (!h->child) keyed.emplace_back((int64_t)(offA[n_local] + (size_t)dest_row[k] + (size_t)dest_col[k] * h->ld[n_local]), k);
   std::stable_sort(keyed.begin(), keyed.end(), [](const auto &a, const auto &b) {
@@ -671,7 +721,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
   h->asm_dst.upload(dst);
   h->asm_ptr.upload(ptr);
   h->asm_src.upload(src);
-  if (h->vals.n < (size_t)std::max<int64_t>(nvals, 1)) h->vals.alloc((size_t)std::max<int64_t>(nvals, 1));
+  if (h->vals.n < (size_t)(nvals + PP_SHIFT_SLOTS)) h->vals.alloc((size_t)(nvals + PP_SHIFT_SLOTS));
+  CK(cudaMemset(h->vals.p + nvals, 0, PP_SHIFT_SLOTS * sizeof(double)));
 
   // ---- plans on the device: supernode headers, packed entry targets, one int table ----
   std::vector<int> ti;
@@ -769,6 +820,7 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
     B.plan = h->block_plan[f];
     B.root = f;
     B.val_off = first_k[f] < 0 ? 0 : first_k[f];
+    B.slot_base = nvals;
     B.L = h->arenaL.p + oL[f];
     B.cb = h->arenaStack.p + oS[f];
     B.vec = B.cb + P.cb_total + 8;
@@ -857,6 +909,12 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
         rb[(size_t)g].push_back({(int)b, k});
       }
     }
+    if (h->have_classes) {
+      for (int64_t a = 0; a < ldim; ++a)
+        if (h->cls_local[(size_t)a] > 0) rl[(size_t)a].push_back({(int)a, nvals + (h->cls_local[(size_t)a] - 1)});
+      for (int g = 0; g < m_c; ++g)
+        if (h->cls_c[(size_t)g] > 0) rq[(size_t)g].push_back({g, nvals + (h->cls_c[(size_t)g] - 1)});
+    }
     auto flat = [](const std::vector<std::vector<std::pair<int, long long>>> &rows, DevBuf<long long> &ptr,
                    DevBuf<int> &col, DevBuf<long long> &src) {
       std::vector<long long> hp(rows.size() + 1, 0), hs;
@@ -941,6 +999,10 @@ static int setup_coupling(pp_handle *h) {
     const auto it = std::lower_bound(L.rowidx.begin() + a, L.rowidx.begin() + b, qrow[i]);
     qs.emplace_back((int64_t)(it - L.rowidx.begin()), qk[i]);
   }
+  if (h->have_classes && (int)h->cls_c.size() == m_c)
+    for (int g = 0; g < m_c; ++g)
+      if (h->cls_c[(size_t)g] > 0)   // the diagonal is the first entry of column g
+        qs.emplace_back(L.colptr[(size_t)g], h->nvals + (h->cls_c[(size_t)g] - 1));
   std::stable_sort(qs.begin(), qs.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
   std::vector<int64_t> qptr((size_t)nnz + 1, 0), qsrc(qs.size());
   for (size_t i = 0; i < qs.size(); ++i) { qptr[(size_t)qs[i].first + 1]++; qsrc[i] = qs[i].second; }
@@ -1037,6 +1099,41 @@ int pp_set_coupling_cliques(pp_handle *h, int32_t n_cliques, const int64_t *ptr,
 
 int64_t pp_schur_size(const pp_handle *h) { return h ? h->schur_size : 0; }
 
+int pp_set_diagonal_classes(pp_handle *h, int64_t n_local_rows, const int8_t *cls_local, int32_t m_c,
+                            const int8_t *cls_c) {
+  if (!h) return misuse("pp_set_diagonal_classes: null handle");
+  if (n_local_rows < 0 || m_c < 0 || (n_local_rows > 0 && !cls_local && cls_c) || (m_c > 0 && !cls_c && cls_local))
+    return misuse("pp_set_diagonal_classes: bad argument");
+  return guarded([&]() {
+    h->have_classes = cls_local != nullptr || cls_c != nullptr;
+    h->cls_local.clear();
+    h->cls_c.clear();
+    if (h->have_classes) {
+      for (int64_t i = 0; i < n_local_rows; ++i)
+        if (cls_local[i] < 0 || cls_local[i] > PP_SHIFT_SLOTS) return misuse("pp_set_diagonal_classes: class out of range");
+      for (int i = 0; i < m_c; ++i)
+        if (cls_c[i] < 0 || cls_c[i] > PP_SHIFT_SLOTS) return misuse("pp_set_diagonal_classes: class out of range");
+      h->cls_local.assign(cls_local, cls_local + n_local_rows);
+      h->cls_c.assign(cls_c, cls_c + m_c);
+    }
+    h->have_symbolic = false;  // the plans must be rebuilt with the classified diagonal entries
+    for (int k = 0; k < PP_SHIFT_SLOTS; ++k) h->shifts[k] = 0.0;
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
+int pp_set_shifts(pp_handle *h, const double *shifts) {
+  if (!h || !shifts) return misuse("pp_set_shifts: null argument");
+  for (int k = 0; k < PP_SHIFT_SLOTS; ++k) {
+    if (!std::isfinite(shifts[k])) return misuse("pp_set_shifts: non-finite shift");
+    if (shifts[k] != 0.0 && !h->have_classes) return misuse("pp_set_shifts: pp_set_diagonal_classes required first");
+    h->shifts[k] = shifts[k];
+  }
+  return PP_SUCCESSFUL;
+}
+
+int64_t pp_value_uploads(const pp_handle *h) { return h ? h->value_uploads : 0; }
+
 int pp_coupling_stats(pp_handle *h, int64_t out[8]) {
   if (!h || !h->have_symbolic || !out) return misuse("pp_coupling_stats: bad argument");
   int levels = 0;
@@ -1078,7 +1175,6 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
       dim3 g((h->max_leaves + per - 1) / per, h->n_local);
       const size_t lsm = per * align16(fb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
       auto kern = lg == 8 ? subtree_leaf_kernel<8> : (lg == 16 ? subtree_leaf_kernel<16> : subtree_leaf_kernel<32>);
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
       kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, dvals, h->pivot_threshold, h->pivot_tol,
                                   h->inertia.p, h->leaf_cap);
       h->launches++;
@@ -1131,15 +1227,19 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
 int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *schur_local_dev,
                      void *stream) {
   if (!h || !h->have_symbolic) return misuse("pp_numeric_local: symbolic factorization required first");
-  if (h->nvals > 0 && !values) return misuse("pp_numeric_local: null values");
+  if (h->nvals > 0 && !values && on_device != PP_VALUES_REUSE) return misuse("pp_numeric_local: null values");
   if (!schur_local_dev) return misuse("pp_numeric_local: null schur buffer");
   return guarded([&]() {
     DeviceGuard dev_guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     h->local_factored = h->coupling_factored = h->forward_done = false;
     const double *dvals = values;
-    if (!on_device && h->nvals > 0 && h->staged_from == (const void *)values) {
+    if (on_device == PP_VALUES_REUSE) {
+      if (!h->last_vals) return misuse("pp_numeric_local: no previous values to reuse");
+      dvals = h->last_vals;   // a retry of the inertia-correction loop: same values, new shifts
+    } else if (!on_device && h->nvals > 0 && h->staged_from == (const void *)values) {
       dvals = h->vals.p;  // pp_stage_values gathered these values and already queued their transfer
+      h->value_uploads++;
     } else if (!on_device && h->nvals > 0) {
       const double *src = values;
       if (!is_pinned_host(values)) {  // pageable caller memory: stage through the handle's pinned buffer
@@ -1149,6 +1249,17 @@ int pp_numeric_local(pp_handle *h, const double *values, int on_device, double *
       }
       CK(cudaMemcpyAsync(h->vals.p, src, (size_t)h->nvals * sizeof(double), cudaMemcpyHostToDevice, st));
       dvals = h->vals.p;
+      h->value_uploads++;
+    } else if (on_device && h->have_classes && h->nvals > 0 && values != h->vals.p) {
+      // the shift slots live behind the handle's own copy of the values
+      CK(cudaMemcpyAsync(h->vals.p, values, (size_t)h->nvals * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      dvals = h->vals.p;
+    }
+    if (h->have_classes) {
+      if (dvals != h->vals.p) return misuse("pp_numeric_local: diagonal shifts need the handle's copy of the values");
+      h->pin_shifts.ensure(PP_SHIFT_SLOTS);
+      for (int k = 0; k < PP_SHIFT_SLOTS; ++k) h->pin_shifts.p[k] = h->shifts[k];
+      CK(cudaMemcpyAsync(h->vals.p + h->nvals, h->pin_shifts.p, PP_SHIFT_SLOTS * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     h->staged_from = nullptr;
     h->tail_valid = false;
@@ -1341,8 +1452,6 @@ int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
 static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t st);
 static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cudaStream_t st);
 
-static size_t coupling_smem(const pp_handle *h) { return h->child ? 0 : solve_smem(h->m_c); }
-
 static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, cudaStream_t st) {
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_FORWARD, st);
@@ -1352,14 +1461,11 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
       const size_t lsm = per * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
       auto kern = lg == 8 ? subtree_leaf_forward_kernel<8>
                           : (lg == 16 ? subtree_leaf_forward_kernel<16> : subtree_leaf_forward_kernel<32>);
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
       kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p, h->ywork.p, h->leaf_cap);
       h->launches++;
     }
     subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
                                                               h->ywork.p, h->root_rhs.p, h->root_off.p);
-    const size_t sm = std::max(solve_smem(h->nfmax_local), coupling_smem(h));
-    CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
                                                                                   h->root_off64.p);
     h->launches += 2;
@@ -1376,9 +1482,6 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
 static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *drc, double *dx, double *dxc,
                          cudaStream_t st) {
   const int mc = h->m_c;
-  const size_t smax = std::max(solve_smem(h->nfmax_local), coupling_smem(h));
-  CK(cudaFuncSetAttribute(front_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-  CK(cudaFuncSetAttribute(front_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
   if (mc > 0 && h->child) {
     // sparse coupling system: S x_c = r_c + rc_sum is solved by the child level (which recurses the same way);
     // its local vector and its coupling vector are a permutation of this level's coupling variables
@@ -1394,7 +1497,6 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
     h->launches += 2;
   } else if (mc > 0) {
     const size_t sm = solve_smem(mc);
-    CK(cudaFuncSetAttribute(coupling_solve_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     coupling_solve_kernel<512><<<1, 512, sm, st>>>(h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
     h->launches++;
   }
@@ -1410,7 +1512,6 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
       const size_t lsm = per * align16(sb_bytes(h->leaf_cap, h->leaf_cap | 1)) + 16;
       auto kern = lg == 8 ? subtree_leaf_backward_kernel<8>
                           : (lg == 16 ? subtree_leaf_backward_kernel<16> : subtree_leaf_backward_kernel<32>);
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
       kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p, h->vec_off.p, dx, h->leaf_cap);
       h->launches++;
     }

@@ -48,6 +48,7 @@ struct PlanDev {
 struct SparseBlock {
   int plan, root;        // plan index; index of the dense root front
   long long val_off;     // base index of this block's input values
+  long long slot_base;   // index of shift slot 0 (behind the input values): a source s < 0 reads slot -s - 1
   double *L;             // factor arena of the subtree supernodes
   double *cb;            // contribution slots
   double *vec;           // forward-solve contribution vectors
@@ -547,10 +548,13 @@ __device__ int process_front(const SparseBlock &Bk, const PlanDev &P, const doub
     const int2 t = P.tgt[H.ent0 + e];
     const int cntv = t.x >> 16;
     double v;
-    if (cntv == 1) v = vals[Bk.val_off + t.y];
+    if (cntv == 1) v = vals[t.y >= 0 ? Bk.val_off + t.y : Bk.slot_base - t.y - 1];
     else {
       v = 0.0;
-      for (int p = 0; p < cntv; ++p) v += vals[Bk.val_off + P.tgt_src[t.y + p]];
+      for (int p = 0; p < cntv; ++p) {
+        const int sidx = P.tgt_src[t.y + p];
+        v += vals[sidx >= 0 ? Bk.val_off + sidx : Bk.slot_base - sidx - 1];
+      }
     }
     int r = t.x & 255;
     if (r >= nc) r += nd_in;

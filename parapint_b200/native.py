@@ -32,6 +32,9 @@ SIGNATURES = {
     "pp_cplan_create": (C.c_int, [C.c_int32, C.c_int32, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, C.c_double, C.POINTER(_vp)]),
     "pp_cplan_get": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64, _i64p]),
     "pp_cplan_destroy": (C.c_int, [_vp]),
+    "pp_set_diagonal_classes": (C.c_int, [_vp, C.c_int64, _vp, C.c_int32, _vp]),
+    "pp_set_shifts": (C.c_int, [_vp, _f64p]),
+    "pp_value_uploads": (C.c_int64, [_vp]),
     "pp_numeric_local": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "pp_numeric_coupling": (C.c_int, [_vp, _vp, _vp]),
     "pp_inertia_local": (C.c_int, [_vp, _i64p]),

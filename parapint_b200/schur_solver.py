@@ -23,6 +23,7 @@ import numpy as np
 from . import native, structure
 from .comm import Communicator
 from .interface import LinearSolverInterface, LinearSolverResults, LinearSolverStatus
+from .regularization import RegularizedKKT
 
 _OK = (LinearSolverStatus.successful, LinearSolverStatus.warning)
 # severity order of the status values for cross-rank agreement
@@ -123,11 +124,33 @@ class CudaBackend:
         self.values = self.values_pin.numpy()
         return code
 
+    # -- device-side regularisation ------------------------------------------------------------
+    def set_classes(self, cls_local, cls_c):
+        """Diagonal classes of the local rows / coupling rows (``pp_set_diagonal_classes``); before ``symbolic``."""
+        if cls_local is None:
+            self._check(self.lib.pp_set_diagonal_classes(self.handle, 0, None, 0, None), "pp_set_diagonal_classes")
+            return
+        a = np.ascontiguousarray(cls_local, dtype=np.int8)
+        b = np.ascontiguousarray(cls_c, dtype=np.int8)
+        self._check(self.lib.pp_set_diagonal_classes(self.handle, a.size, native.np_ptr(a), b.size, native.np_ptr(b)),
+                    "pp_set_diagonal_classes")
+
+    def set_shifts(self, shifts):
+        arr = (C.c_double * 3)(*[float(v) for v in shifts])
+        self._check(self.lib.pp_set_shifts(self.handle, arr), "pp_set_shifts")
+
+    def value_uploads(self):
+        return int(self.lib.pp_value_uploads(self.handle))
+
     # -- numeric -----------------------------------------------------------------------------
-    def numeric_local(self):
-        """Factor the local fronts from ``self.values``; returns (status code, device S_local)."""
-        code = self.lib.pp_numeric_local(self.handle, C.c_void_p(self.values_pin.data_ptr()), 0,
-                                         C.c_void_p(self.schur.data_ptr()), self._stream())
+    def numeric_local(self, reuse=False):
+        """Factor the local fronts from ``self.values`` (``reuse``: from the values of the previous call, which are
+        still on the device -- a retry with new diagonal shifts); returns (status code, device S_local)."""
+        if reuse:
+            code = self.lib.pp_numeric_local(self.handle, None, 2, C.c_void_p(self.schur.data_ptr()), self._stream())
+        else:
+            code = self.lib.pp_numeric_local(self.handle, C.c_void_p(self.values_pin.data_ptr()), 0,
+                                             C.c_void_p(self.schur.data_ptr()), self._stream())
         return self._check(code, "pp_numeric_local"), self.schur
 
     def schur_tail(self):
@@ -266,11 +289,17 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
     device: CUDA device index (default: current device).
     comm: ``Communicator`` (default: the ``torch.distributed`` world if initialised, else 1 rank).
     options: native tunables, e.g. ``{"pivot_tol": 0.0, "panel_width": 64}``.
+    regularization_classes: ``interface.regularization_classes()`` of a ``DeviceRegularizationMixin`` interface, so
+        that the diagonal entries the inertia-correction loop shifts are reserved by the first symbolic phase.
     """
 
     def __init__(self, subproblem_solvers=None, schur_complement_solver=None, device=None, comm=None,
-                 options=None, backend=None, refine_tol=2e-11, max_refine=2):
+                 options=None, backend=None, refine_tol=2e-11, max_refine=2, regularization_classes=None):
         self.subproblem_solvers = subproblem_solvers
+        # (per diagonal block, coupling) diagonal classes for device-side inertia correction (regularization.py);
+        # learnt from the first RegularizedKKT otherwise (at the price of one more symbolic phase)
+        self._classes = regularization_classes
+        self._uploaded_token = None
         self.refine_tol = float(refine_tol)
         self.max_refine = int(max_refine)
         self.last_residual = None
@@ -340,6 +369,17 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         hint = np.zeros(st.nvals)
         structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
         self._copiers = [None, None]               # pointer tables of the old structure are stale
+        self._uploaded_token = None
+        if self._classes is not None:
+            per_block, coupling = self._classes
+            parts = [np.asarray(per_block[i], dtype=np.int8) for i in st.local_blocks]
+            for f, (i, part) in enumerate(zip(st.local_blocks, parts)):
+                if part.size != st.block_n[f]:
+                    raise ValueError(f"regularization classes of block {i} have size {part.size}, expected {st.block_n[f]}")
+            cls_c = np.asarray(coupling, dtype=np.int8)
+            if cls_c.size != st.m_c:
+                raise ValueError(f"regularization classes of the coupling rows have size {cls_c.size}, expected {st.m_c}")
+            self.backend.set_classes(np.concatenate(parts) if parts else np.zeros(0, dtype=np.int8), cls_c)
         cliques = None
         if self.comm.size > 1:
             # the pattern of S is the union over the blocks of EVERY rank (mpi...:244-247 all-gathers the same lists)
@@ -357,6 +397,10 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         ``mpi...:165-255``).  Collective over the communicator."""
         timer = timer or _NullTimer()
         timer.start("sc_structure")
+        if isinstance(matrix, RegularizedKKT):
+            if self._classes is None:
+                self._classes = matrix.classes
+            matrix = matrix.base
         code = self._analyse(matrix)
         timer.stop("sc_structure")
         return self._finish(code, raise_on_error, "Symbolic factorization")
@@ -367,10 +411,26 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         if self._st is None:
             raise RuntimeError("do_symbolic_factorization must be called before do_numeric_factorization")
         timer = timer or _NullTimer()
+        shifts, token = (0.0, 0.0, 0.0), getattr(matrix, "_pp_token", None)
+        if isinstance(matrix, RegularizedKKT):
+            # base matrix + diagonal shifts (regularization.py): the shifts are applied on the device, and when the
+            # values of `base` are the ones already there (same evaluation) nothing is gathered or uploaded
+            shifts, token = matrix.shifts, matrix.token
+            if self._classes is None:
+                # first regularisation and the classes were not given at construction: reserve the diagonal entries
+                # now (one more symbolic phase; every rank is here together -- the IPM loop is SPMD)
+                self._classes = matrix.classes
+                sym = self._finish(self._analyse(matrix.base), False, "Symbolic factorization")
+                if sym.status not in _OK:
+                    return self._result(sym.status.value, raise_on_error, "Numeric factorization")
+            matrix = matrix.base
         self.block_matrix = matrix
         be = self.backend
         timer.start("form SC")
-        changed = not structure.gather_values(matrix, self._st, be.values, self._copier(0))
+        reuse = token is not None and token == self._uploaded_token
+        changed = False if reuse else not structure.gather_values(matrix, self._st, be.values, self._copier(0))
+        self._uploaded_token = None
+        has_shifts = self._classes is not None or any(shifts)
         if self.comm.size == 1:
             if changed:
                 # COO pattern / ordering changed since the symbolic phase (happens after the first
@@ -383,9 +443,13 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 if not structure.gather_values(matrix, self._st, be.values, self._copier(0)):
                     raise RuntimeError("could not gather the matrix values after re-analysis")
             timer.start("factorize")
-            code, schur_local = be.numeric_local()
+            if has_shifts:
+                be.set_shifts(shifts)
+            code, schur_local = be.numeric_local(reuse and not changed)
             timer.stop("factorize")
             self._tail = None
+            if code in (0, LinearSolverStatus.singular.value):
+                self._uploaded_token = token   # the values of this evaluation are on the device
             if code != 0:   # not deferred (or a run-time failure): nothing to factor in the coupling phase
                 timer.stop("form SC")
                 return self._result(code, raise_on_error, "Numeric factorization")
@@ -414,8 +478,10 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 timer.start("factorize")
                 if sync:
                     be.set_option("defer_status", 0)
+                if has_shifts:
+                    be.set_shifts(shifts)
                 try:
-                    local_code, schur_local = be.numeric_local()
+                    local_code, schur_local = be.numeric_local(reuse)
                 finally:
                     if sync:
                         be.set_option("defer_status", 2)
@@ -446,6 +512,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                     code = sym.status.value
                     break
                 be = self.backend
+                reuse = False
                 changed = not structure.gather_values(matrix, self._st, be.values, self._copier(0))
                 continue
             if tail[1] > 0:
@@ -455,6 +522,8 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 sync = True                            # the overflowing rank re-analyses densely
                 continue
             break
+        if code in (0, LinearSolverStatus.singular.value):
+            self._uploaded_token = token
         timer.stop("form SC")
         return self._result(code, raise_on_error, "Numeric factorization")
 
@@ -475,6 +544,8 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             rc.fill_(float("nan"))      # a run-time failure on this rank: every rank sees it after the reduction
         self.comm.allreduce_sum_(rc)
         x_local, x_c = be.solve_backward(rc)
+        if be.failed and self.comm.size == 1:
+            raise RuntimeError(f"back solve failed: {be.last_error}")
         x_local, x_c = self._refine(x_local, x_c)
         if be.failed or not np.all(np.isfinite(x_c[: st.m_c])):
             raise RuntimeError("back solve failed" + (f": {be.last_error}" if be.last_error else ""))
@@ -504,6 +575,12 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         for step in range(self.max_refine + 1):
             if step == 0 and getattr(be, "norms_ready", lambda: False)():
                 r2, b2 = be.residual_norms(None)            # formed by pp_solve_backward ("auto_residual")
+            elif getattr(be, "failed", False):
+                # this rank's solve failed at run time: keep the collectives aligned, every rank sees NaN norms
+                buf = be.resbuf
+                buf.fill_(float("nan"))
+                self.comm.allreduce_sum_(buf)
+                r2 = b2 = float("nan")
             else:
                 buf = be.residual_local()
                 self.comm.allreduce_sum_(buf)

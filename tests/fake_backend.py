@@ -18,9 +18,25 @@ class FakeBackend:
         self.failed = False
         self.fail_symbolic = self.fail_numeric = False   # test hooks: a run-time failure on this rank
         self.ints = torch.zeros(4, dtype=torch.int64)
+        self.cls_local = self.cls_c = None
+        self.shifts = np.zeros(4)
+        self.uploads = 0
+        self.device_values = None
 
     def set_option(self, name, value):
         pass
+
+    # device-side regularisation (pp_set_diagonal_classes / pp_set_shifts / PP_VALUES_REUSE)
+    def set_classes(self, cls_local, cls_c):
+        self.cls_local = None if cls_local is None else np.asarray(cls_local, dtype=np.int64)
+        self.cls_c = None if cls_c is None else np.asarray(cls_c, dtype=np.int64)
+        self.shifts = np.zeros(4)
+
+    def set_shifts(self, shifts):
+        self.shifts = np.concatenate(([0.0], np.asarray(shifts, dtype=float)))
+
+    def value_uploads(self):
+        return self.uploads
 
     def symbolic(self, st, values_hint=None, cliques=None):
         self.st = st
@@ -32,6 +48,7 @@ class FakeBackend:
         self.schur = torch.zeros(max(self.schur_size, 1) + 8, dtype=torch.float64)
         self.rc = torch.zeros(mc, dtype=torch.float64)
         self.ints = torch.zeros(4, dtype=torch.int64)
+        self.device_values = None
         self.values_pin = torch.zeros(max(st.nvals, 1), dtype=torch.float64)
         self.rhs_pin = torch.zeros(max(st.local_dim, 1), dtype=torch.float64)
         self.x_pin = torch.zeros(max(st.local_dim, 1), dtype=torch.float64)
@@ -47,11 +64,21 @@ class FakeBackend:
         for k in range(st.nvals):
             f = st.dest_front[k]
             if f >= 0:
-                fronts[f][st.dest_row[k], st.dest_col[k]] += self.values[k]
+                fronts[f][st.dest_row[k], st.dest_col[k]] += self.device_values[k]
+        if self.cls_local is not None:
+            for f in range(st.n_local):
+                n = int(st.block_n[f])
+                d = self.shifts[self.cls_local[st.rhs_offsets[f]:st.rhs_offsets[f + 1]]]
+                fronts[f][np.arange(n), np.arange(n)] += d
+            fronts[-1][np.arange(st.m_c), np.arange(st.m_c)] += self.shifts[self.cls_c]
         return [np.tril(F) + np.tril(F, -1).T for F in fronts]
 
-    def numeric_local(self):
+    def numeric_local(self, reuse=False):
         st = self.st
+        if not reuse:
+            self.device_values = self.values.copy()
+            self.uploads += 1
+        assert self.device_values is not None
         if self.fail_numeric:
             self.last_error = "injected numeric failure"
             return 3, self.schur

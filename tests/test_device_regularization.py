@@ -1,0 +1,122 @@
+"""Device-side inertia correction: the regularised KKT matrix travels as base + three shifts.
+
+The inertia-correction loop of interior_point.py:369-395 must take the same decisions as with the interface's own
+regularize_* methods (interface.py:590-619, sc_ip_interface.py:903-933,1736-1757), while the retries upload nothing
+and never repeat the symbolic phase."""
+import numpy as np
+import pytest
+
+from oracle.ipm import (DynamicInterface, StochasticInterface, device_regularized, dynamics_time_blocks, ip_solve,
+                        random_stochastic_qp)
+from oracle.schur_oracle import OraclePlugin, sym_full
+from parapint_b200 import B200SchurComplementLinearSolver
+from parapint_b200.regularization import RegularizedKKT
+from tests.fake_backend import FakeBackend
+
+ARGS = (1, 4, 40, 14, 6, 4, 0.3)    # nonconvex two-stage QP: dozens of retries
+
+
+def _setup(cls, device):
+    scen, fs = random_stochastic_qp(*ARGS)
+    return (device_regularized(cls) if device else cls)(scen, fs)
+
+
+def test_wrapper_equals_the_interface_regularisation():
+    """materialize() of the wrapper == what the reference-style regularize_* produce, including the accumulation of the
+    Hessian shift over retries and the SET semantics of the other two classes."""
+    plain, dev = _setup(StochasticInterface, False), _setup(StochasticInterface, True)
+    for itf in (plain, dev):
+        itf.set_barrier_parameter(0.1)
+        for s in itf.sc:
+            s.nlp.x = np.full(s.nlp.n, 0.3)
+    k0, k1 = plain.evaluate_primal_dual_kkt_matrix(), dev.evaluate_primal_dual_kkt_matrix()
+    a, b = k0.copy(), k1.copy()
+    for delta in (1e-8, 1e-7, 1e-6):
+        a = plain.regularize_equality_gradient(kkt=a, coef=-delta, copy_kkt=False)
+        a = plain.regularize_hessian(kkt=a, coef=delta, copy_kkt=False)
+        b = dev.regularize_equality_gradient(kkt=b, coef=-delta, copy_kkt=False)
+        b = dev.regularize_hessian(kkt=b, coef=delta, copy_kkt=False)
+        assert isinstance(b, RegularizedKKT) and b.bshape == a.bshape
+        assert np.allclose(sym_full(b.materialize()).toarray(), sym_full(a).toarray(), rtol=1e-14, atol=1e-22)
+    assert b.shifts == (1e-8 + 1e-7 + 1e-6, -1e-6, 1e-6)
+    # the dynamic layout: forward multipliers (coupling side) are class 2, the coupling variables class 3
+    blocks, st, en, _ = dynamics_time_blocks()
+    p, d = DynamicInterface(blocks, st, en), device_regularized(DynamicInterface)(blocks, st, en)
+    for itf in (p, d):
+        itf.set_barrier_parameter(0.1)
+    a, b = p.evaluate_primal_dual_kkt_matrix().copy(), d.evaluate_primal_dual_kkt_matrix().copy()
+    for delta in (1e-4, 1e-3):
+        a = p.regularize_hessian(p.regularize_equality_gradient(a, -delta, False), delta, False)
+        b = d.regularize_hessian(d.regularize_equality_gradient(b, -delta, False), delta, False)
+    assert np.allclose(sym_full(b.materialize()).toarray(), sym_full(a).toarray(), rtol=1e-14, atol=1e-22)
+
+
+def test_ipm_trajectory_and_counts_on_the_cpu_stand_in():
+    """Host logic on CPU (numpy stand-in of the C ABI): same regularisation log and iterates as the plain interface;
+    one value upload per IPM iteration instead of one per factorisation; one symbolic phase in total."""
+    ref = ip_solve(_setup(StochasticInterface, False), OraclePlugin(inertia_method="eigvalsh"))
+    itf = _setup(StochasticInterface, True)
+    solver = B200SchurComplementLinearSolver(backend=FakeBackend(), regularization_classes=itf.regularization_classes())
+    out = ip_solve(itf, solver)
+    assert ref["status"] == out["status"] == "optimal" and out["iterations"] == ref["iterations"]
+    assert [(r[1], r[2], r[3], r[4]) for r in out["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
+    assert abs(out["objective"] - ref["objective"]) <= 1e-8 * max(1.0, abs(ref["objective"]))
+    n_fact = len(out["reg"])
+    assert n_fact > out["iterations"] + 10                       # the loop did retry
+    assert solver.backend.value_uploads() == out["iterations"]   # one upload per KKT evaluation, none for retries
+    assert solver.symbolic_calls == 1
+    # classes learnt lazily from the first wrapper: one more symbolic phase, same answers
+    itf2 = _setup(StochasticInterface, True)
+    lazy = B200SchurComplementLinearSolver(backend=FakeBackend())
+    out2 = ip_solve(itf2, lazy)
+    assert out2["iterations"] == ref["iterations"] and lazy.symbolic_calls == 2
+    assert [(r[1], r[2], r[3], r[4]) for r in out2["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [ARGS, (2, 6, 220, 120, 12, 6, 0.15)])
+def test_ipm_retries_are_refactor_only_on_b200(args):
+    """zero re-symbolic calls and zero value uploads for the retries, same trajectory."""
+    def run(solver, device):
+        scen, fs = random_stochastic_qp(*args)
+        itf = (device_regularized(StochasticInterface) if device else StochasticInterface)(scen, fs)
+        return itf, ip_solve(itf, solver)
+
+    _, ref = run(OraclePlugin(inertia_method="ldl"), False)
+    plain_solver = B200SchurComplementLinearSolver()
+    _, plain = run(plain_solver, False)
+    scen, fs = random_stochastic_qp(*args)
+    itf = device_regularized(StochasticInterface)(scen, fs)
+    solver = B200SchurComplementLinearSolver(regularization_classes=itf.regularization_classes())
+    out = ip_solve(itf, solver)
+    for res in (plain, out):
+        assert res["status"] == ref["status"] == "optimal" and res["iterations"] == ref["iterations"]
+        assert [(r[1], r[2], r[3], r[4]) for r in res["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
+        assert abs(res["objective"] - ref["objective"]) <= 1e-8 * max(1.0, abs(ref["objective"]))
+    assert len(out["reg"]) > out["iterations"]                    # retries happened
+    assert solver.symbolic_calls == 1                             # never re-analysed
+    assert solver.backend.value_uploads() == out["iterations"]    # uploads: one per KKT evaluation
+    assert plain_solver.backend.value_uploads() == len(plain["reg"])   # the plain interface uploads for every retry
+    assert plain_solver.symbolic_calls > 1                        # ... and re-analyses when the Hessian pattern grows
+
+
+@pytest.mark.gpu
+def test_dynamics_example_with_device_regularisation_on_b200():
+    """The dynamic layout's classes (forward multipliers on the coupling side) through a full solve; a negative
+    curvature term is added to the objective of one block so that the loop regularises."""
+    def build(device):
+        blocks, st, en, _ = dynamics_time_blocks(num_finite_elements=60, num_time_blocks=6)
+        H = blocks[2].H.tocsr().copy()
+        H[3, 3] = -0.5
+        blocks[2].H = H.tocoo()
+        cls = device_regularized(DynamicInterface) if device else DynamicInterface
+        return cls(blocks, st, en)
+
+    ref = ip_solve(build(False), OraclePlugin(inertia_method="ldl"))
+    itf = build(True)
+    solver = B200SchurComplementLinearSolver(regularization_classes=itf.regularization_classes())
+    out = ip_solve(itf, solver)
+    assert ref["status"] == out["status"] == "optimal" and out["iterations"] == ref["iterations"]
+    assert [(r[1], r[2], r[3], r[4]) for r in out["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
+    assert any(r[1] > 0 for r in out["reg"])
+    assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == out["iterations"]
