@@ -440,19 +440,25 @@ int pp_create(int device, pp_handle **out) {
     CK(cudaFuncSetAttribute(front_small_kernel, lim, (int)SM_SMEM));
     CK(cudaFuncSetAttribute(subtree_forward_kernel, lim, (int)SV_SMEM));
     CK(cudaFuncSetAttribute(subtree_backward_kernel, lim, (int)SV_SMEM));
-    CK(cudaFuncSetAttribute(front_forward_kernel<512>, lim, optin));
-    CK(cudaFuncSetAttribute(front_backward_kernel<512>, lim, optin));
-    CK(cudaFuncSetAttribute(coupling_solve_kernel<512>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_kernel<8>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_kernel<16>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_kernel<32>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<8>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<16>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_forward_kernel<32>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<8>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<16>, lim, optin));
-    CK(cudaFuncSetAttribute(subtree_leaf_backward_kernel<32>, lim, optin));
-    h_optin_smem = (size_t)optin;
+    // (the opt-in limit covers static + dynamic shared memory of a kernel)
+    auto allow_all = [&](auto kern) {
+      cudaFuncAttributes fa;
+      CK(cudaFuncGetAttributes(&fa, kern));
+      CK(cudaFuncSetAttribute(kern, lim, optin - (int)fa.sharedSizeBytes));
+    };
+    allow_all(front_forward_kernel<512>);
+    allow_all(front_backward_kernel<512>);
+    allow_all(coupling_solve_kernel<512>);
+    allow_all(subtree_leaf_kernel<8>);
+    allow_all(subtree_leaf_kernel<16>);
+    allow_all(subtree_leaf_kernel<32>);
+    allow_all(subtree_leaf_forward_kernel<8>);
+    allow_all(subtree_leaf_forward_kernel<16>);
+    allow_all(subtree_leaf_forward_kernel<32>);
+    allow_all(subtree_leaf_backward_kernel<8>);
+    allow_all(subtree_leaf_backward_kernel<16>);
+    allow_all(subtree_leaf_backward_kernel<32>);
+    h_optin_smem = (size_t)optin - 1024;
     auto *h = new pp_handle();
     h->device = device;
     h->flag.alloc(8);

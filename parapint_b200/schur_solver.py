@@ -53,7 +53,8 @@ class CudaBackend:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.handle = C.c_void_p()
-        self._check(self.lib.pp_create(self.device_index, C.byref(self.handle)), "pp_create")
+        if self._check(self.lib.pp_create(self.device_index, C.byref(self.handle)), "pp_create") != 0 or not self.handle:
+            raise RuntimeError(f"pp_create failed: {native.last_error()}")
         for key, val in (options or {}).items():
             self._check(self.lib.pp_set_option(self.handle, key.encode(), float(val)), "pp_set_option")
         self.st = None
