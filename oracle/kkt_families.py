@@ -107,9 +107,9 @@ def dynamic_ipm_system(seed, n_blocks, n_x, n_eq, n_in, n_s, same_pattern=True, 
             cols += list(n - nb + np.arange(nb))
             vals += [-1.0] * n_s
         kkt.set_block(N, i, sp.coo_matrix((vals, (rows, cols)), shape=(m_c, n)))
-    idx = np.arange(nf_tot)
-    Q = sp.coo_matrix((np.concatenate([np.zeros(m_c), -np.ones(nf_tot)]),
-                       (np.concatenate([np.arange(m_c), nf_tot + idx]), np.concatenate([np.arange(m_c), idx]))),
+    idx = np.arange(nf_tot)   # both triangles are stored, as the reference's nested Q block holds (1,0) and (0,1)
+    Q = sp.coo_matrix((np.concatenate([np.zeros(m_c), -np.ones(nf_tot), -np.ones(nf_tot)]),
+                       (np.concatenate([np.arange(m_c), nf_tot + idx, idx]), np.concatenate([np.arange(m_c), idx, nf_tot + idx]))),
                       shape=(m_c, m_c))
     kkt.set_block(N, N, Q)
     for i in range(N):

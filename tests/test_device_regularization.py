@@ -101,22 +101,39 @@ def test_ipm_retries_are_refactor_only_on_b200(args):
 
 
 @pytest.mark.gpu
-def test_dynamics_example_with_device_regularisation_on_b200():
-    """The dynamic layout's classes (forward multipliers on the coupling side) through a full solve; a negative
-    curvature term is added to the objective of one block so that the loop regularises."""
-    def build(device):
-        blocks, st, en, _ = dynamics_time_blocks(num_finite_elements=60, num_time_blocks=6)
-        H = blocks[2].H.tocsr().copy()
-        H[3, 3] = -0.5
-        blocks[2].H = H.tocoo()
-        cls = device_regularized(DynamicInterface) if device else DynamicInterface
-        return cls(blocks, st, en)
-
-    ref = ip_solve(build(False), OraclePlugin(inertia_method="ldl"))
-    itf = build(True)
-    solver = B200SchurComplementLinearSolver(regularization_classes=itf.regularization_classes())
-    out = ip_solve(itf, solver)
-    assert ref["status"] == out["status"] == "optimal" and out["iterations"] == ref["iterations"]
-    assert [(r[1], r[2], r[3], r[4]) for r in out["reg"]] == [(r[1], r[2], r[3], r[4]) for r in ref["reg"]]
-    assert any(r[1] > 0 for r in out["reg"])
-    assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == out["iterations"]
+def test_dynamic_layout_shifts_on_b200():
+    """The dynamic layout's classes (forward multipliers on the coupling side are class 2, interface states class 3):
+    the device applies the three shifts exactly where the interface's regularize_* put them -- same solution and
+    inertia as the reference algorithm on the materialised matrix, with and without the sparse coupling path; a second
+    factorisation with other shifts re-uses the values on the device."""
+    from oracle.schur_oracle import SchurOracle
+    blocks, st, en, _ = dynamics_time_blocks(num_finite_elements=120, num_time_blocks=12)
+    itf = device_regularized(DynamicInterface)(blocks, st, en)
+    itf.set_barrier_parameter(0.1)
+    rng = np.random.default_rng(0)
+    for s_ in itf.sc:
+        s_.nlp.x = rng.uniform(0.2, 1.5, s_.nlp.n)
+    kkt = itf.evaluate_primal_dual_kkt_matrix()
+    rhs = itf.evaluate_primal_dual_kkt_rhs()
+    for options in ({}, {"coupling_min_sparse": 8}):
+        solver = B200SchurComplementLinearSolver(regularization_classes=itf.regularization_classes(), options=options)
+        assert solver.do_symbolic_factorization(kkt).status.value == 0
+        assert solver.do_numeric_factorization(kkt).status.value == 0
+        base_inertia = solver.get_inertia()
+        reg = kkt.copy()
+        for delta in (1e-3, 1e-1):
+            reg = itf.regularize_equality_gradient(kkt=reg, coef=-delta, copy_kkt=False)
+            reg = itf.regularize_hessian(kkt=reg, coef=delta, copy_kkt=False)
+            assert solver.do_numeric_factorization(reg).status.value == 0
+            x = solver.do_back_solve(rhs).flatten()
+            full = reg.materialize()
+            o = SchurOracle(compute_inertia=True, inertia_method="ldl")
+            o.symbolic(full)
+            assert o.numeric(full) == 0
+            x_ref = o.solve(rhs).flatten()
+            assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) <= 1e-8
+            assert solver.get_inertia() == o.inertia()
+        assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == 1
+        # back to the unregularised matrix: shifts are cleared, values still on the device
+        assert solver.do_numeric_factorization(kkt).status.value == 0 and solver.get_inertia() == base_inertia
+        assert solver.backend.value_uploads() == 1
