@@ -40,6 +40,7 @@ class FakeBackend:
 
     def symbolic(self, st, values_hint=None, cliques=None):
         self.st = st
+        self.cliques = cliques
         if self.fail_symbolic:
             self.last_error = "injected symbolic failure"
             return 3

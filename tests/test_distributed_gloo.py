@@ -67,6 +67,19 @@ def _worker(rank, world, port, case, out_dir):
                 raise AssertionError("expected RuntimeError on every rank")
             except RuntimeError:
                 pass
+        elif case == "cliques":
+            # the pattern of a sparse Schur complement needs the nonzero border rows of the blocks of EVERY rank
+            # (mpi_explicit_schur_complement.py:244-247): every rank hands the same global list to the native symbolic phase
+            from tests.helpers import dynamic_ipm_system
+            N = 7
+            full, sizes = dynamic_ipm_system(2, N, 30, 12, 3, 2)
+            kkt, _ = dynamic_ipm_system(2, N, 30, 12, 3, 2, local_blocks=[i for i in range(N) if i % world == rank])
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            ptr, rows = solver.backend.cliques
+            assert len(ptr) == N + 1 and ptr[-1] == rows.size
+            got = sorted(tuple(rows[ptr[k]:ptr[k + 1]]) for k in range(N))
+            want = sorted(tuple(np.unique(full.get_block(N, i).tocoo().row)) for i in range(N))
+            assert got == want
         elif case == "rank_local_failure":
             # a run-time failure on ONE rank must become the same status on EVERY rank (no hang, no
             # exception on one rank only), in the symbolic phase and in the numeric phase.
@@ -115,7 +128,7 @@ def _worker(rank, world, port, case, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["generator", "singular", "rank_local_failure", "pattern_change_one_rank"])
+@pytest.mark.parametrize("case", ["generator", "singular", "rank_local_failure", "pattern_change_one_rank", "cliques"])
 def test_world_size_2(tmp_path, case):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)

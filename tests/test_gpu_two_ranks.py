@@ -79,12 +79,59 @@ def _worker(rank, world, port, case, out_dir):
             solver.do_symbolic_factorization(kkt)
             res = solver.do_numeric_factorization(kkt, raise_on_error=False)
             assert res.status == LinearSolverStatus.singular  # every rank agrees (mpi...:19-30)
+        elif case == "sparse_coupling":
+            # time-decomposed layout, blocks dealt over two ranks: the pattern of S needs the borders of BOTH ranks'
+            # blocks (all-gathered in the symbolic phase), the all-reduce moves the pattern values only, every rank
+            # factorises S level by level and gets the same coupling solution
+            from tests.helpers import dynamic_ipm_system
+            N = 21
+            full, sizes = dynamic_ipm_system(6, N, 60, 30, 5, 4)
+            kkt, _ = dynamic_ipm_system(6, N, 60, 30, 5, 4, local_blocks=[i for i in range(N) if i % world == rank])
+            rhs = block_vector(np.random.default_rng(6).standard_normal(sum(sizes)), sizes)
+            solver = B200SchurComplementLinearSolver(comm=comm, options={"coupling_min_sparse": 16})
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            cs = solver.backend.coupling_stats()
+            assert cs["levels"] >= 1 and solver.backend.schur_size == cs["schur_size"] < cs["m_c"] ** 2 // 2
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful
+            x = solver.do_back_solve(rhs)
+            dense = sym_full(full).toarray()
+            x_ref = np.linalg.solve(dense, rhs.flatten())
+            off = np.concatenate(([0], np.cumsum(sizes)))
+            for i in list(solver.local_block_indices) + [N]:
+                assert np.allclose(np.asarray(x.get_block(i)).ravel(), x_ref[off[i]:off[i + 1]], rtol=1e-7, atol=1e-8)
+            assert solver.get_inertia() == dense_inertia(dense, "ldl")
+            assert solver.last_residual is not None and solver.last_residual <= 1e-10
+        elif case == "device_regularization":
+            # shifts on the device under the multi-rank control flow: the retry re-uses the values on every rank
+            from oracle.ipm import StochasticInterface, device_regularized, random_stochastic_qp
+            from oracle.schur_oracle import SchurOracle
+            scen, fs = random_stochastic_qp(1, 4, 40, 14, 6, 4, 0.3)
+            itf = device_regularized(StochasticInterface)(scen, fs)
+            itf.set_barrier_parameter(0.1)
+            for s_ in itf.sc:
+                s_.nlp.x = np.full(s_.nlp.n, 0.3)
+            kkt, rhs = itf.evaluate_primal_dual_kkt_matrix(), itf.evaluate_primal_dual_kkt_rhs()
+            solver = B200SchurComplementLinearSolver(comm=comm, regularization_classes=itf.regularization_classes())
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            assert solver.do_numeric_factorization(kkt, raise_on_error=False).status in (LinearSolverStatus.successful, LinearSolverStatus.singular)
+            reg = itf.regularize_hessian(itf.regularize_equality_gradient(kkt.copy(), -1e-2, False), 1e-2, False)
+            assert solver.do_numeric_factorization(reg).status == LinearSolverStatus.successful
+            x = solver.do_back_solve(rhs)
+            o = SchurOracle(compute_inertia=True, inertia_method="ldl")
+            full = reg.materialize()
+            o.symbolic(full)
+            assert o.numeric(full) == 0
+            x_ref = o.solve(rhs)
+            for i in list(solver.local_block_indices) + [4]:
+                assert np.allclose(np.asarray(x.get_block(i)).flatten(), np.asarray(x_ref.get_block(i)).flatten(), rtol=1e-7, atol=1e-9)
+            assert solver.get_inertia() == o.inertia()
+            assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == 1
         open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["generator", "overflow", "singular"])
+@pytest.mark.parametrize("case", ["generator", "overflow", "singular", "sparse_coupling", "device_regularization"])
 def test_two_ranks_on_one_gpu(tmp_path, case):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
