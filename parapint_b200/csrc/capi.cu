@@ -114,6 +114,8 @@ struct pp_handle {
   bool use_cluster = true;
   bool panel_onchip = true;       // cluster panel kernel with the panel's rows of L in registers / shared memory
   int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
+  int subtree_cluster = 0;        // 0 = automatic; 1, 2, 4, 8 force the CTAs per block of the subtree kernels
+  int sm_count = 148;
   int defer_status = 0;           // 1 single rank: one host sync per factorisation (status + inertia read together);
                                   // 2 several ranks: pp_numeric_local does not synchronise, its status and overflow
                                   //   flag travel in the tail of the Schur buffer the caller all-reduces
@@ -264,6 +266,33 @@ bool is_pinned_host(const void *p) {
     return false;
   }
   return at.type == cudaMemoryTypeHost;
+}
+
+// CTAs per block for the subtree kernels.  Measured on B200 with config-2 blocks (tools/cluster_probe.py): the
+// kernels are bound by the DEPTH of the assembly tree (8 blocks take 148 us, 64 blocks 176 us), so more CTAs per block
+// buy little -- two CTAs shave 5 % off the factorisation (the two levels with ~24 medium fronts need fewer rounds),
+// more only add cluster barriers, and the solves (a few microseconds per level) lose to the barriers altogether.
+int subtree_csize(const pp_handle *h, bool factor) {
+  if (h->subtree_cluster > 0) return h->subtree_cluster;
+  return (factor && h->n_local * 2 <= h->sm_count) ? 2 : 1;
+}
+
+// launch `kern` with one thread-block cluster of `csize` CTAs per block
+template <class... P, class... A>
+void launch_clustered(void (*kern)(P...), int nblocks, int csize, int threads, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nblocks * csize));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...));
 }
 
 // Factor fronts [first, first+count): fixed schedule of (panel, interchange, update) launches.  A
@@ -461,6 +490,7 @@ int pp_create(int device, pp_handle **out) {
     h_optin_smem = (size_t)optin - 1024;
     auto *h = new pp_handle();
     h->device = device;
+    CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     h->flag.alloc(8);
     h->inertia.alloc(8);
     CK(cudaMemset(h->inertia.p, 0, 8 * sizeof(unsigned long long)));
@@ -498,6 +528,10 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("cluster_size must be 0, 1, 2, 4 or 8");
     h->cluster_size = c;
+  } else if (key == "subtree_cluster") {
+    const int c = (int)value;
+    if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("subtree_cluster must be 0, 1, 2, 4 or 8");
+    h->subtree_cluster = c;
   } else if (key == "small_front") {
     h->use_small = value != 0.0;
   } else if (key == "auto_residual") {
@@ -1185,8 +1219,8 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
                                   h->inertia.p, h->leaf_cap);
       h->launches++;
     }
-    subtree_factor_kernel<<<h->n_local, SF_NT, SF_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->fronts.p, dvals,
-                                                             h->pivot_threshold, h->pivot_tol, h->inertia.p);
+    launch_clustered(subtree_factor_kernel, h->n_local, subtree_csize(h, true), SF_NT, SF_SMEM, st, h->blocks_dev.p,
+                     h->plans_dev.p, h->fronts.p, dvals, h->pivot_threshold, h->pivot_tol, h->inertia.p);
     h->launches++;
   }
   factor_fronts(h, 0, h->n_local, st);
@@ -1198,8 +1232,9 @@ static int numeric_local_once(pp_handle *h, const double *dvals, double *schur_l
     h->launches++;
   } else if (h->m_c > 0) {
     ProfSpan sp(h, PP_PROF_SCHUR, st);
-    dim3 g((h->m_c + 127) / 128, h->m_c);
-    schur_gather_kernel<<<g, 128, 0, st>>>(h->fronts.p, h->arenaA.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
+    const bool warp_per_entry = h->m_c <= 256;   // few entries with many sources each: a warp per entry
+    dim3 g(warp_per_entry ? (h->m_c + 7) / 8 : (h->m_c + 127) / 128, h->m_c);
+    (warp_per_entry ? schur_gather_warp_kernel : schur_gather_kernel)<<<g, warp_per_entry ? 256 : 128, 0, st>>>(h->fronts.p, h->arenaA.p, h->src_ptr.p, h->src_front.p, h->src_pos.p,
                                            h->src_aoff.p, h->src_ld.p, h->brow_ptr.p, h->brow.p, h->m_c,
                                            schur_local_dev);
     h->launches++;
@@ -1314,6 +1349,15 @@ static void enqueue_coupling(pp_handle *h, const double *schur_sum_dev, cudaStre
     return;
   }
   const Front C = h->hfronts[h->n_local];
+  if (h->use_small && mc <= SM_CAP) {
+    // small coupling system: S = Q + sum, its LDL^T and its inertia in one launch
+    ProfSpan sp(h, PP_PROF_PANEL, st);
+    front_small_kernel<<<1, SF_NT, SM_SMEM, st>>>(h->fronts.p + h->n_local, h->pivot_threshold, h->pivot_tol,
+                                                  schur_sum_dev, mc, h->inertia.p + 3);
+    h->launches++;
+    CK(cudaGetLastError());
+    return;
+  }
   dim3 g((mc + 127) / 128, mc);
   coupling_add_kernel<<<g, 128, 0, st>>>(C, schur_sum_dev, mc);
   h->launches++;
@@ -1470,8 +1514,8 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
       kern<<<g, LF_NT, lsm, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p, h->ywork.p, h->leaf_cap);
       h->launches++;
     }
-    subtree_forward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, drhs, h->vec_off.p,
-                                                              h->ywork.p, h->root_rhs.p, h->root_off.p);
+    launch_clustered(subtree_forward_kernel, h->n_local, subtree_csize(h, false), SF_NT, SV_SMEM, st, h->blocks_dev.p,
+                     h->plans_dev.p, drhs, h->vec_off.p, h->ywork.p, h->root_rhs.p, h->root_off.p);
     front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
                                                                                   h->root_off64.p);
     h->launches += 2;
@@ -1510,8 +1554,8 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
     ProfSpan sp(h, PP_PROF_BACKWARD, st);
     front_backward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(
         h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, h->root_x.p, h->root_off64.p);
-    subtree_backward_kernel<<<h->n_local, SF_NT, SV_SMEM, st>>>(h->blocks_dev.p, h->plans_dev.p, h->ywork.p,
-                                                               h->vec_off.p, h->root_x.p, h->root_off.p, dx);
+    launch_clustered(subtree_backward_kernel, h->n_local, subtree_csize(h, false), SF_NT, SV_SMEM, st, h->blocks_dev.p,
+                     h->plans_dev.p, h->ywork.p, h->vec_off.p, h->root_x.p, h->root_off.p, dx);
     if (h->max_leaves > 0) {
       const int lg = h->leaf_cap <= 8 ? 8 : (h->leaf_cap <= 16 ? 16 : 32), per = LF_NT / lg;
       dim3 g((h->max_leaves + per - 1) / per, h->n_local);

@@ -14,8 +14,12 @@ namespace ppb {
 constexpr int SM_CAP = 164, SM_LD = SM_CAP + 1;   // 164 x 165 doubles = 211 KB of the 227 KB a CTA may use
 constexpr size_t SM_SMEM = fb_bytes(SM_CAP, SM_LD) + 16;
 
+// `add` (optional, one front only): an m_c x m_c column-major matrix added to the front while it is loaded -- the reduced
+// Schur sum joining Q in the coupling front -- and `inertia_out` (optional) receives the pivot signs of the front, so
+// that the coupling phase S = Q + sum, LDL^T, inertia is ONE launch instead of four.
 __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restrict__ fronts, double u,
-                                                            double pivtol) {
+                                                            double pivtol, const double *__restrict__ add = nullptr,
+                                                            int add_ld = 0, unsigned long long *inertia_out = nullptr) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ int cnt[3];
   const Front F = fronts[blockIdx.x];
@@ -34,7 +38,9 @@ __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restr
     const int j = idx / S, i = idx - j * S;
     if (i < j) continue;
     const int si = i < n ? i : nb + (i - n), sj = j < n ? j : nb + (j - n);
-    B.F[i + j * SM_LD] = A[si + (size_t)sj * ldA];
+    double v = A[si + (size_t)sj * ldA];
+    if (add) v += add[si + (size_t)sj * add_ld];
+    B.F[i + j * SM_LD] = v;
   }
   for (int i = tid; i < S; i += SF_NT) {
     B.fid[i] = i;
@@ -181,6 +187,8 @@ __global__ void __launch_bounds__(SF_NT) front_small_kernel(const Front *__restr
     F.state[ST_KCUR] = n;
     if (t < n && F.state[ST_INFO] == 0) F.state[ST_INFO] = t + 1;
   }
+  if (inertia_out && tid < 3)   // pivots counted by factor_front; columns that found no pivot are zeros
+    inertia_out[tid] = (unsigned long long)(cnt[tid] + (tid == 2 ? n - t : 0));
 }
 
 }  // namespace ppb

@@ -105,6 +105,47 @@ __global__ void schur_gather_kernel(const Front *__restrict__ fronts, const doub
   S[(size_t)c + (size_t)r * m_c] = s;
 }
 
+// The same gather for SMALL coupling systems (few entries, many sources each: 64 scenarios x 50 first-stage variables):
+__global__ void schur_gather_warp_kernel(const Front *__restrict__ fronts, const double *__restrict__ arenaA,
+                                    const int64_t *__restrict__ src_ptr, const int32_t *__restrict__ src_front,
+                                    const int32_t *__restrict__ src_pos, const int64_t *__restrict__ src_aoff,
+                                    const int32_t *__restrict__ src_ld, const int64_t *__restrict__ brow_ptr,
+                                    const int32_t *__restrict__ brow, int m_c, double *__restrict__ S) {
+  // one WARP per entry (r, c) of the lower triangle: lane l adds sources l, l + 32, ... in that order, then a fixed
+  // shuffle tree combines the lanes -- every load of an entry is in flight at once (64 scenarios: two per lane) and
+  // the summation order is the same in every run.  src_aoff[p] is the arena offset of (row of r, first border column)
+  // in the source front and src_ld[p] its leading dimension -- negated when the front carries only part of the
+  // coupling rows and c has to be located first.
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int c = blockIdx.y;
+  if (r >= m_c || r < c) return;
+  double s = 0.0;
+  const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
+  for (int64_t p = p0 + lane; p < p1; p += 32) {
+    const int ldf = src_ld[p];
+    int lo = c;
+    if (ldf < 0) {  // partial border: locate c among the front's border rows (c <= r => position <= a)
+      const int f = src_front[p], a = src_pos[p];
+      const int32_t *br = brow + brow_ptr[f];
+      int hi = a;
+      lo = 0;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (br[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      if (br[lo] != c) continue;
+    }
+    s += arenaA[src_aoff[p] + (int64_t)lo * (ldf < 0 ? -ldf : ldf)];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    S[(size_t)r + (size_t)c * m_c] = s;
+    S[(size_t)c + (size_t)r * m_c] = s;
+  }
+}
+
 // The same gather for a SPARSE Schur complement (time-decomposed problems): one thread per pattern entry (r, c), the
 // result goes to slot p of the value array -- the role of sc_data_slices in mpi_explicit_schur_complement.py:249-254,
 // 326-331, where the all-reduce then moves sc_nnz values instead of m_c^2.

@@ -11,6 +11,7 @@
 // front_small_kernel (small.cuh) or the batched Bunch-Kaufman kernels of factor.cuh finish (they also see the
 // delayed columns, so no pivot is ever forced: the inertia stays exact).  All sums run in a fixed order: results are reproducible.
 #pragma once
+#include <cooperative_groups.h>
 #include "front.cuh"
 
 namespace ppb {
@@ -813,15 +814,23 @@ __global__ void __launch_bounds__(LF_NT, 4) subtree_leaf_kernel(const SparseBloc
   if (threadIdx.x < 3 && cnt[threadIdx.x]) atomicAdd(&inertia[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
 
+// One thread-block CLUSTER per block (1, 2, 4 or 8 CTAs, chosen by the host so that blocks x CTAs fills the GPU
+// once): the fronts of a level are independent, so its tiny / medium / big fronts are dealt over the CTAs of the
+// cluster; contribution blocks travel through HBM as before and a cluster barrier (release / acquire) closes each
+// level.  With few blocks per GPU (strong scaling, or 64 blocks on 148 SMs) the levels with many fronts run on
+// several SMs instead of one.
 __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock *__restrict__ blocks,
                                                                const PlanDev *__restrict__ plans,
                                                                Front *__restrict__ fronts,
                                                                const double *__restrict__ vals, double u,
                                                                double pivtol, unsigned long long *inertia) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int C = (int)cl.num_blocks(), cr = (int)cl.block_rank();
   extern __shared__ __align__(16) unsigned char sm_raw[];
   int *cnt = reinterpret_cast<int *>(sm_raw + SF_WORK);  // [0..2] inertia, [3] failed, [4] deferred count
   int *deferred = cnt + 16;                              // up to 64 deferred fronts per level
-  const SparseBlock Bk = blocks[blockIdx.x];
+  const SparseBlock Bk = blocks[blockIdx.x / C];
   const PlanDev P = plans[Bk.plan];
   const Front R = fronts[Bk.root];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = tid / SF_MG;
@@ -832,14 +841,14 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
   const Stage mstg = carve_stage(sm_raw + (size_t)grp * SF_MED_BYTES + SF_MED_FB, SF_MSTG, SF_MMAXCH);
   const FrontBuf mine = carve(sm_raw + (size_t)warp * SF_TINY_BYTES, SF_TBUF, SF_TLD);
   if (tid < 8) cnt[tid] = 0;
-  if (tid == 0) Bk.info[3] = 0;
+  if (tid == 0 && cr == 0) { Bk.info[3] = 0; Bk.info[6] = 0; }
   __syncthreads();
 
   for (int l = 0; l < P.nlevels; ++l) {
     PP_TR(4 * l);
     // ---- small fronts: one warp each, all warps concurrently (the leaves were done by
     //      subtree_leaf_kernel, spread over the whole GPU) ----
-    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+    for (int k = P.tiny_ptr[l] + warp + SF_NW * cr; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW * C) {
       const int s = P.tiny_idx[k];
       const int rc = process_front<32>(Bk, P, vals, s, mine, u, pivtol, cnt, mstg);
       if (lane == 0) {
@@ -852,7 +861,7 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     __syncthreads();
     PP_TR(4 * l + 1);
     // ---- medium fronts (up to 32 rows, any number of children): two warps each, eight at a time ----
-    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+    for (int k = P.med_ptr[l] + grp + SF_NG * cr; k < P.med_ptr[l + 1]; k += SF_NG * C) {
       const int s = P.med_idx[k];
       const int rc = process_front<SF_MG>(Bk, P, vals, s, med, u, pivtol, cnt, mstg);
       if ((tid & (SF_MG - 1)) == 0) {
@@ -876,18 +885,27 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
       if (process_front<SF_NT>(Bk, P, vals, s, big, u, pivtol, cnt, stg) != PF_OK && tid == 0) cnt[3] = 1;
       __syncthreads();
     }
-    for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+    for (int k = P.big_ptr[l] + cr; k < P.big_ptr[l + 1]; k += C) {
       if (process_front<SF_NT>(Bk, P, vals, P.big_idx[k], big, u, pivtol, cnt, stg) != PF_OK && tid == 0) cnt[3] = 1;
       __syncthreads();
     }
     if (tid == 0) cnt[4] = 0;
-    __syncthreads();
+    // a failed front leaves its (structurally valid) previous record in place, so the other fronts can go on safely;
+    // the failure is reported at the end -- no early exit that the CTAs of a cluster would have to agree on
+    if (C > 1) cl.sync(); else __syncthreads();
     PP_TR(4 * l + 3);
-    if (cnt[3]) break;
   }
+  if (tid == 0) {
+    if (cnt[3]) atomicOr(&Bk.info[6], 1);
+    if (cnt[0]) atomicAdd(&inertia[0], (unsigned long long)cnt[0]);
+    if (cnt[1]) atomicAdd(&inertia[1], (unsigned long long)cnt[1]);
+    if (cnt[2]) atomicAdd(&inertia[2], (unsigned long long)cnt[2]);
+  }
+  if (C > 1) { __threadfence(); cl.sync(); }
+  if (cr != 0) return;
   // ---- children of the root: add their contribution blocks into the dense root front ----
   int ndroot = 0;
-  bool failed = cnt[3] != 0 || Bk.info[2] != 0;
+  bool failed = *((volatile int *)&Bk.info[6]) != 0 || cnt[3] != 0 || Bk.info[2] != 0;
   for (int k = 0; k < P.nrootch && !failed; ++k) {
     const int s = P.root_children[k];
     const int ne = Bk.meta[3 * s], S = Bk.meta[3 * s + 1], ndo = Bk.meta[3 * s + 2];
@@ -925,9 +943,6 @@ __global__ void __launch_bounds__(SF_NT) subtree_factor_kernel(const SparseBlock
     Bk.info[2] = 0;  // leaf-failure flag consumed
     PP_TR(4 * P.nlevels);
     fronts[Bk.root].n = P.nT + ndroot;  // pivot candidates of the dense root: static columns + delayed ones
-    atomicAdd(&inertia[0], (unsigned long long)cnt[0]);
-    atomicAdd(&inertia[1], (unsigned long long)cnt[1]);
-    atomicAdd(&inertia[2], (unsigned long long)cnt[2]);
   }
 }
 
@@ -1193,8 +1208,11 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
                                                                 double *__restrict__ ywork,
                                                                 double *__restrict__ root_rhs,
                                                                 const long long *__restrict__ root_off) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int C = (int)cl.num_blocks(), cr = (int)cl.block_rank(), bid = blockIdx.x / C;  // one cluster per block
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  const SparseBlock Bk = blocks[blockIdx.x];
+  const SparseBlock Bk = blocks[bid];
   const PlanDev P = plans[Bk.plan];
   const int tid = threadIdx.x, warp = tid >> 5, grp = tid / SF_MG;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
@@ -1202,39 +1220,43 @@ __global__ void __launch_bounds__(SF_NT) subtree_forward_kernel(const SparseBloc
   const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
   const Stage mstg = carve_stage(sm_raw + (size_t)grp * SV_MED_BYTES + SV_MED_SB, SF_MSTG, SF_MMAXCH);
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
-  const double *r = rhs + vec_off[blockIdx.x];
-  double *y = ywork + vec_off[blockIdx.x];
+  const double *r = rhs + vec_off[bid];
+  double *y = ywork + vec_off[bid];
   for (int l = 0; l < P.nlevels; ++l) {
     PP_TR(1024 + 4 * l);
-    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+    for (int k = P.tiny_ptr[l] + warp + SF_NW * cr; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW * C) {
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_TBUF) forward_front<32>(Bk, P, s, mine, r, y, mstg);
     }
     __syncthreads();
     PP_TR(1024 + 4 * l + 1);
-    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+    for (int k = P.med_ptr[l] + grp + SF_NG * cr; k < P.med_ptr[l + 1]; k += SF_NG * C) {
       const int s = P.med_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_MBUF) forward_front<SF_MG>(Bk, P, s, med, r, y, mstg);
     }
     __syncthreads();
     PP_TR(1024 + 4 * l + 2);
+    // whole-CTA fronts of the level (those that outgrew their group, and the big ones), dealt over the cluster
+    int turn = 0;
     for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {  // fronts that outgrew their group
       const int s = P.tiny_idx[k];
-      if (Bk.meta[3 * s + 1] > SF_TBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
+      if (Bk.meta[3 * s + 1] > SF_TBUF && (turn++ % C) == cr) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
     }
     for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) {
       const int s = P.med_idx[k];
-      if (Bk.meta[3 * s + 1] > SF_MBUF) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
+      if (Bk.meta[3 * s + 1] > SF_MBUF && (turn++ % C) == cr) { forward_front<SF_NT>(Bk, P, s, big, r, y, stg); __syncthreads(); }
     }
     for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+      if ((turn++ % C) != cr) continue;
       forward_front<SF_NT>(Bk, P, P.big_idx[k], big, r, y, stg);
       __syncthreads();
     }
-    __syncthreads();
+    if (C > 1) cl.sync(); else __syncthreads();
     PP_TR(1024 + 4 * l + 3);
   }
+  if (cr != 0) return;
   // root right-hand side: own entries + contributions of the root's children (fixed order)
-  double *rr = root_rhs + root_off[blockIdx.x];
+  double *rr = root_rhs + root_off[bid];
   for (int p = tid; p < P.nT + P.DR; p += SF_NT) rr[p] = p < P.nT ? r[P.rootcols[p]] : 0.0;
   __syncthreads();
   int ndroot = 0;
@@ -1258,45 +1280,51 @@ __global__ void __launch_bounds__(SF_NT) subtree_backward_kernel(const SparseBlo
                                                                  const double *__restrict__ root_x,
                                                                  const long long *__restrict__ root_off,
                                                                  double *__restrict__ xout) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int C = (int)cl.num_blocks(), cr = (int)cl.block_rank(), bid = blockIdx.x / C;  // one cluster per block
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  const SparseBlock Bk = blocks[blockIdx.x];
+  const SparseBlock Bk = blocks[bid];
   const PlanDev P = plans[Bk.plan];
   const int tid = threadIdx.x, warp = tid >> 5, grp = tid / SF_MG;
   const SolveBuf big = carve_solve(sm_raw, SF_SBUF, SF_LDF);
   const SolveBuf med = carve_solve(sm_raw + (size_t)grp * SV_MED_BYTES, SF_MBUF, SF_MLD);
   const SolveBuf mine = carve_solve(sm_raw + (size_t)warp * SV_TINY_BYTES, SF_TBUF, SF_TLD);
-  const double *y = ywork + vec_off[blockIdx.x];
-  double *x = xout + vec_off[blockIdx.x];
-  const double *rx = root_x + root_off[blockIdx.x];
-  for (int p = tid; p < P.nT + P.DR; p += SF_NT) {
-    const int id = Bk.rootids[p];
-    if (id >= 0) x[id] = rx[p];
-  }
-  __syncthreads();
+  const double *y = ywork + vec_off[bid];
+  double *x = xout + vec_off[bid];
+  const double *rx = root_x + root_off[bid];
+  if (cr == 0)
+    for (int p = tid; p < P.nT + P.DR; p += SF_NT) {
+      const int id = Bk.rootids[p];
+      if (id >= 0) x[id] = rx[p];
+    }
+  if (C > 1) { __threadfence(); cl.sync(); } else __syncthreads();
   for (int l = P.nlevels - 1; l >= 0; --l) {
+    int turn = 0;  // whole-CTA fronts of the level are dealt over the CTAs of the cluster
     for (int k = P.big_ptr[l]; k < P.big_ptr[l + 1]; ++k) {
+      if ((turn++ % C) != cr) continue;
       backward_front<SF_NT>(Bk, P, P.big_idx[k], big, y, x);
       __syncthreads();
     }
     for (int k = P.med_ptr[l]; k < P.med_ptr[l + 1]; ++k) {
       const int s = P.med_idx[k];
-      if (Bk.meta[3 * s + 1] > SF_MBUF) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
+      if (Bk.meta[3 * s + 1] > SF_MBUF && (turn++ % C) == cr) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
     }
     for (int k = P.tiny_ptr[l]; l > 0 && k < P.tiny_ptr[l + 1]; ++k) {
       const int s = P.tiny_idx[k];
-      if (Bk.meta[3 * s + 1] > SF_TBUF) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
+      if (Bk.meta[3 * s + 1] > SF_TBUF && (turn++ % C) == cr) { backward_front<SF_NT>(Bk, P, s, big, y, x); __syncthreads(); }
     }
     __syncthreads();
-    for (int k = P.med_ptr[l] + grp; k < P.med_ptr[l + 1]; k += SF_NG) {
+    for (int k = P.med_ptr[l] + grp + SF_NG * cr; k < P.med_ptr[l + 1]; k += SF_NG * C) {
       const int s = P.med_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_MBUF) backward_front<SF_MG>(Bk, P, s, med, y, x);
     }
     __syncthreads();
-    for (int k = P.tiny_ptr[l] + warp; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW) {
+    for (int k = P.tiny_ptr[l] + warp + SF_NW * cr; l > 0 && k < P.tiny_ptr[l + 1]; k += SF_NW * C) {
       const int s = P.tiny_idx[k];
       if (Bk.meta[3 * s + 1] <= SF_TBUF) backward_front<32>(Bk, P, s, mine, y, x);
     }
-    __syncthreads();
+    if (C > 1) cl.sync(); else __syncthreads();
   }
 }
 
