@@ -232,6 +232,14 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
                  int to_staging, int threads);
 
 /*
+ * Host-side helper (no CUDA): *equal = 1 when the bytes of a[k] and b[k] (len[k] each) agree for every k.  An
+ * interface that rebuilds its KKT matrix every iteration (interfaces/interface.py:432-491) hands over fresh index
+ * arrays; they are compared with the analysed pattern by up to `threads` workers in one call instead of one numpy
+ * comparison per leaf (the check mumps_interface.py:82-83 makes before re-using its analysis).
+ */
+int pp_host_equal(int64_t nseg, void *const *a, void *const *b, const int64_t *len, int threads, int *equal);
+
+/*
  * pp_host_copy + the host-to-device transfer of the values, pipelined: the segments (which must tile the `nvals`
  * doubles of the analysed pattern in order) are gathered into the pinned `staging` buffer in `chunks` shares and
  * every share is sent to the device as soon as it is complete, so the transfer of one overlaps the gather of the

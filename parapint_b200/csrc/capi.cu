@@ -1818,6 +1818,19 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
   return PP_SUCCESSFUL;
 }
 
+int pp_host_equal(int64_t nseg, void *const *a, void *const *b, const int64_t *len, int threads, int *equal) {
+  if (nseg < 0 || !equal || (nseg > 0 && (!a || !b || !len))) return misuse("pp_host_equal: null argument");
+  for (int64_t k = 0; k < nseg; ++k)
+    if (len[k] < 0 || (len[k] > 0 && (!a[k] || !b[k]))) return misuse("pp_host_equal: bad segment");
+  try {
+    *equal = CopyPool::instance().equal(nseg, a, b, len, threads) ? 1 : 0;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return PP_ERROR;
+  }
+  return PP_SUCCESSFUL;
+}
+
 int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {
   if (!h) return misuse("pp_profile: null handle");
   return guarded([&]() {

@@ -60,26 +60,14 @@ class CopyPool {
   // segs[k]: `len[k]` bytes at `ptr[k]` <-> staging offset `off[k]`; to_staging selects the direction
   void run(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, char *staging, bool to_staging,
            int threads) {
-    int64_t total = 0;
-    for (int64_t k = 0; k < nseg; ++k) total += len[k];
-    int T = (int)std::min<int64_t>(std::max(threads, 1), 1 + total / (256 << 10));  // >= 256 KB per thread
-    T = std::min(T, kMax);
-    if (T <= 1) {
-      copy_range(nseg, ptr, off, len, staging, to_staging, 0, total);
-      return;
-    }
-    std::lock_guard<std::mutex> serial(api_);
-    ensure_workers(T - 1);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      job_ = {nseg, ptr, off, len, staging, to_staging, total, T};
-      pending_ = T - 1;
-      ++gen_;
-    }
-    cv_.notify_all();
-    copy_range(nseg, ptr, off, len, staging, to_staging, 0, total / T);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [&] { return pending_ == 0; });
+    dispatch({nseg, ptr, off, len, staging, to_staging, 0, 0, nullptr}, threads);
+  }
+  // true when the bytes of a[k] and b[k] (len[k] each) agree for every k: the index arrays of a freshly built KKT
+  // matrix against the analysed pattern, compared by a few threads instead of one numpy call per leaf
+  bool equal(int64_t nseg, void *const *a, void *const *b, const int64_t *len, int threads) {
+    mismatch_.store(0, std::memory_order_relaxed);
+    dispatch({nseg, a, nullptr, len, nullptr, false, 0, 0, b}, threads);
+    return mismatch_.load(std::memory_order_relaxed) == 0;
   }
 
  private:
@@ -92,7 +80,48 @@ class CopyPool {
     bool to_staging;
     int64_t total;
     int T;
+    void *const *other;   // non-null: compare ptr[k] with other[k] instead of copying
   };
+  void dispatch(Job j, int threads) {
+    int64_t total = 0;
+    for (int64_t k = 0; k < j.nseg; ++k) total += j.len[k];
+    int T = (int)std::min<int64_t>(std::max(threads, 1), 1 + total / (256 << 10));  // >= 256 KB per thread
+    T = std::min(T, kMax);
+    j.total = total;
+    j.T = T;
+    if (T <= 1) {
+      work(j, 0, total);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(api_);
+    ensure_workers(T - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = j;
+      pending_ = T - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    work(j, 0, total / T);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+  void work(const Job &j, int64_t b0, int64_t b1) {
+    if (!j.other) {
+      copy_range(j.nseg, j.ptr, j.off, j.len, j.staging, j.to_staging, b0, b1);
+      return;
+    }
+    int64_t pos = 0;
+    for (int64_t k = 0; k < j.nseg && pos < b1; ++k) {
+      const int64_t lo = std::max(pos, b0), hi = std::min(pos + j.len[k], b1);
+      if (lo < hi && std::memcmp(static_cast<const char *>(j.ptr[k]) + (lo - pos),
+                                 static_cast<const char *>(j.other[k]) + (lo - pos), (size_t)(hi - lo)) != 0) {
+        mismatch_.store(1, std::memory_order_relaxed);
+        return;
+      }
+      pos += j.len[k];
+    }
+  }
   // copy the part of the concatenated byte stream [b0, b1) (segments in order)
   static void copy_range(int64_t nseg, void *const *ptr, const int64_t *off, const int64_t *len, char *staging,
                          bool to_staging, int64_t b0, int64_t b1) {
@@ -125,7 +154,7 @@ class CopyPool {
         seen = gen_;
         j = job_;
       }
-      copy_range(j.nseg, j.ptr, j.off, j.len, j.staging, j.to_staging, j.total * id / j.T, j.total * (id + 1) / j.T);
+      work(j, j.total * id / j.T, j.total * (id + 1) / j.T);
       {
         std::lock_guard<std::mutex> lk(mu_);
         if (--pending_ == 0) done_.notify_one();
@@ -141,6 +170,7 @@ class CopyPool {
     cv_.notify_all();
     for (auto &t : workers_) t.join();
   }
+  std::atomic<int> mismatch_{0};
   std::mutex api_, mu_;
   std::condition_variable cv_, done_;
   std::vector<std::thread> workers_;

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pp_refine_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
     "pp_schur_tail": (C.c_int, [_vp, _f64p]),
     "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "pp_host_equal": (C.c_int, [C.c_int64, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "pp_stage_values": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),
@@ -135,6 +136,23 @@ class HostCopier:
         self._keep = list(arrays)
         self._tables = (ptr, off, ln, np_ptr(ptr), np_ptr(off), np_ptr(ln))
         return self._tables
+
+    def all_equal(self, pairs):
+        """True when ``a`` and ``b`` hold the same bytes for every pair (index arrays of fresh leaves against the
+        analysed pattern); None when a pair does not qualify for the byte comparison (the caller uses numpy)."""
+        import numpy as np
+        if not pairs:
+            return True
+        for a, b in pairs:
+            if a.dtype != b.dtype or a.size != b.size or not a.flags.c_contiguous or not b.flags.c_contiguous:
+                return None
+        pa = np.array([a.__array_interface__["data"][0] for a, _ in pairs], dtype=np.uintp)
+        pb = np.array([b.__array_interface__["data"][0] for _, b in pairs], dtype=np.uintp)
+        ln = np.array([a.nbytes for a, _ in pairs], dtype=np.int64)
+        out = C.c_int(0)
+        if self.lib.pp_host_equal(len(pairs), np_ptr(pa), np_ptr(pb), np_ptr(ln), self.threads, C.byref(out)) != 0:
+            raise RuntimeError(f"pp_host_equal failed: {last_error()}")
+        return bool(out.value)
 
     def copy(self, arrays, offsets, staging, to_staging=True):
         """``arrays[k]`` (float64, contiguous) <-> ``staging[offsets[k] : offsets[k] + arrays[k].size]``.

@@ -219,6 +219,7 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
     N = st.n_blocks
     get = matrix.get_block
     datas, starts = [], []
+    pending = []   # (fresh index array, analysed index array) pairs compared in one threaded call at the end
     seen = st.__dict__.setdefault("_leaf_seen", [None] * len(st.segments))
     recipes = st.recipes if st.recipes else [None] * len(st.segments)
     for k, ((kind, i, lo, hi), (prow, pcol)) in enumerate(zip(st.segments, st.patterns)):
@@ -259,8 +260,15 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             data = blk.data
         else:
             c = blk.tocoo()
-            if not (_same_index(c.row, prow) and _same_index(c.col, pcol)):
-                return False
+            for fresh, ref in ((c.row, prow), (c.col, pcol)):
+                if fresh is ref:
+                    continue
+                if fresh.size != ref.size:
+                    return False
+                if copier is not None and fresh.dtype == ref.dtype:
+                    pending.append((fresh, ref))
+                elif not np.array_equal(fresh, ref):
+                    return False
             data = c.data
         if data.size != hi - lo:
             return False
@@ -269,6 +277,12 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             and blk.row is prow and blk.col is pcol else None
         datas.append(data)
         starts.append(lo)
+    if pending:
+        same = copier.all_equal(pending)
+        if same is None:
+            same = all(np.array_equal(a, b) for a, b in pending)
+        if not same:
+            return False
     if copier is None or not copier.copy(datas, starts, out):
         for lo, data in zip(starts, datas):
             out[lo:lo + data.size] = data

@@ -314,3 +314,26 @@ def test_nested_blocks_are_gathered_by_recipe():
     assert np.array_equal(out, expect)
     assert not structure.gather_values(system([4, 5, 6], shift=True), st, out)   # a sub-leaf's column index moved
     assert not structure.gather_values(system([4, 5, 6], extra=True), st, out)   # an extra sub-block appeared
+
+
+def test_fresh_objects_are_validated_by_the_threaded_comparison():
+    """A matrix rebuilt from scratch (new leaf objects, new index arrays) is accepted when its pattern equals the
+    analysed one and rejected when a single index differs -- through pp_host_equal + pp_host_copy (host-only)."""
+    from oracle.kkt_generator import EstimationModel
+    m = EstimationModel(5, 40, 3, 6)
+    st = structure.analyse(m.build_kkt())
+    copier = native.HostCopier(4)
+    out = np.zeros(st.nvals)
+    fresh = m.build_kkt()
+    assert structure.gather_values(fresh, st, out, copier)
+    ref = np.zeros(st.nvals)
+    assert structure.gather_values(fresh, st, ref)                   # numpy path
+    assert np.array_equal(out, ref)
+    other = m.build_kkt()
+    K = other.get_block(2, 2).tocoo()
+    row = K.row.copy()
+    row[7], row[8] = row[8], row[7]                                   # same entries, different order: a pattern change
+    import scipy.sparse as sp
+    other.set_block(2, 2, sp.coo_matrix((K.data, (row, K.col)), shape=K.shape))
+    assert not structure.gather_values(other, st, out, copier)
+    assert not structure.gather_values(other, st, out)
