@@ -61,7 +61,9 @@ int pp_destroy(pp_handle *h);
  * (0/1: whole-front shared-memory factorisation when every front of a batch has <= 164 rows), "defer_status"
  * (0/1, single-rank use: pp_numeric_local returns a provisional PP_SUCCESSFUL without synchronising and
  * pp_numeric_coupling -- which must then be given the local Schur buffer -- reports the status of both phases and
- * caches the inertia, one host synchronisation per factorisation), "auto_residual" (0/1, single-rank use:
+ * caches the inertia, one host synchronisation per factorisation), "overlap_groups" (0/1: large dense fronts are
+ * factorised as two groups on two streams so that the latency-bound panels of one overlap the updates of the other),
+ * "subtree_cluster" (0 = automatic, or 1/2/4/8 CTAs per block for the subtree kernels), "auto_residual" (0/1, single-rank use:
  * pp_solve_backward with host outputs also forms the residual norms, which pp_residual_norms then returns without
  * launching or waiting), "no_fallback", "profile". */
 int pp_set_option(pp_handle *h, const char *name, double value);

@@ -114,6 +114,10 @@ struct pp_handle {
   bool use_cluster = true;
   bool panel_onchip = true;       // cluster panel kernel with the panel's rows of L in registers / shared memory
   int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
+  int overlap_groups = 2;         // groups of fronts on separate streams: panels of one overlap updates of the others
+  std::vector<cudaStream_t> aux_streams;
+  std::vector<cudaEvent_t> aux_events;
+  cudaEvent_t ev_fork = nullptr;
   int subtree_cluster = 0;        // 0 = automatic; 1, 2, 4, 8 force the CTAs per block of the subtree kernels
   int sm_count = 148;
   int defer_status = 0;           // 1 single rank: one host sync per factorisation (status + inertia read together);
@@ -208,6 +212,9 @@ struct pp_handle {
   ~pp_handle() {
     for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto e : aux_events) cudaEventDestroy(e);
+    for (auto a : aux_streams) cudaStreamDestroy(a);
     delete child;
   }
 };
@@ -298,7 +305,43 @@ void launch_clustered(void (*kern)(P...), int nblocks, int csize, int threads, s
 // Factor fronts [first, first+count): fixed schedule of (panel, interchange, update) launches.  A
 // panel eliminates NB-1 or NB columns, so after launch `it` front f has done at least
 // min(n_f, (it+1)(NB-1)) columns; that bounds the tile grid of the update from the host side.
+void factor_group(pp_handle *h, int first, int count, cudaStream_t st);
+
+// The panel kernel is latency-bound (a chain of pivot columns per front), the trailing update throughput-bound, and
+// inside ONE front they cannot overlap: Bunch-Kaufman may pick its pivot anywhere in the trailing matrix, so a panel
+// needs the whole update before it.  Different fronts are independent, though: the batch is cut into two groups that
+// run the same launch sequence on two streams, so one group's panels fill the gaps of the other group's updates.
 void factor_fronts(pp_handle *h, int first, int count, cudaStream_t st) {
+  if (count == 0) return;
+  int nfmax = 0;
+  for (int f = first; f < first + count; ++f) nfmax = std::max(nfmax, h->nf[f]);
+  const int G = std::min(h->overlap_groups, count);
+  if (G < 2 || nfmax < 512) {
+    factor_group(h, first, count, st);
+    return;
+  }
+  if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  while ((int)h->aux_streams.size() < G - 1) {
+    cudaStream_t s2;
+    cudaEvent_t e2;
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    h->aux_streams.push_back(s2);
+    h->aux_events.push_back(e2);
+  }
+  CK(cudaEventRecord(h->ev_fork, st));
+  for (int g = 1; g < G; ++g) CK(cudaStreamWaitEvent(h->aux_streams[g - 1], h->ev_fork, 0));
+  for (int g = 0; g < G; ++g) {
+    const int lo = (int)((int64_t)count * g / G), hi = (int)((int64_t)count * (g + 1) / G);
+    factor_group(h, first + lo, hi - lo, g == 0 ? st : h->aux_streams[g - 1]);
+  }
+  for (int g = 1; g < G; ++g) {
+    CK(cudaEventRecord(h->aux_events[g - 1], h->aux_streams[g - 1]));
+    CK(cudaStreamWaitEvent(st, h->aux_events[g - 1], 0));
+  }
+}
+
+void factor_group(pp_handle *h, int first, int count, cudaStream_t st) {
   if (count == 0) return;
   const int NB = h->panel_width;
   const Front *fr = h->fronts.p + first;
@@ -478,6 +521,9 @@ int pp_create(int device, pp_handle **out) {
     allow_all(front_forward_kernel<512>);
     allow_all(front_backward_kernel<512>);
     allow_all(coupling_solve_kernel<512>);
+    allow_all(front_forward_cluster_kernel);
+    allow_all(front_backward_cluster_kernel);
+    allow_all(coupling_solve_cluster_kernel);
     allow_all(subtree_leaf_kernel<8>);
     allow_all(subtree_leaf_kernel<16>);
     allow_all(subtree_leaf_kernel<32>);
@@ -528,6 +574,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("cluster_size must be 0, 1, 2, 4 or 8");
     h->cluster_size = c;
+  } else if (key == "overlap_groups") {
+    h->overlap_groups = std::max(1, std::min((int)value, 8));
   } else if (key == "subtree_cluster") {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("subtree_cluster must be 0, 1, 2, 4 or 8");
@@ -699,7 +747,8 @@ static int do_symbolic(pp_handle *h, bool force_dense) {
       h->nmax_local = std::max(h->nmax_local, h->n[f]);
       h->nfmax_local = std::max(h->nfmax_local, h->nf[f]);
     }
-    if (solve_smem(h->nf[f]) > h_optin_smem) return fail("pp_symbolic: dense front too large for the in-smem solve (nf > ~28000)");
+    if (cluster_solve_smem(h->nf[f], CS_MAXC) > h_optin_smem)
+      return fail("pp_symbolic: dense front too large for the shared-memory solve vector (more than ~200 000 rows)");
   }
   h->arenaA_elems = totA;
   h->arenaA.alloc(totA);
@@ -1070,6 +1119,7 @@ static int setup_coupling(pp_handle *h) {
   c->use_cluster = h->use_cluster;
   c->panel_onchip = h->panel_onchip;
   c->use_small = h->use_small;
+  c->overlap_groups = h->overlap_groups;
   c->use_sparse = false;     // the blocks of S are dense
   c->defer_status = 1;
   rc = pp_symbolic(c, L.n_blocks, L.block_n.data(), L.border_ptr.data(), L.border_rows.data(), L.m_next, nnz,
@@ -1502,6 +1552,17 @@ int pp_inertia_coupling(pp_handle *h, int64_t out[3]) {
 static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t st);
 static void enqueue_residual_norms(pp_handle *h, const double *buf_sum_dev, cudaStream_t st);
 
+// CTAs per front for the dense triangular sweeps: one CTA when there are enough fronts to fill the GPU (or the
+// fronts are short), a cluster of up to 8 when a few tall fronts would otherwise stream their factors through a few
+// SMs; at least 256 rows per CTA, and as many CTAs as the solve vector needs to fit in shared memory.
+static int solve_csize(const pp_handle *h, int count, int nfmax) {
+  int c = 1;
+  if (nfmax >= 1024)
+    while (c < CS_MAXC && count * c * 2 <= h->sm_count && nfmax / (c * 2) >= 256) c *= 2;
+  while (c < CS_MAXC && solve_smem(nfmax) > h_optin_smem && cluster_solve_smem(nfmax, c) > h_optin_smem) c *= 2;
+  return c;
+}
+
 static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, cudaStream_t st) {
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_FORWARD, st);
@@ -1516,8 +1577,13 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
     }
     launch_clustered(subtree_forward_kernel, h->n_local, subtree_csize(h, false), SF_NT, SV_SMEM, st, h->blocks_dev.p,
                      h->plans_dev.p, drhs, h->vec_off.p, h->ywork.p, h->root_rhs.p, h->root_off.p);
-    front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
-                                                                                  h->root_off64.p);
+    const int cs = solve_csize(h, h->n_local, h->nfmax_local);
+    if (cs > 1)
+      launch_clustered(front_forward_cluster_kernel, h->n_local, cs, CS_NT, cluster_solve_smem(h->nfmax_local, cs), st,
+                       h->fronts.p, h->root_rhs.p, h->root_off64.p);
+    else
+      front_forward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(h->fronts.p, h->root_rhs.p,
+                                                                                    h->root_off64.p);
     h->launches += 2;
   }
   if (h->m_c > 0) {
@@ -1546,14 +1612,23 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
     if (nc > 0) scatter_perm_kernel<<<(nc + 255) / 256, 256, 0, st>>>(c->xc.p, h->sp_perm_c.p, nc, dxc);
     h->launches += 2;
   } else if (mc > 0) {
-    const size_t sm = solve_smem(mc);
-    coupling_solve_kernel<512><<<1, 512, sm, st>>>(h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
+    const int cs = solve_csize(h, 1, mc);
+    if (cs > 1)
+      launch_clustered(coupling_solve_cluster_kernel, 1, cs, CS_NT, cluster_solve_smem(mc, cs), st,
+                       h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
+    else
+      coupling_solve_kernel<512><<<1, 512, solve_smem(mc), st>>>(h->fronts.p + h->n_local, drc, rc_sum_dev, dxc);
     h->launches++;
   }
   if (h->n_local > 0) {
     ProfSpan sp(h, PP_PROF_BACKWARD, st);
-    front_backward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(
-        h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, h->root_x.p, h->root_off64.p);
+    const int cs = solve_csize(h, h->n_local, h->nfmax_local);
+    if (cs > 1)
+      launch_clustered(front_backward_cluster_kernel, h->n_local, cs, CS_NT, cluster_solve_smem(h->nfmax_local, cs), st,
+                       h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, h->root_x.p, h->root_off64.p);
+    else
+      front_backward_kernel<512><<<h->n_local, 512, solve_smem(h->nfmax_local), st>>>(
+          h->fronts.p, dxc, h->brow_ptr.p, h->brow.p, h->root_x.p, h->root_off64.p);
     launch_clustered(subtree_backward_kernel, h->n_local, subtree_csize(h, false), SF_NT, SV_SMEM, st, h->blocks_dev.p,
                      h->plans_dev.p, h->ywork.p, h->vec_off.p, h->root_x.p, h->root_off.p, dx);
     if (h->max_leaves > 0) {
@@ -1760,6 +1835,14 @@ int64_t pp_kernel_launches(const pp_handle *h) {
   return tot;
 }
 
+#ifdef PP_TRACE_SOLVE
+extern "C" int pp_debug_cs_trace(long long *out, int reset) {
+  if (cudaMemcpyFromSymbol(out, ppb::g_cs_trace, sizeof(long long) * 8) != cudaSuccess) return 3;
+  long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (reset) cudaMemcpyToSymbol(ppb::g_cs_trace, z, sizeof(z));
+  return 0;
+}
+#endif
 #ifdef PP_TRACE
 extern "C" int pp_debug_trace_reset() {
   int z = 0;
