@@ -113,6 +113,7 @@ struct pp_handle {
   bool no_fallback = false;
   bool use_cluster = true;
   bool panel_onchip = true;       // cluster panel kernel with the panel's rows of L in registers / shared memory
+  bool panel_spec = true;         // speculative panel: all diagonals assumed to pass, one reduction per panel
   int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
   int overlap_groups = 2;         // groups of fronts on separate streams: panels of one overlap updates of the others
   std::vector<cudaStream_t> aux_streams;
@@ -376,7 +377,7 @@ void factor_group(pp_handle *h, int first, int count, cudaStream_t st) {
       ProfSpan sp(h, PP_PROF_PANEL, st);
       if (small) {
         front_panel_kernel<128><<<count, 128, 0, st>>>(fr, NB, h->pivot_tol);
-      } else if (csize > 1) {
+      } else if (csize > 1 || (h->panel_spec && h->panel_onchip)) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(count * csize);
         cfg.blockDim = dim3(PC_NT);
@@ -391,7 +392,7 @@ void factor_group(pp_handle *h, int first, int count, cudaStream_t st) {
         cfg.numAttrs = 1;
         if (h->panel_onchip) {
           cfg.dynamicSmemBytes = OC_SMEM;
-          CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_oc_kernel, fr, NB, h->pivot_tol));
+          CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_oc_kernel, fr, NB, h->pivot_tol, h->panel_spec ? 1 : 0));
         } else {
           CK(cudaLaunchKernelEx(&cfg, front_panel_cluster_kernel, fr, NB, h->pivot_tol));
         }
@@ -570,6 +571,8 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->use_sparse = value != 0.0;
   } else if (key == "panel_onchip") {
     h->panel_onchip = value != 0.0;
+  } else if (key == "panel_spec") {
+    h->panel_spec = value != 0.0;
   } else if (key == "cluster_size") {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("cluster_size must be 0, 1, 2, 4 or 8");
@@ -1118,6 +1121,7 @@ static int setup_coupling(pp_handle *h) {
   c->panel_width = h->panel_width;
   c->use_cluster = h->use_cluster;
   c->panel_onchip = h->panel_onchip;
+  c->panel_spec = h->panel_spec;
   c->use_small = h->use_small;
   c->overlap_groups = h->overlap_groups;
   c->use_sparse = false;     // the blocks of S are dense
@@ -1836,6 +1840,12 @@ int64_t pp_kernel_launches(const pp_handle *h) {
 }
 
 #ifdef PP_TRACE_SOLVE
+extern "C" int pp_debug_pc_trace(long long *out, int reset) {
+  if (cudaMemcpyFromSymbol(out, ppb::g_pc_trace, sizeof(long long) * 24) != cudaSuccess) return 3;
+  long long z[24] = {0};
+  if (reset) cudaMemcpyToSymbol(ppb::g_pc_trace, z, sizeof(z));
+  return 0;
+}
 extern "C" int pp_debug_cs_trace(long long *out, int reset) {
   if (cudaMemcpyFromSymbol(out, ppb::g_cs_trace, sizeof(long long) * 8) != cudaSuccess) return 3;
   long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};

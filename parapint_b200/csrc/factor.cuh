@@ -428,11 +428,28 @@ __global__ void front_swaps_left_kernel(const Front *__restrict__ fronts) {
 }
 
 // The same panel factorisation with the panel's rows of L kept on chip (see inside).  Used when fronts are tall and few.
+#ifdef PP_TRACE_SOLVE
+__device__ long long g_pc_trace[24];
+#define PC_TR(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); g_pc_trace[k] += t_ - t_last; t_last = t_; } } while (0)
+#define PC_CNT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_pc_trace[k] += 1; } while (0)
+#else
+#define PC_TR(k) do { } while (0)
+#define PC_CNT(k) do { } while (0)
+#endif
+// exact maximum over a warp of the bit patterns of non-negative doubles (two 32-bit redux.sync operations)
+__device__ __forceinline__ unsigned long long warp_max_bits(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned lo = hi == mh ? (unsigned)v : 0u;
+  const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 constexpr int OC_REG = 16, OC_SM = NBMAX - OC_REG;
-constexpr size_t OC_SMEM = (size_t)OC_SM * PC_NT * sizeof(double);
+constexpr size_t OC_SMEM = ((size_t)OC_SM * PC_NT + (size_t)NBMAX * NBMAX) * sizeof(double);
 
 __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Front *__restrict__ fronts, int NB,
-                                                                    double pivtol) {
+                                                                    double pivtol, int spec) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
   const int C = (int)cl.num_blocks(), rank = (int)cl.block_rank();
@@ -458,19 +475,25 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
   // ([column][thread]: conflict-free).  Rows are dealt once per panel (row0 = k0 + gtid), not per column, so the
   // lazy sweep of a column is kw fused multiply-adds from registers / shared memory instead of kw loads from L2
   // (130 kB per CTA and column at 4 000 rows).  Rows beyond the first GT of a very tall front use the L2 path.
-  extern __shared__ double Ls[];  // [OC_SM][PC_NT]
+  extern __shared__ double Ls[];  // [OC_SM][PC_NT], then (speculative prologue) the NBMAX x NBMAX diagonal block
+  double *const Wd = Ls + (size_t)OC_SM * PC_NT;
+  __shared__ unsigned long long s_colmax[NBMAX];
+  __shared__ double s_rd[NBMAX];
+  __shared__ unsigned s_bad[2];
+  __shared__ int s_nacc;
   double Lr[OC_REG];
 #pragma unroll
   for (int j = 0; j < OC_REG; ++j) Lr[j] = 0.0;
   const int row0 = k0 + gtid;
-  auto dot_onchip = [&](int kw) {
+  auto dot_row = [&](int kw, const double *__restrict__ wr) {
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < OC_REG; ++j)
-      if (j < kw) acc += Lr[j] * wrow[j];
-    for (int j = OC_REG; j < kw; ++j) acc += Ls[(j - OC_REG) * PC_NT + tid] * wrow[j];
+      if (j < kw) acc += Lr[j] * wr[j];
+    for (int j = OC_REG; j < kw; ++j) acc += Ls[(j - OC_REG) * PC_NT + tid] * wr[j];
     return acc;
   };
+  auto dot_onchip = [&](int kw) { return dot_row(kw, wrow); };
   auto store_onchip = [&](int slot, double v) {
     if (slot < OC_REG) {
 #pragma unroll
@@ -483,11 +506,185 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
 
   const bool last_panel = (n - k0 <= NB);
   int k = k0;
+  if (spec) {
+    // ---- speculative panel ---------------------------------------------------------------------------------
+    // Measured on the 4 082 columns of a config-5 root and its coupling front: every column accepts its diagonal at
+    // once (no second column, no interchange, no 2x2 pivot), and each still pays a cluster-wide arg-max.  So the
+    // panel is first factorised AS IF every diagonal passed: (A) the CTA that owns the panel's rows factorises the
+    // w x w diagonal block in shared memory (right-looking, one barrier per column); (B) every row then runs its own
+    // w-column recurrence
+    //   W(i,c) = A(i,c) - sum_{j<c} L(i,j) W(c,j),  L(i,c) = W(i,c) / d_c
+    // against that block with no communication at all, row chunk by row chunk with the chunk's L on chip, writing W
+    // and folding |W(i,c)| into per-column maxima; (C) ONE reduction over the cluster gives all w column maxima and
+    // the Bunch-Kaufman tests are checked in order.  Columns before the first failure are exactly what the
+    // column-by-column loop below would have produced (same tests, same pivots) and are committed; from the failing
+    // column on that loop takes over for the rest of the panel.
+    const int w = last_panel ? n - k0 : NB - 1;
+#ifdef PP_TRACE_SOLVE
+    long long t_last = clock64();
+#endif
+    PC_CNT(23);
+    for (int idx = tid; idx < NBMAX * NBMAX; idx += PC_NT) {
+      const int r = idx % NBMAX, c = idx / NBMAX;   // Wd[c * NBMAX + r] = entry (row k0 + r, column k0 + c), r >= c
+      Wd[idx] = (r < w && c <= r) ? A[(k0 + r) + (size_t)(k0 + c) * ld] : 0.0;
+    }
+    if (tid < NBMAX) s_colmax[tid] = 0ull;
+    __syncthreads();
+    PC_TR(12);
+    if (rank == 0) {
+      // (A) the diagonal block, right-looking in shared memory with the whole CTA: at step c the remaining lower
+      // triangle takes the rank-one update of column c (every entry receives its updates in ascending column order,
+      // as the rows below do), one barrier per column; column c is left holding W(:, c)
+      for (int c = 0; c < w; ++c) {
+        const double rd = __drcp_rn(Wd[c * NBMAX + c]);
+        if (tid == 0) s_rd[c] = rd;
+        const int m = w - 1 - c;
+        for (int idx = tid; idx < m * m; idx += PC_NT) {
+          const int rr = c + 1 + idx % m, cc = c + 1 + idx / m;   // consecutive threads walk down a column
+          if (cc <= rr) Wd[cc * NBMAX + rr] -= (Wd[c * NBMAX + rr] * rd) * Wd[c * NBMAX + cc];
+        }
+        __syncthreads();
+      }
+      // column maxima of the block's part of the tests, and the block itself (W of the panel's rows) to global
+      // memory: for the other CTAs and for the update kernel
+      for (int c = tid >> 5; c < w; c += PC_NT / 32) {
+        const int l = tid & 31;
+        double mx = 0.0;
+        for (int r = c + 1 + l; r < w && k0 + r < n; r += 32) mx = fmax(mx, fabs(Wd[c * NBMAX + r]));
+        const unsigned long long mb = warp_max_bits((unsigned long long)__double_as_longlong(mx));
+        if (l == 0) s_colmax[c] = mb;
+      }
+      for (int idx = tid; idx < NBMAX * NBMAX; idx += PC_NT) {
+        const int r = idx % NBMAX, c = idx / NBMAX;
+        if (r < w && c <= r) W[(k0 + r) + (size_t)c * ld] = Wd[idx];
+      }
+    }
+    PC_TR(13);
+    if (C > 1) { __threadfence(); cl.sync(); } else __syncthreads();
+    PC_TR(14);
+    if (rank != 0) {
+      for (int idx = tid; idx < NBMAX * NBMAX; idx += PC_NT) {
+        const int r = idx % NBMAX, c = idx / NBMAX;
+        Wd[idx] = (r < w && c <= r) ? W[(k0 + r) + (size_t)c * ld] : 0.0;
+      }
+      __syncthreads();
+    }
+    if (rank != 0 && tid < NBMAX) s_rd[tid] = tid < w ? __drcp_rn(Wd[tid * NBMAX + tid]) : 0.0;
+    __syncthreads();
+    // (B) rows below the block, one chunk of GT rows at a time (the chunk's L lives in Lr / Ls); rows are dealt as
+    // in the loop below: row0, row0 + GT, ...
+    for (int i = row0;; i += GT) {
+      if (!__syncthreads_or(i < nf)) break;   // uniform exit: every thread of the CTA is past the last row
+      const bool on = i >= k0 + w && i < nf;
+      // eight columns at a time: the part against the columns before the block is a small GEMV in which one entry
+      // of this row's L meets eight multipliers (two 16-byte broadcast loads per pair), then the 8 x 8 triangle
+      for (int c0 = 0; c0 < w; c0 += 8) {
+        double acc[8], lb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = (on && c0 + q < w) ? A[i + (size_t)(k0 + c0 + q) * ld] : 0.0;
+        auto gemv8 = [&](double lj, int j) {
+          const double2 *mp = reinterpret_cast<const double2 *>(Wd + j * NBMAX + c0);   // W(c0 .. c0+7, j)
+          const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+          acc[0] -= lj * m0.x; acc[1] -= lj * m0.y; acc[2] -= lj * m1.x; acc[3] -= lj * m1.y;
+          acc[4] -= lj * m2.x; acc[5] -= lj * m2.y; acc[6] -= lj * m3.x; acc[7] -= lj * m3.y;
+        };
+        if (c0 >= 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gemv8(Lr[j], j);
+        }
+        if (c0 >= 16) {
+#pragma unroll
+          for (int j = 8; j < 16; ++j) gemv8(Lr[j], j);
+        }
+        for (int j = OC_REG; j < c0; ++j) gemv8(Ls[(j - OC_REG) * PC_NT + tid], j);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = c0 + q;
+#pragma unroll
+          for (int pq = 0; pq < 8; ++pq)
+            if (pq < q) acc[q] -= lb[pq] * Wd[(c0 + pq) * NBMAX + c];
+          lb[q] = c < w ? acc[q] * s_rd[c] : 0.0;
+          if (on && c < w) {
+            W[i + (size_t)c * ld] = acc[q];
+            store_onchip(c, lb[q]);
+          }
+          const unsigned long long mb =
+              warp_max_bits((on && c < w && i < n) ? (unsigned long long)__double_as_longlong(fabs(acc[q])) : 0ull);
+          if ((tid & 31) == 0 && mb > *((volatile unsigned long long *)&s_colmax[c < w ? c : 0])) atomicMax(&s_colmax[c], mb);
+        }
+      }
+    }
+    __syncthreads();
+    PC_TR(15);
+    // (C) column maxima over the cluster (the chunk scratch is free now: Ls doubles as the exchange area)
+    unsigned long long *xcm = reinterpret_cast<unsigned long long *>(Ls);
+    if (C > 1) {
+      cl.sync();   // every CTA is done with its Ls before anybody writes into it remotely
+      if (tid < NBMAX)
+        for (int q = 0; q < C; ++q) cl.map_shared_rank(xcm, q)[rank * NBMAX + tid] = s_colmax[tid];
+      cl.sync();
+      if (tid < NBMAX) {
+        unsigned long long m = 0ull;
+        for (int q = 0; q < C; ++q) m = max(m, xcm[q * NBMAX + tid]);
+        s_colmax[tid] = m;
+      }
+      __syncthreads();
+    }
+    if (tid < NBMAX) {
+      bool ok = true;
+      if (tid < w) {
+        const double d = Wd[tid * NBMAX + tid], absakk = fabs(d);
+        const double colmax = __longlong_as_double((long long)s_colmax[tid]);
+        ok = (fmax(absakk, colmax) > pivtol) && (absakk >= BK_ALPHA * colmax) && (absakk > pivtol) && isfinite(d);
+      }
+      const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+      if ((tid & 31) == 0) s_bad[tid >> 5] = bad;
+    }
+    __syncthreads();
+    if (tid == 0) s_nacc = s_bad[0] ? __ffs(s_bad[0]) - 1 : (s_bad[1] ? 32 + __ffs(s_bad[1]) - 1 : w);
+    __syncthreads();
+    const int nacc = s_nacc;
+    PC_TR(16);
+    // commit the accepted columns: L = W / d (the same expression the column-by-column loop uses), pivot records
+    for (int i = k0 + 1 + gtid; i < nf; i += GT) {   // row i gets its entries of the columns c < min(nacc, i - k0)
+      const int cend = min(nacc, i - k0);
+      for (int c0 = 0; c0 < cend; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = c0 + q < cend ? W[i + (size_t)(c0 + q) * ld] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < cend) A[i + (size_t)(k0 + c0 + q) * ld] = v[q] * s_rd[c0 + q];
+      }
+    }
+    if (gtid < nacc) {
+      A[(k0 + gtid) + (size_t)(k0 + gtid) * ld] = Wd[gtid * NBMAX + gtid];
+      F.ipiv[k0 + gtid] = k0 + gtid;
+      F.bsz[k0 + gtid] = 1;
+    }
+    k = k0 + nacc;
+    PC_TR(17);
+    if (k < n && (last_panel || (k - k0) < NB - 1)) {
+      // a column failed its test: the general loop continues from it; this thread's first row goes back on chip
+      if (C > 1) { __threadfence(); cl.sync(); } else __syncthreads();
+#pragma unroll
+      for (int j = 0; j < OC_REG; ++j) Lr[j] = 0.0;
+      if (row0 < nf)
+        for (int j = 0; j < nacc; ++j) store_onchip(j, row0 > k0 + j ? A[row0 + (size_t)(k0 + j) * ld] : 0.0);
+      __syncthreads();
+    }
+  }
+#ifdef PP_TRACE_SOLVE
+  long long t_last = clock64();
+#endif
   while (k < n && (last_panel || (k - k0) < NB - 1)) {
     const int kw = k - k0;
     double *__restrict__ Wk = W + (size_t)kw * ld;
+    PC_TR(0);
+    PC_CNT(8);
     for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[k + (size_t)j * ld];
     __syncthreads();
+    PC_TR(1);
     double best = -1.0, akk = 0.0;
     int besti = -1;
     for (int i = row0; i < nf; i += GT) {
@@ -507,7 +704,9 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
       }
       if (i == k) s_akk = acc;  // travels with the exchange from the CTA that owns row k
     }
+    PC_TR(2);
     cluster_argmax(cl, best, besti, akk, sval, sidx, xval, xidx, xextra, parity, &s_akk, ((k - k0) % GT) / PC_NT);
+    PC_TR(3);
     const double colmax = besti >= 0 ? best : 0.0;
     const int imax = besti;
     const double absakk = fabs(akk);
@@ -520,6 +719,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
       kp = k;
     } else {
       double *__restrict__ Wk1 = W + (size_t)(kw + 1) * ld;
+      PC_CNT(9);
       for (int j = tid; j < kw; j += PC_NT) wrow[j] = W[imax + (size_t)j * ld];
       __syncthreads();
       double rbest = -1.0, wimax = 0.0;
@@ -558,10 +758,12 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
     }
     // everything the interchange below reads was written before the barrier inside the last cluster_argmax --
     // except the copy above, whose rows belong to other CTAs (the decision is the same in every CTA)
+    PC_TR(4);
     if (copied) cl.sync(); else __syncthreads();
 
     const int kk = k + kstep - 1;
     if (kp != kk) {
+      PC_CNT(10);
       if (gtid == 0) {
         A[kp + (size_t)kp * ld] = A[kk + (size_t)kk * ld];
         const int t = F.perm[kk];
@@ -588,6 +790,8 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
         for (int j = 0; j < kw; ++j) store_onchip(j, A[row0 + (size_t)(k0 + j) * ld]);
     }
 
+    PC_TR(5);
+    if (kstep == 2) PC_CNT(11);
     if (kstep == 1) {
       const double d = Wk[k];
       const bool bad = zero_pivot || !(fabs(d) > pivtol) || !isfinite(d);
@@ -634,6 +838,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
     // candidate's diagonal entry travelled with the exchange, and a copy or an interchange is followed by its own
     // cluster barrier above.
     __syncthreads();
+    PC_TR(6);
     k += kstep;
   }
   if (gtid == 0) {
