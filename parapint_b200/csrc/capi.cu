@@ -377,7 +377,8 @@ void factor_group(pp_handle *h, int first, int count, cudaStream_t st) {
       ProfSpan sp(h, PP_PROF_PANEL, st);
       if (small) {
         front_panel_kernel<128><<<count, 128, 0, st>>>(fr, NB, h->pivot_tol);
-      } else if (csize > 1 || (h->panel_spec && h->panel_onchip)) {
+      } else if (csize > 1 || (h->panel_spec && h->panel_onchip && (nfmax >= 1024 || count * 2 <= h->sm_count))) {
+        // (the on-chip kernel needs an SM per CTA: many mid-sized fronts are better off several to an SM below)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(count * csize);
         cfg.blockDim = dim3(PC_NT);

@@ -506,7 +506,12 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
 
   const bool last_panel = (n - k0 <= NB);
   int k = k0;
-  if (spec) {
+  // Speculation pays when the pivots are benign (the generator's KKT blocks: every diagonal passes); on fronts whose
+  // tests fail early (late-IPM blocks with delayed pivots) the attempt is wasted, so a panel that committed less than
+  // half of its columns switches speculation off for the front's next three panels (state[3], reset per factorisation).
+  const int spec_penalty = F.state[3];
+  int spec_next = spec_penalty > 0 ? spec_penalty - 1 : 0;
+  if (spec && spec_penalty == 0) {
     // ---- speculative panel ---------------------------------------------------------------------------------
     // Measured on the 4 082 columns of a config-5 root and its coupling front: every column accepts its diagonal at
     // once (no second column, no interchange, no 2x2 pivot), and each still pays a cluster-wide arg-max.  So the
@@ -644,6 +649,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
     if (tid == 0) s_nacc = s_bad[0] ? __ffs(s_bad[0]) - 1 : (s_bad[1] ? 32 + __ffs(s_bad[1]) - 1 : w);
     __syncthreads();
     const int nacc = s_nacc;
+    if (2 * nacc < w) spec_next = 3;
     PC_TR(16);
     // commit the accepted columns: L = W / d (the same expression the column-by-column loop uses), pivot records
     for (int i = k0 + 1 + gtid; i < nf; i += GT) {   // row i gets its entries of the columns c < min(nacc, i - k0)
@@ -844,6 +850,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
   if (gtid == 0) {
     F.state[ST_KPREV] = k0;
     F.state[ST_KCUR] = k;
+    F.state[3] = spec_next;
   }
 }
 

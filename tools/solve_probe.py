@@ -6,9 +6,10 @@ from oracle.kkt_generator import EstimationModel
 from parapint_b200 import B200SchurComplementLinearSolver
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 groups = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+extra = dict(kv.split("=") for kv in sys.argv[3:])
 m = EstimationModel(nb, 2000, 4, 2000)
 kkt, rhs = m.build_kkt(), m.build_rhs()
-s = B200SchurComplementLinearSolver(options={"profile": 1, "overlap_groups": groups})
+s = B200SchurComplementLinearSolver(options={"profile": 1, "overlap_groups": groups, **{k: float(v) for k, v in extra.items()}})
 s.do_symbolic_factorization(kkt)
 for _ in range(2):
     s.do_numeric_factorization(kkt); x = s.do_back_solve(rhs)
@@ -19,7 +20,7 @@ for _ in range(reps):
     s.do_numeric_factorization(kkt); x = s.do_back_solve(rhs)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / reps * 1e3
 p = s.backend.profile()
-print(f"blocks {nb} groups {groups}: step {dt:.2f} ms  " + "  ".join(f"{k} {v['ms']/reps:.2f}" for k, v in p.items()), flush=True)
+print(f"blocks {nb} groups {groups} {extra}: step {dt:.2f} ms  " + "  ".join(f"{k} {v['ms']/reps:.2f}" for k, v in p.items()), flush=True)
 print("inertia ok", s.get_inertia() == m.expected_inertia(), "residual", s.last_residual, "max_err", m.check_result(x))
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(reps):
