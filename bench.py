@@ -216,7 +216,7 @@ def run_leg(name, kkt, rhs, comm, dev, flush, reps=3, warmup=2, options=None, ex
     def dev_step():
         flush.fill_(1.0)
         _, s_local = be.numeric_local_device(values_dev)
-        comm.allreduce_sum_(s_local)
+        s_local = comm.allreduce_sum_(s_local)
         code = be.numeric_coupling(s_local)
         be.inertia_coupling()
         be.solve_device(rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=comm.allreduce_sum_)
@@ -616,7 +616,7 @@ def main():
     def dev_step():
         flush.fill_(1.0)
         code, s_local = be.numeric_local_device(values_dev)
-        comm.allreduce_sum_(s_local)
+        s_local = comm.allreduce_sum_(s_local)
         code2 = be.numeric_coupling(s_local)
         loc = be.inertia_local()
         cpl = be.inertia_coupling()

@@ -251,6 +251,20 @@ int pp_stage_values(pp_handle *h, int64_t nseg, void *const *ptr, const int64_t 
                     void *staging, int threads, int chunks, void *stream);
 
 /*
+ * One-shot all-reduce (SUM) of a small device buffer over peer memory -- the exchange step of the path
+ * (mpi_explicit_schur_complement.py:343 for the S values, :387 for the coupling right-hand side) when the payload
+ * is latency-bound (20 kB and 400 B at BASELINE config 2).  bufs[q] / signal_pads[q] are rank q's contribution buffer
+ * and signal pad as mapped in THIS process (e.g. torch symmetric memory: buffer_ptrs, signal_pad_ptrs); `slot` is
+ * the first of `world` 32-bit words of the pads reserved for this channel; `seq` is a sequence number that every
+ * rank increases by one per call on the channel (the pads start at zero, the first call uses 1).  One kernel on
+ * `stream`: announce, wait for the peers, add the contributions in rank order into out_dev (n doubles, local).
+ * Every rank gets bit-identical sums.  The caller must not rewrite a contribution buffer before the NEXT call on the
+ * channel has been enqueued on every rank (use two buffers alternately).
+ */
+int pp_peer_allreduce(int world, int rank, const void *const *bufs, void *const *signal_pads, int slot, uint32_t seq,
+                      int64_t n, double *out_dev, void *stream);
+
+/*
  * Per-kernel-class device timing (measurement aid; enabled with pp_set_option(h, "profile", 1)).
  * CUDA events are recorded on the launching stream around every launch of each class; this call
  * waits for them and returns accumulated milliseconds and launch counts per class.

@@ -20,6 +20,7 @@
 #include "symbolic.hpp"
 #include "hostcopy.hpp"
 #include "coupling.hpp"
+#include "peer.cuh"
 #include <map>
 
 using namespace ppb;
@@ -1923,6 +1924,25 @@ int pp_host_equal(int64_t nseg, void *const *a, void *const *b, const int64_t *l
     return PP_ERROR;
   }
   return PP_SUCCESSFUL;
+}
+
+int pp_peer_allreduce(int world, int rank, const void *const *bufs, void *const *signal_pads, int slot, uint32_t seq,
+                      int64_t n, double *out_dev, void *stream) {
+  if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || !bufs || !signal_pads || n < 0 || slot < 0 ||
+      (n > 0 && !out_dev) || n > (1 << 24))
+    return misuse("pp_peer_allreduce: bad argument");
+  return guarded([&]() {
+    PeerPtrs P;
+    for (int q = 0; q < PEER_MAX; ++q) {
+      P.buf[q] = q < world ? static_cast<const double *>(bufs[q]) : nullptr;
+      P.sig[q] = q < world ? static_cast<uint32_t *>(signal_pads[q]) : nullptr;
+      if (q < world && (!P.buf[q] || !P.sig[q])) return misuse("pp_peer_allreduce: null peer pointer");
+    }
+    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, (n + 31) / 32 * 32));
+    peer_allreduce_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(P, rank, world, slot, seq, (int)n, out_dev);
+    CK(cudaGetLastError());
+    return (int)PP_SUCCESSFUL;
+  });
 }
 
 int pp_profile(pp_handle *h, double *ms, int64_t *launches, int reset) {

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pp_schur_tail": (C.c_int, [_vp, _f64p]),
     "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "pp_host_equal": (C.c_int, [C.c_int64, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "pp_peer_allreduce": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_uint32, C.c_int64, _vp, _vp]),
     "pp_stage_values": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
     "pp_local_dim": (C.c_int64, [_vp]),

@@ -78,7 +78,16 @@ class CudaBackend:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _release_exchange(self):
+        comm = getattr(self, "_comm", None)
+        if comm is not None:
+            for bufs in (getattr(self, "_schur_bufs", None), getattr(self, "_rc_bufs", None), getattr(self, "_res_bufs", None)):
+                comm.release_buffers(bufs)
+        self._schur_bufs = self._rc_bufs = self._res_bufs = None
+
     def close(self):
+        # (peer-mapped exchange buffers are NOT handed back here: close() may run from the garbage collector, at
+        #  different moments on different ranks, and the pool must evolve identically everywhere)
         if getattr(self, "handle", None) is not None and self.handle:
             self.lib.pp_destroy(self.handle)
             self.handle = C.c_void_p()
@@ -90,8 +99,9 @@ class CudaBackend:
             pass
 
     # -- buffers -----------------------------------------------------------------------------
-    def symbolic(self, st: structure.Structure, values_hint=None, cliques=None):
-        """``cliques``: (ptr, rows) of the nonzero border rows of the blocks of ALL ranks (several ranks only)."""
+    def symbolic(self, st: structure.Structure, values_hint=None, cliques=None, comm=None):
+        """``cliques``: (ptr, rows) of the nonzero border rows of the blocks of ALL ranks (several ranks only);
+        ``comm``: the communicator that will reduce the exchange buffers (it may hand out peer-mapped ones)."""
         torch = self.torch
         self.st = st
         if cliques is not None:
@@ -113,10 +123,20 @@ class CudaBackend:
             return code
         mc = max(st.m_c, 1)
         self.schur_size = int(self.lib.pp_schur_size(self.handle))   # m_c^2, or the pattern size of a sparse S
+        self._release_exchange()
         with torch.cuda.device(self.device):
-            self.schur = torch.zeros(max(self.schur_size, 1) + SCHUR_TAIL, dtype=torch.float64, device=self.device)
-            self.rc = torch.zeros(mc, dtype=torch.float64, device=self.device)
-            self.resbuf = torch.zeros(mc + 2, dtype=torch.float64, device=self.device)
+            if comm is not None and comm.size > 1:
+                self._comm = comm
+                # the three exchange steps of the path; small ones may get peer-mapped double buffers
+                self._schur_bufs = comm.exchange_buffers(max(self.schur_size, 1) + SCHUR_TAIL, self.device)
+                self._rc_bufs = comm.exchange_buffers(mc, self.device)
+                self._res_bufs = comm.exchange_buffers(mc + 2, self.device)
+            else:
+                self._schur_bufs = [torch.zeros(max(self.schur_size, 1) + SCHUR_TAIL, dtype=torch.float64, device=self.device)]
+                self._rc_bufs = [torch.zeros(mc, dtype=torch.float64, device=self.device)]
+                self._res_bufs = [torch.zeros(mc + 2, dtype=torch.float64, device=self.device)]
+            self._turn = [0, 0, 0]
+            self.schur, self.rc, self.resbuf = self._schur_bufs[0], self._rc_bufs[0], self._res_bufs[0]
         self.values_pin = torch.empty(max(st.nvals, 1), dtype=torch.float64, pin_memory=True)
         self.rhs_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
         self.x_pin = torch.empty(max(st.local_dim, 1), dtype=torch.float64, pin_memory=True)
@@ -143,10 +163,18 @@ class CudaBackend:
     def value_uploads(self):
         return int(self.lib.pp_value_uploads(self.handle))
 
+    def _next(self, which, bufs):
+        """The exchange buffer to fill now: peer-mapped buffers come in pairs used alternately (a contribution may only
+        be rewritten once every rank has passed the following exchange, see ``csrc/peer.cuh``)."""
+        t = bufs[self._turn[which] % len(bufs)]
+        self._turn[which] += 1
+        return t
+
     # -- numeric -----------------------------------------------------------------------------
     def numeric_local(self, reuse=False):
         """Factor the local fronts from ``self.values`` (``reuse``: from the values of the previous call, which are
         still on the device -- a retry with new diagonal shifts); returns (status code, device S_local)."""
+        self.schur = self._next(0, self._schur_bufs)
         if reuse:
             code = self.lib.pp_numeric_local(self.handle, None, 2, C.c_void_p(self.schur.data_ptr()), self._stream())
         else:
@@ -176,6 +204,7 @@ class CudaBackend:
     # -- solve -------------------------------------------------------------------------------
     def solve_forward(self):
         """Forward sweep on ``self.rhs_pin``; returns the device coupling contribution."""
+        self.rc = self._next(1, self._rc_bufs)
         code = self.lib.pp_solve_forward(self.handle, C.c_void_p(self.rhs_pin.data_ptr()), 0,
                                          C.c_void_p(self.rc.data_ptr()), self._stream())
         self._check(code, "pp_solve_forward")
@@ -193,6 +222,7 @@ class CudaBackend:
     def residual_local(self):
         """This rank's part of r = b - K x for the last solve; returns the device buffer
         ``[partial coupling rows (m_c) | |r_loc|^2 | |b_loc|^2]`` the caller sum-reduces."""
+        self.resbuf = self._next(2, self._res_bufs)
         self._check(self.lib.pp_residual_local(self.handle, C.c_void_p(self.resbuf.data_ptr()), self._stream()),
                     "pp_residual_local")
         return self.resbuf
@@ -207,6 +237,7 @@ class CudaBackend:
         return float(out[0]), float(out[1])
 
     def refine_forward(self):
+        self.rc = self._next(1, self._rc_bufs)
         self._check(self.lib.pp_refine_forward(self.handle, C.c_void_p(self.rc.data_ptr()), self._stream()),
                     "pp_refine_forward")
         return self.rc
@@ -220,16 +251,17 @@ class CudaBackend:
 
     # -- device-resident variants (inputs / outputs already in HBM; used by bench.py `value`) ----
     def numeric_local_device(self, values_dev):
+        self.schur = self._next(0, self._schur_bufs)
         code = self.lib.pp_numeric_local(self.handle, C.c_void_p(values_dev.data_ptr()), 1,
                                          C.c_void_p(self.schur.data_ptr()), self._stream())
         return self._check(code, "pp_numeric_local"), self.schur
 
     def solve_device(self, rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=None):
+        self.rc = self._next(1, self._rc_bufs)
         self._check(self.lib.pp_solve_forward(self.handle, C.c_void_p(rhs_dev.data_ptr()), 1,
                                               C.c_void_p(self.rc.data_ptr()), self._stream()), "pp_solve_forward")
-        if reduce is not None:
-            reduce(self.rc)
-        self._check(self.lib.pp_solve_backward(self.handle, C.c_void_p(self.rc.data_ptr()),
+        rc = reduce(self.rc) if reduce is not None else self.rc
+        self._check(self.lib.pp_solve_backward(self.handle, C.c_void_p(rc.data_ptr()),
                                                C.c_void_p(rhsc_dev.data_ptr()), 1, C.c_void_p(x_dev.data_ptr()),
                                                C.c_void_p(xc_dev.data_ptr()), self._stream()), "pp_solve_backward")
 
@@ -387,7 +419,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             parts = self.comm.allgather_object((np.diff(st.border_ptr), st.border_rows))
             lens = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=np.int64)
             cliques = (np.concatenate(([0], np.cumsum(lens))), np.concatenate([p[1] for p in parts]))
-        code = self.backend.symbolic(st, hint, cliques)
+        code = self.backend.symbolic(st, hint, cliques, self.comm)
         self._st = st
         self._status = None
         self.symbolic_calls += 1
@@ -471,7 +503,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         for _ in range(4):
             n_s = be.schur_size
             if changed:
-                schur_local = be.schur
+                schur_local = be.schur = be._next(0, be._schur_bufs) if hasattr(be, "_next") else be.schur
                 schur_local.zero_()
                 schur_local[n_s + 5] = 1.0
                 local_code = -1                       # this rank has nothing factorised
@@ -490,7 +522,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 if local_code in (LinearSolverStatus.error.value, LinearSolverStatus.not_enough_memory.value):
                     schur_local[n_s:n_s + SCHUR_TAIL] = float("nan")   # seen by every rank after the reduction
             timer.start("communicate")
-            self.comm.allreduce_sum_(schur_local)
+            schur_local = self.comm.allreduce_sum_(schur_local)
             timer.stop("communicate")
             if local_code in (0, LinearSolverStatus.singular.value):
                 code = be.numeric_coupling(schur_local)   # reads the reduced tail: same answer on every rank
@@ -543,7 +575,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         rc = be.solve_forward()
         if be.failed:
             rc.fill_(float("nan"))      # a run-time failure on this rank: every rank sees it after the reduction
-        self.comm.allreduce_sum_(rc)
+        rc = self.comm.allreduce_sum_(rc)
         x_local, x_c = be.solve_backward(rc)
         if be.failed and self.comm.size == 1:
             raise RuntimeError(f"back solve failed: {be.last_error}")
@@ -578,21 +610,19 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 r2, b2 = be.residual_norms(None)            # formed by pp_solve_backward ("auto_residual")
             elif getattr(be, "failed", False):
                 # this rank's solve failed at run time: keep the collectives aligned, every rank sees NaN norms
-                buf = be.resbuf
+                buf = be.resbuf = be._next(2, be._res_bufs) if hasattr(be, "_next") else be.resbuf
                 buf.fill_(float("nan"))
                 self.comm.allreduce_sum_(buf)
                 r2 = b2 = float("nan")
             else:
-                buf = be.residual_local()
-                self.comm.allreduce_sum_(buf)
+                buf = self.comm.allreduce_sum_(be.residual_local())
                 r2, b2 = be.residual_norms(buf)
             rel = float(np.sqrt(r2 / b2)) if b2 > 0 else float(np.sqrt(r2))
             stalled = self.last_residual is not None and not rel < 0.25 * self.last_residual
             self.last_residual = rel if self.last_residual is None else min(rel, self.last_residual)
             if stalled or not np.isfinite(rel) or rel <= self.refine_tol or step == self.max_refine:
                 break                                   # converged, or at the floor eps*|K||x|/|b| of this system
-            rc = be.refine_forward()
-            self.comm.allreduce_sum_(rc)
+            rc = self.comm.allreduce_sum_(be.refine_forward())
             x_local, x_c = be.refine_backward(rc)
             self.refine_steps += 1
         return x_local, x_c

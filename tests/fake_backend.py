@@ -38,7 +38,7 @@ class FakeBackend:
     def value_uploads(self):
         return self.uploads
 
-    def symbolic(self, st, values_hint=None, cliques=None):
+    def symbolic(self, st, values_hint=None, cliques=None, comm=None):
         self.st = st
         self.cliques = cliques
         if self.fail_symbolic:
