@@ -732,6 +732,8 @@ def main():
                 "fresh_objects_ms": fresh_ms,
                 "fresh_objects_note": "same step on newly built BlockMatrix / BlockVector objects every time (no identity fast path)"},
         "gpu_launches": int(launches),
+        "exchange": {"small_payloads": "one-shot peer all-reduce over symmetric memory (csrc/peer.cuh)" if comm._peer else
+                     ("none (one rank)" if world == 1 else "NCCL all-reduce"), "fallback_reason": comm.peer_error},
         "roofline": roofline,
         "kernels_ms_per_step": per_step,
         "symbolic": {k: stats[k] for k in ("supernodes", "root_cols", "delay_slots", "nnz_l_subtree", "max_front",

@@ -1939,7 +1939,8 @@ int pp_peer_allreduce(int world, int rank, const void *const *bufs, void *const 
       if (q < world && (!P.buf[q] || !P.sig[q])) return misuse("pp_peer_allreduce: null peer pointer");
     }
     const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, (n + 31) / 32 * 32));
-    peer_allreduce_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(P, rank, world, slot, seq, (int)n, out_dev);
+    const int ctas = (int)std::min<int64_t>(32, std::max<int64_t>(1, (n + 2047) / 2048));   // about two elements per thread
+    peer_allreduce_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>(P, rank, world, slot, seq, (int)n, out_dev);
     CK(cudaGetLastError());
     return (int)PP_SUCCESSFUL;
   });

@@ -36,18 +36,21 @@ __device__ __forceinline__ double ld_peer(const double *p) {  // never from a st
   return v;
 }
 
-// one CTA; flags of channel `slot`: sig[q][slot + r] = last sequence number rank r announced to rank q
+// flags of channel `slot`: sig[q][slot + r] = last sequence number rank r announced to rank q.  A few CTAs: the first
+// one announces, every one waits for the peers' flags itself (no grid barrier) and sums its share of the elements.
 __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerPtrs P, int rank, int world, int slot, uint32_t seq,
                                                               int n, double *__restrict__ out) {
   if ((int)threadIdx.x < world) {
     const int q = threadIdx.x;
-    __threadfence_system();
-    st_release_sys(P.sig[q] + slot + rank, seq);            // "my contribution number seq is complete"
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(P.sig[q] + slot + rank, seq);          // "my contribution number seq is complete"
+    }
     const uint32_t *mine = P.sig[rank] + slot + q;
     while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) { }    // rank q's contribution is complete (wrap-safe)
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double v[PEER_MAX];
 #pragma unroll
     for (int q = 0; q < PEER_MAX; ++q) v[q] = q < world ? ld_peer(P.buf[q] + i) : 0.0;   // all loads in flight

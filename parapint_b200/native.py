@@ -117,7 +117,7 @@ class HostCopier:
         else:
             # share the host cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
             ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-            self.threads = max(1, min(4, (os.cpu_count() or 2) // (2 * ranks)))
+            self.threads = max(1, min(8, (os.cpu_count() or 2) // (2 * ranks)))
         self._keep = None
         self._tables = None
         self.stage = None   # (handle, stream getter): gather straight into a transfer (see copy)
