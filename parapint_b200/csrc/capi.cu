@@ -117,6 +117,7 @@ struct pp_handle {
   bool panel_spec = true;         // speculative panel: all diagonals assumed to pass, one reduction per panel
   int cluster_size = 0;           // 0 = automatic; 1, 2, 4, 8 force the CTAs per front of the cluster panel kernel
   int overlap_groups = 2;         // groups of fronts on separate streams: panels of one overlap updates of the others
+  int update_strip = -1;          // tiles per CTA of the pipelined trailing update: -1 automatic, 0/1 one-tile kernel, 2..8
   std::vector<cudaStream_t> aux_streams;
   std::vector<cudaEvent_t> aux_events;
   cudaEvent_t ev_fork = nullptr;
@@ -410,18 +411,39 @@ void factor_group(pp_handle *h, int first, int count, cudaStream_t st) {
       h->launches++;
     }
     int ntiles = 0;
+    int64_t all_tiles = 0;
     for (int f = first; f < first + count; ++f) {
       if (h->n[f] <= it * (NB - 1)) continue;  // finished in an earlier launch
       // lower bound on the columns done: a root eliminates at least its static columns (nmin), the
       // delayed-pivot slots may be unused
       const int done = std::min(h->nmin[f], (it + 1) * (NB - 1));
       if (done >= h->nf[f]) continue;
-      ntiles = std::max(ntiles, update_tile_count(h->nf[f], done));
+      const int t = update_tile_count(h->nf[f], done);
+      ntiles = std::max(ntiles, t);
+      all_tiles += t;
     }
     if (ntiles > 0) {
       ProfSpan sp(h, PP_PROF_UPDATE, st);
-      dim3 g(ntiles, count);
-      front_update_kernel<<<g, UPD_THREADS, UPD_SMEM, st>>>(fr);
+      // strips of S tiles per CTA (software-pipelined kernel, one CTA per SM) when strips of at least eight tiles still
+      // fill the GPU four times over; otherwise one tile per CTA, two CTAs per SM (measured, tools/update_probe.cu:
+      // 32 / 16 / 4 fronts of the config-5 root shape: 0.96 / 0.51 / 0.16 ms with strips against 1.06 / 0.54 / 0.15 ms)
+      int S = h->update_strip >= 0 ? h->update_strip : (int)std::min<int64_t>(12, all_tiles / (4 * (int64_t)h->sm_count));
+      if (h->update_strip < 0 && S < 8) S = 0;
+      S = std::min(S, UPS_MAX);
+      if (S >= 2) {
+        int nstrips = 0;
+        for (int f = first; f < first + count; ++f) {
+          if (h->n[f] <= it * (NB - 1)) continue;
+          const int done = std::min(h->nmin[f], (it + 1) * (NB - 1));
+          if (done >= h->nf[f]) continue;
+          nstrips = std::max(nstrips, update_strip_count(h->nf[f], done, S));
+        }
+        dim3 g(nstrips, count);
+        front_update_strip_kernel<<<g, UPD_THREADS, UPS_SMEM, st>>>(fr, S);
+      } else {
+        dim3 g(ntiles, count);
+        front_update_kernel<<<g, UPD_THREADS, UPD_SMEM, st>>>(fr);
+      }
       h->launches++;
     }
   }
@@ -510,6 +532,7 @@ int pp_create(int device, pp_handle **out) {
     if ((size_t)optin < SM_SMEM) return fail("pp_create: the device offers too little shared memory per block");
     const auto lim = cudaFuncAttributeMaxDynamicSharedMemorySize;
     CK(cudaFuncSetAttribute(front_update_kernel, lim, (int)UPD_SMEM));
+    CK(cudaFuncSetAttribute(front_update_strip_kernel, lim, (int)UPS_SMEM));
     CK(cudaFuncSetAttribute(front_panel_cluster_oc_kernel, lim, (int)OC_SMEM));
     CK(cudaFuncSetAttribute(subtree_factor_kernel, lim, (int)SF_SMEM));
     CK(cudaFuncSetAttribute(front_small_kernel, lim, (int)SM_SMEM));
@@ -581,6 +604,10 @@ int pp_set_option(pp_handle *h, const char *name, double value) {
     h->cluster_size = c;
   } else if (key == "overlap_groups") {
     h->overlap_groups = std::max(1, std::min((int)value, 8));
+  } else if (key == "update_strip") {
+    const int c = (int)value;
+    if (c < -1 || c > UPS_MAX) return misuse("update_strip must be -1 (automatic) or in [0, 16]");
+    h->update_strip = c;
   } else if (key == "subtree_cluster") {
     const int c = (int)value;
     if (c != 0 && c != 1 && c != 2 && c != 4 && c != 8) return misuse("subtree_cluster must be 0, 1, 2, 4 or 8");
@@ -1126,6 +1153,7 @@ static int setup_coupling(pp_handle *h) {
   c->panel_spec = h->panel_spec;
   c->use_small = h->use_small;
   c->overlap_groups = h->overlap_groups;
+  c->update_strip = h->update_strip;
   c->use_sparse = false;     // the blocks of S are dense
   c->defer_status = 1;
   rc = pp_symbolic(c, L.n_blocks, L.block_n.data(), L.border_ptr.data(), L.border_rows.data(), L.m_next, nnz,

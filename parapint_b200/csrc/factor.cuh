@@ -865,6 +865,13 @@ constexpr int UCOL = UTN + 4;
 constexpr int UPD_THREADS = 256;
 constexpr size_t UPD_SMEM = (size_t)NBMAX * (UROW + UCOL) * sizeof(double);  // 100 KB: two CTAs per SM
 
+#ifdef PP_UPDATE_PROBE
+__device__ int g_update_probe = 0;
+#define UPD_PROBE(bit) (g_update_probe & (bit))
+#else
+#define UPD_PROBE(bit) 0
+#endif
+
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -903,6 +910,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) front_update_kernel(const Fron
   if (ti >= tend) return;
   const int tj = c0 + rem;
   const int row0 = ti * UT, col0 = tj * UTN;
+  // rows / columns [n, nb) are the unused delayed-pivot slots: exactly zero in A, L and W, nothing to update
+  if ((row0 >= F.n && row0 + UT <= F.nb) || (col0 >= F.n && col0 + UTN <= F.nb)) return;
 
   extern __shared__ __align__(16) double smem[];
   double *sA = smem;                 // [kpad][UROW]  L(row0 + r, kprev + k)
@@ -937,7 +946,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) front_update_kernel(const Fron
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int r = rbase + fm * 8, c = cbase + fn * 8 + e;
-          const bool ok = r < nf && c >= kcur && r >= c;
+          const bool ok = r < nf && c >= kcur && r >= c && !UPD_PROBE(1);
           acc[fm][fn][e] = ok ? F.A[r + (size_t)c * ld] : 0.0;
         }
   }
@@ -947,7 +956,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) front_update_kernel(const Fron
 
   const double *pa = sA + q * UROW + wm * 32 + g;
   const double *pb = sB + q * UCOL + wn * 32 + g;
-  for (int k = 0; k < kpad; k += 4) {
+  for (int k = 0; k < (UPD_PROBE(8) ? 4 : kpad); k += 4) {
     double a[4], b[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
@@ -966,8 +975,250 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) front_update_kernel(const Fron
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int r = rbase + fm * 8, c = cbase + fn * 8 + e;
-        if (r < nf && c >= kcur && r >= c) F.A[r + (size_t)c * ld] = acc[fm][fn][e];
+        if (r < nf && c >= kcur && r >= c && !(UPD_PROBE(2) && acc[fm][fn][e] != 1.2345e300)) F.A[r + (size_t)c * ld] = acc[fm][fn][e];
       }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same update, software-pipelined.  One CTA per *strip*: up to `S` consecutive 128 x 64 tiles of one tile row.
+//
+// What bounds the one-tile kernel above (tools/update_probe.cu, 32 fronts of the config-5 root shape, one launch):
+// full 1.06 ms; staging of the L / W panels alone 0.35 ms (96 KB per tile out of L2 = 4.1 TB/s); C in + out without
+// the k-loop 0.78 ms; k-loop + staging without any C traffic 0.89 ms; the useful flops at the DMMA peak 0.52 ms.
+// Every tile moves 224 KB between L2 and the SM for 1.05 MFLOP, nothing of it under the tile's own k-loop.
+// Here: the strip's 128 rows of L (A operand, 64 KB) are staged once and stay in shared memory (5 KB per tile at
+// S = 12 instead of 64); the W rows (B operand, 32 KB) and the OLD VALUES OF THE C TILE (64 KB) of tile t + 1 arrive by
+// cp.async -- 16 B per thread, whole 128 B lines per request, two running pointers per thread and tile -- while the
+// tensor pipe works on tile t, so a tile costs 165 KB of traffic.  At the start of a tile the accumulators are loaded
+// from the staged C tile (acc = C, acc += (-L) W^T with the staged L negated once per strip: the summation order of the
+// kernel above, results are bit-identical), the k-loop reads double-buffered fragments from shared memory, and the
+// results of an interior tile leave from registers four at a time between the DMMA batches of the next tile's k-loop.
+// 204 KB of shared memory, one CTA per SM, 8 warps of 32 x 32.
+// Measured (same probe): 0.96 ms at S = 16, 20.0 TFLOP/s of useful flops = 56 % of cuBLAS DGEMM (22 TFLOP/s counting the
+// diagonal / edge tiles' masked work); ncu stall samples: k-loop 62 %, start of a strip (A panel, nothing to overlap
+// it with at one CTA per SM) 11 %, per-tile staging issue / barriers / accumulator loads 22 %.  A rank-64 update is
+// balanced between the tensor pipe (0.57 ms) and the C stream (2.6 GB, 0.57 ms at 4.5 TB/s): what is left needs fewer
+// passes over C (rank-128 updates), not a better pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int UCP = UT + 2;       // pitch of the staged C tile: 2 * UCP % 16 == 4 -> conflict-free accumulator loads
+constexpr size_t UPS_SMEM = ((size_t)NBMAX * (UROW + 2 * UCOL) + (size_t)UTN * UCP) * sizeof(double);  // 203 776 B
+constexpr int UPS_MAX = 16;  // longest strip (tiles)
+
+// strips of the trailing region that starts at `kcur`: every tile row's tiles are cut into ceil(cnt / S) nearly equal runs
+__host__ __device__ inline int update_strip_count(int nf, int kcur, int S) {
+  const int t0 = kcur / UT, c0 = kcur / UTN, tend = (nf + UT - 1) / UT, cend = (nf + UTN - 1) / UTN;
+  int total = 0;
+  for (int t = t0; t < tend; ++t) total += (min(2 * t + 2, cend) - c0 + S - 1) / S;
+  return total;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS, 1) front_update_strip_kernel(const Front *__restrict__ fronts, int S) {
+  const Front F = fronts[blockIdx.y];
+  const int kprev = F.state[ST_KPREV], kcur = F.state[ST_KCUR];
+  const int kw = kcur - kprev;
+  const int nf = F.nf, ld = F.ld;
+  if (kw == 0 || kcur >= nf) return;
+  const int t0 = kcur / UT, c0 = kcur / UTN, tend = (nf + UT - 1) / UT, cend = (nf + UTN - 1) / UTN;
+  int rem = blockIdx.x, ti = t0, cnt = 0, ns = 0;
+  for (; ti < tend; ++ti) {
+    cnt = min(2 * ti + 2, cend) - c0;
+    ns = (cnt + S - 1) / S;
+    if (rem < ns) break;
+    rem -= ns;
+  }
+  if (ti >= tend) return;
+  // run `rem` of `ns` nearly equal runs of the row's `cnt` tiles
+  const int base = cnt / ns, extra = cnt % ns;
+  const int tj0 = c0 + rem * base + min(rem, extra);
+  const int ntj = base + (rem < extra ? 1 : 0);
+  const int row0 = ti * UT;
+  // rows / columns [n, nb) are the unused delayed-pivot slots: exactly zero in A, L and W, nothing to update
+  const int gap0 = F.n, gap1 = F.nb;
+  if (row0 >= gap0 && row0 + UT <= gap1) return;
+
+  extern __shared__ __align__(16) double smem[];
+  double *sA = smem;                                  // [kpad][UROW]     -L(row0 + r, kprev + k)
+  double *sB = smem + NBMAX * UROW;                   // 2 x [kpad][UCOL] W(col0 + c, k) of the current / next tile
+  double *sC = smem + NBMAX * (UROW + 2 * UCOL);      // [UTN][UCP]       old A(row0 + r, col0 + c) of the NEXT tile
+  const int kpad = (kw + 7) & ~7;
+  const int tid = threadIdx.x;
+  {
+    const double *gA = F.A + (size_t)kprev * ld + row0;
+    for (int idx = tid; idx < kpad * (UT / 2); idx += UPD_THREADS) {
+      const int k = idx / (UT / 2), r = (idx % (UT / 2)) * 2;
+      const bool ok = k < kw && row0 + r < nf;
+      cp_async16(sA + k * UROW + r, ok ? gA + (size_t)k * ld + r : F.A, ok);
+    }
+  }
+  auto skipped = [&](int tj) { return tj * UTN >= gap0 && tj * UTN + UTN <= gap1; };
+  // Staging of tile tj: W rows and old C values, one cp.async group.  Thread `tid` always moves the same 16-byte
+  // column of the W block (rows k = tid / 32 + 8 j) and of the C tile (columns c = tid / 64 + 4 j): two running
+  // pointers per tile, no index arithmetic per request.
+  const int brow = tid >> 5, bcol = (tid & 31) * 2;   // W: k = brow + 8 j, entries col0 + bcol, + 1
+  const int ccol = tid >> 6, crow = (tid & 63) * 2;   // C: column col0 + ccol + 4 j, rows row0 + crow, + 1
+  const double *const wsrc0 = F.W + (size_t)brow * ld + bcol;
+  const double *const csrc0 = F.A + (size_t)ccol * ld + row0 + crow;
+  const bool full_k = kw == kpad;
+  auto stage = [&](int tj, int buf) {
+    if (!skipped(tj)) {
+      const int col0 = tj * UTN;
+      double *dst = sB + buf * NBMAX * UCOL + brow * UCOL + bcol;
+      const double *src = wsrc0 + col0;
+      if (full_k && col0 + UTN <= nf) {
+#pragma unroll
+        for (int j = 0; j < NBMAX / 8; ++j) cp_async16(dst + j * 8 * UCOL, src + (size_t)j * 8 * ld, true);
+      } else {
+        for (int j = 0; j < kpad / 8; ++j) {
+          const bool ok = brow + 8 * j < kw && col0 + bcol < nf;
+          cp_async16(dst + j * 8 * UCOL, ok ? src + (size_t)j * 8 * ld : F.A, ok);
+        }
+      }
+      double *cd = sC + ccol * UCP + crow;
+      const double *cs = csrc0 + (size_t)col0 * ld;
+      if (UPD_PROBE(1)) {
+      } else if (row0 >= col0 + UTN - 1 && row0 + UT <= nf) {   // whole tile on or below the diagonal, inside the front
+#pragma unroll
+        for (int j = 0; j < UTN / 4; ++j) cp_async16(cd + j * 4 * UCP, cs + (size_t)j * 4 * ld, true);
+      } else {
+        // rows in pairs: a pair is fetched when its second row can hold an entry on or below the diagonal
+#pragma unroll 4
+        for (int j = 0; j < UTN / 4; ++j) {
+          const int c = col0 + ccol + 4 * j;
+          const bool ok = row0 + crow + 1 >= c && row0 + crow < nf && c < nf;
+          cp_async16(cd + j * 4 * UCP, ok ? cs + (size_t)j * 4 * ld : F.A, ok);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  stage(tj0, 0);  // group 0 = A panel + first tile
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps of 32 x 32
+  const int g = lane >> 2, q = lane & 3;
+  const int rbase = row0 + wm * 32 + g;
+  const double *pa = sA + q * UROW + wm * 32 + g;
+  const double *pc = sC + (wn * 32 + q * 2) * UCP + wm * 32 + g;
+
+  // the A operand is negated once per strip (acc = C, acc += (-L) W^T, store acc: the summation order of the
+  // one-tile kernel), each thread flipping the entries it staged itself
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  for (int idx = tid; idx < kpad * (UT / 2); idx += UPD_THREADS) {
+    double2 *p2 = reinterpret_cast<double2 *>(sA + (idx / (UT / 2)) * UROW + (idx % (UT / 2)) * 2);
+    double2 v = *p2;
+    v.x = -v.x;
+    v.y = -v.y;
+    *p2 = v;
+  }
+
+  // Results of an interior tile are not stored in its own epilogue: they wait in `outv` and leave four at a time
+  // between the DMMA batches of the NEXT tile's k-loop (stores need issue slots only, the loop has fifteen spare per
+  // DMMA), so the tensor pipe does not idle behind 32 store instructions per thread and tile.
+  double outv[4][4][2];
+  double *optr = nullptr;
+  auto flush_from = [&](int first) {
+#pragma unroll
+    for (int ce = 0; ce < 8; ++ce)
+      if (ce >= first) {
+#pragma unroll
+        for (int fm = 0; fm < 4; ++fm) optr[(size_t)((ce >> 1) * 8 + (ce & 1)) * ld + fm * 8] = outv[fm][ce >> 1][ce & 1];
+      }
+    optr = nullptr;
+  };
+
+  for (int t = 0; t < ntj; ++t) {
+    const int col0 = (tj0 + t) * UTN;
+    const int cbase = col0 + wn * 32 + q * 2;
+    const bool active = row0 + wm * 32 + 31 >= col0 + wn * 32 && !skipped(tj0 + t);  // not strictly above the diagonal
+    // all 32 x 32 entries inside the front, right of the eliminated columns and on or below the diagonal
+    const bool interior = active && row0 + wm * 32 >= col0 + wn * 32 + 31 && col0 + wn * 32 >= kcur && row0 + wm * 32 + 31 < nf;
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();  // tile t's W rows and old C values are visible
+    double acc[4][4][2];
+    double a0[4], b0[4], a1[4], b1[4];
+    const double *pb = sB + (t & 1) * NBMAX * UCOL + q * UCOL + wn * 32 + g;
+    if (active) {
+#pragma unroll
+      for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[fm][fn][e] = pc[(fn * 8 + e) * UCP + fm * 8];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {   // first fragments: their latency hides behind the barrier and the staging below
+        a0[f] = pa[f * 8];
+        b0[f] = pb[f * 8];
+      }
+    }
+    __syncthreads();  // sC is free again, and so is the W buffer of tile t - 1
+    if (t + 1 < ntj) stage(tj0 + t + 1, (t + 1) & 1);
+    if (!active) {
+      if (optr) flush_from(0);
+      continue;
+    }
+#pragma unroll
+    for (int it = 0; it < NBMAX / 8; ++it) {
+      const int k = it * 8;
+      if (k < (UPD_PROBE(8) ? 8 : kpad)) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          a1[f] = pa[(k + 4) * UROW + f * 8];
+          b1[f] = pb[(k + 4) * UCOL + f * 8];
+        }
+#pragma unroll
+        for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+          for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a0[fm], b0[fn]);
+        if (optr) {
+#pragma unroll
+          for (int fm = 0; fm < 4; ++fm) optr[(size_t)((it >> 1) * 8 + (it & 1)) * ld + fm * 8] = outv[fm][it >> 1][it & 1];
+        }
+        if (k + 8 < kpad) {
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            a0[f] = pa[(k + 8) * UROW + f * 8];
+            b0[f] = pb[(k + 8) * UCOL + f * 8];
+          }
+        }
+#pragma unroll
+        for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+          for (int fn = 0; fn < 4; ++fn) dmma884(acc[fm][fn][0], acc[fm][fn][1], a1[fm], b1[fn]);
+      }
+    }
+    if (optr) {
+      if (kpad < NBMAX) flush_from(kpad / 8);   // a narrow (last) panel ran fewer batches than there are columns
+      optr = nullptr;
+    }
+    if (UPD_PROBE(2)) {
+      double sum = 0.0;
+#pragma unroll
+      for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) sum += acc[fm][fn][0] + acc[fm][fn][1];
+      if (sum == 1.2345e300) F.A[0] = sum;
+    } else if (interior) {
+      optr = F.A + rbase + (size_t)cbase * ld;
+#pragma unroll
+      for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn) {
+          outv[fm][fn][0] = acc[fm][fn][0];
+          outv[fm][fn][1] = acc[fm][fn][1];
+        }
+    } else {
+#pragma unroll
+      for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+        for (int fn = 0; fn < 4; ++fn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = rbase + fm * 8, c = cbase + fn * 8 + e;
+            if (r < nf && c >= kcur && r >= c) F.A[r + (size_t)c * ld] = acc[fm][fn][e];
+          }
+    }
+  }
+  if (optr) flush_from(0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -221,11 +221,16 @@ def test_iterative_refinement():
 
 @pytest.mark.parametrize("shape,options", [((2, 300, 4, 200), {}), ((2, 800, 3, 800), {}),
                                            ((2, 800, 3, 800), {"panel_onchip": 0}),
-                                           ((2, 800, 3, 800), {"cluster_panel": 0})])
+                                           ((2, 800, 3, 800), {"cluster_panel": 0}),
+                                           ((2, 800, 3, 800), {"update_strip": 2}),
+                                           ((2, 800, 3, 800), {"update_strip": 5, "overlap_groups": 1}),
+                                           ((2, 800, 3, 800), {"update_strip": 8}),
+                                           ((2, 800, 3, 800), {"update_strip": 0})])
 def test_wide_border_sparse_blocks(shape, options):
     """Config-5-shaped blocks (family G with a wide border): sparse subtree + a dense root front of
     `root columns + border rows` factorised by the panel kernel (single-CTA and, for the taller one, thread-block
-    clusters with the panel's rows of L on chip or re-read from L2) and the DMMA update, with the root's pivot count set on the device.  Checked against the closed-form
+    clusters with the panel's rows of L on chip or re-read from L2) and the DMMA update (one tile per CTA, or the
+    software-pipelined kernel with strips of 2 / 5 / 8 tiles per CTA), with the root's pivot count set on the device.  Checked against the closed-form
     inertia, the residual bar, and the reference algorithm (oracle) on the same system."""
     m = EstimationModel(*shape)
     kkt, rhs = m.build_kkt(), m.build_rhs()
