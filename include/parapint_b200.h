@@ -323,6 +323,42 @@ int pp_cplan_destroy(pp_cplan *plan);
 int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_t *ld, int32_t *piv,
                    int32_t *bsz);
 
+/*
+ * Interior-point vector kernels: the O(n) passes parapint's IPM loop makes over its iterates
+ * between two linear solves -- fraction_to_the_boundary (algorithms/interior_point.py:655-758), the bound-multiplier
+ * steps (interfaces/interface.py:548-570), the complementarity / scaling terms of check_convergence (:241-251,
+ * :274-315), the infeasibility maxima (:253-269) and the step update (:587-626) -- each ONE streaming pass over
+ * device-resident vectors with the reduction finished on the device.  Stateless (no handle): every pointer is a
+ * device pointer; `workspace` is pp_ipm_workspace_bytes() of device memory, zero-filled once by the caller and then
+ * only passed along (calls that share a workspace must be ordered on one stream); results are accumulated into small
+ * device buffers the caller seeds with pp_ipm_fill and reads back when it needs them.  The arithmetic follows the
+ * reference's NumPy expressions operation by operation (no fused multiply-add), so minima and maxima are bit-identical
+ * to the reference; sums are formed in a fixed order.  "One group" = the primals with primals_lb / primals_ub and
+ * their multipliers, or the slacks with ineq_lb / ineq_ub and theirs; infinite bounds behave as in the reference.
+ *
+ * pp_ipm_fraction_to_boundary: out2[0] = min(out2[0], largest alpha with x + alpha dx inside the tau-shrunk bounds),
+ *     out2[1] = min(out2[1], the same for zl, zu against 0 with their steps formed on the fly).  Seed out2 with 1.
+ * pp_ipm_complementarity: out6[0] = max(out6[0], max |(x - lb) zl - barrier| over lb > -inf), out6[1] likewise for ub,
+ *     out6[2] += sum |zl|, out6[3] += sum |zu|, out6[4] += #finite lb, out6[5] += #finite ub.  Seed with 0.
+ * pp_ipm_max_abs: out2[0] = max(out2[0], max |a - b|) (b may be NULL: max |a|), out2[1] += sum |a|.  Seed with 0.
+ * pp_ipm_step: the group's update with alpha3 = [alpha_primal, alpha_dual, line-search step] READ FROM DEVICE MEMORY
+ *     (normally what pp_ipm_fraction_to_boundary left there): multiplier steps from the values before the update,
+ *     then x += ls (alpha_p dx), zl += ls (alpha_d dzl), zu += ls (alpha_d dzu).
+ * pp_ipm_axpy: y += ls (alpha3[which] dy) for the equality / inequality multipliers (which = 1) or any primal-like
+ *     vector (which = 0).
+ */
+int64_t pp_ipm_workspace_bytes(void);
+int pp_ipm_fill(double *out, int32_t n, double value, void *stream);
+int pp_ipm_fraction_to_boundary(int64_t n, double tau, double barrier, const double *x, const double *dx,
+                                const double *lb, const double *ub, const double *zl, const double *zu,
+                                double *out2, void *workspace, void *stream);
+int pp_ipm_complementarity(int64_t n, double barrier, const double *x, const double *lb, const double *ub,
+                           const double *zl, const double *zu, double *out6, void *workspace, void *stream);
+int pp_ipm_max_abs(int64_t n, const double *a, const double *b, double *out2, void *workspace, void *stream);
+int pp_ipm_step(int64_t n, const double *alpha3, double barrier, double *x, const double *dx, const double *lb,
+                const double *ub, double *zl, double *zu, void *stream);
+int pp_ipm_axpy(int64_t n, const double *alpha3, int32_t which, double *y, const double *dy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -709,8 +709,12 @@ def numeric_factorization(interface, kkt, solver, opts, inertia_coef, log):
     return final
 
 
-def ip_solve(interface, solver, opts=None):
-    """:405-631.  Returns a dict with status, iteration count, objective history and the regularisation log."""
+def ip_solve(interface, solver, opts=None, check_convergence=None, fraction_to_the_boundary=None):
+    """:405-631.  Returns a dict with status, iteration count, objective history and the regularisation log.
+    ``check_convergence`` / ``fraction_to_the_boundary``: replacements for the two module functions of the same names
+    (the tests pass the device versions of ``parapint_b200.ipm_vectors`` and demand the identical trajectory)."""
+    check_convergence = check_convergence or globals()["check_convergence"]
+    fraction_to_the_boundary = fraction_to_the_boundary or globals()["fraction_to_the_boundary"]
     opts = opts or IPOptions()
     interface.set_bounds_relaxation_factor(opts.bounds_relaxation_factor)
     barrier = opts.init_barrier_parameter

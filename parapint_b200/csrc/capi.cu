@@ -21,6 +21,7 @@
 #include "hostcopy.hpp"
 #include "coupling.hpp"
 #include "peer.cuh"
+#include "ipmvec.cuh"
 #include <map>
 
 using namespace ppb;
@@ -2186,6 +2187,96 @@ int pp_debug_front(pp_handle *h, int32_t f, double *out, int64_t out_len, int32_
     if (bsz) CK(cudaMemcpy(bsz, F.bsz, (size_t)F.n * sizeof(int), cudaMemcpyDeviceToHost));
     return (int)PP_SUCCESSFUL;
   });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Interior-point vector kernels (N3; csrc/ipmvec.cuh).  Stateless: device pointers in, results in a device buffer.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+int g_iv_sms = 0;
+int iv_grid(int64_t n) {
+  if (!g_iv_sms) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    g_iv_sms = sms;
+  }
+  // whole multiples of the SM count, eight CTAs of 256 threads per SM at most, one element pair per thread at least
+  const int64_t want = (n / 2 + IV_NT - 1) / IV_NT;
+  int64_t per_sm = (want + g_iv_sms - 1) / g_iv_sms;
+  per_sm = std::max<int64_t>(1, std::min<int64_t>(per_sm, IV_MAXCTA / 148));
+  return (int)std::min<int64_t>(per_sm * g_iv_sms, IV_MAXCTA);
+}
+bool iv_aligned(std::initializer_list<const void *> ps) {
+  for (const void *p : ps)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15u)) return false;
+  return true;
+}
+double *iv_ws(void *workspace) { return reinterpret_cast<double *>(workspace) + 2; }
+unsigned int *iv_counter(void *workspace) { return reinterpret_cast<unsigned int *>(workspace); }
+int iv_done(const char *what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  return PP_SUCCESSFUL;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t pp_ipm_workspace_bytes(void) { return (int64_t)(2 + (size_t)IV_MAXCTA * IV_SLOTS) * sizeof(double); }
+
+int pp_ipm_fill(double *out, int32_t n, double value, void *stream) {
+  if (!out || n < 0 || n > 1024) return misuse("pp_ipm_fill: bad arguments");
+  if (n) ipm_fill_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, n, value);
+  return iv_done("pp_ipm_fill");
+}
+
+int pp_ipm_fraction_to_boundary(int64_t n, double tau, double barrier, const double *x, const double *dx,
+                                const double *lb, const double *ub, const double *zl, const double *zu,
+                                double *out2, void *workspace, void *stream) {
+  if (n < 0 || !out2 || !workspace || (n && (!x || !dx || !lb || !ub || !zl || !zu)))
+    return misuse("pp_ipm_fraction_to_boundary: null pointer");
+  if (n == 0) return PP_SUCCESSFUL;   // an empty group leaves the running minima as they are (:660-661)
+  ipm_ftb_kernel<<<iv_grid(n), IV_NT, 0, (cudaStream_t)stream>>>(n, tau, barrier, x, dx, lb, ub, zl, zu, iv_ws(workspace),
+                                                                 iv_counter(workspace), out2,
+                                                                 iv_aligned({x, dx, lb, ub, zl, zu}) ? 1 : 0);
+  return iv_done("pp_ipm_fraction_to_boundary");
+}
+
+int pp_ipm_complementarity(int64_t n, double barrier, const double *x, const double *lb, const double *ub,
+                           const double *zl, const double *zu, double *out6, void *workspace, void *stream) {
+  if (n < 0 || !out6 || !workspace || (n && (!x || !lb || !ub || !zl || !zu)))
+    return misuse("pp_ipm_complementarity: null pointer");
+  if (n == 0) return PP_SUCCESSFUL;
+  ipm_compl_kernel<<<iv_grid(n), IV_NT, 0, (cudaStream_t)stream>>>(n, barrier, x, lb, ub, zl, zu, iv_ws(workspace),
+                                                                   iv_counter(workspace), out6,
+                                                                   iv_aligned({x, lb, ub, zl, zu}) ? 1 : 0);
+  return iv_done("pp_ipm_complementarity");
+}
+
+int pp_ipm_max_abs(int64_t n, const double *a, const double *b, double *out2, void *workspace, void *stream) {
+  if (n < 0 || !out2 || !workspace || (n && !a)) return misuse("pp_ipm_max_abs: null pointer");
+  if (n == 0) return PP_SUCCESSFUL;
+  ipm_maxabs_kernel<<<iv_grid(n), IV_NT, 0, (cudaStream_t)stream>>>(n, a, b, iv_ws(workspace), iv_counter(workspace), out2,
+                                                                    iv_aligned({a, b}) ? 1 : 0);
+  return iv_done("pp_ipm_max_abs");
+}
+
+int pp_ipm_step(int64_t n, const double *alpha3, double barrier, double *x, const double *dx, const double *lb,
+                const double *ub, double *zl, double *zu, void *stream) {
+  if (n < 0 || !alpha3 || (n && (!x || !dx || !lb || !ub || !zl || !zu))) return misuse("pp_ipm_step: null pointer");
+  if (n == 0) return PP_SUCCESSFUL;
+  ipm_step_kernel<<<iv_grid(2 * n), IV_NT, 0, (cudaStream_t)stream>>>(n, alpha3, barrier, x, dx, lb, ub, zl, zu);
+  return iv_done("pp_ipm_step");
+}
+
+int pp_ipm_axpy(int64_t n, const double *alpha3, int32_t which, double *y, const double *dy, void *stream) {
+  if (n < 0 || !alpha3 || which < 0 || which > 1 || (n && (!y || !dy))) return misuse("pp_ipm_axpy: bad arguments");
+  if (n == 0) return PP_SUCCESSFUL;
+  ipm_axpy_kernel<<<iv_grid(2 * n), IV_NT, 0, (cudaStream_t)stream>>>(n, alpha3, which, y, dy);
+  return iv_done("pp_ipm_axpy");
 }
 
 }  // extern "C"

@@ -61,6 +61,14 @@ SIGNATURES = {
     "pp_plan_scalar": (C.c_int, [_vp, C.c_char_p, _i64p]),
     "pp_plan_destroy": (C.c_int, [_vp]),
     "pp_debug_front": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _vp, _vp]),
+    # interior-point vector kernels (N3)
+    "pp_ipm_workspace_bytes": (C.c_int64, []),
+    "pp_ipm_fill": (C.c_int, [_vp, C.c_int32, C.c_double, _vp]),
+    "pp_ipm_fraction_to_boundary": (C.c_int, [C.c_int64, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_ipm_complementarity": (C.c_int, [C.c_int64, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_ipm_max_abs": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "pp_ipm_step": (C.c_int, [C.c_int64, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pp_ipm_axpy": (C.c_int, [C.c_int64, _vp, C.c_int32, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -51,6 +51,22 @@ def test_null_handle_calls_fail_cleanly():
     assert lib.pp_set_option(None, b"pivot_tol", 0.0) == -1
 
 
+def test_ipm_vector_entry_points_reject_misuse_and_need_a_gpu():
+    """pp_ipm_* (N3): argument errors are PP_MISUSE before anything is launched; the host module has no CPU path."""
+    import torch
+    lib = native.load()
+    assert lib.pp_ipm_workspace_bytes() >= 8 * 148 * 8 * 8
+    assert lib.pp_ipm_fraction_to_boundary(10, 0.99, 0.1, None, None, None, None, None, None, None, None, None) == -1
+    assert b"pp_ipm_fraction_to_boundary" in lib.pp_last_error()
+    assert lib.pp_ipm_complementarity(-1, 0.1, None, None, None, None, None, None, None, None) == -1
+    assert lib.pp_ipm_max_abs(5, None, None, None, None, None) == -1
+    assert lib.pp_ipm_axpy(5, None, 7, None, None, None) == -1
+    if not torch.cuda.is_available():
+        from parapint_b200.ipm_vectors import IpmKernels
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            IpmKernels()
+
+
 def test_solver_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
