@@ -123,9 +123,14 @@ class HostCopier:
         if threads:
             self.threads = int(threads)
         else:
-            # share the host cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+            # share the host cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE): this rank's
+            # share of the cores it may run on, less one for the interpreter thread that drives the GPU
             ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-            self.threads = max(1, min(8, (os.cpu_count() or 2) // (2 * ranks)))
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cores = os.cpu_count() or 2
+            self.threads = max(1, min(8, cores // ranks - 1))
         self._keep = None
         self._tables = None
         self.stage = None   # (handle, stream getter): gather straight into a transfer (see copy)
