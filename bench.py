@@ -113,10 +113,16 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel_class):
+    """DRAM bytes per launch of the kernels of a profile class at the HEADLINE workload, from the committed ncu
+    captures (profiles/ncu_traffic_r02.json, generated by tools/ncu_summary.py --traffic from profiles/ncu_full_r02_*.json:
+    `ncu --set full` of tools/profile_case.py 64 2 = config 2)."""
+    parts = {"subtree": ("subtree_factor", "subtree_leaf_kernel"), "forward": ("subtree_forward",),
+             "backward": ("subtree_backward",), "panel": ("front_small",)}.get(kernel_class)
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-            return json.load(fh).get(kernel)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as fh:
+            table = json.load(fh)
+        return float(sum(table[p]["bytes"] for p in parts)) if parts else None
     except Exception:  # noqa: BLE001
         return None
 
