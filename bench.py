@@ -596,6 +596,18 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1 and os.environ.get("PARAPINT_B200_PIN", "1") != "0":
+        # every rank keeps to its own share of the cores this job may use (before any worker thread exists: the host
+        # copy pool and the NCCL helpers inherit the mask), so that eight interpreters do not migrate over each other
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            share = cores[local_rank * len(cores) // local_world:(local_rank + 1) * len(cores) // local_world]
+            if share:
+                os.sched_setaffinity(0, share)
+                os.environ.setdefault("PARAPINT_B200_HOST_THREADS", str(max(1, min(8, len(share) - 1))))
+        except (AttributeError, OSError):
+            pass
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN") else None
         # (NCCL prints a version banner on stdout at VERSION/WARN level; stdout must stay the one JSON line)
