@@ -596,7 +596,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1 and os.environ.get("PARAPINT_B200_PIN", "1") != "0":
+    if world > 1 and os.environ.get("PARAPINT_B200_PIN", "0") == "1":   # measured on this pool (one NUMA node, 32 vCPUs): no gain, off by default
         # every rank keeps to its own share of the cores this job may use (before any worker thread exists: the host
         # copy pool and the NCCL helpers inherit the mask), so that eight interpreters do not migrate over each other
         try:
