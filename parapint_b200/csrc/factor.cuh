@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_kernel(const Front 
     F.state[ST_KPREV] = k0;
     F.state[ST_KCUR] = k;
   }
+  if (C > 1) cl.sync();   // see front_panel_cluster_oc_kernel: nobody leaves while a peer may still read its candidates
 }
 
 // Apply the interchanges of the last panel to the columns of L left of it (one thread per column).
@@ -852,6 +853,9 @@ __global__ void __launch_bounds__(PC_NT) front_panel_cluster_oc_kernel(const Fro
     F.state[ST_KCUR] = k;
     F.state[3] = spec_next;
   }
+  // cluster_argmax PULLS the candidates out of the peers' shared memory after its barrier: a CTA that ran ahead must
+  // not leave while a peer may still be reading (distributed shared memory lives only as long as its CTA does)
+  if (C > 1) cl.sync();
 }
 
 // ---------------------------------------------------------------------------------------------
