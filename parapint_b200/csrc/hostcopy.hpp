@@ -99,12 +99,24 @@ class CopyPool {
       std::lock_guard<std::mutex> lk(mu_);
       job_ = j;
       pending_ = T - 1;
+      left_.store(T - 1, std::memory_order_relaxed);
       ++gen_;
+      gen_pub_.store(gen_, std::memory_order_release);
     }
     cv_.notify_all();
     work(j, 0, total / T);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [&] { return pending_ == 0; });
+    // the shares are equal, so the workers finish within microseconds of this thread: spin before sleeping
+    for (int spin = 0; spin < kSpin && left_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
+    if (left_.load(std::memory_order_acquire) != 0) {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    while (left_.load(std::memory_order_acquire) != 0) cpu_relax();   // every worker is out of its bookkeeping
+  }
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
   }
   void work(const Job &j, int64_t b0, int64_t b1) {
     if (!j.other) {
@@ -147,18 +159,23 @@ class CopyPool {
     uint64_t seen = 0;
     for (;;) {
       Job j;
+      // a gather comes in a few shares a few microseconds apart (pp_stage_values): stay awake for a moment after a job
+      // instead of paying a futex wake-up per share
+      for (int spin = 0; spin < kSpin && gen_pub_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && id < job_.T); });
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
         if (stop_) return;
         seen = gen_;
         j = job_;
       }
+      if (id >= j.T) continue;   // this job uses fewer threads
       work(j, j.total * id / j.T, j.total * (id + 1) / j.T);
       {
         std::lock_guard<std::mutex> lk(mu_);
         if (--pending_ == 0) done_.notify_one();
       }
+      left_.fetch_sub(1, std::memory_order_acq_rel);   // last: the dispatcher may start the next job once this is 0
     }
   }
   CopyPool() = default;
@@ -170,7 +187,10 @@ class CopyPool {
     cv_.notify_all();
     for (auto &t : workers_) t.join();
   }
+  static constexpr int kSpin = 20000;   // ~50 us of pause instructions
   std::atomic<int> mismatch_{0};
+  std::atomic<int> left_{0};
+  std::atomic<uint64_t> gen_pub_{0};
   std::mutex api_, mu_;
   std::condition_variable cv_, done_;
   std::vector<std::thread> workers_;
