@@ -1777,7 +1777,7 @@ static void enqueue_residual_local(pp_handle *h, double *buf_dev, cudaStream_t s
                                                        h->res_part.p, h->local_dim);
     h->launches++;
   }
-  residual_border_kernel<<<std::max(1, (h->m_c + 127) / 128), 128, 0, st>>>(
+  residual_border_kernel<<<std::max(1, (h->m_c + 3) / 4), 128, 0, st>>>(   // a warp per coupling row
       h->rb_ptr.p, h->rb_col.p, h->rb_src.p, h->last_vals, h->last_x, h->m_c, h->res_part.p, h->res_blocks, buf_dev);
   h->launches++;
 }

@@ -269,18 +269,23 @@ __global__ void residual_border_kernel(const long long *__restrict__ ptr, const 
                                        const long long *__restrict__ src, const double *__restrict__ vals,
                                        const double *__restrict__ x, int m_c, const double *__restrict__ part,
                                        int nparts, double *__restrict__ buf) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per coupling row: the row's entries (one per block that touches it) are dealt over the lanes, every lane
+  // adds its entries in list order and a fixed shuffle tree adds the lanes -- reproducible, and a row with 64 entries
+  // costs one round of dependent loads instead of eight
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ln = threadIdx.x & 31;
   if (g < m_c) {
     double s = 0.0;
     const long long p0 = ptr[g], p1 = ptr[g + 1];
-    for (long long pb = p0; pb < p1; pb += 8) {  // eight products in flight; the additions keep their order
-      double t[8];
+    for (long long pb = p0 + ln; pb < p1; pb += 128) {  // four products in flight per lane
+      double t[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t[q] = pb + q < p1 ? vals[src[pb + q]] * x[col[pb + q]] : 0.0;
+      for (int q = 0; q < 4; ++q) t[q] = pb + 32 * q < p1 ? vals[src[pb + 32 * q]] * x[col[pb + 32 * q]] : 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s += t[q];
+      for (int q = 0; q < 4; ++q) s += t[q];
     }
-    buf[g] = -s;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (ln == 0) buf[g] = -s;
   }
   if (blockIdx.x == 0 && threadIdx.x < 64) {
     // the two norms: warp w sums the partials of component w, each lane a strided subset, then a fixed tree
