@@ -1622,7 +1622,7 @@ static void run_forward(pp_handle *h, const double *drhs, double *rc_local_dev, 
     h->launches += 2;
   }
   if (h->m_c > 0) {
-    rc_gather_kernel<<<(h->m_c + 127) / 128, 128, 0, st>>>(h->arenaZ.p, h->src_ptr.p, h->src_boff.p, h->m_c,
+    rc_gather_kernel<<<(h->m_c + 3) / 4, 128, 0, st>>>(h->arenaZ.p, h->src_ptr.p, h->src_boff.p, h->m_c,
                                                           rc_local_dev);
     h->launches++;
   }

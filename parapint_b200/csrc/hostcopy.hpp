@@ -3,6 +3,7 @@
 // over the Python heap; copying them one by one from Python costs more than the GPU spends factorising them.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -106,7 +107,7 @@ class CopyPool {
     cv_.notify_all();
     work(j, 0, total / T);
     // the shares are equal, so the workers finish within microseconds of this thread: spin before sleeping
-    for (int spin = 0; spin < kSpin && left_.load(std::memory_order_acquire) != 0; ++spin) cpu_relax();
+    for (const auto t0 = now_ns(); left_.load(std::memory_order_acquire) != 0 && now_ns() - t0 < kSpinNs;) cpu_relax();
     if (left_.load(std::memory_order_acquire) != 0) {
       std::unique_lock<std::mutex> lk(mu_);
       done_.wait(lk, [&] { return pending_ == 0; });
@@ -161,7 +162,7 @@ class CopyPool {
       Job j;
       // a gather comes in a few shares a few microseconds apart (pp_stage_values): stay awake for a moment after a job
       // instead of paying a futex wake-up per share
-      for (int spin = 0; spin < kSpin && gen_pub_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
+      for (const auto t0 = now_ns(); gen_pub_.load(std::memory_order_acquire) == seen && now_ns() - t0 < kSpinNs;) cpu_relax();
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
@@ -187,7 +188,10 @@ class CopyPool {
     cv_.notify_all();
     for (auto &t : workers_) t.join();
   }
-  static constexpr int kSpin = 20000;   // ~50 us of pause instructions
+  static constexpr int64_t kSpinNs = 30000;   // spin for at most 30 us (by the clock: a `pause` is 10-140 cycles)
+  static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
   std::atomic<int> mismatch_{0};
   std::atomic<int> left_{0};
   std::atomic<uint64_t> gen_pub_{0};

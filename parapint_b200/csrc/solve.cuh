@@ -212,18 +212,23 @@ __global__ void coupling_add_kernel(Front F, const double *__restrict__ Ssum, in
 
 __global__ void rc_gather_kernel(const double *__restrict__ zarena, const int64_t *__restrict__ src_ptr,
                                  const int64_t *__restrict__ src_boff, int m_c, double *__restrict__ rc) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per coupling row: the sources (one per front that touches the row) are dealt over the lanes, every lane
+  // adds its sources in front order, a fixed shuffle tree adds the lanes (reproducible; one round of dependent loads
+  // for 64 fronts instead of eight)
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, ln = threadIdx.x & 31;
   if (r >= m_c) return;
   double s = 0.0;
   const int64_t p0 = src_ptr[r], p1 = src_ptr[r + 1];
-  for (int64_t pb = p0; pb < p1; pb += 8) {  // eight sources in flight; the additions keep their (front) order
-    double v[8];
+  for (int64_t pb = p0 + ln; pb < p1; pb += 128) {  // four sources in flight per lane
+    double v[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = pb + q < p1 ? zarena[src_boff[pb + q]] : 0.0;
+    for (int q = 0; q < 4; ++q) v[q] = pb + 32 * q < p1 ? zarena[src_boff[pb + 32 * q]] : 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += v[q];
+    for (int q = 0; q < 4; ++q) s += v[q];
   }
-  rc[r] = s;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (ln == 0) rc[r] = s;
 }
 
 __global__ void vec_add_kernel(const double *__restrict__ a, const double *__restrict__ b, int n,
