@@ -160,9 +160,16 @@ class HostCopier:
         for a, b in pairs:
             if a.dtype != b.dtype or a.size != b.size or not a.flags.c_contiguous or not b.flags.c_contiguous:
                 return None
-        pa = np.array([a.__array_interface__["data"][0] for a, _ in pairs], dtype=np.uintp)
-        pb = np.array([b.__array_interface__["data"][0] for _, b in pairs], dtype=np.uintp)
-        ln = np.array([a.nbytes for a, _ in pairs], dtype=np.int64)
+        pa = np.array([a.ctypes.data for a, _ in pairs], dtype=np.uintp)
+        # the analysed side is the same list of arrays call after call: its pointer / length tables are kept
+        cache = getattr(self, "_eq_ref", None)
+        if cache is not None and len(cache[0]) == len(pairs) and all(b is r for (_, b), r in zip(pairs, cache[0])):
+            pb, ln = cache[1], cache[2]
+        else:
+            refs = [b for _, b in pairs]
+            pb = np.array([b.ctypes.data for b in refs], dtype=np.uintp)
+            ln = np.array([b.nbytes for b in refs], dtype=np.int64)
+            self._eq_ref = (refs, pb, ln)
         out = C.c_int(0)
         if self.lib.pp_host_equal(len(pairs), np_ptr(pa), np_ptr(pb), np_ptr(ln), self.threads, C.byref(out)) != 0:
             raise RuntimeError(f"pp_host_equal failed: {last_error()}")
