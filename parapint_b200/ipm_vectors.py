@@ -107,10 +107,24 @@ class DeviceIpmVectors:
     GROUPS = (("primals", "primals_lb", "primals_ub", "duals_primals_lb", "duals_primals_ub", "delta_primals"),
               ("slacks", "ineq_lb", "ineq_ub", "duals_slacks_lb", "duals_slacks_ub", "delta_slacks"))
 
-    def __init__(self, device=None, kernels=None):
+    def __init__(self, device=None, kernels=None, comm=None):
+        """``comm``: a :class:`parapint_b200.comm.Communicator` when every rank holds the iterates of its own blocks
+        (the reference's ``MPIBlockVector`` reductions, ``interior_point.py:253-315`` on distributed vectors): step
+        lengths and maxima are then MIN / MAX-reduced, sums and counts SUM-reduced over the ranks -- two small
+        all-reduces per call.  Replicated vectors (the coupling variables) must be loaded on one rank only."""
         self.k = kernels if kernels is not None else IpmKernels(device)
+        self.comm = comm
         self.v = {}
         self.alpha = self.k.torch.ones(3, dtype=self.k.torch.float64, device=self.k.device)
+
+    def _reduce(self, t, maxima, sums):
+        """In-place reduction over the ranks: ``t[maxima]`` by MAX, ``t[sums]`` by SUM (slices of one device tensor)."""
+        if self.comm is None or self.comm.size == 1:
+            return
+        if maxima is not None:
+            self.comm.allreduce_max_(t[maxima])
+        if sums is not None:
+            self.comm.allreduce_sum_(t[sums])
 
     def load(self, interface):
         up = self.k.to_device
@@ -134,6 +148,10 @@ class DeviceIpmVectors:
         k.fill(self.alpha, 1.0)
         for x, lb, ub, zl, zu, dx in self.GROUPS:
             k.fraction_to_boundary(self.alpha, tau, barrier, v[x], v[dx], v[lb], v[ub], v[zl], v[zu])
+        if self.comm is not None and self.comm.size > 1:      # min over the ranks = -max(-x)
+            self.alpha[:2].neg_()
+            self._reduce(self.alpha, slice(0, 2), None)
+            self.alpha[:2].neg_()
         a = self.alpha[:2].cpu().numpy()
         return float(a[0]), float(a[1])
 
@@ -146,8 +164,19 @@ class DeviceIpmVectors:
             k.complementarity(out[:6], barrier, v[x], v[lb], v[ub], v[zl], v[zu])
         k.max_abs(out[6:8], v["duals_eq"])
         k.max_abs(out[8:10], v["duals_ineq"])
-        o = out[:10].cpu().numpy()
-        return _scalings(o, v["duals_eq"].numel(), v["duals_ineq"].numel(), error_scaling)
+        n_eq, n_in = v["duals_eq"].numel(), v["duals_ineq"].numel()
+        if self.comm is not None and self.comm.size > 1:
+            # regroup as [maxima | sums and counts] so that two all-reduces do: o[0], o[1] MAX; the rest SUM
+            out[10], out[11] = float(n_eq), float(n_in)
+            packed = k.torch.cat([out[0:2], out[2:6], out[7:8], out[9:10], out[10:12]])
+            self._reduce(packed, slice(0, 2), slice(2, 10))
+            p = packed.cpu().numpy()
+            o = np.zeros(10)
+            o[0:2], o[2:6], o[7], o[9] = p[0:2], p[2:6], p[6], p[7]
+            n_eq, n_in = int(round(p[8])), int(round(p[9]))
+        else:
+            o = out[:10].cpu().numpy()
+        return _scalings(o, n_eq, n_in, error_scaling)
 
     def take_step(self, barrier, line_search_step=1.0, unified_step=False):
         """``interior_point.py:571-574,587-626`` with the step lengths already in ``self.alpha`` (device)."""

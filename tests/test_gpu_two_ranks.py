@@ -126,12 +126,49 @@ def _worker(rank, world, port, case, out_dir):
                 assert np.allclose(np.asarray(x.get_block(i)).flatten(), np.asarray(x_ref.get_block(i)).flatten(), rtol=1e-7, atol=1e-9)
             assert solver.get_inertia() == o.inertia()
             assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == 1
+        elif case == "ipm_vectors":
+            # the interior-point vector kernels on distributed iterates: every rank holds half of the entries, the step
+            # lengths / maxima / sums are reduced over the ranks (the reference's MPIBlockVector reductions)
+            from oracle import ipm as O
+            from parapint_b200.ipm_vectors import DeviceIpmVectors
+            from tests.test_gpu_ipm_vectors import _random_group, _ref_ftb
+            rng = np.random.default_rng(9)
+            gx, gs = _random_group(rng, 4001), _random_group(rng, 1203)       # (x, dx, lb, ub, zl, zu) of primals / slacks
+            lam_eq, lam_in = rng.standard_normal(777), rng.standard_normal(1203)
+            tau, barrier = 0.99, 2e-3
+            mine = lambda v: v[rank::world].copy()                            # noqa: E731 - this rank's entries
+            dv = DeviceIpmVectors(comm=comm)
+            names = (("primals", "delta_primals", "primals_lb", "primals_ub", "duals_primals_lb", "duals_primals_ub"),
+                     ("slacks", "delta_slacks", "ineq_lb", "ineq_ub", "duals_slacks_lb", "duals_slacks_ub"))
+            for grp, nm in zip((gx, gs), names):
+                for v, name in zip(grp, nm):
+                    dv.v[name] = dv.k.to_device(mine(v))
+            dv.v["duals_eq"], dv.v["duals_ineq"] = dv.k.to_device(mine(lam_eq)), dv.k.to_device(mine(lam_in))
+            a_p, a_d = dv.fraction_to_the_boundary(tau, barrier)
+            with np.errstate(all="ignore"):
+                rx, rs = _ref_ftb(tau, barrier, *gx), _ref_ftb(tau, barrier, *gs)
+            assert a_p == min(rx[0], rs[0], 1.0) and a_d == min(rx[1], rs[1], 1.0)          # bit-exact on every rank
+            c_inf, dual_scaling, compl_scaling = dv.complementarity(barrier, 100.0)
+
+            def resid(x, lb, ub, zl, zu):
+                lb_m, ub_m = np.where(np.isneginf(lb), 0.0, lb), np.where(np.isinf(ub), 0.0, ub)
+                r_l, r_u = (x - lb_m) * zl - barrier, (ub_m - x) * zu - barrier
+                r_l[np.isneginf(lb)] = 0
+                r_u[np.isinf(ub)] = 0
+                return max(O._max_abs(r_l), O._max_abs(r_u))
+            assert c_inf == max(resid(gx[0], gx[2], gx[3], gx[4], gx[5]), resid(gs[0], gs[2], gs[3], gs[4], gs[5]))
+            bsum = sum(np.abs(g[4]).sum() + np.abs(g[5]).sum() for g in (gx, gs))
+            nb = sum(np.isfinite(g[2]).sum() + np.isfinite(g[3]).sum() for g in (gx, gs))
+            ds = (np.abs(lam_eq).sum() + np.abs(lam_in).sum() + bsum) / (lam_eq.size + lam_in.size + nb)
+            assert np.isclose(dual_scaling, max(100.0, ds) / 100.0, rtol=1e-13)
+            assert np.isclose(compl_scaling, max(100.0, bsum / nb) / 100.0, rtol=1e-13)
         open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["generator", "overflow", "singular", "sparse_coupling", "device_regularization"])
+@pytest.mark.parametrize("case", ["generator", "overflow", "singular", "sparse_coupling", "device_regularization",
+                                  "ipm_vectors"])
 def test_two_ranks_on_one_gpu(tmp_path, case):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
