@@ -255,12 +255,14 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             if pos != hi:
                 return False
             continue
-        # a COO leaf that still carries the analysed index arrays (values updated in place)
-        if getattr(blk, "format", None) == "coo" and blk.row is prow and blk.col is pcol:
-            data = blk.data
-        else:
-            c = blk.tocoo()
-            for fresh, ref in ((c.row, prow), (c.col, pcol)):
+        # (scipy's row / col / format are properties: every access costs; the index tuple is read once per leaf)
+        is_coo = getattr(blk, "format", None) == "coo"
+        c = blk if is_coo else blk.tocoo()
+        coords = getattr(c, "coords", None)
+        frow, fcol = coords if coords is not None else (c.row, c.col)
+        same = frow is prow and fcol is pcol      # still carries the analysed index arrays (values updated in place)
+        if not same:
+            for fresh, ref in ((frow, prow), (fcol, pcol)):
                 if fresh is ref:
                     continue
                 if fresh.size != ref.size:
@@ -269,12 +271,10 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
                     pending.append((fresh, ref))
                 elif not np.array_equal(fresh, ref):
                     return False
-            data = c.data
+        data = c.data
         if data.size != hi - lo:
             return False
-        coords = getattr(blk, "coords", None)
-        seen[k] = (blk, coords) if coords is not None and getattr(blk, "format", None) == "coo" \
-            and blk.row is prow and blk.col is pcol else None
+        seen[k] = (blk, coords) if (is_coo and same and coords is not None) else None
         datas.append(data)
         starts.append(lo)
     if pending:
