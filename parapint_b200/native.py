@@ -73,6 +73,11 @@ SIGNATURES = {
 
 _lib = None
 
+try:   # pointer tables of many arrays in one call (csrc/fastptr.c, built by __graft_entry__.build())
+    from . import _pp_fastptr as _fp
+except ImportError:   # host bookkeeping only: the interpreter builds the same tables, slower
+    _fp = None
+
 
 class NativeLibraryMissing(RuntimeError):
     pass
@@ -139,39 +144,50 @@ class HostCopier:
         import numpy as np
         keep = self._keep
         off = np.asarray(offsets, dtype=np.int64) * 8
-        if keep is not None and len(keep) == len(arrays) and all(a is b for a, b in zip(arrays, keep)) \
-                and np.array_equal(off, self._tables[1]):   # same arrays AND same destinations
-            return self._tables
-        for a in arrays:
-            if a.dtype != np.float64 or not a.flags.c_contiguous:
+        if keep is not None:
+            same = _fp.same(arrays, keep) if _fp is not None else \
+                (len(keep) == len(arrays) and all(a is b for a, b in zip(arrays, keep)))
+            if same and np.array_equal(off, self._tables[1]):   # same arrays AND same destinations
+                return self._tables
+        n = len(arrays)
+        ptr = np.empty(n, dtype=np.uintp)
+        ln = np.empty(n, dtype=np.int64)
+        if _fp is not None:
+            if _fp.fill(arrays, ptr, ln, "d") != n:   # an entry is not a contiguous float64 buffer
                 return None
-        ptr = np.array([a.__array_interface__["data"][0] for a in arrays], dtype=np.uintp)
-        ln = np.array([a.size * 8 for a in arrays], dtype=np.int64)
+        else:
+            for k, a in enumerate(arrays):
+                if a.dtype != np.float64 or not a.flags.c_contiguous:
+                    return None
+                ptr[k] = a.__array_interface__["data"][0]
+                ln[k] = a.size * 8
         self._keep = list(arrays)
         self._tables = (ptr, off, ln, np_ptr(ptr), np_ptr(off), np_ptr(ln))
         return self._tables
 
-    def all_equal(self, pairs):
-        """True when ``a`` and ``b`` hold the same bytes for every pair (index arrays of fresh leaves against the
-        analysed pattern); None when a pair does not qualify for the byte comparison (the caller uses numpy)."""
+    def all_equal(self, fresh, refs):
+        """True when ``fresh[k]`` and ``refs[k]`` hold the same bytes for every k (index arrays of fresh leaves against
+        the analysed pattern); None when a pair does not qualify for the byte comparison -- different types or
+        lengths, not contiguous -- and the caller has to compare with numpy."""
         import numpy as np
-        if not pairs:
+        n = len(fresh)
+        if n == 0:
             return True
-        for a, b in pairs:
-            if a.dtype != b.dtype or a.size != b.size or not a.flags.c_contiguous or not b.flags.c_contiguous:
+        if n != len(refs):
+            return None
+        pa = np.empty(n, dtype=np.uintp)
+        pb = np.empty(n, dtype=np.uintp)
+        ln = np.empty(n, dtype=np.int64)
+        if _fp is not None:
+            if _fp.pairs(fresh, refs, pa, pb, ln) != n:
                 return None
-        pa = np.array([a.ctypes.data for a, _ in pairs], dtype=np.uintp)
-        # the analysed side is the same list of arrays call after call: its pointer / length tables are kept
-        cache = getattr(self, "_eq_ref", None)
-        if cache is not None and len(cache[0]) == len(pairs) and all(b is r for (_, b), r in zip(pairs, cache[0])):
-            pb, ln = cache[1], cache[2]
         else:
-            refs = [b for _, b in pairs]
-            pb = np.array([b.ctypes.data for b in refs], dtype=np.uintp)
-            ln = np.array([b.nbytes for b in refs], dtype=np.int64)
-            self._eq_ref = (refs, pb, ln)
+            for k, (a, b) in enumerate(zip(fresh, refs)):
+                if a.dtype != b.dtype or a.size != b.size or not a.flags.c_contiguous or not b.flags.c_contiguous:
+                    return None
+                pa[k], pb[k], ln[k] = a.ctypes.data, b.ctypes.data, b.nbytes
         out = C.c_int(0)
-        if self.lib.pp_host_equal(len(pairs), np_ptr(pa), np_ptr(pb), np_ptr(ln), self.threads, C.byref(out)) != 0:
+        if self.lib.pp_host_equal(n, np_ptr(pa), np_ptr(pb), np_ptr(ln), self.threads, C.byref(out)) != 0:
             raise RuntimeError(f"pp_host_equal failed: {last_error()}")
         return bool(out.value)
 

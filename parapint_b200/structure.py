@@ -17,8 +17,15 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List
 
+import operator
+
 import numpy as np
 import scipy.sparse as sp
+
+try:   # identity comparison of two lists in one call (csrc/fastptr.c); the interpreter does the same, slower
+    from . import _pp_fastptr as _fp
+except ImportError:
+    _fp = None
 
 
 def _coo(block):
@@ -31,45 +38,80 @@ def _is_nested(block) -> bool:
     return hasattr(block, "bshape") and hasattr(block, "get_block")
 
 
-def _walk_leaves(block, path=()):
-    """COO sub-leaves of a nested block matrix in row-major block order (the order ``tocoo()`` concatenates them):
-    list of (path, leaf); None when a sub-block is neither nested nor a COO matrix."""
-    out = []
+_KIND_BY_TYPE = {}   # class -> 0 (COO leaf) / 1 (nested block matrix) / 2 (anything else)
+
+
+def _kind(sub):
+    """0 for a COO leaf, 1 for a nested block matrix, 2 otherwise.  For SciPy's sparse classes and for block-matrix
+    classes the answer is a property of the class and is remembered per class (``format`` is a Python-level property
+    in SciPy: asking ~30 sub-leaves per scenario and iteration costs as much as walking them)."""
+    cls = type(sub)
+    kind = _KIND_BY_TYPE.get(cls)
+    if kind is None:
+        if _is_nested(sub):
+            kind = _KIND_BY_TYPE[cls] = 1
+        elif sp.issparse(sub):
+            kind = _KIND_BY_TYPE[cls] = 0 if sub.format == "coo" else 2
+        else:   # a duck-typed leaf: its format may be an instance attribute, ask every time
+            kind = 0 if getattr(sub, "format", None) == "coo" else 2
+    return kind
+
+
+def _walk_leaves(block, leaves, sig):
+    """COO sub-leaves of a nested block matrix in row-major block order (the order ``tocoo()`` concatenates them),
+    appended to ``leaves``; ``sig`` receives the shape of the walk as a flat list of integers (position of every
+    leaf, entry / exit marks of every nested sub-block), so that two walks visited the same positions exactly when
+    their signatures are equal.  Returns False when a sub-block is neither nested nor a COO matrix."""
     nbr, nbc = block.bshape
     get = block.get_block
+    kinds = _KIND_BY_TYPE
+    pos = 0
     for i in range(nbr):
         for j in range(nbc):
             sub = get(i, j)
-            if sub is None:
-                continue
-            if _is_nested(sub):
-                inner = _walk_leaves(sub, path + ((i, j),))
-                if inner is None:
-                    return None
-                out.extend(inner)
-            elif getattr(sub, "format", None) == "coo":
-                out.append((path + ((i, j),), sub))
-            else:
-                return None
-    return out
+            if sub is not None:
+                kind = kinds.get(type(sub))
+                if kind is None:
+                    kind = _kind(sub)
+                if kind == 0:
+                    leaves.append(sub)
+                    sig.append(pos)
+                elif kind == 1:
+                    sig.append(-1 - pos)
+                    if not _walk_leaves(sub, leaves, sig):
+                        return False
+                    sig.append(-1 - nbr * nbc)
+                else:
+                    return False
+            pos += 1
+    return True
+
+
+def _leaf_index(leaf):
+    """(row, col) index arrays of a COO leaf without copying (scipy's ``row`` / ``col`` are properties of ``coords``)."""
+    coords = getattr(leaf, "coords", None)
+    return coords if coords is not None else (leaf.row, leaf.col)
 
 
 def _flatten_recipe(block, data):
     """How to gather the values of a nested leaf without flattening it every iteration (parapint builds a new
     nested 4x4 BlockMatrix per scenario and iteration, ``interface.py:432-491``; its ``tocoo()`` costs far more
-    than the factorisation): the COO sub-leaves in concatenation order with their index arrays.  The recipe is
-    only kept when concatenating the sub-leaves' values reproduces ``tocoo().data`` exactly."""
+    than the factorisation): the walk's signature and the index arrays of the COO sub-leaves in concatenation order.
+    The recipe is only kept when concatenating the sub-leaves' values reproduces ``tocoo().data`` exactly."""
     if not _is_nested(block):
         return None
-    leaves = _walk_leaves(block)
-    if not leaves:
+    leaves, sig = [], []
+    if not _walk_leaves(block, leaves, sig) or not leaves:
         return None
-    parts = [np.asarray(leaf.data, dtype=np.float64) for _, leaf in leaves]
+    parts = [np.asarray(leaf.data, dtype=np.float64) for leaf in leaves]
     if sum(p.size for p in parts) != data.size or not np.array_equal(np.concatenate(parts), data):
         return None
-    # the index arrays are kept both as arrays and as bytes: comparing bytes is 4x cheaper than np.array_equal on the
-    # few-thousand-entry leaves this is for, and it is done ~30 times per scenario and iteration
-    return [(path, leaf.row, leaf.col, leaf.row.tobytes(), leaf.col.tobytes()) for path, leaf in leaves]
+    index = [_leaf_index(leaf) for leaf in leaves]
+    sizes = [p.size for p in parts]
+    rel = [0]
+    for n in sizes[:-1]:
+        rel.append(rel[-1] + n)
+    return sig, [ix[0] for ix in index], [ix[1] for ix in index], sizes, rel
 
 
 @dataclass
@@ -202,8 +244,21 @@ def analyse(matrix, rank=0, size=1) -> Structure:
         segments=segments, patterns=patterns, recipes=recipes, rhs_offsets=offs)
 
 
+def _same_objects(a, b) -> bool:
+    """Both lists hold the same objects (identity, not equality)."""
+    if _fp is not None:
+        return _fp.same(a, b)
+    return len(a) == len(b) and all(map(operator.is_, a, b))
+
+
 def _same_index(a, b) -> bool:
-    return a is b or (a.size == b.size and np.array_equal(a, b))
+    if a is b:
+        return True
+    if a.size != b.size:
+        return False
+    if a.dtype == b.dtype and a.flags.c_contiguous and b.flags.c_contiguous:
+        return a.tobytes() == b.tobytes()   # 4x cheaper than np.array_equal on leaves of a few thousand entries
+    return bool(np.array_equal(a, b))
 
 
 def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
@@ -214,12 +269,15 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
     ``native.HostCopier``) moves the leaves with a few threads instead of one numpy slice assignment each.
 
     Three paths per leaf, fastest first: the very object validated last time (values updated in place); a nested
-    block matrix walked sub-leaf by sub-leaf against the recipe recorded by :func:`analyse` (index arrays compared,
-    nothing concatenated); ``tocoo()`` and a comparison of the flattened index arrays."""
+    block matrix walked sub-leaf by sub-leaf against the recipe recorded by :func:`analyse` (index arrays compared
+    unless the sub-leaves are the objects validated last time, nothing concatenated); ``tocoo()`` and a comparison
+    of the flattened index arrays.  All index comparisons of a call are made together at the end, by the copier's
+    threads when there is one."""
     N = st.n_blocks
     get = matrix.get_block
     datas, starts = [], []
-    pending = []   # (fresh index array, analysed index array) pairs compared in one threaded call at the end
+    fresh_idx, ref_idx = [], []   # fresh / analysed index arrays, compared in one threaded call at the end
+    validated = []                # (segment, leaf object(s), index tuple(s)) that pass once that comparison has passed
     seen = st.__dict__.setdefault("_leaf_seen", [None] * len(st.segments))
     recipes = st.recipes if st.recipes else [None] * len(st.segments)
     for k, ((kind, i, lo, hi), (prow, pcol)) in enumerate(zip(st.segments, st.patterns)):
@@ -236,53 +294,63 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             starts.append(lo)
             continue
         recipe = recipes[k]
-        if recipe is not None and _is_nested(blk):
-            leaves = _walk_leaves(blk)
-            if leaves is None or len(leaves) != len(recipe):
+        kind_blk = _KIND_BY_TYPE.get(type(blk))
+        if kind_blk is None:
+            kind_blk = _kind(blk)
+        if recipe is not None and kind_blk == 1:
+            leaves, sig = [], []
+            if not _walk_leaves(blk, leaves, sig) or sig != recipe[0]:
                 return False
-            pos = lo
-            for (path, leaf), (rpath, rrow, rcol, rrow_b, rcol_b) in zip(leaves, recipe):
-                lrow, lcol = leaf.row, leaf.col
-                if path != rpath:
-                    return False
-                if not (lrow is rrow or lrow.tobytes() == rrow_b or _same_index(lrow, rrow)):
-                    return False
-                if not (lcol is rcol or lcol.tobytes() == rcol_b or _same_index(lcol, rcol)):
-                    return False
-                datas.append(leaf.data)
-                starts.append(pos)
-                pos += leaf.data.size
-            if pos != hi:
+            coords = [getattr(leaf, "coords", None) for leaf in leaves]
+            if None in coords:
+                coords = [(leaf.row, leaf.col) for leaf in leaves]
+            # the sub-leaves validated last time, index tuples untouched: nothing to compare
+            if last is None or not (_same_objects(leaves, last[0]) and _same_objects(coords, last[1])):
+                for (lrow, lcol), rrow, rcol in zip(coords, recipe[1], recipe[2]):
+                    if lrow is not rrow:
+                        fresh_idx.append(lrow)
+                        ref_idx.append(rrow)
+                    if lcol is not rcol:
+                        fresh_idx.append(lcol)
+                        ref_idx.append(rcol)
+                seen[k] = None
+                validated.append((k, leaves, coords))
+            part = [leaf.data for leaf in leaves]
+            if [d.size for d in part] != recipe[3]:
                 return False
+            datas.extend(part)
+            starts.extend([lo + r for r in recipe[4]] if lo else recipe[4])
             continue
         # (scipy's row / col / format are properties: every access costs; the index tuple is read once per leaf)
-        is_coo = getattr(blk, "format", None) == "coo"
+        is_coo = kind_blk == 0
         c = blk if is_coo else blk.tocoo()
         coords = getattr(c, "coords", None)
         frow, fcol = coords if coords is not None else (c.row, c.col)
         same = frow is prow and fcol is pcol      # still carries the analysed index arrays (values updated in place)
         if not same:
-            for fresh, ref in ((frow, prow), (fcol, pcol)):
-                if fresh is ref:
-                    continue
-                if fresh.size != ref.size:
-                    return False
-                if copier is not None and fresh.dtype == ref.dtype:
-                    pending.append((fresh, ref))
-                elif not np.array_equal(fresh, ref):
-                    return False
+            # (sizes and types are checked by the comparison at the end)
+            if frow is not prow:
+                fresh_idx.append(frow)
+                ref_idx.append(prow)
+            if fcol is not pcol:
+                fresh_idx.append(fcol)
+                ref_idx.append(pcol)
         data = c.data
         if data.size != hi - lo:
             return False
-        seen[k] = (blk, coords) if (is_coo and same and coords is not None) else None
+        seen[k] = None
+        if is_coo and coords is not None:
+            validated.append((k, blk, coords))
         datas.append(data)
         starts.append(lo)
-    if pending:
-        same = copier.all_equal(pending)
-        if same is None:
-            same = all(np.array_equal(a, b) for a, b in pending)
+    if fresh_idx:
+        same = copier.all_equal(fresh_idx, ref_idx) if copier is not None else None
+        if same is None:   # no threaded comparison, or a pair of different types / lengths
+            same = all(map(_same_index, fresh_idx, ref_idx))
         if not same:
             return False
+    for k, obj, coords in validated:   # these objects now count as validated while their index tuples stay untouched
+        seen[k] = (obj, coords)
     if copier is None or not copier.copy(datas, starts, out):
         for lo, data in zip(starts, datas):
             out[lo:lo + data.size] = data

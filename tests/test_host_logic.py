@@ -353,3 +353,110 @@ def test_fresh_objects_are_validated_by_the_threaded_comparison():
     other.set_block(2, 2, sp.coo_matrix((K.data, (row, K.col)), shape=K.shape))
     assert not structure.gather_values(other, st, out, copier)
     assert not structure.gather_values(other, st, out)
+
+
+def test_fastptr_tables():
+    """csrc/fastptr.c (CPython helper of the host binding): addresses / byte lengths of many buffers in one call,
+    -1 for anything that is not a contiguous buffer of the requested type."""
+    from parapint_b200 import _pp_fastptr as fp
+    rng = np.random.default_rng(5)
+    arrays = [rng.standard_normal(int(k)) for k in rng.integers(0, 500, size=50)]
+    ptr, ln = np.zeros(50, dtype=np.uintp), np.zeros(50, dtype=np.int64)
+    assert fp.fill(arrays, ptr, ln, "d") == 50
+    assert all(int(p) == a.ctypes.data for p, a in zip(ptr, arrays) if a.size) and np.array_equal(ln, [a.nbytes for a in arrays])
+    assert fp.fill(tuple(arrays), ptr, ln) == 50                                   # any sequence, any type
+    assert fp.fill(arrays[:3] + [np.zeros(4, dtype=np.int64)], ptr, ln, "d") == -1  # wrong type
+    assert fp.fill([np.zeros((4, 4))[:, 1]], ptr, ln, "d") == -1                    # strided
+    assert fp.fill([object()], ptr, ln) == -1                                       # no buffer
+    with pytest.raises(ValueError):
+        fp.fill(arrays, np.zeros(3, dtype=np.uintp), ln)
+    ro = np.arange(5.0)
+    ro.setflags(write=False)
+    assert fp.fill([ro], ptr, ln, "d") == 1 and int(ptr[0]) == ro.ctypes.data        # read-only sources are fine
+    a = [np.arange(7, dtype=np.int32), np.arange(3, dtype=np.int64)]
+    b = [x.copy() for x in a]
+    pa, pb = np.zeros(2, dtype=np.uintp), np.zeros(2, dtype=np.uintp)
+    assert fp.pairs(a, b, pa, pb, ln) == 2 and list(ln[:2]) == [28, 24]
+    assert [int(v) for v in pb] == [x.ctypes.data for x in b]
+    assert fp.pairs(a, [b[0], b[1].astype(np.float64)], pa, pb, ln) == -1          # same size, other type
+    assert fp.pairs(a, [b[0], np.arange(4, dtype=np.int64)], pa, pb, ln) == -1     # other length
+    assert fp.pairs(a, b[:1], pa, pb, ln) == -1
+    assert fp.same(a, list(a)) and fp.same(a, tuple(a)) and not fp.same(a, b) and not fp.same(a, a[:1])
+
+
+def test_gather_paths_agree_with_and_without_the_pointer_helper(monkeypatch):
+    """The interpreter builds the same pointer tables as csrc/fastptr.c: flat and nested systems, fresh and re-used
+    objects, pattern changes detected on both paths."""
+    from oracle.kkt_generator import EstimationModel
+    m = EstimationModel(5, 40, 3, 6)
+    st = structure.analyse(m.build_kkt())
+    fresh, other = m.build_kkt(), m.build_kkt()
+    K = other.get_block(2, 2).tocoo()
+    col = K.col.copy()
+    col[3] += 1 if col[3] + 1 < K.shape[1] else -1
+    other.set_block(2, 2, sp.coo_matrix((K.data, (K.row, col)), shape=K.shape))
+    ref = np.zeros(st.nvals)
+    assert structure.gather_values(fresh, st, ref)
+    for helper in (True, False):
+        if not helper:
+            monkeypatch.setattr(native, "_fp", None)
+            monkeypatch.setattr(structure, "_fp", None)
+        copier = native.HostCopier(3)
+        st.__dict__.pop("_leaf_seen", None)
+        for _ in range(2):       # second pass: the objects validated by the first one
+            out = np.zeros(st.nvals)
+            assert structure.gather_values(fresh, st, out, copier) and np.array_equal(out, ref)
+        assert not structure.gather_values(other, st, out, copier)
+        assert structure.gather_values(fresh, st, out, copier) and np.array_equal(out, ref)
+
+
+def test_validated_objects_are_revalidated_when_their_index_tuple_changes():
+    """A leaf that passed the comparison is taken on trust afterwards only while it is the same object with the same
+    index tuple: a new index tuple on the same object (or a new sub-leaf inside the same nested block) is compared
+    again -- and rejected when it differs."""
+    from parapint_b200.carriers import BlockMatrix
+
+    def nested(seed):
+        r = np.random.default_rng(seed)
+        H = sp.coo_matrix((r.standard_normal(5), ([0, 1, 2, 3, 3], [0, 1, 2, 3, 0])), shape=(4, 4))
+        J = sp.coo_matrix((r.standard_normal(3), ([0, 1, 1], [0, 2, 3])), shape=(2, 4))
+        K = BlockMatrix(2, 2)
+        K.set_block(0, 0, H)
+        K.set_block(1, 0, J)
+        K.set_block(0, 1, J.transpose().tocoo())
+        K.set_block(1, 1, sp.coo_matrix((2, 2)))
+        return K
+
+    def system(seed):
+        kkt = BlockMatrix(3, 3)
+        for i in range(2):
+            kkt.set_block(i, i, nested(10 * seed + i))
+            kkt.set_block(2, i, sp.coo_matrix(([-1.0], ([0], [i])), shape=(1, 6)))
+        kkt.set_block(2, 2, sp.coo_matrix((1, 1)))
+        return kkt
+
+    st = structure.analyse(system(1))
+    copier = native.HostCopier(2)
+    kkt = system(2)
+    out = np.zeros(st.nvals)
+    for scale in (1.0, 3.0):                    # the second call takes the validated objects on trust
+        assert structure.gather_values(kkt, st, out, copier)
+        assert np.array_equal(out, np.concatenate([kkt.get_block(i, i).tocoo().data if kind == "K" else
+                                                   kkt.get_block(2, i).tocoo().data for kind, i, _, _ in st.segments]))
+        kkt.get_block(0, 0).get_block(0, 0).data[:] *= scale
+    seen = st.__dict__["_leaf_seen"]
+    assert all(s is not None for s in seen)
+    # same nested object, one sub-leaf replaced by one with another pattern
+    J = kkt.get_block(1, 1).get_block(1, 0)
+    kkt.get_block(1, 1).set_block(1, 0, sp.coo_matrix((J.data, (J.row, np.array([0, 1, 3]))), shape=J.shape))
+    assert not structure.gather_values(kkt, st, out, copier)
+    # same flat leaf object, index tuple swapped for an equal one: compared again and accepted
+    A = kkt.get_block(2, 0)
+    kkt2 = system(2)
+    assert structure.gather_values(kkt2, st, out, copier)
+    A2 = kkt2.get_block(2, 0)
+    if hasattr(A2, "coords"):
+        A2.coords = (A2.coords[0].copy(), A2.coords[1].copy())
+        assert structure.gather_values(kkt2, st, out, copier)
+        A2.coords = (A2.coords[0].copy(), np.array([1], dtype=A2.coords[1].dtype))
+        assert not structure.gather_values(kkt2, st, out, copier)
