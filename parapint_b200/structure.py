@@ -275,6 +275,20 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
     threads when there is one."""
     N = st.n_blocks
     get = matrix.get_block
+    # whole-matrix fast path: every segment is the flat COO leaf validated last time and carries the index tuple it had
+    # then (an interior-point loop that updates the values in place): four list passes, no per-leaf branching
+    fast = st.__dict__.get("_fast_leaves")
+    if fast is not None:
+        blks = [get(i, j) for i, j in fast[0]]
+        if _same_objects(blks, fast[1]) and _same_objects([b.coords for b in blks], fast[2]):
+            datas = [b.data for b in blks]
+            if [d.size for d in datas] != fast[3]:
+                return False
+            starts = st.segment_starts
+            if copier is None or not copier.copy(datas, starts, out):
+                for lo, data in zip(starts, datas):
+                    out[lo:lo + data.size] = data
+            return True
     datas, starts = [], []
     fresh_idx, ref_idx = [], []   # fresh / analysed index arrays, compared in one threaded call at the end
     validated = []                # (segment, leaf object(s), index tuple(s)) that pass once that comparison has passed
@@ -351,6 +365,13 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
             return False
     for k, obj, coords in validated:   # these objects now count as validated while their index tuples stay untouched
         seen[k] = (obj, coords)
+    flat = [sk for sk in seen if sk is not None and type(sk[1]) is tuple]
+    if len(flat) == len(seen):   # every segment is a flat leaf with an index tuple: remember them for the fast path
+        keys = [(i, i) if kind != "A" else (N, i) for kind, i, _, _ in st.segments]
+        st.__dict__["_fast_leaves"] = (keys, [sk[0] for sk in flat], [sk[1] for sk in flat],
+                                       [hi - lo for _, _, lo, hi in st.segments])
+    else:
+        st.__dict__.pop("_fast_leaves", None)
     if copier is None or not copier.copy(datas, starts, out):
         for lo, data in zip(starts, datas):
             out[lo:lo + data.size] = data
@@ -359,9 +380,13 @@ def gather_values(matrix, st: Structure, out: np.ndarray, copier=None) -> bool:
 
 def pack_rhs(rhs, st: Structure, out: np.ndarray, copier=None):
     if copier is not None:
-        blocks = [rhs.get_block(i) for i in st.local_blocks]
-        if all(type(b) is np.ndarray and b.ndim == 1 and b.size == st.rhs_offsets[f + 1] - st.rhs_offsets[f]
-               for f, b in enumerate(blocks)) and copier.copy(blocks, st.rhs_offsets[:-1], out):
+        get = rhs.get_block
+        blocks = [get(i) for i in st.local_blocks]
+        sizes = st.__dict__.get("_rhs_sizes")
+        if sizes is None:
+            sizes = st.__dict__["_rhs_sizes"] = [int(n) for n in np.diff(st.rhs_offsets)]
+        if {type(b) for b in blocks} <= {np.ndarray} and [b.size for b in blocks] == sizes \
+                and copier.copy(blocks, st.rhs_offsets[:-1], out):   # (the copier insists on contiguous float64)
             return
     for f, i in enumerate(st.local_blocks):
         blk = rhs.get_block(i)
