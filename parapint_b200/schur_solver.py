@@ -337,7 +337,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.max_refine = int(max_refine)
         self.last_residual = None
         self.refine_steps = 0
-        self._copiers = [None, None]
+        self._copiers = [None, None, None]
         env = os.environ.get("PARAPINT_B200_HOST_THREADS")   # 0 disables the threaded host gather
         self.host_threads = int(env) if env not in (None, "") else None
         self.schur_complement_solver = schur_complement_solver
@@ -401,7 +401,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         self.local_block_indices = list(st.local_blocks)
         hint = np.zeros(st.nvals)
         structure.gather_values(matrix, st, hint)  # values only steer the ordering (2x2 pivot pre-selection)
-        self._copiers = [None, None]               # pointer tables of the old structure are stale
+        self._copiers = [None, None, None]               # pointer tables of the old structure are stale
         self._uploaded_token = None
         if self._classes is not None:
             per_block, coupling = self._classes
@@ -582,12 +582,13 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         x_local, x_c = self._refine(x_local, x_c)
         if be.failed or not np.all(np.isfinite(x_c[: st.m_c])):
             raise RuntimeError("back solve failed" + (f": {be.last_error}" if be.last_error else ""))
-        out = structure.unpack_solution(rhs, st, x_local, x_c[: st.m_c])
+        out = structure.unpack_solution(rhs, st, x_local, x_c[: st.m_c], self._copier(2))
         timer.stop("back_solve")
         return out
 
     def _copier(self, which):
-        """Threaded host gather for the CUDA backend (values: slot 0, right-hand side: slot 1)."""
+        """Threaded host gather / scatter for the CUDA backend (values: slot 0, right-hand side: slot 1, solution:
+        slot 2; one pointer-table cache each)."""
         if not isinstance(self.backend, CudaBackend) or self.host_threads == 0:
             return None
         if self._copiers[which] is None:

@@ -431,12 +431,25 @@ def _nested_like(template, values):
         return blk
 
 
-def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray):
+THREADED_UNPACK_BYTES = 4 << 20   # solutions of at least this size leave the pinned buffer through the copy pool
+
+
+def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray, copier=None):
     """New vector with the block structure of ``rhs`` (``mpi_explicit_schur_complement.py:390``;
     nested blocks keep their structure as the SciPy leaf does, ``scipy_interface.py:57-60``).
-    The blocks are views of one freshly allocated array (nothing aliases solver buffers)."""
+    The blocks are views of one freshly allocated array (nothing aliases solver buffers); ``copier`` (a
+    ``native.HostCopier``) fills that array with a few threads when the solution is large (20 MB per rank at
+    BASELINE configs 3 and 4: 4 ms for one thread)."""
     out = rhs.empty_like_structure() if hasattr(rhs, "empty_like_structure") else rhs.copy_structure()
-    flat = np.array(x_local[: st.local_dim], dtype=np.float64)  # one copy out of the pinned buffer
+    n = st.local_dim
+    flat = None
+    if copier is not None and n * 8 >= THREADED_UNPACK_BYTES and x_local.dtype == np.float64 \
+            and x_local.flags.c_contiguous:
+        flat = np.empty(n, dtype=np.float64)
+        if not copier.copy([flat], [0], x_local, to_staging=False):
+            flat = None
+    if flat is None:
+        flat = np.array(x_local[:n], dtype=np.float64)  # one copy out of the pinned buffer
     offs = st.rhs_offsets
     get, put = rhs.get_block, out.set_block
     for f, i in enumerate(st.local_blocks):

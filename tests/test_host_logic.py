@@ -460,3 +460,38 @@ def test_validated_objects_are_revalidated_when_their_index_tuple_changes():
         assert structure.gather_values(kkt2, st, out, copier)
         A2.coords = (A2.coords[0].copy(), np.array([1], dtype=A2.coords[1].dtype))
         assert not structure.gather_values(kkt2, st, out, copier)
+
+
+def test_large_solutions_are_unpacked_by_the_copy_pool(monkeypatch):
+    """unpack_solution hands a solution of several MB to the threaded copy (pp_host_copy, staging -> array): same
+    blocks as the single-threaded path, nothing aliases the staging buffer."""
+    from parapint_b200.carriers import BlockVector
+    rng = np.random.default_rng(8)
+    sizes = [70001, 3, 90000, 50000]
+    rhs = BlockVector(len(sizes) + 1)
+    for i, n in enumerate(sizes):
+        rhs.set_block(i, np.zeros(n))
+    inner = BlockVector(2)
+    inner.set_block(0, np.zeros(2))
+    inner.set_block(1, np.zeros(3))
+    rhs.set_block(len(sizes), inner)
+    st = structure.Structure(n_blocks=len(sizes), m_c=5, local_blocks=list(range(len(sizes))),
+                             block_n=np.asarray(sizes, dtype=np.int32), border_ptr=np.zeros(len(sizes) + 1, dtype=np.int64),
+                             border_rows=np.zeros(0, dtype=np.int32), dest_front=np.zeros(0, dtype=np.int32),
+                             dest_row=np.zeros(0, dtype=np.int32), dest_col=np.zeros(0, dtype=np.int32),
+                             rhs_offsets=np.concatenate(([0], np.cumsum(sizes))).astype(np.int64))
+    staging = rng.standard_normal(st.local_dim + 7)      # (the pinned buffer may be longer than the solution)
+    x_c = rng.standard_normal(5)
+    monkeypatch.setattr(structure, "THREADED_UNPACK_BYTES", 1 << 20)
+    copier = native.HostCopier(3)
+    calls = []
+    real = copier.copy
+    copier.copy = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    a = structure.unpack_solution(rhs, st, staging, x_c, copier)
+    b = structure.unpack_solution(rhs, st, staging, x_c)
+    assert calls, "the threaded path was not taken"
+    for i in range(len(sizes)):
+        assert np.array_equal(a.get_block(i), b.get_block(i))
+        assert np.array_equal(a.get_block(i), staging[st.rhs_offsets[i]:st.rhs_offsets[i + 1]])
+        assert not np.shares_memory(a.get_block(i), staging)
+    assert np.array_equal(a.get_block(len(sizes)).flatten(), x_c) and a.get_block(len(sizes)).nblocks == 2
