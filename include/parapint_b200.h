@@ -242,6 +242,16 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
 int pp_host_equal(int64_t nseg, void *const *a, void *const *b, const int64_t *len, int threads, int *equal);
 
 /*
+ * Host-side helper (no CUDA): announce that a pp_host_copy / pp_stage_values / pp_host_equal call follows shortly --
+ * typically issued just before the caller blocks on the GPU (the scatter of the solution follows the wait) or starts
+ * walking the matrix whose values it is about to gather.  The pool's workers (up to `threads`) wake up now and spin for
+ * the job for at most `spin_ns` nanoseconds (capped at 2 ms) instead of being woken by it, which costs tens of
+ * microseconds: as much as the copy of a megabyte.  Without a following job they go back to sleep.  No counterpart in
+ * the reference (its per-block copies are single-threaded NumPy, explicit_schur_complement.py:96-101).
+ */
+int pp_host_wake(int threads, int64_t spin_ns);
+
+/*
  * pp_host_copy + the host-to-device transfer of the values, pipelined: the segments (which must tile the `nvals`
  * doubles of the analysed pattern in order) are gathered into the pinned `staging` buffer in `chunks` shares and
  * every share is sent to the device as soon as it is complete, so the transfer of one overlaps the gather of the

@@ -1942,6 +1942,17 @@ int pp_host_copy(int64_t nseg, void *const *ptr, const int64_t *off, const int64
   return PP_SUCCESSFUL;
 }
 
+int pp_host_wake(int threads, int64_t spin_ns) {
+  if (threads < 0 || spin_ns < 0) return misuse("pp_host_wake: negative argument");
+  try {
+    CopyPool::instance().wake(threads, spin_ns);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return PP_ERROR;
+  }
+  return PP_SUCCESSFUL;
+}
+
 int pp_host_equal(int64_t nseg, void *const *a, void *const *b, const int64_t *len, int threads, int *equal) {
   if (nseg < 0 || !equal || (nseg > 0 && (!a || !b || !len))) return misuse("pp_host_equal: null argument");
   for (int64_t k = 0; k < nseg; ++k)

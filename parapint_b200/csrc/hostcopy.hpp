@@ -70,6 +70,22 @@ class CopyPool {
     dispatch({nseg, a, nullptr, len, nullptr, false, 0, 0, b}, threads);
     return mismatch_.load(std::memory_order_relaxed) == 0;
   }
+  // A job follows shortly (the caller is about to wait for the GPU and will scatter the result, or is walking the
+  // matrix whose values it will gather): wake the workers now and let them spin for it for at most `spin_ns`, so the
+  // job does not pay a futex wake-up (tens of microseconds -- as much as copying a megabyte).  Bounded: without a job
+  // the workers go back to sleep when the window closes.
+  void wake(int threads, int64_t spin_ns) {
+    const int T = std::min(std::max(threads, 1), kMax);
+    if (T <= 1 || spin_ns <= 0) return;
+    std::lock_guard<std::mutex> serial(api_);
+    ensure_workers(T - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      ++ping_;
+      ping_spin_ns_ = std::min(spin_ns, kMaxWakeNs);
+    }
+    cv_.notify_all();
+  }
 
  private:
   static constexpr int kMax = 8;
@@ -157,17 +173,25 @@ class CopyPool {
     }
   }
   void loop(int id) {
-    uint64_t seen = 0;
+    uint64_t seen = 0, seen_ping = 0;
+    int64_t window = kSpinNs;
     for (;;) {
       Job j;
       // a gather comes in a few shares a few microseconds apart (pp_stage_values): stay awake for a moment after a job
-      // instead of paying a futex wake-up per share
-      for (const auto t0 = now_ns(); gen_pub_.load(std::memory_order_acquire) == seen && now_ns() - t0 < kSpinNs;) cpu_relax();
+      // instead of paying a futex wake-up per share; after a wake-up call (wake) for as long as the caller asked
+      for (const auto t0 = now_ns(); gen_pub_.load(std::memory_order_acquire) == seen && now_ns() - t0 < window;) cpu_relax();
+      window = kSpinNs;
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen || ping_ != seen_ping; });
         if (stop_) return;
+        if (gen_ == seen) {   // a wake-up call, no job yet: spin at the top of the loop for the job that follows
+          seen_ping = ping_;
+          window = ping_spin_ns_;
+          continue;
+        }
         seen = gen_;
+        seen_ping = ping_;
         j = job_;
       }
       if (id >= j.T) continue;   // this job uses fewer threads
@@ -189,6 +213,7 @@ class CopyPool {
     for (auto &t : workers_) t.join();
   }
   static constexpr int64_t kSpinNs = 30000;   // spin for at most 30 us (by the clock: a `pause` is 10-140 cycles)
+  static constexpr int64_t kMaxWakeNs = 2000000;   // a wake-up call keeps the workers spinning for at most 2 ms
   static int64_t now_ns() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
   }
@@ -199,7 +224,8 @@ class CopyPool {
   std::condition_variable cv_, done_;
   std::vector<std::thread> workers_;
   Job job_{};
-  uint64_t gen_ = 0;
+  uint64_t gen_ = 0, ping_ = 0;
+  int64_t ping_spin_ns_ = 0;
   int pending_ = 0;
   bool stop_ = false;
 };

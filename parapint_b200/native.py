@@ -48,6 +48,7 @@ SIGNATURES = {
     "pp_schur_tail": (C.c_int, [_vp, _f64p]),
     "pp_host_copy": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "pp_host_equal": (C.c_int, [C.c_int64, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "pp_host_wake": (C.c_int, [C.c_int, C.c_int64]),
     "pp_peer_allreduce": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_uint32, C.c_int64, _vp, _vp]),
     "pp_stage_values": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "pp_factor_bytes": (C.c_int64, [_vp]),
@@ -123,22 +124,33 @@ class HostCopier:
     an interior-point loop updates the KKT values in place); strong references are held so ids cannot be reused."""
 
     def __init__(self, threads=None):
-        import os
         self.lib = load()
         if threads:
             self.threads = int(threads)
         else:
-            # share the host cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE): this rank's
-            # share of the cores it may run on, less one for the interpreter thread that drives the GPU
-            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-            try:
-                cores = len(os.sched_getaffinity(0))
-            except (AttributeError, OSError):
-                cores = os.cpu_count() or 2
-            self.threads = max(1, min(8, cores // ranks - 1))
+            # share the host cores with the other ranks of this node: this rank's share of the cores it may run on,
+            # less one for the interpreter thread that drives the GPU
+            self.threads = max(1, min(8, self._cores_per_rank() - 1))
+        env = os.environ.get("PARAPINT_B200_WAKE_US")
+        if env not in (None, ""):
+            self.wake_us = float(env)
+        else:
+            # workers that spin through the GPU waits need cores of their own: with fewer than eight per rank the pool
+            # is woken by its jobs as before
+            self.wake_us = 400.0 if self._cores_per_rank() >= 8 else 0.0
         self._keep = None
         self._tables = None
         self.stage = None   # (handle, stream getter): gather straight into a transfer (see copy)
+
+    @staticmethod
+    def _cores_per_rank():
+        """Host cores this rank may count on (torchrun exports LOCAL_WORLD_SIZE)."""
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 2
+        return cores // ranks
 
     def _table(self, arrays, offsets):
         import numpy as np
@@ -164,6 +176,14 @@ class HostCopier:
         self._keep = list(arrays)
         self._tables = (ptr, off, ln, np_ptr(ptr), np_ptr(off), np_ptr(ln))
         return self._tables
+
+    def wake(self, spin_us=None):
+        """A copy follows shortly (after a wait for the GPU, or after walking the matrix): the pool's workers wake up
+        now and spin for it, for at most ``spin_us`` microseconds (``pp_host_wake``; default: the
+        ``PARAPINT_B200_WAKE_US`` environment variable, 400; 0 disables)."""
+        us = self.wake_us if spin_us is None else spin_us
+        if us > 0 and self.threads > 1:
+            self.lib.pp_host_wake(self.threads, int(us * 1000))
 
     def all_equal(self, fresh, refs):
         """True when ``fresh[k]`` and ``refs[k]`` hold the same bytes for every k (index arrays of fresh leaves against

@@ -461,6 +461,8 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         be = self.backend
         timer.start("form SC")
         reuse = token is not None and token == self._uploaded_token
+        if not reuse:
+            self._wake(0)   # the copy pool wakes up while the matrix is being walked
         changed = False if reuse else not structure.gather_values(matrix, self._st, be.values, self._copier(0))
         self._uploaded_token = None
         has_shifts = self._classes is not None or any(shifts)
@@ -488,6 +490,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
                 return self._result(code, raise_on_error, "Numeric factorization")
             timer.stop("form SC")
             timer.start("factor SC")
+            self._wake(1)   # ... and stays awake through the wait for the GPU: the right-hand side is packed next
             code = be.numeric_coupling(schur_local)
             timer.stop("factor SC")
             return self._result(code, raise_on_error, "Numeric factorization")
@@ -525,6 +528,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             schur_local = self.comm.allreduce_sum_(schur_local)
             timer.stop("communicate")
             if local_code in (0, LinearSolverStatus.singular.value):
+                self._wake(1)
                 code = be.numeric_coupling(schur_local)   # reads the reduced tail: same answer on every rank
                 tail = be.schur_tail()
             else:
@@ -576,6 +580,7 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         if be.failed:
             rc.fill_(float("nan"))      # a run-time failure on this rank: every rank sees it after the reduction
         rc = self.comm.allreduce_sum_(rc)
+        self._wake(2)   # the solution is scattered by the copy pool right after the wait for the GPU
         x_local, x_c = be.solve_backward(rc)
         if be.failed and self.comm.size == 1:
             raise RuntimeError(f"back solve failed: {be.last_error}")
@@ -596,6 +601,12 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
             if which == 0:
                 self._copiers[0].stage = (self.backend.handle, self.backend._stream)
         return self._copiers[which]
+
+    def _wake(self, which):
+        """Announce a host copy to the pool behind the copiers (``pp_host_wake``; bounded spin, see native.HostCopier)."""
+        copier = self._copier(which)
+        if copier is not None:
+            copier.wake()
 
     def _refine(self, x_local, x_c):
         """Iterative refinement with the values that were factorised: while ||b - K x|| > refine_tol ||b||,

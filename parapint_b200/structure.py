@@ -431,7 +431,8 @@ def _nested_like(template, values):
         return blk
 
 
-THREADED_UNPACK_BYTES = 4 << 20   # solutions of at least this size leave the pinned buffer through the copy pool
+THREADED_UNPACK_BYTES = 4 << 20   # solutions of at least this size leave the pinned buffer through the copy pool ...
+AWAKE_UNPACK_BYTES = 256 << 10    # ... or of this size when the pool has been told to stay awake for them (copier.wake_us)
 
 
 def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray, copier=None):
@@ -443,7 +444,10 @@ def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray, co
     out = rhs.empty_like_structure() if hasattr(rhs, "empty_like_structure") else rhs.copy_structure()
     n = st.local_dim
     flat = None
-    if copier is not None and n * 8 >= THREADED_UNPACK_BYTES and x_local.dtype == np.float64 \
+    limit = THREADED_UNPACK_BYTES
+    if copier is not None and getattr(copier, "wake_us", 0) > 0 and getattr(copier, "threads", 1) > 1:
+        limit = min(limit, AWAKE_UNPACK_BYTES)
+    if copier is not None and n * 8 >= limit and x_local.dtype == np.float64 \
             and x_local.flags.c_contiguous:
         flat = np.empty(n, dtype=np.float64)
         if not copier.copy([flat], [0], x_local, to_staging=False):

@@ -495,3 +495,42 @@ def test_large_solutions_are_unpacked_by_the_copy_pool(monkeypatch):
         assert np.array_equal(a.get_block(i), staging[st.rhs_offsets[i]:st.rhs_offsets[i + 1]])
         assert not np.shares_memory(a.get_block(i), staging)
     assert np.array_equal(a.get_block(len(sizes)).flatten(), x_c) and a.get_block(len(sizes)).nblocks == 2
+
+
+@pytest.mark.timeout(120)
+def test_copy_pool_wake_calls_interleave_with_jobs():
+    """pp_host_wake only changes WHEN the pool's workers are awake: any interleaving of wake-up calls, gathers,
+    scatters and comparisons gives the results of the plain calls (and terminates)."""
+    import time
+    lib = native.load()
+    rng = np.random.default_rng(21)
+    assert lib.pp_host_wake(-1, 10) < 0 and lib.pp_host_wake(4, -5) < 0        # misuse is reported, not executed
+    cp = native.HostCopier(6)
+    cp.wake_us = 50.0
+    for it in range(400):
+        op = rng.integers(0, 5)
+        if op == 0:
+            cp.wake(float(rng.choice([1, 20, 200, 3000])))
+            if rng.integers(0, 4) == 0:
+                time.sleep(float(rng.choice([0.0, 2e-5, 5e-4])))                # sometimes no job follows in time
+            continue
+        n = int(rng.choice([3, 2000, 40000, 300000]))
+        k = int(rng.integers(1, 6))
+        arrays = [rng.standard_normal(int(rng.integers(0, n + 1))) for _ in range(k)]
+        offs = np.concatenate(([0], np.cumsum([a.size for a in arrays])))
+        staging = np.full(offs[-1] + 3, np.nan)
+        if op in (1, 2):
+            assert cp.copy(arrays, offs[:-1], staging)
+            assert np.array_equal(staging[: offs[-1]], np.concatenate(arrays)) and np.all(np.isnan(staging[offs[-1]:]))
+        elif op == 3:
+            staging[: offs[-1]] = rng.standard_normal(offs[-1])
+            back = [np.zeros_like(a) for a in arrays]
+            assert cp.copy(back, offs[:-1], staging, to_staging=False)
+            assert np.array_equal(np.concatenate(back), staging[: offs[-1]])
+        else:
+            other = [a.copy() for a in arrays]
+            assert cp.all_equal(arrays, other) is True
+            big = [j for j, a in enumerate(other) if a.size]
+            if big:
+                other[big[-1]][-1] += 1.0
+                assert cp.all_equal(arrays, other) is False
