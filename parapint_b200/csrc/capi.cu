@@ -1680,8 +1680,23 @@ static void run_backward(pp_handle *h, const double *rc_sum_dev, const double *d
   CK(cudaGetLastError());
 }
 
+// A second stream of the handle and the events to fork it from / join it into the caller's stream.
+static cudaStream_t aux_stream(pp_handle *h, int g) {
+  if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  while ((int)h->aux_streams.size() <= g) {
+    cudaStream_t s2;
+    cudaEvent_t e2;
+    CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    h->aux_streams.push_back(s2);
+    h->aux_events.push_back(e2);
+  }
+  return h->aux_streams[g];
+}
+
+// `join`: work on another stream (the residual check) that the synchronisation has to cover as well
 static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *x_local, double *x_c,
-                     cudaStream_t st) {
+                     cudaStream_t st, cudaEvent_t join = nullptr) {
   const int mc = h->m_c;
   // pinned caller buffers receive the device data directly; pageable ones go through the handle's staging buffer
   const bool direct = (h->local_dim == 0 || is_pinned_host(x_local)) && (mc == 0 || is_pinned_host(x_c));
@@ -1689,6 +1704,7 @@ static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *
     if (h->local_dim > 0)
       CK(cudaMemcpyAsync(x_local, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mc > 0) CK(cudaMemcpyAsync(x_c, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (join) CK(cudaStreamWaitEvent(st, join, 0));
     CK(cudaStreamSynchronize(st));
     return;
   }
@@ -1697,6 +1713,7 @@ static void copy_out(pp_handle *h, const double *dx, const double *dxc, double *
     CK(cudaMemcpyAsync(h->pin_vec.p, dx, (size_t)h->local_dim * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (mc > 0)
     CK(cudaMemcpyAsync(h->pin_vec.p + h->local_dim, dxc, (size_t)mc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (join) CK(cudaStreamWaitEvent(st, join, 0));
   CK(cudaStreamSynchronize(st));
   if (h->local_dim > 0) std::memcpy(x_local, h->pin_vec.p, (size_t)h->local_dim * sizeof(double));
   if (mc > 0) std::memcpy(x_c, h->pin_vec.p + h->local_dim, (size_t)mc * sizeof(double));
@@ -1755,15 +1772,22 @@ int pp_solve_backward(pp_handle *h, const double *rc_sum_dev, const double *rhs_
     h->last_xc = dxc;
     h->solved = true;
     h->norms_valid = false;
+    cudaEvent_t join = nullptr;
     if (!on_device && h->auto_residual) {
-      // single rank: nothing to reduce, so the residual norms ride on the synchronisation of the copy-out
+      // single rank: nothing to reduce, so the residual norms ride on the synchronisation of the copy-out.  The check
+      // only reads x: it runs on a second stream beside the device-to-host copy of x instead of in front of it.
       if (h->res_buf.n < (size_t)mc + 2) h->res_buf.alloc((size_t)mc + 2);
-      enqueue_residual_local(h, h->res_buf.p, st);
-      enqueue_residual_norms(h, h->res_buf.p, st);
+      cudaStream_t s2 = aux_stream(h, 0);
+      CK(cudaEventRecord(h->ev_fork, st));
+      CK(cudaStreamWaitEvent(s2, h->ev_fork, 0));
+      enqueue_residual_local(h, h->res_buf.p, s2);
+      enqueue_residual_norms(h, h->res_buf.p, s2);
       CK(cudaGetLastError());
+      join = h->aux_events[0];
+      CK(cudaEventRecord(join, s2));
     }
     if (!on_device) {
-      copy_out(h, dx, dxc, x_local, x_c, st);
+      copy_out(h, dx, dxc, x_local, x_c, st, join);
       h->norms_valid = h->auto_residual;
     }
     return (int)PP_SUCCESSFUL;
