@@ -135,9 +135,9 @@ class HostCopier:
         if env not in (None, ""):
             self.wake_us = float(env)
         else:
-            # workers that spin through the GPU waits need cores of their own: with fewer than eight per rank the pool
+            # workers that spin through the GPU waits need cores of their own: with fewer than twelve per rank the pool
             # is woken by its jobs as before
-            self.wake_us = 400.0 if self._cores_per_rank() >= 8 else 0.0
+            self.wake_us = 400.0 if self._cores_per_rank() >= 12 else 0.0
         self._keep = None
         self._tables = None
         self.stage = None   # (handle, stream getter): gather straight into a transfer (see copy)
