@@ -454,20 +454,24 @@ def unpack_solution(rhs, st: Structure, x_local: np.ndarray, x_c: np.ndarray, co
             flat = None
     if flat is None:
         flat = np.array(x_local[:n], dtype=np.float64)  # one copy out of the pinned buffer
-    offs = st.rhs_offsets
+    bounds = st.__dict__.get("_rhs_bounds")
+    if bounds is None:   # plain integers: slicing with NumPy scalars costs a conversion per bound
+        offs = [int(v) for v in st.rhs_offsets]
+        bounds = st.__dict__["_rhs_bounds"] = list(zip(offs[:-1], offs[1:]))
     get, put = rhs.get_block, out.set_block
-    for f, i in enumerate(st.local_blocks):
+    ndarray = np.ndarray
+    for i, (lo, hi) in zip(st.local_blocks, bounds):
         template = get(i)
-        seg = flat[offs[f]:offs[f + 1]]
-        if hasattr(template, "nblocks"):
+        seg = flat[lo:hi]
+        if type(template) is ndarray or not hasattr(template, "nblocks"):
+            put(i, seg)
+        else:
             try:
                 put(i, _views_like(template, seg))
             except Exception:  # noqa: BLE001 - an unusual vector class
                 blk = template.copy_structure()
                 blk.copyfrom(seg)
                 put(i, blk)
-        else:
-            put(i, seg)
     template = get(st.n_blocks)
     if hasattr(template, "nblocks"):
         put(st.n_blocks, _nested_like(template, x_c))
