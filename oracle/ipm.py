@@ -241,7 +241,22 @@ class StochasticInterface:
 
     def evaluate_ineq_constraints(self): return np.concatenate([s.nlp.ineq() for s in self.sc])
 
+    # The scenarios are closed-form QPs: every constraint is linear, so both Jacobians are constant.  They are
+    # assembled once (N x (N + 1) blocks through ``bmat`` cost more than the rest of an iteration) and the same CSR
+    # object is handed out afterwards; callers only read it.
     def evaluate_jacobian_eq(self):
+        jac = self.__dict__.get("_jac_eq")
+        if jac is None:
+            jac = self._jac_eq = self._assemble_jacobian_eq()
+        return jac
+
+    def evaluate_jacobian_ineq(self):
+        jac = self.__dict__.get("_jac_ineq")
+        if jac is None:
+            jac = self._jac_ineq = self._assemble_jacobian_ineq()
+        return jac
+
+    def _assemble_jacobian_eq(self):
         rows = []
         for i, (s, L, C) in enumerate(zip(self.sc, self.L, self.C)):
             row = [None] * (self.N + 1)
@@ -253,7 +268,7 @@ class StochasticInterface:
             rows.append(row)
         return sp.bmat(rows).tocsr()
 
-    def evaluate_jacobian_ineq(self):
+    def _assemble_jacobian_ineq(self):
         blocks = [s.nlp.A_in for s in self.sc]
         J = sp.block_diag(blocks) if blocks else sp.coo_matrix((0, 0))
         return sp.hstack([J, sp.coo_matrix((J.shape[0], self.n_c))]).tocsr()
@@ -422,7 +437,7 @@ class DynamicInterface(StochasticInterface):
                                                self.Lf[i] @ s.nlp.x - self.Cf[i] @ self.z])
                                for i, s in enumerate(self.sc)])
 
-    def evaluate_jacobian_eq(self):                                # :254-272,753-765
+    def _assemble_jacobian_eq(self):                               # :254-272,753-765
         rows = []
         for i, s in enumerate(self.sc):
             row = [sp.coo_matrix((s.nlp.n_eq + self.nb[i] + self.nf[i], t.nlp.n)) for t in self.sc] + [None]

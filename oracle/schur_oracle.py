@@ -75,22 +75,39 @@ def dense_inertia(dense, method="eigvals", tol=1e-8):
     elif method == "eigvalsh":
         eig = sla.eigvalsh((dense + dense.T) * 0.5)
     elif method == "ldl":
-        _, d, _ = sla.ldl(np.tril(dense) + np.tril(dense, -1).T, lower=True)
-        pos = neg = zero = 0
+        # LAPACK dsytrf called directly (scipy.linalg.ldl runs the same routine and then spends most of its time
+        # rebuilding L and D in Python); lower storage: ipiv[k] > 0 is a 1x1 pivot, ipiv[k] = ipiv[k+1] < 0 a 2x2
+        # pivot whose off-diagonal entry sits at (k+1, k)
+        lwork, _ = sla.lapack.dsytrf_lwork(n, lower=1)      # blocked variant, as scipy.linalg.ldl asks for
+        ldu, ipiv, info = sla.lapack.dsytrf(np.asfortranarray(dense), lower=1, lwork=max(int(lwork), 1))
+        if info < 0:
+            raise ValueError(f"dsytrf: illegal argument {-info}")
+        diag = np.diagonal(ldu)
+        first = np.zeros(n, dtype=bool)         # first column of every 2x2 pivot
         k = 0
+        neg_piv = ipiv < 0
         while k < n:
-            if k + 1 < n and d[k + 1, k] != 0.0:
-                ev = np.linalg.eigvalsh(d[k:k + 2, k:k + 2])
-                pos += int(np.count_nonzero(ev > 0))
-                neg += int(np.count_nonzero(ev < 0))
-                zero += int(np.count_nonzero(ev == 0))
+            if neg_piv[k]:
+                first[k] = True
                 k += 2
             else:
-                pos += d[k, k] > 0
-                neg += d[k, k] < 0
-                zero += d[k, k] == 0
                 k += 1
-        return int(pos), int(neg), int(zero)
+        k2 = np.flatnonzero(first)
+        single = np.ones(n, dtype=bool)
+        single[k2] = False
+        single[k2 + 1] = False
+        d1 = diag[single]
+        pos, neg, zero = int(np.count_nonzero(d1 > 0)), int(np.count_nonzero(d1 < 0)), int(np.count_nonzero(d1 == 0))
+        if k2.size:
+            off = ldu[k2 + 1, k2]
+            blocks = np.empty((k2.size, 2, 2))
+            blocks[:, 0, 0], blocks[:, 1, 1] = diag[k2], diag[k2 + 1]
+            blocks[:, 0, 1] = blocks[:, 1, 0] = off
+            ev = np.linalg.eigvalsh(blocks)     # one LAPACK call per block, batched by NumPy
+            pos += int(np.count_nonzero(ev > 0))
+            neg += int(np.count_nonzero(ev < 0))
+            zero += int(np.count_nonzero(ev == 0))
+        return pos, neg, zero
     else:
         raise ValueError(method)
     pos = int(np.count_nonzero(eig > tol))

@@ -124,3 +124,40 @@ def test_restatement_equals_reference_live():
         o.numeric(k)
         assert np.array_equal(o.solve(m.build_rhs()).flatten(), x_ref.flatten())
         assert o.inertia() == tuple(int(v) for v in s.get_inertia())
+
+
+def test_pivot_sign_inertia_matches_scipy_ldl():
+    """``dense_inertia(..., "ldl")`` calls LAPACK ``dsytrf`` directly; the count of pivot signs must be the one
+    ``scipy.linalg.ldl`` (same routine, D rebuilt in Python) gives, on KKT-shaped matrices with zero (2,2) blocks,
+    diagonals over eight decades and a structurally zero row -- and only the lower triangle may be read."""
+    import scipy.linalg as sla
+
+    def by_scipy(dense):
+        n = dense.shape[0]
+        _, d, _ = sla.ldl(np.tril(dense) + np.tril(dense, -1).T, lower=True)
+        pos = neg = zero = k = 0
+        while k < n:
+            if k + 1 < n and d[k + 1, k] != 0.0:
+                ev = np.linalg.eigvalsh(d[k:k + 2, k:k + 2])
+                pos, neg, zero = pos + int((ev > 0).sum()), neg + int((ev < 0).sum()), zero + int((ev == 0).sum())
+                k += 2
+            else:
+                pos, neg, zero = pos + int(d[k, k] > 0), neg + int(d[k, k] < 0), zero + int(d[k, k] == 0)
+                k += 1
+        return pos, neg, zero
+
+    rng = np.random.default_rng(7)
+    for t in range(120):
+        n = int(rng.integers(1, 70))
+        m = int(rng.integers(0, n + 1))
+        H = rng.standard_normal((n, n))
+        H = H + H.T if t % 3 else np.diag(10.0 ** rng.uniform(-4, 4, n))
+        A = rng.standard_normal((m, n))
+        K = np.block([[H, A.T], [A, np.zeros((m, m))]])
+        if t % 7 == 0:
+            K[:, -1] = 0
+            K[-1, :] = 0
+        lower_only = np.tril(K) + np.triu(rng.standard_normal(K.shape), 1)
+        got = dense_inertia(lower_only, "ldl")
+        assert got == by_scipy(K), t
+        assert sum(got) == n + m
