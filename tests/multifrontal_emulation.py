@@ -8,8 +8,13 @@ safe in any order (the tests use diagonally dominant ones).  It validates the sy
 import numpy as np
 
 
-def emulate(plan, values, n, m):
-    """Returns the dense root front (lower triangle, before its factorisation) and the eliminated pivots."""
+def emulate(plan, values, n, m, block=False):
+    """Returns the dense root front (lower triangle, before its factorisation) and the eliminated pivots.
+
+    ``block``: eliminate the columns of a supernode all at once (``F22 - F21 F11^-1 F12``, which is what any pivot
+    order *inside* the front arrives at) -- for matrices whose fronts need 2x2 pivots, e.g. KKT blocks with zero
+    diagonals whose multiplier columns the analysis paired with a partner; ``pivots`` then holds the eigenvalues of
+    the ``F11`` blocks (their signs add up to the inertia of the eliminated part)."""
     nT, DR, ns = plan["nT"], plan["DR"], plan["ns"]
     nroot = nT + DR + m
     root = np.zeros((nroot, nroot))
@@ -41,7 +46,10 @@ def emulate(plan, values, n, m):
                     a, b = max(rel[i], rel[j]), min(rel[i], rel[j])
                     F[a, b] += M[i, j]
         F = np.tril(F) + np.tril(F, -1).T
-        for k in range(nc):
+        if block:
+            pivots.extend(np.linalg.eigvalsh(F[:nc, :nc]))
+            F[nc:, nc:] -= F[nc:, :nc] @ np.linalg.solve(F[:nc, :nc], F[:nc, nc:])
+        for k in range(0 if block else nc):
             d = F[k, k]
             pivots.append(d)
             l = F[k + 1:, k] / d

@@ -125,3 +125,23 @@ def test_interior_dissection_shortens_a_chain():
         R = np.tril(root) + np.tril(root, -1).T
         schur = R[nr:, nr:] - R[nr:, :nr] @ np.linalg.solve(R[:nr, :nr], R[:nr, nr:])
         assert np.allclose(schur, -A @ np.linalg.solve(K.toarray(), A.T), rtol=1e-9, atol=1e-11)
+
+
+def test_plan_fuzz_structured_patterns():
+    """A slice of ``tools/fuzz_symbolic.py``: banded, arrow, disconnected, grid, diagonal-only and KKT-shaped patterns
+    (multiplier columns without a diagonal entry -> ordered as 2x2 pivots with a partner), duplicated and shuffled
+    entries, every ordering and front-size cap; plan invariants, the Schur complement and the determinant must come out
+    of the numpy walk of the plan."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_symbolic.py")
+    spec = importlib.util.spec_from_file_location("fuzz_symbolic", path)
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(11)
+    walked = 0
+    with np.errstate(all="ignore"):
+        for case in range(35):
+            walked += not fuzz.one(rng, case).startswith("skipped")
+    assert walked >= 30
