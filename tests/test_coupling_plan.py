@@ -157,3 +157,18 @@ def test_dense_and_small_systems_stay_dense():
     ptr, rows = pack(cliques)
     assert not native.coupling_plan(m_c, ptr, rows, np.zeros(0), np.zeros(0))["sparse"]
     assert native.coupling_plan(m_c, ptr, rows, np.zeros(0), np.zeros(0), min_mc=10, max_density=0.9)["sparse"]
+
+
+def test_fuzz_clique_structures():
+    """A slice of ``tools/fuzz_coupling.py``: chains, random subsets, stars (scenario groups sharing first-stage
+    variables), trees, 2-D grids, disconnected islands with repeated / empty cliques and variables in no clique."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_coupling.py")
+    spec = importlib.util.spec_from_file_location("fuzz_coupling", path)
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(4)
+    for case in range(24):
+        fuzz.one(rng, case)
