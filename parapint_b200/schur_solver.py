@@ -652,6 +652,8 @@ class B200SchurComplementLinearSolver(LinearSolverInterface):
         return int(tot[0]), int(tot[1]), int(tot[2])
 
     def increase_memory_allocation(self, factor):
-        """Factor storage is sized exactly in the symbolic phase, so ``not_enough_memory`` is never
-        returned and there is nothing to grow (``explicit...:174-177`` forwards to the leaves)."""
+        """Factor storage is sized exactly in the symbolic phase (a block that outgrows its delayed-pivot capacity
+        is re-analysed as dense fronts inside the numeric phase), so there is no work array to grow
+        (``explicit...:174-177`` forwards to the leaves).  ``not_enough_memory`` is only reported when an allocation
+        itself fails (host ``bad_alloc`` / ``cudaMalloc``), which a growth factor cannot cure."""
         return None
