@@ -234,6 +234,7 @@ def run_leg(name, kkt, rhs, comm, dev, flush, reps=3, warmup=2, options=None, ex
         solver.get_inertia()
         return solver.do_back_solve(rhs)
 
+    be.set_option("profile", 0)     # per-kernel events only in the `value` region below
     for _ in range(warmup):
         e2e_step()
     sync_all()
@@ -258,6 +259,7 @@ def run_leg(name, kkt, rhs, comm, dev, flush, reps=3, warmup=2, options=None, ex
         be.solve_device(rhs_dev, rhsc_dev, x_dev, xc_dev, reduce=comm.allreduce_sum_)
         return code
 
+    be.set_option("profile", 1)
     for _ in range(warmup):
         dev_step()
     be.profile(reset=True)
@@ -656,6 +658,9 @@ def main():
     max_err = model.check_result(x)
 
     # ---- end-to-end through the plugin API (host buffers) ----------------------------------------
+    # (no instrumentation here: the per-kernel CUDA events of `pp_profile` -- two cudaEventRecord per launch -- are
+    #  what a user of the plugin never switches on; they are recorded in the `value` region, where the roofline needs them)
+    be.set_option("profile", 0)
     flush = torch.empty(20 * 1024 * 1024, dtype=torch.float64, device=dev)  # 160 MB > 126 MB of L2
 
     def e2e_step():
@@ -724,6 +729,7 @@ def main():
         return code, code2, loc, cpl
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # NVML init takes milliseconds: before the barrier
+    be.set_option("profile", 1)
     for _ in range(args.warmup):
         dev_step()
     be.profile(reset=True)
@@ -833,6 +839,7 @@ def main():
         "config": {"workload": workload_name(world), "blocks_per_gpu": BLOCKS_PER_GPU, "block_rows": model.block_dim,
                    "coupling": N_THETA, "l2": "L2 flushed by a 160 MB device write (> 126 MB of L2) before every step (inside the timed region)",
                    "value_excludes": "the residual check / iterative refinement that do_back_solve runs (e2e includes it)",
+                   "instrumentation": "per-kernel CUDA events (pp_profile, for the roofline) are recorded inside the value region only; e2e runs without them",
                    "parallelism": f"blocks round-robin over {world} GPU(s); Schur complement + coupling rhs all-reduced (NCCL)"},
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "wall_ms": e2e_wall_ms, "api": "B200SchurComplementLinearSolver.do_numeric_factorization + get_inertia + do_back_solve",
