@@ -123,12 +123,67 @@ def _worker(rank, world, port, case, out_dir):
             for i in local.local_blocks:
                 assert np.allclose(x.get_block(i), x_ref.get_block(i), rtol=1e-9, atol=1e-9)
             assert solver.get_inertia() == full.expected_inertia()
+        elif case == "device_regularization":
+            # the inertia-correction retry under the multi-rank control flow: base matrix + diagonal shifts, the values
+            # of the evaluation are re-used on every rank (no second gather, no second symbolic phase), and a whole
+            # interior-point solve takes the path of the single-process reference algorithm
+            from oracle.ipm import StochasticInterface, device_regularized, ip_solve, random_stochastic_qp
+            from oracle.schur_oracle import OraclePlugin, SchurOracle
+            args = (1, 4, 40, 14, 6, 4, 0.3)
+            scen, fs = random_stochastic_qp(*args)
+            itf = device_regularized(StochasticInterface)(scen, fs)
+            itf.set_barrier_parameter(0.1)
+            for s_ in itf.sc:
+                s_.nlp.x = np.full(s_.nlp.n, 0.3)
+            kkt, rhs = itf.evaluate_primal_dual_kkt_matrix(), itf.evaluate_primal_dual_kkt_rhs()
+            solver = B200SchurComplementLinearSolver(backend=FakeBackend(), comm=comm,
+                                                     regularization_classes=itf.regularization_classes())
+            assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful
+            first = solver.do_numeric_factorization(kkt, raise_on_error=False).status
+            assert first in (LinearSolverStatus.successful, LinearSolverStatus.singular)
+            reg = itf.regularize_hessian(itf.regularize_equality_gradient(kkt.copy(), -1e-2, False), 1e-2, False)
+            assert solver.do_numeric_factorization(reg).status == LinearSolverStatus.successful
+            x = solver.do_back_solve(rhs)
+            o = SchurOracle(compute_inertia=True, inertia_method="ldl")
+            full = reg.materialize()
+            o.symbolic(full)
+            assert o.numeric(full) == 0
+            x_ref = o.solve(rhs)
+            for i in list(solver.local_block_indices) + [4]:
+                assert np.allclose(np.asarray(x.get_block(i)).flatten(), np.asarray(x_ref.get_block(i)).flatten(),
+                                   rtol=1e-7, atol=1e-9)
+            assert solver.get_inertia() == o.inertia()
+            assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == 1
+
+            class Gathered:          # the restated loop keeps its iterates replicated: every rank needs every block
+                def __init__(self, s): self.s = s
+                def __getattr__(self, name): return getattr(self.s, name)
+                def do_back_solve(self, rhs):
+                    sol = self.s.do_back_solve(rhs)
+                    for part in comm.allgather_object({i: sol.get_block(i) for i in self.s.local_block_indices}):
+                        for i, blk in part.items():
+                            sol.set_block(i, blk)
+                    return sol
+
+            scen, fs = random_stochastic_qp(*args)
+            itf = device_regularized(StochasticInterface)(scen, fs)
+            solver = B200SchurComplementLinearSolver(backend=FakeBackend(), comm=comm,
+                                                     regularization_classes=itf.regularization_classes())
+            out = ip_solve(itf, Gathered(solver))
+            scen, fs = random_stochastic_qp(*args)
+            ref = ip_solve(StochasticInterface(scen, fs), OraclePlugin(inertia_method="ldl"))
+            assert out["status"] == ref["status"] == "optimal" and out["iterations"] == ref["iterations"]
+            assert [r[1:] for r in out["reg"]] == [r[1:] for r in ref["reg"]]          # same retries, same inertia
+            assert abs(out["objective"] - ref["objective"]) <= 1e-8 * max(1.0, abs(ref["objective"]))
+            assert len(out["reg"]) > out["iterations"]                                  # there were retries ...
+            assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == out["iterations"]   # ... for free
         open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["generator", "singular", "rank_local_failure", "pattern_change_one_rank", "cliques"])
+@pytest.mark.parametrize("case", ["generator", "singular", "rank_local_failure", "pattern_change_one_rank", "cliques",
+                                  "device_regularization"])
 def test_world_size_2(tmp_path, case):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
