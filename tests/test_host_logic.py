@@ -534,3 +534,19 @@ def test_copy_pool_wake_calls_interleave_with_jobs():
             if big:
                 other[big[-1]][-1] += 1.0
                 assert cp.all_equal(arrays, other) is False
+
+
+def test_fuzz_input_forms():
+    """A slice of ``tools/fuzz_host.py``: random block-bordered systems as COO / CSR / CSC leaves, nested block matrices
+    and vectors, absent border blocks, absent Q, duplicates, explicit zeros, garbage in the unread upper triangle; values
+    refreshed in place, as fresh objects and with a changed pattern between factorisations -- solution and inertia
+    against dense linear algebra, ``rhs`` untouched, structure of ``rhs`` preserved."""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_host.py")
+    spec = importlib.util.spec_from_file_location("fuzz_host", path)
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rng = np.random.default_rng(21)
+    for case in range(40):
+        fuzz.one(rng, case)
