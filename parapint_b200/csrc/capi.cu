@@ -2158,6 +2158,10 @@ int pp_cplan_create(int32_t m_c, int32_t n_cliques, const int64_t *ptr, const in
     std::vector<int64_t> cp(1, 0);
     std::vector<int32_t> cr;
     if (n_cliques > 0) {
+      if (ptr[0] != 0) return misuse("pp_cplan_create: clique_ptr must start at 0");
+      for (int k = 0; k < n_cliques; ++k)
+        if (ptr[k + 1] < ptr[k]) return misuse("pp_cplan_create: clique_ptr must not decrease");
+      if (ptr[n_cliques] > 0 && !rows) return misuse("pp_cplan_create: null clique rows");
       cp.assign(ptr, ptr + n_cliques + 1);
       cr.assign(rows, rows + ptr[n_cliques]);
     }

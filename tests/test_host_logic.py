@@ -550,3 +550,50 @@ def test_fuzz_input_forms():
     rng = np.random.default_rng(21)
     for case in range(40):
         fuzz.one(rng, case)
+
+
+def test_handle_free_entry_points_reject_malformed_descriptions():
+    """``pp_plan_create`` / ``pp_cplan_create`` (the analyses, callable without a GPU) answer PP_MISUSE (-1) to entries
+    outside the lower triangle, indices out of range, negative sizes and a decreasing clique pointer -- and survive
+    random garbage."""
+    lib = native.load()
+
+    def plan(n, m, rows, cols):
+        rows, cols = np.ascontiguousarray(rows, dtype=np.int32), np.ascontiguousarray(cols, dtype=np.int32)
+        out = ctypes.c_void_p()
+        code = lib.pp_plan_create(n, m, rows.size, native.np_ptr(rows), native.np_ptr(cols), -1, -1, 16, ctypes.byref(out))
+        if code == 0:
+            lib.pp_plan_destroy(out)
+        return code
+
+    def cplan(m_c, ptr, rows, qr, qc):
+        ptr, rows = np.ascontiguousarray(ptr, dtype=np.int64), np.ascontiguousarray(rows, dtype=np.int32)
+        qr, qc = np.ascontiguousarray(qr, dtype=np.int32), np.ascontiguousarray(qc, dtype=np.int32)
+        out = ctypes.c_void_p()
+        code = lib.pp_cplan_create(m_c, ptr.size - 1, native.np_ptr(ptr), native.np_ptr(rows), qr.size, native.np_ptr(qr),
+                                   native.np_ptr(qc), 8, 0.9, ctypes.byref(out))
+        if code == 0:
+            lib.pp_cplan_destroy(out)
+        return code
+
+    assert plan(50, 2, [0, 1, 3], [0, 5, 3]) == -1          # upper-triangle entry
+    assert plan(50, 2, [0, 60], [0, 5]) == -1               # row beyond n + m
+    assert plan(50, 2, [0, -1], [0, 0]) == -1
+    assert plan(50, 2, [51], [50]) == -1                    # border entry in a column that does not exist
+    assert plan(-5, 0, [], []) == -1
+    assert plan(0, 0, [], []) == 0 and plan(1, 0, [0], [0]) == 0 and plan(100, 0, [], []) == 0
+    assert cplan(10, [0, 3], [1, 2, 50], [0], [0]) == -1
+    assert cplan(10, [0, 3], [1, -2, 5], [0], [0]) == -1
+    assert cplan(10, [0, 3, 2], [1, 2, 5], [0], [0]) == -1  # decreasing pointer
+    assert cplan(10, [1, 3], [1, 2, 5], [0], [0]) == -1     # pointer not starting at 0
+    assert cplan(10, [0, 3], [1, 2, 5], [11], [0]) == -1
+    assert cplan(0, [0], [], [], []) == 0
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n, m, k = int(rng.integers(0, 120)), int(rng.integers(0, 5)), int(rng.integers(0, 400))
+        assert plan(n, m, rng.integers(-3, n + m + 3, size=k), rng.integers(-3, n + 3, size=k)) in (0, -1)
+        m_c, nc = int(rng.integers(0, 80)), int(rng.integers(0, 10))
+        ptr = np.concatenate(([0], np.cumsum(rng.integers(0, 8, size=nc))))
+        nq = int(rng.integers(0, 20))
+        assert cplan(m_c, ptr, rng.integers(-2, m_c + 2, size=int(ptr[-1])), rng.integers(-2, m_c + 2, size=nq),
+                     rng.integers(-2, m_c + 2, size=nq)) in (0, -1)
