@@ -686,10 +686,8 @@ inline PatternPlan build_plan_with(int n, int m, const std::vector<int> &rows, c
       continue;
     }
     // the entry belongs to the front of whichever endpoint is eliminated first
-    int first = c, other = r;
-    if (!cs || (rs && epos(r) < epos(c))) { first = r; other = c; }
+    const int first = (!cs || (rs && epos(r) < epos(c))) ? r : c;
     ent_of[sn_of[first]].push_back((int)k);
-    (void)other;
   }
   P.ent_ptr.assign(1, 0);
   P.tgt_src_ptr.assign(1, 0);
