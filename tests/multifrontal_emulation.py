@@ -47,7 +47,11 @@ def emulate(plan, values, n, m, block=False):
                     F[a, b] += M[i, j]
         F = np.tril(F) + np.tril(F, -1).T
         if block:
-            pivots.extend(np.linalg.eigvalsh(F[:nc, :nc]))
+            ev = np.linalg.eigvalsh(F[:nc, :nc])
+            if nc and np.abs(ev).min() <= 1e-10 * max(np.abs(ev).max(), 1e-300):
+                # e.g. a multiplier column that found no partner: the kernels delay such a pivot to the parent front
+                raise np.linalg.LinAlgError("pivot block of a front is singular: needs delayed pivots")
+            pivots.extend(ev)
             F[nc:, nc:] -= F[nc:, :nc] @ np.linalg.solve(F[:nc, :nc], F[:nc, nc:])
         for k in range(0 if block else nc):
             d = F[k, k]

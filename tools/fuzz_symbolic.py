@@ -111,6 +111,10 @@ def one(rng, case):
     # determinant identity: product of subtree pivots x det(root pivot block) = det(K)
     s1, l1 = np.linalg.slogdet(R[:nr, :nr])
     s2, l2 = np.linalg.slogdet(K.toarray())
+    # Haynsworth: inertia of K = signs of the eliminated pivots (eigenvalues of the pivot blocks) + inertia of the root block
+    er, ek = np.linalg.eigvalsh(R[:plan["nT"], :plan["nT"]]), np.linalg.eigvalsh(K.toarray())   # (the empty delayed-pivot slots hold 1)
+    assert (int((pivots > 0).sum() + (er > 0).sum()), int((pivots < 0).sum() + (er < 0).sum())) == \
+        (int((ek > 0).sum()), int((ek < 0).sum())), tag
     s1 *= np.prod(np.sign(pivots))
     assert s1 == s2 and abs(l1 + np.log(np.abs(pivots)).sum() - l2) <= 1e-6 * max(1.0, abs(l2)), tag
     return tag
