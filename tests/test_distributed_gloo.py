@@ -177,6 +177,17 @@ def _worker(rank, world, port, case, out_dir):
             assert abs(out["objective"] - ref["objective"]) <= 1e-8 * max(1.0, abs(ref["objective"]))
             assert len(out["reg"]) > out["iterations"]                                  # there were retries ...
             assert solver.symbolic_calls == 1 and solver.backend.value_uploads() == out["iterations"]   # ... for free
+        elif case == "fuzz":
+            # tools/fuzz_host.py over several ranks: every rank draws the same random systems (input forms, nested
+            # blocks, absent borders, pattern changes on re-factorisation) and checks its own blocks; with fewer blocks
+            # than ranks a rank owns nothing and still takes part in every collective
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("fuzz_host", os.path.join(ROOT, "tools", "fuzz_host.py"))
+            fuzz = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(fuzz)
+            rng = np.random.default_rng(77)
+            for c in range(30):
+                fuzz.one(rng, c, comm=comm)
         open(os.path.join(out_dir, f"ok_{case}_{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -194,3 +205,10 @@ def test_world_size_3_uneven(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(3, port, "generator", str(tmp_path)), nprocs=3, join=True)
     assert len(os.listdir(tmp_path)) == 3
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fuzzed_inputs_over_ranks(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, "fuzz", str(tmp_path)), nprocs=world, join=True)
+    assert len(os.listdir(tmp_path)) == world

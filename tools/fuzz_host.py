@@ -97,7 +97,9 @@ def build(rng, dense, sizes, forms, absent_border, q_absent):
     return kkt
 
 
-def one(rng, case):
+def one(rng, case, comm=None):
+    """``comm``: a Communicator of several ranks -- every rank draws the same system from the same stream and checks its own
+    blocks (round-robin ownership; a rank may own no block at all) and the replicated coupling block."""
     nblk = int(rng.integers(1, 6))
     sizes = [int(rng.integers(1, 14)) for _ in range(nblk)]
     m_c = int(rng.integers(1, 7))
@@ -138,8 +140,10 @@ def one(rng, case):
             f["dups"] = f["nested"] = False
     kkt = build(rng, dense, sizes, forms, absent_border, q_absent)
     tag = f"case {case}: sizes {sizes} absent border {sorted(absent_border)} q_absent {q_absent} forms {[(f['kind'], int(f['nested'])) for f in forms]}"
-    solver = B200SchurComplementLinearSolver(backend=FakeBackend())
+    solver = B200SchurComplementLinearSolver(backend=FakeBackend()) if comm is None else \
+        B200SchurComplementLinearSolver(backend=FakeBackend(), comm=comm)
     assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful, tag
+    mine = list(solver.local_block_indices) + [nblk]
     want_inertia = dense_inertia(dense, "eigvalsh")
     for rep in range(3):
         b = rng.standard_normal(N)
@@ -152,9 +156,12 @@ def one(rng, case):
         assert solver.get_inertia() == want_inertia, (tag, solver.get_inertia(), want_inertia)
         x = solver.do_back_solve(rhs)
         ref = np.linalg.solve(dense, b)
-        assert np.allclose(x.flatten(), ref, rtol=1e-8, atol=1e-9), (tag, rep)
+        for i in mine:
+            xi = x.get_block(i)
+            xi = xi.flatten() if hasattr(xi, "nblocks") else np.asarray(xi)
+            assert np.allclose(xi, ref[off[i]:off[i + 1]], rtol=1e-8, atol=1e-9), (tag, rep, i)
         assert np.array_equal(rhs.flatten(), rhs_before), tag                  # rhs untouched
-        for i in range(nblk + 1):                                               # structure of the rhs preserved
+        for i in mine:                                                          # structure of the rhs preserved
             tb, xb = rhs.get_block(i), x.get_block(i)
             assert hasattr(tb, "nblocks") == hasattr(xb, "nblocks"), (tag, i)
             if hasattr(tb, "nblocks"):
