@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from oracle.schur_oracle import dense_inertia  # noqa: E402
 from parapint_b200 import B200SchurComplementLinearSolver, LinearSolverStatus  # noqa: E402
 from parapint_b200.carriers import BlockMatrix, BlockVector  # noqa: E402
+from parapint_b200.regularization import RegularizedKKT  # noqa: E402
 from tests.fake_backend import FakeBackend  # noqa: E402
 
 
@@ -140,8 +141,17 @@ def one(rng, case, comm=None):
             f["dups"] = f["nested"] = False
     kkt = build(rng, dense, sizes, forms, absent_border, q_absent)
     tag = f"case {case}: sizes {sizes} absent border {sorted(absent_border)} q_absent {q_absent} forms {[(f['kind'], int(f['nested'])) for f in forms]}"
-    solver = B200SchurComplementLinearSolver(backend=FakeBackend()) if comm is None else \
-        B200SchurComplementLinearSolver(backend=FakeBackend(), comm=comm)
+    # one case in three goes through device-side inertia correction: the matrix travels as base + three diagonal shifts
+    # (class per row: 0 none, 1 / 2 inside the blocks, 3 on the coupling rows), and a retry with new shifts on the same
+    # evaluation must re-use the values that are there
+    classes = None
+    if rng.random() < 0.34:
+        classes = ({i: rng.integers(0, 3, size=sizes[i]).astype(np.int8) for i in range(nblk)},
+                   (rng.integers(0, 2, size=m_c) * 3 * (0 if q_absent else 1)).astype(np.int8))
+    kw = {} if comm is None else {"comm": comm}
+    if classes is not None:
+        kw["regularization_classes"] = classes
+    solver = B200SchurComplementLinearSolver(backend=FakeBackend(), **kw)
     assert solver.do_symbolic_factorization(kkt).status == LinearSolverStatus.successful, tag
     mine = list(solver.local_block_indices) + [nblk]
     want_inertia = dense_inertia(dense, "eigvalsh")
@@ -152,10 +162,25 @@ def one(rng, case, comm=None):
             seg = b[off[i]:off[i + 1]].copy()
             rhs.set_block(i, _nested_vector(rng, seg) if rng.random() < 0.4 else seg)
         rhs_before = rhs.flatten().copy()
-        assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful, tag
+        dense_now = dense
+        if classes is None:
+            assert solver.do_numeric_factorization(kkt).status == LinearSolverStatus.successful, tag
+        else:
+            cls_all = np.concatenate([classes[0][i] for i in range(nblk)] + [classes[1]]).astype(int)
+            for attempt in range(2):          # second attempt: other shifts, same evaluation (same token)
+                uploads = solver.backend.value_uploads()
+                shifts = (float(rng.uniform(0.0, 0.5)), float(rng.uniform(-0.5, 0.0)), float(rng.uniform(-0.5, 0.0)))
+                if attempt == 0 and rng.random() < 0.3:
+                    shifts = (0.0, 0.0, 0.0)
+                reg = RegularizedKKT(kkt, classes, shifts, token=("fuzz", case, rep))
+                assert solver.do_numeric_factorization(reg).status == LinearSolverStatus.successful, tag
+                dense_now = dense + np.diag(np.array((0.0,) + shifts)[cls_all])
+                assert solver.get_inertia() == dense_inertia(dense_now, "eigvalsh"), (tag, attempt)
+            assert solver.backend.value_uploads() == uploads, tag          # the retry uploaded nothing
+            want_inertia = dense_inertia(dense_now, "eigvalsh")
         assert solver.get_inertia() == want_inertia, (tag, solver.get_inertia(), want_inertia)
         x = solver.do_back_solve(rhs)
-        ref = np.linalg.solve(dense, b)
+        ref = np.linalg.solve(dense_now, b)
         for i in mine:
             xi = x.get_block(i)
             xi = xi.flatten() if hasattr(xi, "nblocks") else np.asarray(xi)
