@@ -163,7 +163,7 @@ static PyObject *same(PyObject *self, PyObject *args) {
 }
 
 static PyMethodDef methods[] = {
-    {"fill", fill, METH_VARARGS, "fill(seq, ptr_out, len_out, itemsize=0): addresses and byte lengths of the buffers in seq"},
+    {"fill", fill, METH_VARARGS, "fill(seq, ptr_out, len_out, fmt=\"\"): addresses and byte lengths of the buffers in seq (fmt: required struct format, e.g. \"d\")"},
     {"pairs", pairs, METH_VARARGS, "pairs(a, b, pa_out, pb_out, len_out): address tables of two sequences of equally typed, equally long buffers"},
     {"same", same, METH_VARARGS, "same(a, b): both sequences hold the same objects"},
     {NULL, NULL, 0, NULL}};
