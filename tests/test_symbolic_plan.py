@@ -22,8 +22,45 @@ def _lower_entries(K, A):
     return np.asarray(rows), np.asarray(cols), np.asarray(vals, dtype=float), len(nz)
 
 
-def _check_plan_invariants(plan, n):
+def _check_plan_invariants(plan, n, fmax=64, sbuf=96, tiny=16, medium=24, tiny_max_children=8):
+    """What the subtree kernels rely on: every column eliminated once, postorder, child -> parent maps inside the
+    parent's front, static fronts within ``fmax`` and fronts with their delayed-pivot slots within the shared-memory
+    buffer (``sbuf`` rows), and the per-level work lists (tiny / medium / big) listing every front exactly once, at its
+    own level, after all of its children."""
     ns = plan["ns"]
+    level = np.zeros(ns, dtype=int)
+    for s in range(ns):
+        p = plan["parent"][s]
+        if p >= 0:
+            level[p] = max(level[p], level[s] + 1)
+    listed = np.zeros(ns, dtype=int)
+    for name, ptr, idx in (("tiny", plan["tiny_ptr"], plan["tiny_idx"]), ("med", plan["med_ptr"], plan["med_idx"]),
+                           ("big", plan["big_ptr"], plan["big_idx"])):
+        if ns == 0:
+            continue
+        assert len(ptr) == plan["nlevels"] + 1 and ptr[-1] == len(idx)
+        for lv in range(plan["nlevels"]):
+            for s in idx[ptr[lv]:ptr[lv + 1]]:
+                listed[s] += 1
+                assert level[s] == lv, (name, s, level[s], lv)
+                size = (plan["col_ptr"][s + 1] - plan["col_ptr"][s]) + (plan["row_ptr"][s + 1] - plan["row_ptr"][s])
+                if name == "tiny":
+                    assert size <= tiny and plan["nchild"][s] < tiny_max_children
+                elif name == "med":
+                    assert size <= medium
+    assert np.all(listed == 1)
+    for s in range(ns):
+        nc = plan["col_ptr"][s + 1] - plan["col_ptr"][s]
+        ncb = plan["row_ptr"][s + 1] - plan["row_ptr"][s]
+        assert nc >= 1 and nc + ncb <= fmax, (s, nc, ncb, fmax)
+        assert 0 <= plan["dcap"][s] and nc + ncb + plan["dcap"][s] <= sbuf
+        assert 0 <= plan["dslot"][s] <= nc + plan["dcap"][s]
+        kids = plan["child_idx"][plan["child_ptr"][s]:plan["child_ptr"][s + 1]]
+        assert len(kids) == plan["nchild"][s] and all(plan["parent"][k] == s for k in kids)
+        assert plan["dcap"][s] <= sum(plan["dslot"][k] for k in kids)      # slots only for what the children can delay
+    if ns:
+        assert plan["max_front"] <= sbuf
+        assert sorted(plan["root_children"]) == [s for s in range(ns) if plan["parent"][s] < 0]
     seen = np.zeros(n, dtype=int)
     seen[plan["rootcols"]] += 1
     seen[plan["cols"]] += 1
