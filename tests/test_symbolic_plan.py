@@ -22,7 +22,7 @@ def _lower_entries(K, A):
     return np.asarray(rows), np.asarray(cols), np.asarray(vals, dtype=float), len(nz)
 
 
-def _check_plan_invariants(plan, n, fmax=64, sbuf=96, tiny=16, medium=24, tiny_max_children=8):
+def _check_plan_invariants(plan, n, fmax=64, sbuf=96, tiny=16, medium=24, tiny_max_children=8, nent=None):
     """What the subtree kernels rely on: every column eliminated once, postorder, child -> parent maps inside the
     parent's front, static fronts within ``fmax`` and fronts with their delayed-pivot slots within the shared-memory
     buffer (``sbuf`` rows), and the per-level work lists (tiny / medium / big) listing every front exactly once, at its
@@ -61,6 +61,21 @@ def _check_plan_invariants(plan, n, fmax=64, sbuf=96, tiny=16, medium=24, tiny_m
     if ns:
         assert plan["max_front"] <= sbuf
         assert sorted(plan["root_children"]) == [s for s in range(ns) if plan["parent"][s] < 0]
+        # entry targets: inside the lower triangle of their front, in one of the front's own columns
+        for s in range(ns):
+            nc = plan["col_ptr"][s + 1] - plan["col_ptr"][s]
+            ncb = plan["row_ptr"][s + 1] - plan["row_ptr"][s]
+            e0, e1 = plan["ent_ptr"][s], plan["ent_ptr"][s + 1]
+            r, c = plan["tgt_row"][e0:e1], plan["tgt_col"][e0:e1]
+            assert np.all((0 <= c) & (c < nc) & (c <= r) & (r < nc + ncb)), s
+        nroot = plan["nT"] + plan["DR"] + plan["m"]
+        rr, rc = plan["root_row"], plan["root_col"]
+        assert np.all((0 <= rc) & (rc <= rr) & (rr < nroot) & (rc < plan["nT"]))
+        assert np.all((rr < plan["nT"]) | (rr >= plan["nT"] + plan["DR"]))      # nothing lands in the delayed-pivot slots
+    if nent is not None and ns:
+        # every input entry is used exactly once: in a subtree front or in the root
+        used = np.bincount(np.concatenate([plan["tgt_src"], plan["root_src"]]), minlength=nent)
+        assert used.size == nent and np.all(used == 1)
     seen = np.zeros(n, dtype=int)
     seen[plan["rootcols"]] += 1
     seen[plan["cols"]] += 1

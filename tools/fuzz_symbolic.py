@@ -94,7 +94,7 @@ def one(rng, case):
     if plan["ns"] == 0:
         assert plan["nT"] == n, tag
         return tag
-    _check_plan_invariants(plan, n, fmax=64 if fmax < 0 else fmax)
+    _check_plan_invariants(plan, n, fmax=64 if fmax < 0 else fmax, nent=rows.size)
     try:
         root, pivots = emulate(plan, vals, n, m, block=(kind == "kkt"))
     except np.linalg.LinAlgError:
