@@ -17,8 +17,18 @@ Contents
                       usable in the build container (the reference does not
                       travel to the GPU box) and only used to pin the
                       restatement and to emit ``tests/golden`` fixtures.
+``ipm``               flat restatement of the interior-point loop and of the
+                      stochastic / dynamic interface layouts (farmer LP,
+                      dynamics QP, separable two-stage QPs).  UNPINNED against
+                      ``ip_solve`` itself (pyomo is absent): pinned only by the
+                      reference's end values (farmer acreage, the nine control
+                      values of the dynamics example) and the layout tests.
+``kkt_families``      synthetic IPM-shaped KKT systems at the shapes of BASELINE
+                      configs 3 and 4 (family P); nothing to pin.
+``parallel_baseline`` the reference algorithm partitioned over the host cores
+                      (process per "rank"): the CPU arm of ``bench.py``.
 
-Parity status: PINNED.  ``tests/golden/make_golden.py`` ran the unmodified
+Parity status of ``schur_oracle`` / ``kkt_generator``: PINNED.  ``tests/golden/make_golden.py`` ran the unmodified
 reference solver here and committed its outputs; ``tests/test_oracle.py`` checks
 this restatement against those fixtures and against the reference's own golden
 values (8x8 known-answer system, 3x3 leaf system, max_err 0.3163456780448639).
