@@ -199,17 +199,21 @@ def test_plan_fuzz_structured_patterns():
     assert walked >= 30
 
 
-def test_config2_plan_is_the_measured_one():
-    """The plan of a BASELINE config-2 block as the solver builds it (block + its 50 border rows) has the statistics of
-    the plan the bench records were measured with (``profiles/bench_r02_n1*.json: symbolic``): a change of the ordering
-    or of the amalgamation shows up here before it shows up as a different step time on the GPU."""
+@pytest.mark.parametrize("shape,want", [
+    ((2, 150, 6, 50), {"ns": 931, "nT": 50, "DR": 62, "nnz_l": 10737, "max_front": 86}),           # BASELINE config 2
+    ((2, 2000, 4, 2000), {"ns": 8624, "nT": 2082, "DR": 625, "nnz_l": 113961, "max_front": 84}),   # BASELINE config 5
+])
+def test_generator_plans_are_the_measured_ones(shape, want):
+    """The plan of a generator block as the solver builds it (block + its border rows) has the statistics of the plan
+    the bench records were measured with (``profiles/bench_r02_n1*.json`` / ``bench_r02_n8.json``: ``symbolic``): a
+    change of the ordering or of the amalgamation shows up here before it shows up as a different step time on the GPU."""
     from parapint_b200 import structure
-    m = EstimationModel(2, 150, 6, 50)
+    m = EstimationModel(*shape)
     st = structure.analyse(m.build_kkt())
     sel = st.dest_front == 0
     n, mloc = int(st.block_n[0]), int(st.border_ptr[1] - st.border_ptr[0])
     plan = native.build_plan(n, mloc, st.dest_row[sel], st.dest_col[sel])
     _check_plan_invariants(plan, n, nent=int(sel.sum()))
-    got = {k: plan[k] for k in ("ns", "nT", "DR", "nnz_l", "max_front")}
-    assert got == {"ns": 931, "nT": 50, "DR": 62, "nnz_l": 10737, "max_front": 86}, got
+    got = {k: plan[k] for k in want}
+    assert got == want, got
     assert plan["nlevels"] <= 8
