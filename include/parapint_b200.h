@@ -312,6 +312,10 @@ typedef struct pp_plan pp_plan;
 int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols,
                    int32_t fmax, int32_t dmax, int32_t min_sparse_n, pp_plan **out);
 int pp_plan_set_ordering(int32_t ordering); /* for pp_plan_create: 0 auto, 1 minimum degree, 2 nested dissection */
+/* Representative values of the entries of the NEXT pp_plan_create (the role `values_hint` plays in pp_symbolic: columns
+ * whose diagonal is numerically zero are ordered as 2x2 pivots with a partner); consumed by that call and ignored when
+ * `nent` is not its entry count. */
+int pp_plan_set_hint(const double *values, int64_t nent);
 int pp_plan_get(const pp_plan *plan, const char *name, const int32_t **data, int64_t *len);
 int pp_plan_scalar(const pp_plan *plan, const char *name, int64_t *value);
 int pp_plan_destroy(pp_plan *plan);

@@ -2062,8 +2062,21 @@ int pp_plan_set_ordering(int32_t ordering) {
   return PP_SUCCESSFUL;
 }
 
+// representative values of the entries of the NEXT pp_plan_create (what pp_symbolic's `values_hint` is to a handle):
+// consumed by that call, ignored if its length is not the entry count; NULL / 0 clears it
+static std::vector<double> g_plan_hint;
+int pp_plan_set_hint(const double *values, int64_t nent) {
+  if (nent < 0 || (nent > 0 && !values)) return misuse("pp_plan_set_hint: bad argument");
+  return guarded([&]() {
+    g_plan_hint.assign(values, values + nent);
+    return (int)PP_SUCCESSFUL;
+  });
+}
+
 int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, const int32_t *cols, int32_t fmax,
                    int32_t dmax, int32_t min_sparse_n, pp_plan **out) {
+  std::vector<double> hint;
+  hint.swap(g_plan_hint);   // consumed, whatever happens below
   if (!out || n < 0 || m < 0 || nent < 0 || (nent > 0 && (!rows || !cols))) return misuse("pp_plan_create: bad argument");
   *out = nullptr;
   return guarded([&]() {
@@ -2077,7 +2090,7 @@ int pp_plan_create(int32_t n, int32_t m, int64_t nent, const int32_t *rows, cons
     if (min_sparse_n >= 0) opt.min_sparse_n = min_sparse_n;
     opt.ordering = g_plan_ordering;
     auto *pl = new pp_plan();
-    pl->P = build_plan(n, m, r, c, src, opt, false);
+    pl->P = build_plan(n, m, r, c, src, opt, false, (nent > 0 && (int64_t)hint.size() == nent) ? &hint : nullptr);
     *out = pl;
     return (int)PP_SUCCESSFUL;
   });

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pp_plan_stats": (C.c_int, [_vp, C.c_int32, _i64p]),
     "pp_plan_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "pp_plan_set_ordering": (C.c_int, [C.c_int32]),
+    "pp_plan_set_hint": (C.c_int, [_vp, C.c_int64]),
     "pp_plan_get": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32p), _i64p]),
     "pp_plan_scalar": (C.c_int, [_vp, C.c_char_p, _i64p]),
     "pp_plan_destroy": (C.c_int, [_vp]),
@@ -234,13 +235,22 @@ class HostCopier:
         return True
 
 
-def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1, ordering=0):
-    """Run the host symbolic analysis of one block and return its tables as a dict of numpy arrays."""
+def build_plan(n, m, rows, cols, fmax=-1, dmax=-1, min_sparse_n=-1, ordering=0, values=None):
+    """Run the host symbolic analysis of one block and return its tables as a dict of numpy arrays.
+    ``values``: representative values of the entries (the values hint of ``pp_symbolic``), or None."""
     import numpy as np
     lib = load()
     lib.pp_plan_set_ordering(ordering)
     rows = np.ascontiguousarray(rows, dtype=np.int32)
     cols = np.ascontiguousarray(cols, dtype=np.int32)
+    if values is not None:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.size != rows.size:
+            raise ValueError("values must have one entry per (row, col) pair")
+        if lib.pp_plan_set_hint(np_ptr(values), values.size) != 0:
+            raise RuntimeError(last_error())
+    else:
+        lib.pp_plan_set_hint(None, 0)
     plan = _vp()
     if lib.pp_plan_create(n, m, rows.size, np_ptr(rows), np_ptr(cols), fmax, dmax, min_sparse_n, C.byref(plan)) != 0:
         raise RuntimeError(last_error())

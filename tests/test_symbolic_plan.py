@@ -217,3 +217,34 @@ def test_generator_plans_are_the_measured_ones(shape, want):
     got = {k: plan[k] for k in want}
     assert got == want, got
     assert plan["nlevels"] <= 8
+
+
+@pytest.mark.parametrize("family,want", [
+    ("config4", {"ns": 3679, "nT": 1972, "DR": 631, "nnz_l": 274009, "max_front": 96}),    # 20 200-row scenario, 200 first-stage columns
+    ("config3", {"ns": 920, "nT": 232, "DR": 312, "nnz_l": 157021, "max_front": 96}),      # first time block, 50 interface states
+])
+def test_ipm_shaped_plans_are_the_measured_ones(family, want):
+    """Family-P blocks at the shapes of BASELINE configs 4 and 3, analysed WITH the values hint as ``pp_symbolic`` does
+    (``pp_plan_set_hint``: multiplier columns, whose stored diagonal is an explicit zero, are ordered as 2x2 pivots with
+    a partner): the plans have the statistics recorded by the bench legs on the GPU (``profiles/bench_r02_n8.json``,
+    ``other_workloads.*.symbolic``) and satisfy the invariants the kernels rely on."""
+    from oracle.kkt_families import dynamic_ipm_system, stochastic_ipm_system
+    from parapint_b200 import structure
+    if family == "config4":
+        kkt, _ = stochastic_ipm_system(7, 128, 10000, 8000, 1000, 200, same_pattern=True, local_blocks=[0])
+        st = structure.analyse(kkt, 0, 128)
+    else:
+        kkt, _ = dynamic_ipm_system(9, 256, 5000, 4800, 100, 50, same_pattern=True, local_blocks=[0])
+        st = structure.analyse(kkt, 0, 256)
+    assert st.n_local == 1
+    hint = np.zeros(st.nvals)
+    assert structure.gather_values(kkt, st, hint)
+    sel = st.dest_front == 0
+    n, mloc = int(st.block_n[0]), int(st.border_ptr[1] - st.border_ptr[0])
+    plan = native.build_plan(n, mloc, st.dest_row[sel], st.dest_col[sel], values=hint[sel])
+    _check_plan_invariants(plan, n, nent=int(sel.sum()))
+    got = {k: plan[k] for k in want}
+    assert got == want, got
+    if family == "config4":    # the hint matters: without it the multiplier columns are not paired and the root grows
+        unhinted = native.build_plan(n, mloc, st.dest_row[sel], st.dest_col[sel])
+        assert unhinted["nT"] > plan["nT"] and unhinted["ns"] != plan["ns"]

@@ -60,7 +60,7 @@ def pattern(rng, kind, n, case=0):
             for c in rng.choice(pool, size=min(pool.size, int(rng.integers(0, 3))), replace=False):
                 if c != cols[r]:
                     J[r, c] = 0.3 * rng.standard_normal()
-        return sp.bmat([[H, J.T], [J, None]]).tocsr(), n
+        return sp.bmat([[H, J.T], [J, None]]).tocsr(), n      # (the caller may add explicit zero diagonals + a values hint)
     else:
         raise ValueError(kind)
     M = sp.csr_matrix(M)
@@ -89,7 +89,16 @@ def one(rng, case):
         rows, cols, vals = rows[p], cols[p], vals[p]
     ordering = int(rng.integers(0, 4))
     fmax = int(rng.choice([-1, 32, 64]))
-    plan = native.build_plan(n, m, rows, cols, fmax=fmax, min_sparse_n=int(rng.choice([16, 64])), ordering=ordering)
+    hint = None
+    if kind == "kkt" and rng.random() < 0.5:
+        # the form an interior-point interface hands over: multiplier columns WITH a stored diagonal that is an explicit
+        # zero -- only the values hint tells the analysis that they are weak (pp_plan_set_hint / pp_symbolic's hint)
+        zero_diag = np.flatnonzero(K.diagonal() == 0.0)
+        rows, cols, vals = np.concatenate([rows, zero_diag]), np.concatenate([cols, zero_diag]), np.concatenate([vals, np.zeros(zero_diag.size)])
+        hint = vals
+    elif rng.random() < 0.2:
+        hint = vals            # a hint never changes what a plan computes, only the order
+    plan = native.build_plan(n, m, rows, cols, fmax=fmax, min_sparse_n=int(rng.choice([16, 64])), ordering=ordering, values=hint)
     tag = f"case {case} kind {kind} n {n} m {m} ordering {ordering} fmax {fmax} ns {plan['ns']} nT {plan['nT']}"
     if plan["ns"] == 0:
         assert plan["nT"] == n, tag
